@@ -1,0 +1,200 @@
+/*
+ * kdfusion_b200 -- C ABI of the B200 (sm_100a) kernels behind the camera+LiDAR
+ * distillation training hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * reference (KELVIN-ASU/Lightweight-Multi-Modal-Scene-Understanding-via-
+ * Knowledge-Distillation) is pure Python/PyTorch and has no FFI of its own, so
+ * each entry point names the reference Python lines whose arithmetic it replaces;
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises, nothing allocates (callers pass workspaces), so
+ *     every call can be captured into a CUDA graph;
+ *   - tensors are dense and row-major in the order written, e.g. [B,N,4];
+ *   - return value 0 = success, otherwise an error code; kdf_last_error()
+ *     gives the message of the last failure on the calling thread;
+ *   - dtype codes: KDF_F32 / KDF_BF16 (features, logits, gradients);
+ *     points, index math, statistics and loss scalars are always fp32.
+ */
+#ifndef KDFUSION_B200_H
+#define KDFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDF_ABI_VERSION 1
+
+enum { KDF_F32 = 0, KDF_BF16 = 1 };
+enum { KDF_REDUCE_MAX = 0, KDF_REDUCE_MEAN = 1 };
+enum { KDF_OK = 0, KDF_ERR_ARG = 1, KDF_ERR_CUDA = 2, KDF_ERR_UNSUPPORTED = 3 };
+
+/* ---------------------------------------------------------------- library */
+int         kdf_abi_version(void);
+const char *kdf_last_error(void);
+/* number of SMs / compute capability of the current device (host outputs) */
+int         kdf_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------- (1) LiDAR -> BEV projection
+ * Replaces SpatialLiDAREncoder.points_to_bev_coords + the index/scatter half
+ * of forward_vectorized (reference src/models/lidar_encoder.py:42-55, 69-99).
+ *
+ *   xn = (x - x0) / xspan ; yn = (y - y0) / yspan         one IEEE fp32 rounding per op
+ *   valid = 0 <= xn <= 1 && 0 <= yn <= 1                   closed range, NaN -> invalid
+ *   col = trunc(xn * (W-1)), row = trunc(yn * (H-1))       clamped to the grid
+ *   cell = row*W + col   (-1 when invalid)
+ *
+ * x0/xspan/y0/yspan are the fp32 values of x_range[0], x_range[1]-x_range[0], ...
+ * formed on the host exactly as the reference's buffers do (int64 difference
+ * first when the range is integral).
+ */
+
+/* Index / occupancy only (bit-exact outputs; also the rasterisation primitive).
+ *   points    f32 [B,N,point_stride]  (x,y first; point_stride >= 2 floats, 4 for (x,y,z,i))
+ *   cell      i32 [B,N]   out
+ *   rank      i32 [B,N]   out, may be NULL: arrival rank of the point inside its cell
+ *   count     i32 [B,H*W] out (zeroed by the call): points per cell
+ */
+int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
+                  float x0, float xspan, float y0, float yspan, int H, int W,
+                  int32_t *cell, int32_t *rank, int32_t *count, void *stream);
+
+/* bytes of scratch kdf_bev_project_fwd needs */
+size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W);
+
+/* Full projection: per-cell channel-wise max (scatter_reduce_ amax,
+ * include_self=False into zeros, lidar_encoder.py:85-96) or mean.
+ *   feats     dtype [B,N,C] point-major            (C % 4 == 0)
+ *   grid      dtype [B,H,W,C] out  -- the NHWC memory of the [B,C,H,W] view the
+ *                                     reference returns (lidar_encoder.py:99)
+ *   count     i32 [B,H*W] out
+ *   cell      i32 [B,N]   out
+ *   ties      i32 [B,H*W,C] out, max only, may be NULL: sources equal to the max
+ *   order     i32 [B,N]   out, may be NULL (then taken from workspace): point ids
+ *                          grouped by cell (counting sort), offsets in `offsets`
+ *   offsets   i32 [B,H*W+1] out, may be NULL (then taken from workspace)
+ */
+int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats, int dtype,
+                        int B, int64_t N, int C,
+                        float x0, float xspan, float y0, float yspan, int H, int W, int reduce,
+                        void *grid, int32_t *count, int32_t *cell, int32_t *ties,
+                        int32_t *order, int32_t *offsets,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* Gradient of the projection w.r.t. feats.  max: the cell gradient is split
+ * evenly among the sources equal to the max (ATen ScatterReduceBackward), with
+ * ATen's quirk that a max of exactly 0.0 counts the zero-initialised output as
+ * one more tie.  mean: grad / count.  Points outside the grid get 0.
+ *   grad_grid dtype [B,H*W,C]; grid/ties from the forward (max only);
+ *   grad_feats dtype [B,N,C] out (every row written).
+ */
+int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *grid,
+                        const int32_t *ties, const int32_t *count, const int32_t *cell,
+                        int dtype, int B, int64_t N, int C, int H, int W, int reduce,
+                        void *grad_feats, void *stream);
+
+/* ---------------------------------------------------------------- (2) camera-LiDAR fusion
+ * Inputs are the PRE-BatchNorm outputs of the two 1x1 projection convolutions
+ * in pixel-major (NHWC) layout; BatchNorm is applied as y = x*scale + shift with
+ * per-channel fp32 scale/shift (batch statistics in training, running statistics
+ * in eval), followed by ReLU -- i.e. the tail of the reference's Conv1x1 block
+ * (src/models/fusion_module.py:8-17) fused into the fusion itself.
+ *
+ * weighted  (WeightedFusion, fusion_module.py:107-136, executed inline at :248-253):
+ *      cp = relu(cam*sc+sh), lp = relu(lid*sc+sh)
+ *      a  = W2 . relu(W1 . [cp;lp] + b1) + b2 ;  w = softmax(a)   (2 logits per pixel)
+ *      out = cp*w0 + lp*w1
+ *   M pixels, C channels per branch (C % 32 == 0, C <= 256), hidden width = C.
+ *   w1 f32 [C,2C], b1 f32 [C], w2 f32 [2,C], b2 f32 [2];  attn f32 [M,2] out.
+ */
+int kdf_fusion_weighted_fwd(const void *cam_pre, const void *lid_pre, int dtype, int64_t M, int C,
+                            const float *cam_scale, const float *cam_shift,
+                            const float *lid_scale, const float *lid_shift,
+                            const float *w1, const float *b1, const float *w2, const float *b2,
+                            void *out, float *attn, void *stream);
+
+/* Backward of the above.  Outputs gradients w.r.t. the pre-BN inputs treating
+ * scale/shift as independent inputs (their gradients are returned so autograd
+ * can chain through the batch statistics):
+ *   grad_cam_pre/grad_lid_pre dtype [M,C];
+ *   grad_affine f32 [4,C]  = d/d(cam_scale, cam_shift, lid_scale, lid_shift)   (zeroed by the call)
+ *   grad_w1 f32 [C,2C], grad_b1 f32 [C], grad_w2 f32 [2,C], grad_b2 f32 [2]    (zeroed by the call)
+ */
+int kdf_fusion_weighted_bwd(const void *grad_out, const void *cam_pre, const void *lid_pre,
+                            int dtype, int64_t M, int C,
+                            const float *cam_scale, const float *cam_shift,
+                            const float *lid_scale, const float *lid_shift,
+                            const float *w1, const float *b1, const float *w2, const float *b2,
+                            const float *attn,
+                            void *grad_cam_pre, void *grad_lid_pre, float *grad_affine,
+                            float *grad_w1, float *grad_b1, float *grad_w2, float *grad_b2,
+                            void *stream);
+
+/* minimal (MinimalFusion, fusion_module.py:94-104; inline at :248-255):
+ *      out = relu(cam*sc+sh) + relu(lid*sc+sh)
+ * concat  (first half of ConcatenationFusion, fusion_module.py:89-91; inline :243-245):
+ *      out[M,2C] = [relu(cam*sc+sh) ; relu(lid*sc+sh)]          (mode = 1)
+ */
+int kdf_fusion_affine_relu_pair_fwd(const void *cam_pre, const void *lid_pre, int dtype, int64_t M, int C,
+                                    const float *cam_scale, const float *cam_shift,
+                                    const float *lid_scale, const float *lid_shift,
+                                    int mode /*0 = add, 1 = concat*/, void *out, void *stream);
+int kdf_fusion_affine_relu_pair_bwd(const void *grad_out, const void *cam_pre, const void *lid_pre,
+                                    int dtype, int64_t M, int C,
+                                    const float *cam_scale, const float *cam_shift,
+                                    const float *lid_scale, const float *lid_shift, int mode,
+                                    void *grad_cam_pre, void *grad_lid_pre, float *grad_affine /*[4,C], zeroed*/,
+                                    void *stream);
+
+/* ---------------------------------------------------------------- (3) distillation loss
+ * One pass over logits and mimic taps producing the loss terms AND their
+ * gradients:
+ *   ce  = sum_i w[y_i] * (-log softmax(z_s)_i[y_i]) / sum_i w[y_i]      over y_i != ignore
+ *         (nn.CrossEntropyLoss(ignore_index=-1, weight=w), reference src/training/trainer.py:55,88)
+ *   kl  = T^2 * sum_pixels KL(softmax(z_t/T) || softmax(z_s/T)) / (B*HW)   (not in the reference)
+ *   mse = sum_taps mean((s - t)^2)                                          (not in the reference)
+ *   loss = (1-alpha)*ce + alpha*kl + beta*mse
+ *
+ *   s_logits/t_logits dtype_logits [B,K,HW] (NCHW), K <= 8; t_logits NULL -> no KL term
+ *   labels i64 [B,HW]; class_w f32 [K] or NULL
+ *   taps: up to 2 (s_featX, t_featX dtype_feat, numelX elements; NULL/0 = unused)
+ *   d_logits [B,K,HW] out; d_featX out (same dtype as feats)
+ *   scalars f32 [8] out: loss, ce, kl, mse, wsum, mse_tap0, mse_tap1, n_valid
+ *   grad_scale multiplies every gradient (upstream dL/dloss, 1/world_size, ...)
+ *   workspace: kdf_kd_loss_workspace_bytes() bytes
+ */
+size_t kdf_kd_loss_workspace_bytes(void);
+int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_t *labels,
+                        const float *class_w, int B, int K, int64_t HW, int dtype_logits,
+                        float T, float alpha, float beta, int64_t ignore_index,
+                        const void *s_feat0, const void *t_feat0, void *d_feat0, int64_t numel0,
+                        const void *s_feat1, const void *t_feat1, void *d_feat1, int64_t numel1,
+                        int dtype_feat, float grad_scale,
+                        void *d_logits, float *scalars, void *workspace, void *stream);
+
+/* ---------------------------------------------------------------- training-step helpers
+ * Confusion matrix of SegmentationMetrics.update (trainer.py:18-26):
+ *   conf[t,p] += 1 over pixels with label t != ignore, 0 <= t < K, p = argmax_k logits.
+ *   conf i64 [K,K] is ACCUMULATED into (caller zeroes it at reset()).
+ */
+int kdf_confusion_matrix(const void *logits, const int64_t *labels, int B, int K, int64_t HW,
+                         int dtype_logits, int64_t ignore_index, int64_t *conf, void *stream);
+
+/* AdamW over one flat parameter buffer (torch.optim.AdamW single-tensor maths,
+ * trainer.py:56,90): decoupled weight decay, bias-corrected moments.
+ *   hyper f32 [2] on device = {lr, step}  (step already incremented, >= 1)
+ */
+int kdf_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                   const float *hyper, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDFUSION_B200_H */

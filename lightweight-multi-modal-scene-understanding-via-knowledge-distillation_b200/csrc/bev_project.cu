@@ -1,0 +1,400 @@
+// LiDAR point cloud -> BEV grid projection for sm_100a.
+//
+// Replaces the index math and scatter of SpatialLiDAREncoder.forward_vectorized
+// (reference src/models/lidar_encoder.py:42-55, 69-99) without its temporaries:
+// the reference materialises six [B,N] fp32 tensors, an int64 [B,N,2] index, a
+// boolean-mask gather of the [Nv,C] features and an int64 [Nv,C] expanded index;
+// here a sweep is
+//
+//   index   : one coalesced float4 read per point -> cell id (bit-exact index
+//             math) + warp-aggregated atomic occupancy count / arrival rank
+//   scan    : per-frame exclusive scan of the occupancy -> segment offsets
+//   fill    : counting-sort scatter of point ids into cell order
+//   reduce  : one warp per cell streams that cell's feature rows (each row is a
+//             contiguous, fully coalesced C*sizeof(T) read) and keeps the running
+//             max (+ tie count) or sum in registers; every grid row is written once.
+//
+// Features are therefore read exactly once and never touched by atomics; the only
+// atomics are one 4-byte add per (warp, distinct cell) in `index`.  Outputs are
+// bitwise deterministic for max (order-independent).  HBM-bound: 16 B/point +
+// C*s bytes per valid point + one grid write (kernel table).
+#include <float.h>
+
+#include "kdf_common.cuh"
+
+namespace kdf {
+
+struct BevGeom {
+    float x0, xspan, y0, yspan, sx, sy;   // sx = W-1, sy = H-1 as fp32 (grid_tensor)
+    int H, W;
+};
+
+// lidar_encoder.py:47-53,69-71 -- every operation rounded to fp32 separately
+// (no FMA contraction, IEEE division), exactly like the eager ATen ops.
+__device__ __forceinline__ int bev_cell_of(float x, float y, const BevGeom &g) {
+    const float xn = __fdiv_rn(__fsub_rn(x, g.x0), g.xspan);
+    const float yn = __fdiv_rn(__fsub_rn(y, g.y0), g.yspan);
+    const bool valid = (xn >= 0.f) && (xn <= 1.f) && (yn >= 0.f) && (yn <= 1.f);   // NaN -> false
+    if (!valid) return -1;
+    int col = (int)__fmul_rn(xn, g.sx);      // .long(): truncation toward zero
+    int row = (int)__fmul_rn(yn, g.sy);
+    col = min(max(col, 0), g.W - 1);
+    row = min(max(row, 0), g.H - 1);
+    return row * g.W + col;
+}
+
+// ----------------------------------------------------------------------------- index
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+bev_index_kernel(const float *__restrict__ points, int64_t total, int64_t N, int stride, BevGeom g,
+                 int32_t *__restrict__ cell_out, int32_t *__restrict__ rank_out, int32_t *__restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int HW = g.H * g.W;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count: every lane takes part in the match/shuffle below
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    for (int64_t base = first; base < total; base += nthreads) {
+        const int64_t i = base + lane;
+        int cell = -1;
+        int64_t key = -1;
+        if (i < total) {
+            float x, y;
+            if (VEC4) {
+                const float4 p = ldg_stream_f4(reinterpret_cast<const float4 *>(points) + i);
+                x = p.x; y = p.y;
+            } else {
+                x = __ldg(points + i * stride);
+                y = __ldg(points + i * stride + 1);
+            }
+            cell = bev_cell_of(x, y, g);
+            cell_out[i] = cell;
+            if (cell >= 0) key = (i / N) * HW + cell;
+        }
+        // warp-aggregated atomic: one add per distinct (frame, cell) in the warp
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        int r = 0;
+        if (key >= 0 && lane == leader) r = atomicAdd(count + key, __popc(peers));
+        r = __shfl_sync(0xffffffffu, r, leader);
+        if (key >= 0 && rank_out) rank_out[i] = r + __popc(peers & ((1u << lane) - 1u));
+    }
+}
+
+// ----------------------------------------------------------------------------- scan
+// One CTA per frame: offsets[b, 0..HW] = exclusive prefix of count[b, :].
+__global__ void __launch_bounds__(1024)
+bev_scan_kernel(const int32_t *__restrict__ count, int32_t *__restrict__ offsets, int HW) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int32_t *cnt = count + (int64_t)b * HW;
+    int32_t *off = offsets + (int64_t)b * (HW + 1);
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < HW; c0 += 1024) {
+        const int c = c0 + t;
+        const int v = (c < HW) ? cnt[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_tot[lane] = wi - w;           // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + warp_tot[wid] + incl - v;
+        if (c < HW) off[c] = excl;
+        __syncthreads();
+        if (t == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (t == 0) off[HW] = carry_s;
+}
+
+// ----------------------------------------------------------------------------- fill
+__global__ void __launch_bounds__(256)
+bev_fill_kernel(const int32_t *__restrict__ cell, const int32_t *__restrict__ rank,
+                const int32_t *__restrict__ offsets, int32_t *__restrict__ order,
+                int64_t total, int64_t N, int HW) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+        const int c = cell[i];
+        if (c < 0) continue;
+        const int64_t b = i / N;
+        const int pos = offsets[b * (HW + 1) + c] + rank[i];
+        order[b * N + pos] = (int32_t)(i - b * N);
+    }
+}
+
+// ----------------------------------------------------------------------------- reduce
+// One warp per (frame, cell); lane l owns channels [c0 + 4l, c0 + 4l + 4).
+template <typename T, int REDUCE>
+__global__ void __launch_bounds__(256)
+bev_reduce_kernel(const T *__restrict__ feats, const int32_t *__restrict__ order,
+                  const int32_t *__restrict__ offsets, T *__restrict__ grid, int32_t *__restrict__ ties,
+                  int64_t n_cells, int64_t N, int C, int HW) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
+        const int64_t b = cid / HW;
+        const int c = (int)(cid - b * HW);
+        const int beg = offsets[b * (HW + 1) + c];
+        const int n = offsets[b * (HW + 1) + c + 1] - beg;
+        const int32_t *ord = order + b * N + beg;
+        const T *fb = feats + b * N * C;
+        for (int c0 = 0; c0 < C; c0 += 128) {
+            const int ch = c0 + lane * 4;
+            const bool act = ch < C;
+            float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // running max, or sum for mean
+            int k[4] = {0, 0, 0, 0};
+            if (REDUCE == KDF_REDUCE_MEAN) m[0] = m[1] = m[2] = m[3] = 0.f;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int mine = (j0 + lane < n) ? ord[j0 + lane] : 0;
+                const int lim = min(32, n - j0);
+                for (int jj = 0; jj < lim; jj += 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int p = __shfl_sync(0xffffffffu, mine, (jj + u) & 31);
+                        if (jj + u < lim && act) v[u] = Vec4<T>::load_stream(fb + (int64_t)p * C + ch);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (jj + u < lim && act) {
+                            const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (REDUCE == KDF_REDUCE_MAX) {
+                                    if (f[q] > m[q]) { m[q] = f[q]; k[q] = 1; }
+                                    else if (f[q] == m[q]) { k[q]++; }
+                                } else {
+                                    m[q] += f[q];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (act) {
+                float4 o;
+                if (n == 0) {
+                    o = make_float4(0.f, 0.f, 0.f, 0.f);       // include_self=False into zeros
+                } else if (REDUCE == KDF_REDUCE_MEAN) {
+                    const float d = (float)n;
+                    o = make_float4(m[0] / d, m[1] / d, m[2] / d, m[3] / d);
+                } else {
+                    o = make_float4(m[0], m[1], m[2], m[3]);
+                }
+                Vec4<T>::store(grid + cid * C + ch, o);
+                if (REDUCE == KDF_REDUCE_MAX && ties)
+                    *reinterpret_cast<int4 *>(ties + cid * C + ch) = make_int4(k[0], k[1], k[2], k[3]);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- backward
+// One warp per point row; rows of the same cell hit grid/ties/grad_grid in L2.
+template <typename T, int REDUCE>
+__global__ void __launch_bounds__(256)
+bev_bwd_kernel(const T *__restrict__ grad_grid, const T *__restrict__ feats, const T *__restrict__ grid,
+               const int32_t *__restrict__ ties, const int32_t *__restrict__ count,
+               const int32_t *__restrict__ cell, T *__restrict__ grad_feats,
+               int64_t total, int64_t N, int C, int HW) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;
+    for (int64_t i0 = warp0 * U; i0 < total; i0 += nwarps * U) {
+        int cl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) cl[u] = (i0 + u < total) ? __ldg(cell + i0 + u) : -2;
+        for (int c0 = 0; c0 < C; c0 += 128) {
+            const int ch = c0 + lane * 4;
+            if (ch >= C) continue;
+            float4 f[U], g[U], m[U];
+            int4 t[U];
+            int cnt[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (cl[u] >= 0) {
+                    const int64_t b = (i0 + u) / N;
+                    const int64_t cid = b * HW + cl[u];
+                    g[u] = Vec4<T>::load(grad_grid + cid * C + ch);
+                    if (REDUCE == KDF_REDUCE_MAX) {
+                        f[u] = Vec4<T>::load_stream(feats + (i0 + u) * C + ch);
+                        m[u] = Vec4<T>::load(grid + cid * C + ch);
+                        t[u] = *reinterpret_cast<const int4 *>(ties + cid * C + ch);
+                    } else {
+                        cnt[u] = __ldg(count + cid);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (cl[u] == -2) continue;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cl[u] >= 0) {
+                    if (REDUCE == KDF_REDUCE_MAX) {
+                        // ATen: N_to_distribute = (self == result) + #(src == result); self is 0
+                        o.x = (f[u].x == m[u].x) ? g[u].x / (float)(t[u].x + (m[u].x == 0.f)) : 0.f;
+                        o.y = (f[u].y == m[u].y) ? g[u].y / (float)(t[u].y + (m[u].y == 0.f)) : 0.f;
+                        o.z = (f[u].z == m[u].z) ? g[u].z / (float)(t[u].z + (m[u].z == 0.f)) : 0.f;
+                        o.w = (f[u].w == m[u].w) ? g[u].w / (float)(t[u].w + (m[u].w == 0.f)) : 0.f;
+                    } else {
+                        const float d = (float)cnt[u];
+                        o = make_float4(g[u].x / d, g[u].y / d, g[u].z / d, g[u].w / d);
+                    }
+                }
+                Vec4<T>::store(grad_feats + (i0 + u) * C + ch, o);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+static int check_geom(int B, int64_t N, int H, int W, float xspan, float yspan) {
+    KDF_CHECK_ARG(B >= 0 && N >= 0, "bev: negative B or N");
+    KDF_CHECK_ARG(H > 0 && W > 0 && (int64_t)H * W < (1 << 30), "bev: bad grid %dx%d", H, W);
+    KDF_CHECK_ARG(N < (int64_t)INT32_MAX, "bev: N must fit int32");
+    (void)xspan; (void)yspan;
+    return KDF_OK;
+}
+
+static int grid_for(int64_t work_items, int per_block, int max_waves = 16) {
+    int64_t blocks = (work_items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sm_count() * 8 * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+static int launch_index(const float *points, int B, int64_t N, int stride, const BevGeom &g,
+                        int32_t *cell, int32_t *rank, int32_t *count, cudaStream_t st) {
+    const int64_t total = (int64_t)B * N;
+    KDF_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)B * g.H * g.W, st));
+    if (total == 0) return KDF_OK;
+    const bool vec4 = (stride == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    const int blocks = grid_for(total, 256, 4);
+    if (vec4) bev_index_kernel<true><<<blocks, 256, 0, st>>>(points, total, N, stride, g, cell, rank, count);
+    else      bev_index_kernel<false><<<blocks, 256, 0, st>>>(points, total, N, stride, g, cell, rank, count);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+}  // namespace kdf
+
+using namespace kdf;
+
+extern "C" {
+
+int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
+                  float x0, float xspan, float y0, float yspan, int H, int W,
+                  int32_t *cell, int32_t *rank, int32_t *count, void *stream) {
+    if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
+    KDF_CHECK_ARG(point_stride >= 2, "bev: point_stride must be >= 2");
+    KDF_CHECK_ARG(points && cell && count, "bev: null pointer");
+    BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
+    return launch_index(points, B, N, point_stride, g, cell, rank, count, as_stream(stream));
+}
+
+size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W) {
+    const size_t bn = align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256);
+    const size_t off = align_up(sizeof(int32_t) * (size_t)B * ((size_t)H * W + 1), 256);
+    return 2 * bn + off + 256;
+}
+
+int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats, int dtype,
+                        int B, int64_t N, int C,
+                        float x0, float xspan, float y0, float yspan, int H, int W, int reduce,
+                        void *grid, int32_t *count, int32_t *cell, int32_t *ties,
+                        int32_t *order, int32_t *offsets,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
+    KDF_CHECK_ARG(point_stride >= 2, "bev: point_stride must be >= 2");
+    KDF_CHECK_ARG(C > 0 && C % 4 == 0, "bev: C=%d must be a positive multiple of 4", C);
+    KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "bev: bad dtype %d", dtype);
+    KDF_CHECK_ARG(reduce == KDF_REDUCE_MAX || reduce == KDF_REDUCE_MEAN, "bev: bad reduce %d", reduce);
+    KDF_CHECK_ARG(points && feats && grid && count && cell && workspace, "bev: null pointer");
+    KDF_CHECK_ARG(workspace_bytes >= kdf_bev_workspace_bytes(B, N, H, W), "bev: workspace too small");
+    KDF_CHECK_ARG((reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0,
+                  "bev: feats/grid must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int HW = H * W;
+    const int64_t total = (int64_t)B * N;
+    char *ws = reinterpret_cast<char *>(workspace);
+    const size_t bn = align_up(sizeof(int32_t) * (size_t)total, 256);
+    int32_t *rank = reinterpret_cast<int32_t *>(ws);
+    if (!order) order = reinterpret_cast<int32_t *>(ws + bn);
+    if (!offsets) offsets = reinterpret_cast<int32_t *>(ws + 2 * bn);
+    BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
+    if (B == 0) return KDF_OK;
+
+    if (int e = launch_index(points, B, N, point_stride, g, cell, rank, count, st)) return e;
+    bev_scan_kernel<<<B, 1024, 0, st>>>(count, offsets, HW);
+    KDF_LAUNCH_CHECK();
+    if (total > 0) {
+        bev_fill_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(cell, rank, offsets, order, total, N, HW);
+        KDF_LAUNCH_CHECK();
+    }
+    const int64_t n_cells = (int64_t)B * HW;
+    const int blocks = grid_for(n_cells * 32, 256, 64);
+#define KDF_REDUCE_LAUNCH(T, R)                                                                    \
+    bev_reduce_kernel<T, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
+                                                   reinterpret_cast<T *>(grid), ties, n_cells, N, C, HW)
+    if (dtype == KDF_F32) {
+        if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MAX);
+        else                          KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MEAN);
+    } else {
+        if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MAX);
+        else                          KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MEAN);
+    }
+#undef KDF_REDUCE_LAUNCH
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *grid,
+                        const int32_t *ties, const int32_t *count, const int32_t *cell,
+                        int dtype, int B, int64_t N, int C, int H, int W, int reduce,
+                        void *grad_feats, void *stream) {
+    KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_bwd: bad sizes");
+    KDF_CHECK_ARG(C > 0 && C % 4 == 0, "bev_bwd: C=%d must be a positive multiple of 4", C);
+    KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "bev_bwd: bad dtype %d", dtype);
+    KDF_CHECK_ARG(grad_grid && cell && grad_feats, "bev_bwd: null pointer");
+    if (reduce == KDF_REDUCE_MAX) KDF_CHECK_ARG(feats && grid && ties, "bev_bwd(max): feats/grid/ties required");
+    else if (reduce == KDF_REDUCE_MEAN) KDF_CHECK_ARG(count, "bev_bwd(mean): count required");
+    else KDF_CHECK_ARG(false, "bev_bwd: bad reduce %d", reduce);
+    const int64_t total = (int64_t)B * N;
+    if (total == 0) return KDF_OK;
+    cudaStream_t st = as_stream(stream);
+    const int blocks = grid_for((total + 3) / 4 * 32, 256, 64);
+#define KDF_BWD_LAUNCH(T, R)                                                                         \
+    bev_bwd_kernel<T, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(grad_grid),             \
+        reinterpret_cast<const T *>(feats), reinterpret_cast<const T *>(grid), ties, count, cell,     \
+        reinterpret_cast<T *>(grad_feats), total, N, C, H * W)
+    if (dtype == KDF_F32) {
+        if (reduce == KDF_REDUCE_MAX) KDF_BWD_LAUNCH(float, KDF_REDUCE_MAX);
+        else                          KDF_BWD_LAUNCH(float, KDF_REDUCE_MEAN);
+    } else {
+        if (reduce == KDF_REDUCE_MAX) KDF_BWD_LAUNCH(__nv_bfloat16, KDF_REDUCE_MAX);
+        else                          KDF_BWD_LAUNCH(__nv_bfloat16, KDF_REDUCE_MEAN);
+    }
+#undef KDF_BWD_LAUNCH
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+}  // extern "C"

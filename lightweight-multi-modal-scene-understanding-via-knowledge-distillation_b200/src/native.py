@@ -1,0 +1,95 @@
+"""ctypes binding of libkdfusion_b200.so (the C ABI in include/kdfusion_b200.h).
+
+There is no fallback: if the shared library is missing the import fails loudly,
+and every wrapper refuses tensors that are not on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "libkdfusion_b200.so")
+
+KDF_F32, KDF_BF16 = 0, 1
+REDUCE_MAX, REDUCE_MEAN = 0, 1
+
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+_SIGNATURES = {
+    "kdf_abi_version": (C.c_int, []),
+    "kdf_last_error": (C.c_char_p, []),
+    "kdf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "kdf_bev_index": (C.c_int, [_vp, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "kdf_bev_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
+    "kdf_bev_project_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _i,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "kdf_bev_project_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "kdf_fusion_weighted_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp, _vp, _vp]),
+    "kdf_fusion_weighted_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp] + [_vp] * 7 + [_vp]),
+    "kdf_fusion_affine_relu_pair_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "kdf_fusion_affine_relu_pair_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "kdf_kd_loss_workspace_bytes": (_sz, []),
+    "kdf_kd_loss_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _i64,
+                                      _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
+    "kdf_confusion_matrix": (C.c_int, [_vp, _vp, _i, _i, _i64, _i, _i64, _vp, _vp]),
+    "kdf_adamw_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            f"`python {os.path.join(_PKG_ROOT, 'build.py')}` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI and this table diverge
+        fn.restype, fn.argtypes = res, args
+    if lib.kdf_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.kdf_abi_version()} != 1, rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"kdfusion_b200 {what} failed (code {rc}): {lib.kdf_last_error().decode()}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return KDF_F32
+    if t.dtype == torch.bfloat16:
+        return KDF_BF16
+    raise TypeError(f"kdfusion_b200 supports float32 and bfloat16 features, got {t.dtype}")
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("kdfusion_b200 kernels run on CUDA tensors only (no CPU fallback); "
+                               f"got a tensor on {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,356 @@
+"""torch-facing wrappers (and autograd glue) over the kdfusion_b200 C ABI.
+
+Everything here only moves pointers: tensors are allocated by torch on the
+current CUDA stream, the arithmetic happens in libkdfusion_b200.so.  CUDA tensors
+only -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import native as _n
+from .native import check, dtype_code, lib, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    "bev_range_constants", "bev_index", "bev_project", "BevProjectFn",
+    "fused_fusion", "kd_loss_fwd_bwd", "KDLossFn", "confusion_matrix_", "adamw_flat_",
+]
+
+
+# ----------------------------------------------------------------------------- (1) projection
+def bev_range_constants(point_cloud_range: Sequence) -> Tuple[float, float, float, float]:
+    """fp32 (x0, xspan, y0, yspan) with the reference's promotion rules: the range
+    buffers are int64 when the entries are Python ints (lidar_encoder.py:38-39), so
+    the span is an exact integer difference before it becomes fp32 (:47-48)."""
+    out = []
+    for lo, hi in ((point_cloud_range[0], point_cloud_range[3]), (point_cloud_range[1], point_cloud_range[4])):
+        if isinstance(lo, int) and isinstance(hi, int):
+            x0 = torch.tensor(lo, dtype=torch.float32)
+            span = torch.tensor(hi - lo, dtype=torch.float32)
+        else:
+            x0 = torch.tensor(lo, dtype=torch.float32)
+            span = torch.tensor(hi, dtype=torch.float32) - x0
+        out += [float(x0), float(span)]
+    return tuple(out)
+
+
+def _check_points(points: torch.Tensor) -> Tuple[int, int, int]:
+    require_cuda(points)
+    if points.dim() != 3 or points.shape[-1] < 2:
+        raise ValueError(f"points must be [B, N, >=2], got {tuple(points.shape)}")
+    if points.dtype != torch.float32:
+        raise TypeError("points must stay float32 (index math is fp32 by contract)")
+    return points.shape
+
+
+def bev_index(points: torch.Tensor, geom: Tuple[float, float, float, float], grid_size: Tuple[int, int],
+              want_rank: bool = False):
+    """Cell id per point (int32, -1 outside) and per-cell occupancy (int32 [B,H*W]).
+    Bit-exact with SpatialLiDAREncoder.points_to_bev_coords + the truncation of
+    forward_vectorized (lidar_encoder.py:42-55, 69-71)."""
+    B, N, D = _check_points(points)
+    points = points.contiguous()
+    H, W = grid_size
+    cell = torch.empty(B, N, dtype=torch.int32, device=points.device)
+    count = torch.empty(B, H * W, dtype=torch.int32, device=points.device)
+    rank = torch.empty(B, N, dtype=torch.int32, device=points.device) if want_rank else None
+    check(lib.kdf_bev_index(ptr(points), B, N, D, *geom, H, W, ptr(cell), ptr(rank), ptr(count),
+                            stream_ptr(points.device)), "bev_index")
+    return (cell, count, rank) if want_rank else (cell, count)
+
+
+class BevProjectFn(torch.autograd.Function):
+    """grid[B,C,H,W] (NHWC memory) = per-cell max/mean of point-major feats[B,N,C]."""
+
+    @staticmethod
+    def forward(ctx, points, feats, geom, grid_size, reduce):
+        B, N, D = _check_points(points)
+        require_cuda(points, feats)
+        if feats.dim() != 3 or feats.shape[0] != B or feats.shape[1] != N:
+            raise ValueError(f"feats must be [B={B}, N={N}, C], got {tuple(feats.shape)}")
+        points = points.contiguous()
+        feats = feats.contiguous()
+        C = feats.shape[2]
+        H, W = grid_size
+        dev = points.device
+        grid = torch.empty(B, H, W, C, dtype=feats.dtype, device=dev)
+        count = torch.empty(B, H * W, dtype=torch.int32, device=dev)
+        cell = torch.empty(B, N, dtype=torch.int32, device=dev)
+        need_ties = reduce == _n.REDUCE_MAX and feats.requires_grad
+        ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev) if need_ties else None
+        ws_bytes = lib.kdf_bev_workspace_bytes(B, N, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.kdf_bev_project_fwd(ptr(points), D, ptr(feats), dtype_code(feats), B, N, C, *geom, H, W, reduce,
+                                      ptr(grid), ptr(count), ptr(cell), ptr(ties), None, None,
+                                      ptr(ws), ws_bytes, stream_ptr(dev)), "bev_project_fwd")
+        ctx.reduce, ctx.dims = reduce, (B, N, C, H, W)
+        if reduce == _n.REDUCE_MAX:
+            ctx.save_for_backward(feats, grid, ties, cell)
+        else:
+            ctx.save_for_backward(count, cell)
+        ctx.mark_non_differentiable(count, cell)
+        return grid.permute(0, 3, 1, 2), count, cell      # lidar_encoder.py:99: [B,C,H,W] view of NHWC memory
+
+    @staticmethod
+    def backward(ctx, grad_grid, _gc, _gi):
+        B, N, C, H, W = ctx.dims
+        gg = grad_grid.permute(0, 2, 3, 1).contiguous()
+        if ctx.reduce == _n.REDUCE_MAX:
+            feats, grid, ties, cell = ctx.saved_tensors
+            count = None
+        else:
+            count, cell = ctx.saved_tensors
+            feats = grid = ties = None
+        if gg.dtype != (feats.dtype if feats is not None else gg.dtype):
+            gg = gg.to(feats.dtype)
+        out = torch.empty(B, N, C, dtype=gg.dtype, device=gg.device)
+        check(lib.kdf_bev_project_bwd(ptr(gg), ptr(feats), ptr(grid), ptr(ties), ptr(count), ptr(cell),
+                                      dtype_code(gg), B, N, C, H, W, ctx.reduce, ptr(out), stream_ptr(gg.device)),
+              "bev_project_bwd")
+        return None, out, None, None, None
+
+
+def bev_project(points: torch.Tensor, feats: torch.Tensor, geom, grid_size, reduce: str = "max"):
+    """-> (grid [B,C,H,W] over NHWC memory, count int32 [B,H*W], cell int32 [B,N])."""
+    code = {"max": _n.REDUCE_MAX, "amax": _n.REDUCE_MAX, "mean": _n.REDUCE_MEAN}[reduce]
+    return BevProjectFn.apply(points, feats, tuple(geom), tuple(grid_size), code)
+
+
+# ----------------------------------------------------------------------------- (2) fusion
+_MODES = {"add": 0, "concat": 1, "weighted": 2}
+
+
+class _FusedFusionFn(torch.autograd.Function):
+    """BN-apply + ReLU of both projection branches fused with the fusion itself.
+
+    Inputs are pre-BatchNorm rows [M,C]; (mean, invstd) are the statistics the
+    BatchNorm uses (batch statistics when ``batch_stats`` else running), computed
+    by the caller.  Backward chains through the batch statistics analytically."""
+
+    @staticmethod
+    def forward(ctx, cam_pre, lid_pre, cam_g, cam_b, lid_g, lid_b, cam_mean, cam_invstd, lid_mean, lid_invstd,
+                batch_stats, mode, w1, b1, w2, b2):
+        dev = require_cuda(cam_pre, lid_pre, cam_g, lid_g, w1)
+        cam_pre, lid_pre = cam_pre.contiguous(), lid_pre.contiguous()
+        if cam_pre.shape != lid_pre.shape or cam_pre.dtype != lid_pre.dtype or cam_pre.dim() != 2:
+            raise ValueError("fusion expects two [M,C] row tensors of the same shape and dtype")
+        M, C = cam_pre.shape
+        f32 = torch.float32
+        csc = (cam_g.to(f32) * cam_invstd).contiguous()
+        csh = (cam_b.to(f32) - cam_mean * csc).contiguous()
+        lsc = (lid_g.to(f32) * lid_invstd).contiguous()
+        lsh = (lid_b.to(f32) - lid_mean * lsc).contiguous()
+        dt, st = dtype_code(cam_pre), stream_ptr(dev)
+        attn = None
+        if mode == 2:
+            w1c = w1.reshape(C, 2 * C).to(f32).contiguous()
+            w2c = w2.reshape(2, C).to(f32).contiguous()
+            b1c, b2c = b1.to(f32).contiguous(), b2.to(f32).contiguous()
+            out = torch.empty(M, C, dtype=cam_pre.dtype, device=dev)
+            attn = torch.empty(M, 2, dtype=f32, device=dev)
+            check(lib.kdf_fusion_weighted_fwd(ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh), ptr(lsc), ptr(lsh),
+                                              ptr(w1c), ptr(b1c), ptr(w2c), ptr(b2c), ptr(out), ptr(attn), st),
+                  "fusion_weighted_fwd")
+            ctx.save_for_backward(cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd,
+                                  w1c, b1c, w2c, b2c, attn)
+        else:
+            out = torch.empty(M, C * (2 if mode == 1 else 1), dtype=cam_pre.dtype, device=dev)
+            check(lib.kdf_fusion_affine_relu_pair_fwd(ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh), ptr(lsc),
+                                                      ptr(lsh), mode, ptr(out), st), "fusion_affine_relu_pair_fwd")
+            ctx.save_for_backward(cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd)
+        ctx.mode, ctx.batch_stats = mode, batch_stats
+        ctx.param_dtypes = (cam_g.dtype, w1.dtype if w1 is not None else None)
+        ctx.w_shapes = (w1.shape, w2.shape) if mode == 2 else None
+        if attn is not None:
+            ctx.mark_non_differentiable(attn)
+            return out, attn
+        return out, None
+
+    @staticmethod
+    def backward(ctx, grad_out, _ga):
+        saved = ctx.saved_tensors
+        cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd = saved[:10]
+        M, C = cam_pre.shape
+        dev = cam_pre.device
+        f32 = torch.float32
+        grad_out = grad_out.contiguous().to(cam_pre.dtype)
+        g_cam, g_lid = torch.empty_like(cam_pre), torch.empty_like(lid_pre)
+        gaff = torch.empty(4, C, dtype=f32, device=dev)
+        dt, st = dtype_code(cam_pre), stream_ptr(dev)
+        gw1 = gb1 = gw2 = gb2 = None
+        if ctx.mode == 2:
+            w1c, b1c, w2c, b2c, attn = saved[10:]
+            gw1 = torch.empty(C, 2 * C, dtype=f32, device=dev)
+            gb1 = torch.empty(C, dtype=f32, device=dev)
+            gw2 = torch.empty(2, C, dtype=f32, device=dev)
+            gb2 = torch.empty(2, dtype=f32, device=dev)
+            check(lib.kdf_fusion_weighted_bwd(ptr(grad_out), ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh),
+                                              ptr(lsc), ptr(lsh), ptr(w1c), ptr(b1c), ptr(w2c), ptr(b2c), ptr(attn),
+                                              ptr(g_cam), ptr(g_lid), ptr(gaff), ptr(gw1), ptr(gb1), ptr(gw2), ptr(gb2), st),
+                  "fusion_weighted_bwd")
+            gw1, gw2 = gw1.view(ctx.w_shapes[0]), gw2.view(ctx.w_shapes[1])
+        else:
+            check(lib.kdf_fusion_affine_relu_pair_bwd(ptr(grad_out), ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc),
+                                                      ptr(csh), ptr(lsc), ptr(lsh), ctx.mode, ptr(g_cam), ptr(g_lid),
+                                                      ptr(gaff), st), "fusion_affine_relu_pair_bwd")
+        grads_gb = []
+        for (x, g, scale, mean, invstd, s1, s0) in ((cam_pre, g_cam, csc, cam_mean, cam_invstd, gaff[0], gaff[1]),
+                                                    (lid_pre, g_lid, lsc, lid_mean, lid_invstd, gaff[2], gaff[3])):
+            dgamma = invstd * (s1 - mean * s0)          # sum dy * xhat
+            dbeta = s0
+            if ctx.batch_stats:                         # chain through the batch mean / variance
+                bc = -(scale * invstd * dgamma) / M
+                ac = -(scale * s0) / M - bc * mean
+                g.addcmul_(x, bc.to(f32)).add_(ac)
+            grads_gb.append((dgamma, dbeta))
+        pd = ctx.param_dtypes[0]
+        return (g_cam, g_lid, grads_gb[0][0].to(pd), grads_gb[0][1].to(pd), grads_gb[1][0].to(pd), grads_gb[1][1].to(pd),
+                None, None, None, None, None, None, gw1, gb1, gw2, gb2)
+
+
+def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None):
+    """Fused fusion over pre-BN rows.  ``cam_bn`` / ``lid_bn`` are the BatchNorm2d
+    modules of the two Conv1x1 blocks (their running statistics are updated here
+    exactly like nn.BatchNorm2d does in training); ``attention`` is the
+    ``nn.Sequential(conv, relu, conv, softmax)`` of WeightedFusion.
+    Returns (rows [M,C] or [M,2C], attn [M,2] | None)."""
+    stats = []
+    for x, bn in ((cam_pre, cam_bn), (lid_pre, lid_bn)):
+        use_batch = bn.training or bn.running_mean is None
+        with torch.no_grad():
+            if use_batch:
+                mean, invstd = torch.batch_norm_stats(x, bn.eps)           # fp32 statistics over the M rows
+                if bn.training and bn.track_running_stats and bn.running_mean is not None:
+                    bn.num_batches_tracked += 1
+                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                    M = x.shape[0]
+                    var = invstd.pow(-2) - bn.eps
+                    bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+                    bn.running_var.mul_(1 - mom).add_((var * (M / max(M - 1, 1))).to(bn.running_var.dtype), alpha=mom)
+            else:
+                mean = bn.running_mean.float()
+                invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+        stats.append((mean, invstd, use_batch))
+    if stats[0][2] != stats[1][2]:
+        raise RuntimeError("the two projection BatchNorms must be in the same mode")
+    if mode == "weighted":
+        w1, b1, w2, b2 = attention[0].weight, attention[0].bias, attention[2].weight, attention[2].bias
+    else:
+        w1 = b1 = w2 = b2 = None
+    return _FusedFusionFn.apply(cam_pre, lid_pre, cam_bn.weight, cam_bn.bias, lid_bn.weight, lid_bn.bias,
+                                stats[0][0], stats[0][1], stats[1][0], stats[1][1], stats[0][2], _MODES[mode],
+                                w1, b1, w2, b2)
+
+
+# ----------------------------------------------------------------------------- (3) distillation loss
+def _dense_like(s: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """teacher tensor laid out exactly like the student one (so one flat pass pairs them)."""
+    if t.shape != s.shape:
+        raise ValueError(f"mimic tap shapes differ: {tuple(s.shape)} vs {tuple(t.shape)}")
+    if t.dtype != s.dtype:
+        t = t.to(s.dtype)
+    if t.stride() != s.stride():
+        t = torch.empty_like(s).copy_(t)
+    return t
+
+
+def _dense(s: torch.Tensor) -> torch.Tensor:
+    if s.is_contiguous() or s.is_contiguous(memory_format=torch.channels_last):
+        return s
+    if s.dim() == 4 and s.permute(0, 2, 3, 1).is_contiguous():
+        return s
+    return s.contiguous()
+
+
+def kd_loss_fwd_bwd(student_logits, teacher_logits, labels, class_weights=None,
+                    student_feats: Sequence[torch.Tensor] = (), teacher_feats: Sequence[torch.Tensor] = (),
+                    T: float = 4.0, alpha: float = 0.5, beta: float = 1.0, ignore_index: int = -1,
+                    grad_scale: float = 1.0):
+    """One pass: loss terms + gradients.  -> (scalars f32[8] = loss, ce, kl, mse, wsum, mse0, mse1, n_valid;
+    d_logits like student_logits; [d_feat like each student feat]).  No host sync."""
+    dev = require_cuda(student_logits, teacher_logits, labels, class_weights, *student_feats, *teacher_feats)
+    if student_logits.dim() != 4:
+        raise ValueError("logits must be [B,K,H,W]")
+    if len(student_feats) != len(teacher_feats) or len(student_feats) > 2:
+        raise ValueError("0, 1 or 2 (student, teacher) mimic taps are supported")
+    zs = student_logits.contiguous()
+    zt = None if teacher_logits is None else teacher_logits.to(zs.dtype).contiguous()
+    if zt is not None and zt.shape != zs.shape:
+        raise ValueError("teacher and student logits differ in shape")
+    B, K, H, W = zs.shape
+    if labels.dtype != torch.int64 or tuple(labels.shape) != (B, H, W):
+        raise ValueError(f"labels must be int64 [B,H,W]={B, H, W}, got {labels.dtype} {tuple(labels.shape)}")
+    labels = labels.contiguous()
+    cw = None if class_weights is None else class_weights.to(torch.float32).contiguous()
+    if cw is not None and cw.numel() != K:
+        raise ValueError(f"class_weights has {cw.numel()} entries, logits have {K} classes")
+    s_list = [_dense(s) for s in student_feats]
+    t_list = [_dense_like(s, t) for s, t in zip(s_list, teacher_feats)]
+    if len({s.dtype for s in s_list}) > 1:
+        raise TypeError("mimic taps must share one dtype")
+    d_list = [torch.empty_like(s) for s in s_list]
+    fd = dtype_code(s_list[0]) if s_list else _n.KDF_F32
+    taps = []
+    for i in range(2):
+        if i < len(s_list):
+            taps += [ptr(s_list[i]), ptr(t_list[i]), ptr(d_list[i]), s_list[i].numel()]
+        else:
+            taps += [None, None, None, 0]
+    d_logits = torch.empty_like(zs)
+    scalars = torch.empty(8, dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.kdf_kd_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
+    check(lib.kdf_kd_loss_fwd_bwd(ptr(zs), ptr(zt), ptr(labels), ptr(cw), B, K, H * W, dtype_code(zs),
+                                  float(T), float(alpha), float(beta), int(ignore_index), *taps, fd, float(grad_scale),
+                                  ptr(d_logits), ptr(scalars), ptr(ws), stream_ptr(dev)), "kd_loss_fwd_bwd")
+    return scalars, d_logits, d_list
+
+
+class KDLossFn(torch.autograd.Function):
+    """Autograd face of the fused loss: returns the scalar loss; gradients were
+    produced in the forward pass and are only scaled by the incoming grad."""
+
+    @staticmethod
+    def forward(ctx, student_logits, teacher_logits, labels, class_weights, T, alpha, beta, ignore_index, *feats):
+        n = len(feats) // 2
+        s_feats, t_feats = feats[:n], feats[n:]
+        scalars, d_logits, d_feats = kd_loss_fwd_bwd(student_logits, teacher_logits, labels, class_weights,
+                                                     s_feats, t_feats, T, alpha, beta, ignore_index)
+        ctx.save_for_backward(d_logits, *d_feats)
+        ctx.n = n
+        ctx.mark_non_differentiable(scalars)
+        return scalars[0].clone(), scalars
+
+    @staticmethod
+    def backward(ctx, g_loss, _gs):
+        d_logits, *d_feats = ctx.saved_tensors
+        return (d_logits * g_loss.to(d_logits.dtype), None, None, None, None, None, None, None,
+                *[d * g_loss.to(d.dtype) for d in d_feats], *([None] * ctx.n))
+
+
+# ----------------------------------------------------------------------------- step helpers
+def confusion_matrix_(conf: torch.Tensor, logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -1):
+    """conf[t,p] += 1 (int64 [K,K], on device) -- SegmentationMetrics.update without the host loop."""
+    dev = require_cuda(conf, logits, labels)
+    B, K = logits.shape[0], logits.shape[1]
+    if conf.dtype != torch.int64 or tuple(conf.shape) != (K, K) or not conf.is_contiguous():
+        raise ValueError("conf must be a contiguous int64 [K,K] tensor")
+    logits, labels = logits.contiguous(), labels.contiguous()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    HW = logits.numel() // max(B * K, 1)
+    check(lib.kdf_confusion_matrix(ptr(logits), ptr(labels), B, K, HW, dtype_code(logits), int(ignore_index),
+                                   ptr(conf), stream_ptr(dev)), "confusion_matrix")
+    return conf
+
+
+def adamw_flat_(param, grad, exp_avg, exp_avg_sq, hyper, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    """In-place AdamW step over flat fp32 buffers; hyper = device tensor [lr, step]."""
+    dev = require_cuda(param, grad, exp_avg, exp_avg_sq, hyper)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
+            raise ValueError("adamw_flat_ needs contiguous float32 buffers of one size")
+    check(lib.kdf_adamw_flat(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(hyper),
+                             float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
+                             stream_ptr(dev)), "adamw_flat")

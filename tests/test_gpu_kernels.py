@@ -1,0 +1,410 @@
+"""GPU parity tests: each CUDA kernel, called through the C ABI (ctypes binding in
+src/native.py), against the CPU oracle on the same seeded inputs.
+
+Bars: indices / occupancy / max-grid bit-exact; fp32 losses, fused features and
+gradients within 1e-5 relative; bf16 within the tolerance written in each test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bev_oracle, kd_oracle, model_oracle
+from oracle.weights import make_state_dict, synthetic_frames
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from src import ops as _ops
+    return _ops
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+# ----------------------------------------------------------------------------- projection: indices
+@pytest.mark.parametrize("name", ["g64", "g128", "g48x80f"])
+def test_bev_index_golden_bit_exact(ops, name):
+    """cells + occupancy equal the REFERENCE's own outputs (tests/golden/bev_cells.npz)."""
+    z = np.load(os.path.join(GOLDEN, "bev_cells.npz"))
+    seed, B, N, H, W = (int(v) for v in z[name + "_meta"])
+    rng = [float(v) for v in z[name + "_range"]]
+    if all(v.is_integer() for v in rng):
+        rng = [int(v) for v in rng]
+    _, pts, _ = synthetic_frames(seed, B, N, image_hw=(8, 8), grid_size=(H, W), edge_cases=True)
+    cell, occ = ops.bev_index(pts.cuda(), ops.bev_range_constants(rng), (H, W))
+    np.testing.assert_array_equal(cell.cpu().numpy(), z[name + "_cell"].astype(np.int32))
+    np.testing.assert_array_equal(occ.cpu().numpy(), z[name + "_occ"].astype(np.int32))
+
+
+def test_bev_index_known_answer_survey_s4(ops):
+    """SURVEY.md section 4 known-answer vector (torch CPU RNG, seed 123)."""
+    import hashlib
+    from src.models.lidar_encoder import create_test_point_cloud
+    torch.manual_seed(123)
+    pts = create_test_point_cloud(2, 1500)
+    cell, occ = ops.bev_index(pts.cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64))
+    cell = cell.cpu().numpy()
+    valid = cell >= 0
+    flat = (np.arange(2)[:, None] * 4096 + cell)[valid].astype(np.int64)
+    assert valid.sum() == 1796 and flat.sum() == 7278080
+    assert (occ.cpu().numpy() > 0).sum() == 1594 and occ.max().item() == 4
+    assert hashlib.sha1(flat.tobytes()).hexdigest()[:16] == "9d430af99ab6ca47"
+
+
+@pytest.mark.parametrize("B,N,stride", [(1, 1, 4), (3, 31, 4), (2, 1000, 4), (2, 777, 6), (1, 0, 4), (4, 33, 2)])
+def test_bev_index_ragged_sizes_and_strides(ops, B, N, stride):
+    g = np.random.default_rng(B * 1000 + N)
+    pts = (g.standard_normal((B, N, stride)) * 40).astype(np.float32)
+    cell, occ, rank = ops.bev_index(torch.from_numpy(pts).cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]),
+                                    (64, 64), want_rank=True)
+    ref = bev_oracle.bev_cells(pts, (64, 64))
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref)
+    np.testing.assert_array_equal(occ.cpu().numpy(), bev_oracle.bev_occupancy(ref, (64, 64)))
+    # ranks: a permutation of 0..count-1 inside every cell
+    r, c = rank.cpu().numpy(), cell.cpu().numpy()
+    for b in range(B):
+        for cid in np.unique(c[b][c[b] >= 0]):
+            got = np.sort(r[b][c[b] == cid])
+            np.testing.assert_array_equal(got, np.arange(got.size))
+
+
+def test_bev_index_edge_semantics(ops):
+    """closed range, x=+50 -> last cell, NaN/inf/-50.0001 invalid, zero padding -> cell (31,31)
+    (SURVEY.md section 7 'Validity and edge semantics')."""
+    p = torch.zeros(1, 8, 4)
+    p[0, 0, :2] = torch.tensor([50.0, 50.0])
+    p[0, 1, :2] = torch.tensor([-50.0, -50.0])
+    p[0, 2, 0] = float("nan")
+    p[0, 3, 1] = float("inf")
+    p[0, 4, :2] = torch.tensor([-50.0001, 0.0])
+    p[0, 5, :2] = torch.tensor([49.999996, 0.0])
+    cell, occ = ops.bev_index(p.cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64))
+    c = cell.cpu().numpy()[0]
+    assert c[0] == 63 * 64 + 63 and c[1] == 0 and c[2] == -1 and c[3] == -1 and c[4] == -1
+    assert c[5] == 31 * 64 + 62 and c[6] == 31 * 64 + 31 and c[7] == 31 * 64 + 31
+    np.testing.assert_array_equal(c, bev_oracle.bev_cells(p.numpy(), (64, 64))[0])
+    assert occ.sum().item() == 5
+
+
+def test_bev_index_full_size_properties(ops):
+    """BASELINE size (32 frames x 170k points): size-independent properties."""
+    from src.data_loading.synthetic_frames import make_frames
+    f = make_frames(32, 170_000, seed=3, device="cuda")
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    cell, occ = ops.bev_index(f["points"], geom, (64, 64))
+    assert cell.min().item() >= -1 and cell.max().item() < 4096
+    assert occ.sum(dim=1).tolist() == (cell >= 0).sum(dim=1).tolist()            # checksum of checksums
+    cell2, occ2 = ops.bev_index(f["points"], geom, (64, 64))
+    assert torch.equal(cell, cell2) and torch.equal(occ, occ2)                  # deterministic
+    # a sample of frames against the oracle
+    ref = bev_oracle.bev_cells(f["points"][:2].cpu().numpy(), (64, 64))
+    np.testing.assert_array_equal(cell[:2].cpu().numpy(), ref)
+    x, y = f["points"][..., 0], f["points"][..., 1]
+    inside = (x >= -50) & (x <= 50) & (y >= -50) & (y <= 50)
+    assert torch.equal(inside, cell >= 0)
+
+
+# ----------------------------------------------------------------------------- projection: reduce + backward
+def _proj_inputs(B, N, C, seed, ties=True):
+    _, pts, _ = synthetic_frames(seed, B, N, image_hw=(8, 8), edge_cases=N >= 64)
+    g = np.random.default_rng(seed)
+    feats = np.maximum(g.standard_normal((B, N, C)).astype(np.float32), 0)        # post-ReLU like the MLP output
+    if ties and N >= 64:
+        feats[:, 8:12] = feats[:, 12:13]
+    return pts, torch.from_numpy(feats)
+
+
+@pytest.mark.parametrize("B,N,C", [(2, 6000, 128), (1, 100, 128), (3, 2500, 64), (2, 4000, 256), (1, 1, 4), (2, 0, 128)])
+def test_bev_project_max_fp32_exact(ops, B, N, C):
+    pts, feats = _proj_inputs(B, N, C, seed=B * 100 + C)
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    f = feats.cuda().requires_grad_(True)
+    grid, count, cell = ops.bev_project(pts.cuda(), f, geom, (64, 64), "max")
+    ref_cell = bev_oracle.bev_cells(pts.numpy(), (64, 64))
+    ref_grid, ref_ties = bev_oracle.bev_scatter_max(feats.numpy(), ref_cell, (64, 64))
+    assert grid.shape == (B, C, 64, 64) and grid.stride() == (64 * 64 * C, 1, 64 * C, C)     # NHWC view (lidar_encoder.py:99)
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
+    np.testing.assert_array_equal(count.cpu().numpy(), bev_oracle.bev_occupancy(ref_cell, (64, 64)))
+    np.testing.assert_array_equal(grid.detach().permute(0, 2, 3, 1).reshape(B, 4096, C).cpu().numpy(), ref_grid)
+    # backward: even split among ties (+ ATen's zero-max quirk), zero for points outside
+    gg = torch.from_numpy(np.random.default_rng(1).standard_normal((B, 4096, C)).astype(np.float32))
+    grid.backward(gg.view(B, 64, 64, C).permute(0, 3, 1, 2).cuda())
+    ref_gf = bev_oracle.bev_scatter_max_backward(gg.numpy(), feats.numpy(), ref_grid, ref_ties, ref_cell)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), ref_gf, rtol=1e-6, atol=0)
+
+
+def test_bev_project_outside_points_give_zero_grid(ops):
+    """the reference's own (commented) assertion: all points out of range => output max == 0
+    (test_lidar_encoder.py:227-233)."""
+    pts = torch.full((2, 500, 4), 500.0)
+    feats = torch.rand(2, 500, 128) + 1
+    grid, count, cell = ops.bev_project(pts.cuda(), feats.cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64))
+    assert grid.abs().max().item() == 0.0 and count.sum().item() == 0 and (cell == -1).all()
+
+
+def test_bev_project_all_in_one_cell_and_negative_features(ops):
+    """heavy cell (every point in one cell) and features that are not post-ReLU:
+    include_self=False semantics -> max of the sources even when negative."""
+    B, N, C = 2, 3000, 128
+    pts = torch.zeros(B, N, 4)
+    pts[..., 0] = 10.2
+    pts[..., 1] = -7.7
+    g = np.random.default_rng(5)
+    feats = torch.from_numpy(g.standard_normal((B, N, C)).astype(np.float32) - 3.0)
+    grid, count, cell = ops.bev_project(pts.cuda(), feats.cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64))
+    ref_cell = bev_oracle.bev_cells(pts.numpy(), (64, 64))
+    ref_grid, _ = bev_oracle.bev_scatter_max(feats.numpy(), ref_cell, (64, 64))
+    np.testing.assert_array_equal(grid.permute(0, 2, 3, 1).reshape(B, 4096, C).cpu().numpy(), ref_grid)
+    assert count.max().item() == N and (ref_grid.min() < 0)
+
+
+def test_bev_project_bf16_features_exact_max(ops):
+    """bf16 features: the max of bf16 values is exactly representable, so the grid must equal
+    the oracle run on the bf16-rounded features; points / indices stay fp32."""
+    B, N, C = 2, 5000, 128
+    pts, feats = _proj_inputs(B, N, C, seed=9)
+    fb = feats.to(torch.bfloat16)
+    grid, count, cell = ops.bev_project(pts.cuda(), fb.cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64))
+    ref_cell = bev_oracle.bev_cells(pts.numpy(), (64, 64))
+    ref_grid, _ = bev_oracle.bev_scatter_max(fb.float().numpy(), ref_cell, (64, 64))
+    assert grid.dtype == torch.bfloat16
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
+    np.testing.assert_array_equal(grid.float().permute(0, 2, 3, 1).reshape(B, 4096, C).cpu().numpy(), ref_grid)
+
+
+def test_bev_project_mean(ops):
+    """per-cell mean (north star; not in the reference -> parity unpinned, torch scatter_reduce as oracle)."""
+    B, N, C = 2, 5000, 64
+    pts, feats = _proj_inputs(B, N, C, seed=4, ties=False)
+    f = feats.cuda().requires_grad_(True)
+    grid, count, cell = ops.bev_project(pts.cuda(), f, ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64), "mean")
+    ref_cell = bev_oracle.bev_cells(pts.numpy(), (64, 64))
+    ref = bev_oracle.bev_scatter_mean(feats.numpy(), ref_cell, (64, 64))
+    np.testing.assert_allclose(grid.detach().permute(0, 2, 3, 1).reshape(B, 4096, C).cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    gg = torch.randn(B, C, 64, 64, device="cuda")
+    grid.backward(gg)
+    occ = bev_oracle.bev_occupancy(ref_cell, (64, 64))
+    ggr = gg.permute(0, 2, 3, 1).reshape(B, 4096, C).cpu().numpy()
+    want = np.zeros((B, N, C), np.float32)
+    for b in range(B):
+        v = ref_cell[b] >= 0
+        want[b, v] = ggr[b, ref_cell[b, v]] / occ[b, ref_cell[b, v]][:, None]
+    np.testing.assert_allclose(f.grad.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+
+
+def test_bev_project_full_size_properties(ops):
+    """32 x 170k x 128 bf16 (the bench shape): order independence (point permutation leaves the
+    grid bit-identical), idempotence, occupancy checksum, and max >= any member."""
+    from src.data_loading.synthetic_frames import make_frames
+    B, N, C = 32, 170_000, 128
+    pts = make_frames(B, N, seed=11, device="cuda")["points"]
+    feats = torch.rand(B, N, C, device="cuda", dtype=torch.bfloat16)
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    grid, count, cell = ops.bev_project(pts, feats, geom, (64, 64))
+    perm = torch.randperm(N, device="cuda")
+    grid2, count2, _ = ops.bev_project(pts[:, perm].contiguous(), feats[:, perm].contiguous(), geom, (64, 64))
+    assert torch.equal(grid, grid2) and torch.equal(count, count2)
+    assert count.sum().item() == (cell >= 0).sum().item()
+    # every valid point is <= its cell max; empty cells are exactly zero
+    g = grid.permute(0, 2, 3, 1).reshape(B, 4096, C)
+    b = 5
+    v = cell[b] >= 0
+    assert (feats[b][v] <= g[b][cell[b][v].long()]).all()
+    assert (g[count == 0] == 0).all()
+
+
+# ----------------------------------------------------------------------------- KD loss
+def _kd_inputs(B, K, seed, feat_shapes=((128, 64, 64), (128, 64, 64))):
+    g = torch.Generator().manual_seed(seed)
+    zs = torch.randn(B, K, 64, 64, generator=g) * 2
+    zt = torch.randn(B, K, 64, 64, generator=g) * 2
+    lab = (torch.rand(B, 64, 64, generator=g) < 0.13).long()
+    lab[0, :3] = -1
+    sf = [torch.randn(B, *s, generator=g) for s in feat_shapes]
+    tf = [torch.randn(B, *s, generator=g) for s in feat_shapes]
+    return zs, zt, lab, sf, tf
+
+
+@pytest.mark.parametrize("K,weights", [(2, [0.4, 3.5]), (3, [0.39, 2.61, 33.09]), (2, None)])
+def test_kd_loss_fp32_vs_oracle(ops, K, weights):
+    zs, zt, lab, sf, tf = _kd_inputs(3, K, seed=K)
+    w = None if weights is None else torch.tensor(weights)
+    zs_r = zs.clone().requires_grad_(True)
+    sf_r = [s.clone().requires_grad_(True) for s in sf]
+    ref = kd_oracle.kd_loss(zs_r, zt, lab, w, sf_r, tf, T=4.0, alpha=0.5, beta=1.0)
+    ref["loss"].backward()
+    terms, dz, dfe = ops.kd_loss_fwd_bwd(zs.cuda(), zt.cuda(), lab.cuda(), None if w is None else w.cuda(),
+                                         [s.cuda() for s in sf], [t.cuda() for t in tf], T=4.0, alpha=0.5, beta=1.0)
+    t = terms.cpu()
+    for i, k in enumerate(("loss", "ce", "kl", "mse")):
+        assert t[i].item() == pytest.approx(ref[k].item(), rel=1e-5), k
+    assert rel_err(dz.cpu(), zs_r.grad) < 1e-5
+    for d, s in zip(dfe, sf_r):
+        assert rel_err(d.cpu(), s.grad) < 1e-5
+
+
+def test_kd_loss_ce_only_matches_reference_criterion(ops):
+    """teacher=None, alpha=beta=0 -> exactly nn.CrossEntropyLoss(ignore_index=-1, weight) (trainer.py:55)."""
+    zs, _, lab, _, _ = _kd_inputs(2, 2, seed=7)
+    w = torch.tensor([0.4, 3.5])
+    zs_r = zs.clone().requires_grad_(True)
+    ref = torch.nn.CrossEntropyLoss(ignore_index=-1, weight=w)(zs_r, lab)
+    ref.backward()
+    terms, dz, _ = ops.kd_loss_fwd_bwd(zs.cuda(), None, lab.cuda(), w.cuda(), [], [], alpha=0.0, beta=0.0)
+    assert terms[0].item() == pytest.approx(ref.item(), rel=1e-5) and terms[1].item() == pytest.approx(ref.item(), rel=1e-5)
+    assert rel_err(dz.cpu(), zs_r.grad) < 1e-5
+    assert terms[7].item() == (lab != -1).sum().item()
+
+
+def test_kd_loss_autograd_function_and_nhwc_taps(ops):
+    """KDLossFn through autograd, with channels-last / NHWC-strided taps like the model produces."""
+    zs, zt, lab, sf, tf = _kd_inputs(2, 2, seed=3)
+    w = torch.tensor([0.4, 3.5])
+    zs_r = zs.clone().requires_grad_(True)
+    sf_r = [s.clone().requires_grad_(True) for s in sf]
+    ref = kd_oracle.kd_loss(zs_r, zt, lab, w, sf_r, tf)
+    (ref["loss"] * 0.5).backward()
+    zc = zs.cuda().requires_grad_(True)
+    s_c = [sf[0].cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True),     # NHWC view
+           sf[1].cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)]
+    t_c = [tf[0].cuda(), tf[1].cuda()]
+    loss, terms = ops.KDLossFn.apply(zc, zt.cuda(), lab.cuda(), w.cuda(), 4.0, 0.5, 1.0, -1, *s_c, *t_c)
+    (loss * 0.5).backward()
+    assert loss.item() == pytest.approx(ref["loss"].item(), rel=1e-5)
+    assert rel_err(zc.grad.cpu(), zs_r.grad) < 1e-5
+    for s, r in zip(s_c, sf_r):
+        assert rel_err(s.grad.cpu(), r.grad) < 1e-5
+
+
+def test_kd_loss_bf16_tolerance(ops):
+    """bf16 logits/taps, fp32 accumulation.  Stated tolerance: 1e-3 relative on the
+    scalar terms against the oracle evaluated on the same bf16-rounded inputs, 2e-2 on gradients."""
+    zs, zt, lab, sf, tf = _kd_inputs(4, 2, seed=5)
+    w = torch.tensor([0.4, 3.5])
+    bf = torch.bfloat16
+    zs_b, zt_b = zs.to(bf), zt.to(bf)
+    sf_b, tf_b = [s.to(bf) for s in sf], [t.to(bf) for t in tf]
+    zs_r = zs_b.float().requires_grad_(True)
+    sf_r = [s.float().requires_grad_(True) for s in sf_b]
+    ref = kd_oracle.kd_loss(zs_r, zt_b.float(), lab, w, sf_r, [t.float() for t in tf_b])
+    ref["loss"].backward()
+    terms, dz, dfe = ops.kd_loss_fwd_bwd(zs_b.cuda(), zt_b.cuda(), lab.cuda(), w.cuda(),
+                                         [s.cuda() for s in sf_b], [t.cuda() for t in tf_b])
+    for i, k in enumerate(("loss", "ce", "kl", "mse")):
+        assert terms[i].item() == pytest.approx(ref[k].item(), rel=1e-3), k
+    assert dz.dtype == bf and rel_err(dz.float().cpu(), zs_r.grad) < 2e-2
+    for d, s in zip(dfe, sf_r):
+        assert d.dtype == bf and rel_err(d.float().cpu(), s.grad) < 2e-2
+
+
+def test_kd_loss_all_ignored_is_nan_like_torch(ops):
+    zs, zt, lab, _, _ = _kd_inputs(1, 2, seed=1)
+    lab[:] = -1
+    terms, _, _ = ops.kd_loss_fwd_bwd(zs.cuda(), None, lab.cuda(), None, [], [], alpha=0.0, beta=0.0)
+    assert torch.isnan(terms[1]).item() and torch.isnan(kd_oracle.ce_loss(zs, lab)).item()
+
+
+# ----------------------------------------------------------------------------- fusion
+def _fusion_oracle(cam_feat, lid_feat, sd, fusion_type, train):
+    pre, fused, extras = model_oracle.fusion(cam_feat, lid_feat, sd, fusion_type, "fusion", train)
+    return pre, fused, extras
+
+
+@pytest.mark.parametrize("fusion_type", ["weighted", "minimal", "concat"])
+@pytest.mark.parametrize("train", [True, False])
+def test_fusion_fp32_forward_backward_vs_oracle(ops, fusion_type, train):
+    """Fused fusion block (incl. BatchNorm batch statistics in training) against the oracle's
+    restatement of fusion_module.py:242-256: outputs and every gradient within 1e-5 relative."""
+    from src.models import fusion_module as fm
+    B, C = 2, 128
+    sd_full = make_state_dict(11, fusion_type=fusion_type, random_running_stats=True)
+    sd = {k: v for k, v in sd_full.items() if k.startswith("fusion.")}
+    g = torch.Generator().manual_seed(2)
+    cam = torch.randn(B, C, 64, 64, generator=g).relu()
+    lid = torch.randn(B, C, 64, 64, generator=g).relu() * (torch.rand(B, 1, 64, 64, generator=g) > 0.3)
+    # oracle (CPU autograd)
+    sdo = model_oracle.clone_state(sd, requires_grad=True)
+    cam_o, lid_o = cam.clone().requires_grad_(True), lid.clone().requires_grad_(True)
+    pre_o, fused_o, _ = _fusion_oracle(cam_o, lid_o, sdo, fusion_type, train)
+    gout = torch.randn(fused_o.shape, generator=g)
+    fused_o.backward(gout)
+    # product (CUDA)
+    cls = {"weighted": fm.WeightedFusion, "minimal": fm.MinimalFusion, "concat": fm.ConcatenationFusion}[fusion_type]
+    mod = cls(128, 128, 256) if fusion_type == "concat" else cls(128, 128, 128)
+    mod.load_state_dict({k[len("fusion."):]: v for k, v in sd.items()})
+    mod.cuda().train(train)
+    cam_c = cam.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    lid_c = lid.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    pre_c, fused_c = mod.forward_with_pre(cam_c, lid_c)
+    fused_c.backward(gout.cuda())
+    assert rel_err(pre_c.detach().cpu(), pre_o.detach()) < 1e-5
+    assert rel_err(fused_c.detach().cpu(), fused_o.detach()) < 1e-5
+    assert rel_err(cam_c.grad.cpu(), cam_o.grad) < 2e-5
+    assert rel_err(lid_c.grad.cpu(), lid_o.grad) < 2e-5
+    for name, p in mod.named_parameters():
+        assert rel_err(p.grad.cpu(), sdo["fusion." + name].grad) < 2e-5, name
+    if train:   # running statistics advanced like nn.BatchNorm2d
+        for k, v in mod.state_dict().items():
+            if "running_" in k or "num_batches" in k:
+                assert rel_err(v.cpu().float(), sdo["fusion." + k].float()) < 1e-5, k
+
+
+def test_fusion_weighted_bf16_tolerance(ops):
+    """bf16 rows through the same kernel: stated tolerance 2e-2 relative (bf16 has 8 mantissa bits)
+    against the fp32 oracle on the bf16-rounded inputs."""
+    from src.models import fusion_module as fm
+    sd = {k: v for k, v in make_state_dict(11, fusion_type="weighted").items() if k.startswith("fusion.")}
+    g = torch.Generator().manual_seed(4)
+    cam = torch.randn(2, 128, 64, 64, generator=g).relu().to(torch.bfloat16)
+    lid = torch.randn(2, 128, 64, 64, generator=g).relu().to(torch.bfloat16)
+    with torch.no_grad():
+        _, fused_o, _ = _fusion_oracle(cam.float(), lid.float(), model_oracle.clone_state(sd), "weighted", True)
+    mod = fm.WeightedFusion(128, 128, 128)
+    mod.load_state_dict({k[len("fusion."):]: v for k, v in sd.items()})
+    mod.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = mod(cam.cuda().contiguous(memory_format=torch.channels_last),
+                  lid.cuda().contiguous(memory_format=torch.channels_last))
+    assert out.dtype == torch.bfloat16 and rel_err(out.float().cpu(), fused_o) < 2e-2
+
+
+# ----------------------------------------------------------------------------- step helpers
+def test_confusion_matrix_vs_oracle(ops):
+    g = torch.Generator().manual_seed(0)
+    for K in (2, 3):
+        logits = torch.randn(3, K, 64, 64, generator=g)
+        labels = torch.randint(0, K, (3, 64, 64), generator=g)
+        labels[0, :2] = -1
+        conf = torch.zeros(K, K, dtype=torch.int64, device="cuda")
+        ops.confusion_matrix_(conf, logits.cuda(), labels.cuda())
+        ops.confusion_matrix_(conf, logits.cuda(), labels.cuda())             # accumulates
+        np.testing.assert_array_equal(conf.cpu().numpy(), 2 * kd_oracle.confusion_matrix(logits, labels, K).numpy())
+
+
+def test_adamw_flat_matches_torch_adamw(ops):
+    g = torch.Generator().manual_seed(0)
+    n = 10_007
+    p0 = torch.randn(n, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, weight_decay=1e-3, foreach=False)
+    p = p0.clone().cuda()
+    pad = (n + 3) // 4 * 4
+    buf = [torch.zeros(pad, device="cuda") for _ in range(4)]
+    buf[0][:n] = p
+    hyper = torch.zeros(2, device="cuda")
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g)
+        ref_p.grad = grad.clone()
+        opt.step()
+        buf[1][:n] = grad.cuda() * 4.0
+        hyper.copy_(torch.tensor([1e-3, float(step)]))
+        ops.adamw_flat_(buf[0], buf[1], buf[2], buf[3], hyper, 0.9, 0.999, 1e-8, 1e-3, grad_scale=0.25)
+        assert rel_err(buf[0][:n].cpu(), ref_p.detach()) < 1e-6
