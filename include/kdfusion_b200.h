@@ -87,6 +87,14 @@ int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats
                         int32_t *order, int32_t *offsets,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* The reduce stage alone, over a cell ordering produced earlier (by
+ * kdf_bev_project_fwd with order/offsets supplied, e.g. to share one sort between
+ * the teacher's and the student's projection of the same sweep, or to time the
+ * dominant kernel in isolation).  Same outputs as kdf_bev_project_fwd's grid/ties. */
+int kdf_bev_reduce(const void *feats, int dtype, const int32_t *order, const int32_t *offsets,
+                   int B, int64_t N, int C, int H, int W, int reduce,
+                   void *grid, int32_t *ties, void *stream);
+
 /* Gradient of the projection w.r.t. feats.  max: the cell gradient is split
  * evenly among the sources equal to the max (ATen ScatterReduceBackward), with
  * ATen's quirk that a max of exactly 0.0 counts the zero-initialised output as

