@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""Headline benchmark: teacher->student KD training frames/s on synthetic PandaSet-shaped frames.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # CPU arm (oracle port of the reference)
+
+Workload (BASELINE.json configs[1]; weak scaling for N>1 = configs[3]): frozen concat/256 teacher
+(eval) -> weighted/128 student (train), 2 classes, class weights [0.4, 3.5], KD loss (CE + T^2 KL +
+feature-mimic MSE), AdamW, bf16 activations with fp32 points / index math / statistics, 32 frames
+per GPU, 170k-point Pandar64-shaped sweeps, 256x256 images, 64x64 BEV grid.
+
+One JSON line on stdout (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
+step driven from pinned HOST batches through Trainer.training_step with the H2D copies and a D2H read
+of the loss terms inside the timed region; `roofline` = the dominant hand-written kernel timed alone
+with CUDA events at the step's shapes; `cpu_baseline` = the oracle port of the reference's CPU path
+on a bounded sample (rank 0, N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "lightweight-multi-modal-scene-understanding-via-knowledge-distillation_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "kd_train_frames_per_sec"
+UNIT = "frames/s"
+CLASS_WEIGHTS = [0.4, 3.5]                    # train_with_fusion_ablation.py:47
+FALLBACK_PEAK_GBS = 6650.0                    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=("native", "reference"))
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU (weak scaling)")
+    ap.add_argument("--points", type=int, default=170_000)
+    ap.add_argument("--fp32", action="store_true", help="fp32 activations instead of bf16")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="frames per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
+    ap.add_argument("--graph", action="store_true", help="(reserved) CUDA-graph the step")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "teacher(concat/256, eval) -> student(weighted/128, train) KD training step, 2-class, "
+                        f"{'fp32' if args.fp32 else 'bf16'} activations, {args.batch} frames/GPU, "
+                        f"{args.points}-pt sweeps, 256x256 images, 64x64 BEV",
+            "global_batch": args.batch * n_gpus, "frames_per_gpu": args.batch, "points_per_frame": args.points,
+            "parallelism": f"dp{n_gpus}", "loss": "0.5*CE + 0.5*T^2*KL(T=4) + 1.0*MSE(lidar_feat, camera_feat)",
+            "optimizer": "AdamW lr 1e-3 wd 1e-3 (flat, one kernel)",
+            "l2": "per-step working set (>= 10 GB of activations, 113 MB of inputs) far exceeds the 126 MB L2; no flush"}
+
+
+# ============================================================================= CPU arm (oracle port)
+def cpu_step_runner(batch, points, seed=0):
+    """The reference's CPU path, restated by the oracle: teacher fwd (eval) + student fwd/bwd (train) +
+    KD loss + torch AdamW, eager fp32 on all host threads."""
+    from oracle import kd_oracle, model_oracle
+    from oracle.weights import make_state_dict, synthetic_frames
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_s = model_oracle.clone_state(make_state_dict(5, fusion_type="weighted"), requires_grad=True)
+    sd_t = model_oracle.clone_state(make_state_dict(6, fusion_type="concat", random_running_stats=True))
+    params = [v for v in sd_s.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-3)
+    w = torch.tensor(CLASS_WEIGHTS)
+    img, pts, lab = synthetic_frames(seed, batch, points)
+
+    def step():
+        opt.zero_grad()
+        with torch.no_grad():
+            tl, tm = model_oracle.model_forward(img, pts, sd_t, fusion_type="concat", train=False)
+        sl, sm = model_oracle.model_forward(img, pts, sd_s, fusion_type="weighted", train=True)
+        out = kd_oracle.kd_loss(sl, tl, lab, w, [sm[k] for k in kd_oracle.MIMIC_TAPS], [tm[k] for k in kd_oracle.MIMIC_TAPS])
+        out["loss"].backward()
+        opt.step()
+        return float(out["loss"].detach())
+    return step
+
+
+def time_cpu(batch, points, steps, warmup):
+    step = cpu_step_runner(batch, points)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    sec = statistics.median(ts)
+    return {"value": batch / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{steps} timed + {warmup} warm-up KD steps of {batch} frames x {points} pts on the host "
+                      f"(oracle port of the reference's eager fp32 path, torch {torch.__version__}, "
+                      f"{torch.get_num_threads()} threads), median {sec * 1e3:.0f} ms/step",
+            "ms_per_step": sec * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cb = time_cpu(args.cpu_batch, args.points, max(1, args.steps), max(0, args.warmup))
+    cfg = workload_config(args, args.gpus)
+    cfg["sample"] = f"each step is a bounded sample of {args.cpu_batch} frames of the same workload"
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ============================================================================= clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.cmd = ["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"]
+        except Exception:
+            self.cmd = None
+
+    def __enter__(self):
+        if self.cmd:
+            try:
+                self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for ln in out.splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "samples": len(sm)}
+
+
+# ============================================================================= native arm
+def build_models(device, fp32):
+    from src.models.camera_encoder import TwinLiteEncoder
+    from src.models.fusion_module import CompleteSegmentationModel
+    from src.models.lidar_encoder import LiDAREncoder
+    from src.training.trainer import Trainer
+
+    def make(ft, oc):
+        return CompleteSegmentationModel(TwinLiteEncoder(return_multiscale=True),
+                                         LiDAREncoder("spatial", grid_size=(64, 64), use_vectorized=True), num_classes=2,
+                                         fusion_type=ft, fusion_out_channels=oc,
+                                         camera_fpn_stages=["stage3", "stage4", "stage5"], camera_fpn_channels=128,
+                                         output_mode="same").to(device)
+    torch.manual_seed(0)                                  # identical replicas on every rank
+    student, teacher = make("weighted", 128), make("concat", 256)
+    trainer = Trainer(student, [], [], device, lr=1e-3, weight_decay=1e-3, class_weights=CLASS_WEIGHTS,
+                      save_dir=os.path.join(ROOT, "gpurun_out", "bench_ckpt"), teacher=teacher,
+                      amp_dtype=None if fp32 else torch.bfloat16, verbose=False)
+    student.train()
+    return trainer
+
+
+def peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_PEAK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def time_kernel(fn, iters=20, warm=3):
+    """Average device time of fn() in ms: CUDA events on the launching (current) stream."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def kernel_rooflines(args, device, fp32):
+    """Each hand-written kernel alone at the step's shapes.  Algorithmic bytes follow SURVEY.md 8(d)
+    (stated again in DESIGN.md); inputs per launch are >> L2 for the projection kernels, and a 256 MB
+    buffer is rewritten between launches for the small ones."""
+    from src import native, ops
+    from src.data_loading.synthetic_frames import make_frames
+    B, N, C, H, W = args.batch, args.points, 128, 64, 64
+    s = 4 if fp32 else 2
+    dt = torch.float32 if fp32 else torch.bfloat16
+    pts = make_frames(B, N, seed=123, device=device)["points"]
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    feats = torch.rand(B, N, C, device=device, dtype=dt)
+    peak, peak_src = peak_gbs()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = []
+
+    def add(name, ms, alg_bytes, note):
+        out.append({"kernel": name, "ms": ms, "algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms * 1e-3) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "bound": "hbm",
+                    "traffic": None, "note": note})
+
+    # ---- projection: whole forward call, reduce kernel alone, backward, index only
+    cell, count = ops.bev_index(pts, geom, (H, W))
+    v = (cell >= 0).float().mean().item()
+    grid = torch.empty(B, H, W, C, dtype=dt, device=device)
+    cnt = torch.empty(B, H * W, dtype=torch.int32, device=device)
+    cel = torch.empty(B, N, dtype=torch.int32, device=device)
+    ties = torch.empty(B, H * W, C, dtype=torch.int32, device=device)
+    order = torch.empty(B, N, dtype=torch.int32, device=device)
+    offs = torch.empty(B, H * W + 1, dtype=torch.int32, device=device)
+    wsb = native.lib.kdf_bev_workspace_bytes(B, N, H, W)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+    st = native.stream_ptr(device)
+    p = native.ptr
+
+    def proj_fwd():
+        native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), native.dtype_code(feats), B, N, C, *geom, H, W, 0,
+                    p(grid), p(cnt), p(cel), p(ties), p(order), p(offs), p(ws), wsb, st)
+    fwd_bytes = B * (16 * N + C * s * v * N + C * s * H * W + 4 * H * W)
+    add("bev_project_fwd (index+scan+fill+reduce)", time_kernel(proj_fwd), fwd_bytes,
+        "16N + C*s*v*N + C*s*HW + 4*HW per frame")
+
+    def reduce_only():
+        native.call("kdf_bev_reduce", p(feats), native.dtype_code(feats), p(order), p(offs), B, N, C, H, W, 0,
+                    p(grid), p(ties), st)
+    add("bev_reduce_kernel", time_kernel(reduce_only), B * (C * s * v * N + C * s * H * W),
+        "C*s*v*N + C*s*HW per frame (feature rows of valid points read once, grid written once)")
+
+    gg = torch.rand(B, H * W, C, device=device, dtype=dt)
+    gf = torch.empty(B, N, C, dtype=dt, device=device)
+
+    def proj_bwd():
+        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), native.dtype_code(feats),
+                    B, N, C, H, W, 0, p(gf), st)
+    add("bev_bwd_kernel", time_kernel(proj_bwd), B * (C * s * H * W + C * s * v * N + 4 * N),
+        "C*s*HW + C*s*v*N + 4N per frame (SURVEY 8d; the kernel also re-reads feats for tie detection "
+        "and writes zero rows for points outside)")
+
+    def index_only():
+        native.call("kdf_bev_index", p(pts), B, N, 4, *geom, H, W, p(cel), None, p(cnt), st)
+    add("bev_index_kernel", time_kernel(index_only), B * (16 * N + 4 * N + 4 * H * W), "16N + 4N + 4*HW per frame")
+
+    # ---- fusion (weighted) forward / backward on pre-BN rows
+    M = B * H * W
+    cam_pre = torch.randn(M, C, device=device, dtype=dt)
+    lid_pre = torch.randn(M, C, device=device, dtype=dt)
+    f32 = dict(device=device, dtype=torch.float32)
+    sc = [torch.rand(C, **f32) + 0.5 for _ in range(2)]
+    sh = [torch.randn(C, **f32) * 0.1 for _ in range(2)]
+    w1, b1 = torch.randn(C, 2 * C, **f32) * 0.05, torch.randn(C, **f32) * 0.1
+    w2, b2 = torch.randn(2, C, **f32) * 0.1, torch.randn(2, **f32) * 0.1
+    fo = torch.empty(M, C, dtype=dt, device=device)
+    attn = torch.empty(M, 2, **f32)
+
+    def with_flush(fn):
+        def g():
+            flush.fill_(1)
+            fn()
+        return g
+
+    def fus_fwd():
+        native.call("kdf_fusion_weighted_fwd", p(cam_pre), p(lid_pre), native.dtype_code(cam_pre), M, C, p(sc[0]), p(sh[0]),
+                    p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(fo), p(attn), st)
+    t_flush = time_kernel(lambda: flush.fill_(1))
+    add("fusion_weighted_fwd_kernel", time_kernel(with_flush(fus_fwd)) - t_flush, M * 3 * C * s,
+        "3*C*s per pixel (whole block fused, single pass); L2 flushed between launches")
+    go = torch.randn(M, C, device=device, dtype=dt)
+    g1, g2 = torch.empty_like(cam_pre), torch.empty_like(lid_pre)
+    gaff, gw1, gb1 = torch.empty(4, C, **f32), torch.empty(C, 2 * C, **f32), torch.empty(C, **f32)
+    gw2, gb2 = torch.empty(2, C, **f32), torch.empty(2, **f32)
+
+    def fus_bwd():
+        native.call("kdf_fusion_weighted_bwd", p(go), p(cam_pre), p(lid_pre), native.dtype_code(cam_pre), M, C, p(sc[0]),
+                    p(sh[0]), p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(attn), p(g1), p(g2), p(gaff), p(gw1),
+                    p(gb1), p(gw2), p(gb2), st)
+    add("fusion_weighted_bwd_kernel", time_kernel(with_flush(fus_bwd)) - t_flush, M * 5 * C * s,
+        "5*C*s per pixel (grad_out + 2 inputs read, 2 input grads written)")
+
+    # ---- KD loss forward+backward
+    zs = torch.randn(B, 2, H, W, device=device, dtype=dt)
+    zt = torch.randn(B, 2, H, W, device=device, dtype=dt)
+    lab = (torch.rand(B, H, W, device=device) < 0.13).long()
+    taps_s = [torch.randn(B, H, W, C, device=device, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
+    taps_t = [torch.randn(B, H, W, C, device=device, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
+    cw = torch.tensor(CLASS_WEIGHTS, device=device)
+
+    def kd():
+        ops.kd_loss_fwd_bwd(zs, zt, lab, cw, taps_s, taps_t)
+    K = 2
+    add("kd_loss_kernel (fwd+bwd)", time_kernel(with_flush(kd)) - t_flush, M * (2 * K * s + 8 + K * s + 2 * 3 * C * s),
+        "per pixel 2K*s + 8 + K*s logits/labels + 3*C*s per mimic tap (2 taps)")
+    return out, v
+
+
+def run_native(args):
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+    from src import native
+    from src.data_loading.synthetic_frames import make_frames
+    from src.training.parallel import frame_seed, reduce_max
+
+    trainer = build_models(device, args.fp32)
+    B, N = args.batch, args.points
+    n_data = 3
+    batches = [make_frames(B, N, seed=frame_seed(rank, i), device=device) for i in range(n_data)]
+
+    def step(i, b=None):
+        b = b or batches[i % n_data]
+        return trainer.training_step(b["image"], b["points"], b["segmentation"])
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step(i)
+    fence()
+    k0 = native.launch_stats["kernels"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(device) as clk:
+        e0.record()
+        for i in range(args.steps):
+            terms, _ = step(args.warmup + i)
+        e1.record()
+        fence()
+    launches = native.launch_stats["kernels"] - k0
+    ms = reduce_max(e0.elapsed_time(e1) / args.steps, device)
+    value = B * n_gpus / (ms * 1e-3)
+    loss_terms = [float(x) for x in terms[:4].float().cpu()]
+
+    # ---------------- e2e: pinned host batches, H2D inside the timed region, D2H of the loss terms
+    e2e = None
+    if not args.no_e2e:
+        host = [{k: v.cpu().pin_memory() for k, v in b.items() if torch.is_tensor(v)} for b in batches[:2]]
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        dev_bufs = [{k: torch.empty_like(v, device=device) for k, v in host[0].items()} for _ in range(2)]
+        host_terms = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        total = args.warmup + args.steps
+
+        def prefetch(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[slot])              # the step that last used this slot has finished
+                for k, v in host[i % 2].items():
+                    dev_bufs[slot][k].copy_(v, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        fence()
+        for ev in done:
+            ev.record()
+        prefetch(0)
+        t0 = t1 = None
+        for i in range(total):
+            if i == args.warmup:
+                fence()
+                t0 = torch.cuda.Event(enable_timing=True); t0.record()
+            slot = i % 2
+            torch.cuda.current_stream().wait_event(ready[slot])
+            if i + 1 < total:
+                prefetch(i + 1)                                  # overlaps with this step's compute
+            tt, _ = step(i, dev_bufs[slot])
+            done[slot].record()
+            host_terms[slot].copy_(tt, non_blocking=True)        # D2H read of the step's result
+        t1 = torch.cuda.Event(enable_timing=True); t1.record()
+        fence()
+        ms_e2e = reduce_max(t0.elapsed_time(t1) / args.steps, device)
+        e2e = {"value": B * n_gpus / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+               "ms_per_step": ms_e2e, "api": "src.training.trainer.Trainer.training_step on pinned host batches "
+               "(double-buffered H2D on a copy stream), loss terms copied back every step"}
+
+    # ---------------- per-kernel rooflines (rank 0 only does the work; others wait at the barrier)
+    kernels, roof = [], None
+    if not args.no_kernels and rank == 0:
+        del batches
+        torch.cuda.empty_cache()
+        kernels, valid_frac = kernel_rooflines(args, device, args.fp32)
+        dom = max((k for k in kernels if k["kernel"] != "bev_project_fwd (index+scan+fill+reduce)"), key=lambda k: k["ms"])
+        roof = {"bound": "hbm", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GB/s", "frac": dom["frac"],
+                "traffic": None, "kernel": dom["kernel"], "launch_ms": dom["ms"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "peak_source": peak_gbs()[1],
+                "valid_point_fraction": valid_frac}
+    if world > 1:
+        dist.barrier()
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cb = time_cpu(args.cpu_batch, args.points, args.cpu_steps, 1)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
+                "config": workload_config(args, n_gpus), "clocks": clk.result, "e2e": e2e,
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+                "loss_terms_last_step": dict(zip(("loss", "ce", "kl", "mse"), loss_terms))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()
