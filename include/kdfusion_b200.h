@@ -107,6 +107,33 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
                         int dtype, int B, int64_t N, int C, int H, int W, int reduce,
                         void *grad_feats, void *stream);
 
+/* ---------------------------------------------------------------- BatchNorm (+activation) over rows
+ * Every BatchNorm of the reference (BatchNorm1d in the point MLP, src/models/lidar_encoder.py:25-35;
+ * BatchNorm2d in camera_encoder.py:19-41 and fusion_module.py:11-32) applied to channels-last
+ * data seen as rows x [M,C] (M = B*N points or B*H*W pixels).  act: 0 none, 1 ReLU, 2 ReLU6.
+ *
+ * kdf_rowbn_stats    training statistics in one pass: mean / invstd (biased variance, eps inside the
+ *                    sqrt), the folded scale = gamma*invstd and shift = beta - mean*scale, and the
+ *                    nn.BatchNorm running-stat update (momentum, unbiased variance) when
+ *                    running_mean/var are given.  gamma/beta may be NULL (1 / 0).
+ * kdf_rowbn_apply_fwd  y = act(x*scale + shift) [+ residual]      (residual may be NULL)
+ * kdf_rowbn_bwd      d x, d gamma, d beta from grad_out: dy = g*act'(x*scale+shift);
+ *                    batch_stats != 0 chains through the batch mean / variance (training mode),
+ *                    batch_stats == 0 is eval mode (running statistics are constants).
+ * Workspaces: kdf_rowbn_workspace_bytes(C) for stats, kdf_rowbn_bwd_workspace_bytes(C) for bwd.
+ */
+size_t kdf_rowbn_workspace_bytes(int C);
+size_t kdf_rowbn_bwd_workspace_bytes(int C);
+int kdf_rowbn_stats(const void *x, int dtype, int64_t M, int C, const float *gamma, const float *beta,
+                    float eps, float momentum, float *running_mean, float *running_var,
+                    float *mean, float *invstd, float *scale, float *shift, void *workspace, void *stream);
+int kdf_rowbn_apply_fwd(const void *x, const void *residual, int dtype, int64_t M, int C,
+                        const float *scale, const float *shift, int act, void *y, void *stream);
+int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int C,
+                  const float *scale, const float *shift, const float *mean, const float *invstd,
+                  int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,
+                  void *workspace, void *stream);
+
 /* ---------------------------------------------------------------- (2) camera-LiDAR fusion
  * Inputs are the PRE-BatchNorm outputs of the two 1x1 projection convolutions
  * in pixel-major (NHWC) layout; BatchNorm is applied as y = x*scale + shift with

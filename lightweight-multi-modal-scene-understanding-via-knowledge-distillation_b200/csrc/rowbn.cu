@@ -1,0 +1,395 @@
+// BatchNorm (+ReLU / ReLU6, + residual) over pixel- or point-major rows [M, C]  (sm_100a).
+//
+// Every BatchNorm of the reference -- BatchNorm1d in the point MLP
+// (src/models/lidar_encoder.py:25-35), BatchNorm2d in the camera encoder, FPN, fusion and
+// heads (camera_encoder.py:19-41, fusion_module.py:11-32) -- sees its input here as rows
+// of a channels-last tensor: M = B*N points or B*H*W pixels, C channels contiguous.
+// Training mode needs the batch statistics before anything can be applied, so forward and
+// backward are two streaming passes each, and nothing else:
+//
+//   forward : stats  (read x)            -> mean/invstd, scale/shift, running-stat update
+//             apply  (read x, write y)   y = act(x*scale + shift) [+ residual]
+//   backward: reduce (read g, x)         -> S0 = sum dy, S1 = sum dy*x  => d gamma, d beta,
+//                                           per-channel (A, B) of the statistics chain
+//             apply  (read g, x, write)  dx = dy*scale + B*x + A
+//
+// Both reductions are per-thread fp32 partial sums over a few hundred rows, combined in
+// fp64 in a fixed order by the last CTA (deterministic, no float atomics).  All four
+// kernels are HBM-bound streaming kernels; the per-channel finalisation lives in the last
+// CTA of the reduction so no tiny host-driven launches are needed.
+#include "kdf_common.cuh"
+
+namespace kdf {
+
+constexpr int RB_THREADS = 256;
+constexpr int RB_MAX_BLOCKS = 1184;          // 148 SMs x 8 CTAs
+
+struct RowMap {           // thread -> (row lane r, column group g) for rows of C = G*VEC channels
+    int G, rows, r, g;
+    bool active;
+};
+template <int VEC>
+__device__ __forceinline__ RowMap row_map(int C) {
+    RowMap m;
+    m.G = C / VEC;
+    m.rows = RB_THREADS / m.G;               // >= 1 because C <= 256*VEC is checked on the host
+    m.active = threadIdx.x < m.rows * m.G;
+    m.r = threadIdx.x / m.G;
+    m.g = threadIdx.x - m.r * m.G;
+    return m;
+}
+
+template <typename T, int VEC> struct VecIO;
+template <typename T> struct VecIO<T, 4> {
+    static __device__ __forceinline__ void load(const T *p, float *v) {
+        const float4 a = Vec4<T>::load_stream(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    static __device__ __forceinline__ void store(T *p, const float *v) {
+        Vec4<T>::store(p, make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <> struct VecIO<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
+        const uint4 u = ldg_stream_u4(reinterpret_cast<const uint4 *>(p));
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+        uint4 u;
+        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+        u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(p) = u;
+    }
+};
+
+__device__ __forceinline__ float act_fwd(float y, int act) {
+    if (act == 1) return fmaxf(y, 0.f);
+    if (act == 2) return fminf(fmaxf(y, 0.f), 6.f);
+    return y;
+}
+__device__ __forceinline__ bool act_open(float y, int act) {      // derivative is 1 (else 0)
+    if (act == 1) return y > 0.f;
+    if (act == 2) return y > 0.f && y < 6.f;
+    return true;
+}
+
+struct RowBnWs {            // workspace header followed by partial[blocks][2][C]
+    unsigned int ticket;
+    unsigned int pad[3];
+};
+
+// Two per-channel sums over the rows; `MODE` 0: (x, x^2)   1: (dy, dy*x) with dy = g * act'(x*scale+shift).
+// The last CTA combines the partials in block order and finalises.
+struct ReduceArgs {
+    const void *x, *g;
+    int64_t M;
+    int C, act;
+    const float *scale, *shift;      // MODE 1
+    // MODE 0 finalisation (training statistics)
+    const float *gamma, *beta;
+    float eps, momentum;
+    float *mean, *invstd, *out_scale, *out_shift, *running_mean, *running_var;
+    // MODE 1 finalisation
+    const float *in_mean, *in_invstd;
+    int batch_stats;
+    float *dgamma, *dbeta, *coefA, *coefB;
+    RowBnWs *ws;
+};
+
+template <typename T, int VEC, int MODE>
+__global__ void __launch_bounds__(RB_THREADS)
+rowbn_reduce_kernel(ReduceArgs a) {
+    extern __shared__ float sm[];                     // [rows][G][2*VEC]
+    __shared__ bool last;
+    const RowMap m = row_map<VEC>(a.C);
+    const T *x = reinterpret_cast<const T *>(a.x);
+    const T *g = reinterpret_cast<const T *>(a.g);
+    float s0[VEC], s1[VEC], sc[VEC], sh[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) { s0[q] = 0.f; s1[q] = 0.f; sc[q] = 1.f; sh[q] = 0.f; }
+    if (m.active) {
+        const int c = m.g * VEC;
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { sc[q] = a.scale[c + q]; sh[q] = a.shift[c + q]; }
+        }
+        const int64_t stride = (int64_t)gridDim.x * m.rows;
+        constexpr int U = 4;
+        for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < a.M; row += stride * U) {
+            float xv[U][VEC], gv[U][VEC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t rr = row + u * stride;
+                if (rr < a.M) {
+                    VecIO<T, VEC>::load(x + rr * a.C + c, xv[u]);
+                    if (MODE == 1) VecIO<T, VEC>::load(g + rr * a.C + c, gv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (row + u * stride < a.M) {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        if (MODE == 0) {
+                            s0[q] += xv[u][q];
+                            s1[q] = fmaf(xv[u][q], xv[u][q], s1[q]);
+                        } else {
+                            const float dy = act_open(fmaf(xv[u][q], sc[q], sh[q]), a.act) ? gv[u][q] : 0.f;
+                            s0[q] += dy;
+                            s1[q] = fmaf(dy, xv[u][q], s1[q]);
+                        }
+                    }
+                }
+            }
+        }
+        float *dst = sm + (m.r * m.G + m.g) * 2 * VEC;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { dst[q] = s0[q]; dst[VEC + q] = s1[q]; }
+    }
+    __syncthreads();
+    float *partial = reinterpret_cast<float *>(a.ws + 1);
+    if (m.active && m.r == 0) {
+        for (int rr = 1; rr < m.rows; ++rr) {
+            const float *src = sm + (rr * m.G + m.g) * 2 * VEC;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { s0[q] += src[q]; s1[q] += src[VEC + q]; }
+        }
+        float *p0 = partial + (int64_t)blockIdx.x * 2 * a.C + m.g * VEC;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { p0[q] = s0[q]; p0[a.C + q] = s1[q]; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&a.ws->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const double invM = 1.0 / (double)a.M;
+    for (int c = threadIdx.x; c < a.C; c += RB_THREADS) {
+        double t0 = 0.0, t1 = 0.0;
+        const volatile float *pp = partial + c;
+        for (int b = 0; b < (int)gridDim.x; ++b) {
+            t0 += (double)pp[(int64_t)b * 2 * a.C];
+            t1 += (double)pp[(int64_t)b * 2 * a.C + a.C];
+        }
+        if (MODE == 0) {
+            const double mean = t0 * invM;
+            double var = t1 * invM - mean * mean;                 // biased variance (normalisation)
+            if (var < 0.0) var = 0.0;
+            const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+            a.mean[c] = (float)mean;
+            a.invstd[c] = invstd;
+            const float scl = (a.gamma ? a.gamma[c] : 1.f) * invstd;
+            a.out_scale[c] = scl;
+            a.out_shift[c] = (a.beta ? a.beta[c] : 0.f) - (float)mean * scl;
+            if (a.running_mean) {                                 // nn.BatchNorm: unbiased variance in the running stat
+                const double unb = a.M > 1 ? var * ((double)a.M / (double)(a.M - 1)) : var;
+                a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)mean;
+                a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
+            }
+        } else {
+            const float mean = a.in_mean[c], invstd = a.in_invstd[c], scl = a.scale[c];
+            const float S0 = (float)t0, S1 = (float)t1;
+            const float dgamma = invstd * (S1 - mean * S0);       // sum dy * xhat
+            if (a.dgamma) a.dgamma[c] = dgamma;
+            if (a.dbeta) a.dbeta[c] = S0;
+            float A = 0.f, B = 0.f;
+            if (a.batch_stats) {                                  // chain through batch mean / variance
+                B = -(scl * invstd * dgamma) * (float)invM;
+                A = -(scl * S0) * (float)invM - B * mean;
+            }
+            a.coefA[c] = A;
+            a.coefB[c] = B;
+        }
+    }
+}
+
+// y = act(x*scale + shift) [+ residual]
+template <typename T, int VEC>
+__global__ void __launch_bounds__(RB_THREADS)
+rowbn_apply_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, T *__restrict__ y, int64_t M, int C,
+                       const float *__restrict__ scale, const float *__restrict__ shift, int act) {
+    const RowMap m = row_map<VEC>(C);
+    if (!m.active) return;
+    const int c = m.g * VEC;
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) { sc[q] = scale[c + q]; sh[q] = shift[c + q]; }
+    const int64_t stride = (int64_t)gridDim.x * m.rows;
+    constexpr int U = 4;
+    for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < M; row += stride * U) {
+        float xv[U][VEC], rv[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                VecIO<T, VEC>::load(x + rr * C + c, xv[u]);
+                if (res) VecIO<T, VEC>::load(res + rr * C + c, rv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                float o[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    o[q] = act_fwd(fmaf(xv[u][q], sc[q], sh[q]), act);
+                    if (res) o[q] += rv[u][q];
+                }
+                VecIO<T, VEC>::store(y + rr * C + c, o);
+            }
+        }
+    }
+}
+
+// dx = dy*scale + B*x + A,  dy = g * act'(x*scale + shift)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(RB_THREADS)
+rowbn_apply_bwd_kernel(const T *__restrict__ g, const T *__restrict__ x, T *__restrict__ dx, int64_t M, int C,
+                       const float *__restrict__ scale, const float *__restrict__ shift,
+                       const float *__restrict__ coefA, const float *__restrict__ coefB, int act) {
+    const RowMap m = row_map<VEC>(C);
+    if (!m.active) return;
+    const int c = m.g * VEC;
+    float sc[VEC], sh[VEC], A[VEC], B[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) { sc[q] = scale[c + q]; sh[q] = shift[c + q]; A[q] = coefA[c + q]; B[q] = coefB[c + q]; }
+    const int64_t stride = (int64_t)gridDim.x * m.rows;
+    constexpr int U = 4;
+    for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < M; row += stride * U) {
+        float xv[U][VEC], gv[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                VecIO<T, VEC>::load(x + rr * C + c, xv[u]);
+                VecIO<T, VEC>::load(g + rr * C + c, gv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                float o[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const float dy = act_open(fmaf(xv[u][q], sc[q], sh[q]), act) ? gv[u][q] : 0.f;
+                    o[q] = fmaf(dy, sc[q], fmaf(B[q], xv[u][q], A[q]));
+                }
+                VecIO<T, VEC>::store(dx + rr * C + c, o);
+            }
+        }
+    }
+}
+
+static int rb_vec(int dtype, int C) { return (dtype == KDF_BF16 && C % 8 == 0) ? 8 : 4; }
+
+static int rb_check(int dtype, int64_t M, int C, const char *who) {
+    KDF_CHECK_ARG(M >= 0, "%s: negative M", who);
+    KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "%s: bad dtype %d", who, dtype);
+    KDF_CHECK_ARG(C >= 4 && C % 4 == 0, "%s: C=%d must be a positive multiple of 4", who, C);
+    KDF_CHECK_ARG(C / rb_vec(dtype, C) <= RB_THREADS, "%s: C=%d too wide", who, C);
+    return KDF_OK;
+}
+
+static int rb_blocks(int64_t M, int C, int vec, int per_thread_rows) {
+    const int rows = RB_THREADS / (C / vec);
+    int64_t b = (M + (int64_t)rows * per_thread_rows - 1) / ((int64_t)rows * per_thread_rows);
+    const int cap = sm_count() * 8 < RB_MAX_BLOCKS ? sm_count() * 8 : RB_MAX_BLOCKS;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <int MODE>
+static int launch_reduce(const ReduceArgs &a, int dtype, cudaStream_t st) {
+    const int vec = rb_vec(dtype, a.C);
+    const int blocks = rb_blocks(a.M, a.C, vec, 16);
+    const int rows = RB_THREADS / (a.C / vec);
+    const size_t smem = sizeof(float) * (size_t)rows * (a.C / vec) * 2 * vec;
+    KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs), st));
+    if (dtype == KDF_F32) rowbn_reduce_kernel<float, 4, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
+    else if (vec == 8)    rowbn_reduce_kernel<__nv_bfloat16, 8, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
+    else                  rowbn_reduce_kernel<__nv_bfloat16, 4, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+}  // namespace kdf
+
+using namespace kdf;
+
+extern "C" {
+
+size_t kdf_rowbn_workspace_bytes(int C) { return sizeof(RowBnWs) + sizeof(float) * (size_t)RB_MAX_BLOCKS * 2 * (size_t)C; }
+
+int kdf_rowbn_stats(const void *x, int dtype, int64_t M, int C, const float *gamma, const float *beta,
+                    float eps, float momentum, float *running_mean, float *running_var,
+                    float *mean, float *invstd, float *scale, float *shift, void *workspace, void *stream) {
+    if (int e = rb_check(dtype, M, C, "rowbn_stats")) return e;
+    KDF_CHECK_ARG(M > 0, "rowbn_stats: batch statistics need at least one row");
+    KDF_CHECK_ARG(x && mean && invstd && scale && shift && workspace, "rowbn_stats: null pointer");
+    KDF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "rowbn_stats: running stats come in pairs");
+    ReduceArgs a{};
+    a.x = x; a.M = M; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum;
+    a.mean = mean; a.invstd = invstd; a.out_scale = scale; a.out_shift = shift;
+    a.running_mean = running_mean; a.running_var = running_var;
+    a.ws = reinterpret_cast<RowBnWs *>(workspace);
+    return launch_reduce<0>(a, dtype, as_stream(stream));
+}
+
+int kdf_rowbn_apply_fwd(const void *x, const void *residual, int dtype, int64_t M, int C,
+                        const float *scale, const float *shift, int act, void *y, void *stream) {
+    if (int e = rb_check(dtype, M, C, "rowbn_apply_fwd")) return e;
+    KDF_CHECK_ARG(act >= 0 && act <= 2, "rowbn_apply_fwd: bad activation %d", act);
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(x && y && scale && shift, "rowbn_apply_fwd: null pointer");
+    const int vec = rb_vec(dtype, C);
+    const int blocks = rb_blocks(M, C, vec, 8);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == KDF_F32)
+        rowbn_apply_fwd_kernel<float, 4><<<blocks, RB_THREADS, 0, st>>>((const float *)x, (const float *)residual, (float *)y, M, C, scale, shift, act);
+    else if (vec == 8)
+        rowbn_apply_fwd_kernel<__nv_bfloat16, 8><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)residual, (__nv_bfloat16 *)y, M, C, scale, shift, act);
+    else
+        rowbn_apply_fwd_kernel<__nv_bfloat16, 4><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)residual, (__nv_bfloat16 *)y, M, C, scale, shift, act);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int C,
+                  const float *scale, const float *shift, const float *mean, const float *invstd,
+                  int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,
+                  void *workspace, void *stream) {
+    if (int e = rb_check(dtype, M, C, "rowbn_bwd")) return e;
+    KDF_CHECK_ARG(act >= 0 && act <= 2, "rowbn_bwd: bad activation %d", act);
+    KDF_CHECK_ARG(M > 0, "rowbn_bwd: empty input");
+    KDF_CHECK_ARG(grad_out && x && scale && shift && mean && invstd && grad_x && workspace, "rowbn_bwd: null pointer");
+    cudaStream_t st = as_stream(stream);
+    // coefficient vectors live at the tail of the workspace
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *coefA = reinterpret_cast<float *>(ws + sizeof(RowBnWs) + sizeof(float) * (size_t)RB_MAX_BLOCKS * 2 * (size_t)C);
+    float *coefB = coefA + C;
+    ReduceArgs a{};
+    a.x = x; a.g = grad_out; a.M = M; a.C = C; a.act = act; a.scale = scale; a.shift = shift;
+    a.in_mean = mean; a.in_invstd = invstd; a.batch_stats = batch_stats;
+    a.dgamma = dgamma; a.dbeta = dbeta; a.coefA = coefA; a.coefB = coefB;
+    a.ws = reinterpret_cast<RowBnWs *>(workspace);
+    if (int e = launch_reduce<1>(a, dtype, st)) return e;
+    const int vec = rb_vec(dtype, C);
+    const int blocks = rb_blocks(M, C, vec, 8);
+    if (dtype == KDF_F32)
+        rowbn_apply_bwd_kernel<float, 4><<<blocks, RB_THREADS, 0, st>>>((const float *)grad_out, (const float *)x, (float *)grad_x, M, C, scale, shift, coefA, coefB, act);
+    else if (vec == 8)
+        rowbn_apply_bwd_kernel<__nv_bfloat16, 8><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)grad_out, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)grad_x, M, C, scale, shift, coefA, coefB, act);
+    else
+        rowbn_apply_bwd_kernel<__nv_bfloat16, 4><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)grad_out, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)grad_x, M, C, scale, shift, coefA, coefB, act);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+size_t kdf_rowbn_bwd_workspace_bytes(int C) { return kdf_rowbn_workspace_bytes(C) + sizeof(float) * 2 * (size_t)C; }
+
+}  // extern "C"

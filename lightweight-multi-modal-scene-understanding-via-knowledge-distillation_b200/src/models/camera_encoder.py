@@ -16,6 +16,8 @@ from typing import Dict, List, Union
 import torch
 import torch.nn as nn
 
+from ..ops import run_fused
+
 
 def _conv_bn(cin: int, cout: int, kernel: int, stride: int = 1, groups: int = 1, act: bool = True) -> List[nn.Module]:
     """conv (no bias) -> BatchNorm2d [-> ReLU6], as a flat list so callers control Sequential indices."""
@@ -44,8 +46,8 @@ class InvertedResidual(nn.Module):
         self.conv = nn.Sequential(*seq)
 
     def forward(self, x):
-        y = self.conv(x)
-        return x + y if self.use_residual else y
+        # conv layers on cuDNN; every BatchNorm(+ReLU6) group and the shortcut add on the fused row kernels
+        return run_fused(self.conv, x, residual=x if self.use_residual else None)
 
 
 class TwinLiteEncoder(nn.Module):
@@ -68,9 +70,10 @@ class TwinLiteEncoder(nn.Module):
         self.out_channels = base_channels * 4
 
     def forward(self, x) -> Union[torch.Tensor, Dict[str, torch.Tensor]]:
-        if x.is_cuda and x.dim() == 4:
-            x = x.contiguous(memory_format=torch.channels_last)     # NHWC end to end
-        x = self.stem(x)
+        if not x.is_cuda:
+            raise RuntimeError("TwinLiteEncoder runs on CUDA tensors only (no CPU fallback)")
+        x = x.contiguous(memory_format=torch.channels_last)         # NHWC end to end
+        x = run_fused(self.stem, x)
         feats = {}
         for name, *_ in self._STAGES:
             x = getattr(self, name)(x)

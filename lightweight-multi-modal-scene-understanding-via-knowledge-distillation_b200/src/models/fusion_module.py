@@ -29,7 +29,7 @@ class Conv1x1(nn.Module):
                                   nn.BatchNorm2d(out_ch), nn.ReLU())
 
     def forward(self, x):
-        return self.conv(x)
+        return ops.run_fused(self.conv, x)
 
 
 class DWSeparableConv(nn.Module):
@@ -44,7 +44,7 @@ class DWSeparableConv(nn.Module):
             nn.BatchNorm2d(out_ch), nn.ReLU())
 
     def forward(self, x):
-        return self.net(x)
+        return ops.run_fused(self.net, x)
 
 
 class CameraFPNLite(nn.Module):
@@ -134,7 +134,7 @@ class ConcatenationFusion(_PairFusion):
 
     def forward_with_pre(self, cam_feat, lidar_feat):
         pre, _ = self.fuse_rows(cam_feat, lidar_feat)
-        return pre, self.fuse(pre)
+        return pre, ops.run_fused(self.fuse, pre)
 
     def forward(self, cam_feat, lidar_feat):
         return self.forward_with_pre(cam_feat, lidar_feat)[1]
@@ -192,7 +192,7 @@ class LightweightSegmentationHead(nn.Module):
         self.cls = nn.Conv2d(16, num_classes, kernel_size=3, padding=1)
 
     def forward(self, x):
-        return self.cls(self.up2(self.up1(x)))
+        return self.cls(ops.run_fused(self.up2, ops.run_fused(self.up1, x)))
 
 
 class SameResolutionSegmentationHead(nn.Module):

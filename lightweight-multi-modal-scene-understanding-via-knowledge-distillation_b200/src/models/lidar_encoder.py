@@ -70,7 +70,7 @@ class SpatialLiDAREncoder(nn.Module):
         x = points.reshape(B * N, D)
         for i in range(0, len(self.point_mlp), 3):
             conv, bn = self.point_mlp[i], self.point_mlp[i + 1]
-            x = F.relu(bn(F.linear(x, conv.weight.squeeze(-1), conv.bias)))
+            x = ops.bn_act(F.linear(x, conv.weight.squeeze(-1), conv.bias), bn, "relu")
         return x.view(B, N, -1)
 
     def forward_vectorized(self, points: torch.Tensor) -> torch.Tensor:

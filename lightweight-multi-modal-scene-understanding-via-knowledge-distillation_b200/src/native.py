@@ -29,6 +29,11 @@ _SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kdf_bev_reduce": (C.c_int, [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kdf_bev_project_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "kdf_rowbn_workspace_bytes": (_sz, [_i]),
+    "kdf_rowbn_bwd_workspace_bytes": (_sz, [_i]),
+    "kdf_rowbn_stats": (C.c_int, [_vp, _i, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdf_rowbn_apply_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _i, _vp, _vp]),
+    "kdf_rowbn_bwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_fusion_weighted_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp, _vp, _vp]),
     "kdf_fusion_weighted_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp] + [_vp] * 7 + [_vp]),
     "kdf_fusion_affine_relu_pair_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -71,6 +76,7 @@ KERNELS_PER_CALL = {
     "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
     "kdf_fusion_affine_relu_pair_fwd": 1, "kdf_fusion_affine_relu_pair_bwd": 1,
     "kdf_kd_loss_fwd_bwd": 2, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
+    "kdf_rowbn_stats": 1, "kdf_rowbn_apply_fwd": 1, "kdf_rowbn_bwd": 2,
 }
 launch_stats = {"kernels": 0, "calls": 0}
 

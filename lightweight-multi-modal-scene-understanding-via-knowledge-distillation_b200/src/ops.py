@@ -14,9 +14,135 @@ from . import native as _n
 from .native import call, dtype_code, lib, ptr, require_cuda, stream_ptr
 
 __all__ = [
+    "bn_act", "run_fused",
     "bev_range_constants", "bev_index", "bev_project", "BevProjectFn",
     "fused_fusion", "kd_loss_fwd_bwd", "KDLossFn", "confusion_matrix_", "adamw_flat_",
 ]
+
+
+# ----------------------------------------------------------------------------- BatchNorm (+act) over rows
+_ACT = {None: 0, "none": 0, "relu": 1, "relu6": 2}
+
+
+class _RowBNActFn(torch.autograd.Function):
+    """y = act(x*scale + shift) [+ residual] over rows [M,C]; scale/shift/mean/invstd are the fp32
+    per-channel vectors prepared by ``bn_act`` (batch statistics in training, running statistics in
+    eval).  Backward = kdf_rowbn_bwd (reduce + apply, chaining through the batch statistics)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale, shift, mean, invstd, act, batch_stats, residual):
+        M, C = x.shape
+        y = torch.empty_like(x)
+        call("kdf_rowbn_apply_fwd", ptr(x), ptr(residual), dtype_code(x), M, C, ptr(scale), ptr(shift), act, ptr(y),
+             stream_ptr(x.device))
+        ctx.save_for_backward(x, scale, shift, mean, invstd)
+        ctx.act, ctx.batch_stats = act, batch_stats
+        ctx.has_res = residual is not None
+        ctx.affine = (gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, scale, shift, mean, invstd = ctx.saved_tensors
+        M, C = x.shape
+        g = g.contiguous()
+        if g.dtype != x.dtype:
+            g = g.to(x.dtype)
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        nb = lib.kdf_rowbn_bwd_workspace_bytes(C)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        call("kdf_rowbn_bwd", ptr(g), ptr(x), dtype_code(x), M, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+             ctx.act, int(ctx.batch_stats), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(ws), stream_ptr(x.device))
+        return (dx, dgamma if ctx.affine[0] else None, dbeta if ctx.affine[1] else None,
+                None, None, None, None, None, None, g if ctx.has_res else None)
+
+
+def _eval_affine(bn):
+    """(scale, shift, mean, invstd) of a BatchNorm in eval mode, cached until its tensors change."""
+    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None)
+    cache = getattr(bn, "_kdf_eval_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    with torch.no_grad():
+        mean = bn.running_mean.float()
+        invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+        scale = invstd * bn.weight.float() if bn.weight is not None else invstd.clone()
+        shift = (bn.bias.float() if bn.bias is not None else torch.zeros_like(mean)) - mean * scale
+        vals = tuple(t.contiguous() for t in (scale, shift, mean, invstd))
+    bn._kdf_eval_cache = (key, vals)
+    return vals
+
+
+def _bn_prepare(rows: torch.Tensor, bn):
+    """fp32 per-channel (scale, shift, mean, invstd, batch_stats) for a BatchNorm module over rows [M,C]:
+    batch statistics (one ``kdf_rowbn_stats`` launch, which also advances the running statistics
+    exactly like nn.BatchNorm) in training, cached running-statistics affine in eval."""
+    dev = rows.device
+    M, C = rows.shape
+    use_batch = bn.training or bn.running_mean is None
+    if not use_batch:
+        return (*_eval_affine(bn), False)
+    f32 = dict(dtype=torch.float32, device=dev)
+    mean, invstd, scale, shift = (torch.empty(C, **f32) for _ in range(4))
+    track = bn.training and bn.track_running_stats and bn.running_mean is not None
+    mom = 0.0
+    if track:
+        bn.num_batches_tracked.add_(1)
+        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    ws = torch.empty(lib.kdf_rowbn_workspace_bytes(C), dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        call("kdf_rowbn_stats", ptr(rows), dtype_code(rows), M, C, ptr(bn.weight), ptr(bn.bias), float(bn.eps), float(mom),
+             ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+             ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(ws), stream_ptr(dev))
+    return scale, shift, mean, invstd, True
+
+
+def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(bn(x)) [+ residual]`` with the BatchNorm module's parameters / buffers (updated like
+    nn.BatchNorm does in training).  ``x`` is a channels-last [B,C,H,W] tensor or rows [M,C]."""
+    dev = require_cuda(x, residual)
+    four_d = x.dim() == 4
+    if four_d:
+        B, C, H, W = x.shape
+        rows = x.permute(0, 2, 3, 1).reshape(B * H * W, C)        # free for channels-last, one copy otherwise
+        res = None if residual is None else residual.permute(0, 2, 3, 1).reshape(B * H * W, C)
+    elif x.dim() == 2:
+        rows, res, C = x.contiguous(), (None if residual is None else residual.contiguous()), x.shape[1]
+    else:
+        raise ValueError(f"bn_act expects [B,C,H,W] or [M,C], got {tuple(x.shape)}")
+    if not rows.is_contiguous():
+        rows = rows.contiguous()
+    if res is not None and (res.dtype != rows.dtype or not res.is_contiguous()):
+        res = res.to(rows.dtype).contiguous()
+    scale, shift, mean, invstd, use_batch = _bn_prepare(rows, bn)
+    y = _RowBNActFn.apply(rows, bn.weight, bn.bias, scale, shift, mean, invstd, _ACT[act], use_batch, res)
+    return y.view(B, H, W, C).permute(0, 3, 1, 2) if four_d else y
+
+
+def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run an ``nn.Sequential`` of conv / BatchNorm / ReLU(6) layers with every BatchNorm(+activation)
+    group executed by the fused row kernels; ``residual`` is added after the LAST BatchNorm group.
+    The Sequential keeps its layers (and state_dict keys); only the execution is fused."""
+    import torch.nn as nn
+    mods = list(seq)
+    last_bn = max((i for i, m in enumerate(mods) if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d))), default=-1)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            act, step = None, 1
+            if i + 1 < len(mods) and isinstance(mods[i + 1], (nn.ReLU, nn.ReLU6)):
+                act, step = ("relu6" if isinstance(mods[i + 1], nn.ReLU6) else "relu"), 2
+            x = bn_act(x, m, act, residual if i == last_bn else None)
+            i += step
+        else:
+            x = m(x)
+            i += 1
+    if residual is not None and last_bn < 0:
+        x = x + residual
+    return x
 
 
 # ----------------------------------------------------------------------------- (1) projection
@@ -129,18 +255,14 @@ class _FusedFusionFn(torch.autograd.Function):
     by the caller.  Backward chains through the batch statistics analytically."""
 
     @staticmethod
-    def forward(ctx, cam_pre, lid_pre, cam_g, cam_b, lid_g, lid_b, cam_mean, cam_invstd, lid_mean, lid_invstd,
-                batch_stats, mode, w1, b1, w2, b2):
+    def forward(ctx, cam_pre, lid_pre, cam_g, cam_b, lid_g, lid_b, csc, csh, cam_mean, cam_invstd,
+                lsc, lsh, lid_mean, lid_invstd, batch_stats, mode, w1, b1, w2, b2):
         dev = require_cuda(cam_pre, lid_pre, cam_g, lid_g, w1)
         cam_pre, lid_pre = cam_pre.contiguous(), lid_pre.contiguous()
         if cam_pre.shape != lid_pre.shape or cam_pre.dtype != lid_pre.dtype or cam_pre.dim() != 2:
             raise ValueError("fusion expects two [M,C] row tensors of the same shape and dtype")
         M, C = cam_pre.shape
         f32 = torch.float32
-        csc = (cam_g.to(f32) * cam_invstd).contiguous()
-        csh = (cam_b.to(f32) - cam_mean * csc).contiguous()
-        lsc = (lid_g.to(f32) * lid_invstd).contiguous()
-        lsh = (lid_b.to(f32) - lid_mean * lsc).contiguous()
         dt, st = dtype_code(cam_pre), stream_ptr(dev)
         attn = None
         if mode == 2:
@@ -204,7 +326,7 @@ class _FusedFusionFn(torch.autograd.Function):
             grads_gb.append((dgamma, dbeta))
         pd = ctx.param_dtypes[0]
         return (g_cam, g_lid, grads_gb[0][0].to(pd), grads_gb[0][1].to(pd), grads_gb[1][0].to(pd), grads_gb[1][1].to(pd),
-                None, None, None, None, None, None, gw1, gb1, gw2, gb2)
+                None, None, None, None, None, None, None, None, None, None, gw1, gb1, gw2, gb2)
 
 
 def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None):
@@ -213,31 +335,16 @@ def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None):
     exactly like nn.BatchNorm2d does in training); ``attention`` is the
     ``nn.Sequential(conv, relu, conv, softmax)`` of WeightedFusion.
     Returns (rows [M,C] or [M,2C], attn [M,2] | None)."""
-    stats = []
-    for x, bn in ((cam_pre, cam_bn), (lid_pre, lid_bn)):
-        use_batch = bn.training or bn.running_mean is None
-        with torch.no_grad():
-            if use_batch:
-                mean, invstd = torch.batch_norm_stats(x, bn.eps)           # fp32 statistics over the M rows
-                if bn.training and bn.track_running_stats and bn.running_mean is not None:
-                    bn.num_batches_tracked += 1
-                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                    M = x.shape[0]
-                    var = invstd.pow(-2) - bn.eps
-                    bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
-                    bn.running_var.mul_(1 - mom).add_((var * (M / max(M - 1, 1))).to(bn.running_var.dtype), alpha=mom)
-            else:
-                mean = bn.running_mean.float()
-                invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
-        stats.append((mean, invstd, use_batch))
-    if stats[0][2] != stats[1][2]:
+    cs = _bn_prepare(cam_pre.contiguous(), cam_bn)
+    ls = _bn_prepare(lid_pre.contiguous(), lid_bn)
+    if cs[4] != ls[4]:
         raise RuntimeError("the two projection BatchNorms must be in the same mode")
     if mode == "weighted":
         w1, b1, w2, b2 = attention[0].weight, attention[0].bias, attention[2].weight, attention[2].bias
     else:
         w1 = b1 = w2 = b2 = None
     return _FusedFusionFn.apply(cam_pre, lid_pre, cam_bn.weight, cam_bn.bias, lid_bn.weight, lid_bn.bias,
-                                stats[0][0], stats[0][1], stats[1][0], stats[1][1], stats[0][2], _MODES[mode],
+                                cs[0], cs[1], cs[2], cs[3], ls[0], ls[1], ls[2], ls[3], cs[4], _MODES[mode],
                                 w1, b1, w2, b2)
 
 

@@ -408,3 +408,58 @@ def test_adamw_flat_matches_torch_adamw(ops):
         hyper.copy_(torch.tensor([1e-3, float(step)]))
         ops.adamw_flat_(buf[0], buf[1], buf[2], buf[3], hyper, 0.9, 0.999, 1e-8, 1e-3, grad_scale=0.25)
         assert rel_err(buf[0][:n].cpu(), ref_p.detach()) < 1e-6
+
+
+# ----------------------------------------------------------------------------- BatchNorm (+act) over rows
+@pytest.mark.parametrize("C,act,train,residual", [(64, "relu", True, False), (192, "relu6", True, False),
+                                                   (128, None, True, True), (32, "relu6", False, False),
+                                                   (768, "relu6", True, False), (16, "relu", True, False)])
+def test_rowbn_fp32_vs_torch_batchnorm(ops, C, act, train, residual):
+    """bn_act against nn.BatchNorm2d + activation (+ shortcut add) as the reference composes them
+    (camera_encoder.py:19-51, fusion_module.py:11-32): output, d input, d gamma, d beta and the running
+    statistics within 1e-5 relative (fp32)."""
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(3, C, 20, 28, generator=g) * 2 + 0.5
+    res = torch.randn(3, C, 20, 28, generator=g) if residual else None
+    gout = torch.randn(3, C, 20, 28, generator=g)
+    bn_ref = nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.rand(C, generator=g) + 0.5); bn_ref.bias.copy_(torch.randn(C, generator=g) * 0.2)
+        bn_ref.running_mean.copy_(torch.randn(C, generator=g) * 0.1); bn_ref.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    import copy
+    bn_cuda = copy.deepcopy(bn_ref).cuda()
+    bn_ref.train(train); bn_cuda.train(train)
+    xr = x.clone().requires_grad_(True)
+    y = bn_ref(xr)
+    y = torch.relu(y) if act == "relu" else (torch.nn.functional.relu6(y) if act == "relu6" else y)
+    if residual:
+        y = y + res
+    y.backward(gout)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    rc = None if res is None else res.cuda().contiguous(memory_format=torch.channels_last)
+    yc = ops.bn_act(xc, bn_cuda, act, rc)
+    yc.backward(gout.cuda())
+    assert rel_err(yc.detach().cpu(), y.detach()) < 1e-5
+    assert rel_err(xc.grad.cpu(), xr.grad) < 2e-5
+    assert rel_err(bn_cuda.weight.grad.cpu(), bn_ref.weight.grad) < 2e-5
+    assert rel_err(bn_cuda.bias.grad.cpu(), bn_ref.bias.grad) < 2e-5
+    assert rel_err(bn_cuda.running_mean.cpu(), bn_ref.running_mean) < 1e-5
+    assert rel_err(bn_cuda.running_var.cpu(), bn_ref.running_var) < 1e-5
+    assert bn_cuda.num_batches_tracked.item() == bn_ref.num_batches_tracked.item()
+
+
+def test_rowbn_rows_bf16_and_large_m(ops):
+    """2-D rows (the point MLP case), bf16 storage with fp32 statistics: stated tolerance 1e-2 relative
+    against fp32 BatchNorm1d+ReLU on the bf16-rounded input; M large enough for several CTAs per column."""
+    import torch.nn as nn
+    M, C = 300_000, 128
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(M, C, generator=g) * 3 + 1).to(torch.bfloat16)
+    bn_ref = nn.BatchNorm1d(C)
+    import copy
+    bn_cuda = copy.deepcopy(bn_ref).cuda()
+    y = torch.relu(bn_ref(x.float()))
+    yc = ops.bn_act(x.cuda(), bn_cuda, "relu")
+    assert yc.dtype == torch.bfloat16 and rel_err(yc.float().cpu(), y) < 1e-2
+    assert rel_err(bn_cuda.running_var.cpu(), bn_ref.running_var) < 1e-4
