@@ -278,11 +278,11 @@ def kernel_rooflines(args, device, fp32):
     gf = torch.empty(B, N, C, dtype=dt, device=device)
 
     def proj_bwd():
-        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), native.dtype_code(feats),
-                    B, N, C, H, W, 0, p(gf), st)
+        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order), p(offs),
+                    native.dtype_code(feats), B, N, C, H, W, 0, p(gf), st)
     add("bev_bwd_kernel", time_kernel(proj_bwd), B * (C * s * H * W + C * s * v * N + 4 * N),
-        "C*s*HW + C*s*v*N + 4N per frame (SURVEY 8d; the kernel also re-reads feats for tie detection "
-        "and writes zero rows for points outside)")
+        "C*s*HW + C*s*v*N + 4N per frame (SURVEY 8d); actual traffic is higher: feats re-read for the exact "
+        "tie split (C*s*v*N) and zero rows written for points outside (C*s*(1-v)*N)")
 
     def index_only():
         native.call("kdf_bev_index", p(pts), B, N, 4, *geom, H, W, p(cel), None, p(cnt), st)

@@ -100,10 +100,13 @@ int kdf_bev_reduce(const void *feats, int dtype, const int32_t *order, const int
  * ATen's quirk that a max of exactly 0.0 counts the zero-initialised output as
  * one more tie.  mean: grad / count.  Points outside the grid get 0.
  *   grad_grid dtype [B,H*W,C]; grid/ties from the forward (max only);
+ *   order/offsets: the forward's cell ordering (both or neither); with it the gradient is
+ *   computed cell-major (per-cell rows read once), without it point-major;
  *   grad_feats dtype [B,N,C] out (every row written).
  */
 int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *grid,
                         const int32_t *ties, const int32_t *count, const int32_t *cell,
+                        const int32_t *order, const int32_t *offsets,
                         int dtype, int B, int64_t N, int C, int H, int W, int reduce,
                         void *grad_feats, void *stream);
 
@@ -115,7 +118,9 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
  * kdf_rowbn_stats    training statistics in one pass: mean / invstd (biased variance, eps inside the
  *                    sqrt), the folded scale = gamma*invstd and shift = beta - mean*scale, and the
  *                    nn.BatchNorm running-stat update (momentum, unbiased variance) when
- *                    running_mean/var are given.  gamma/beta may be NULL (1 / 0).
+ *                    running_mean/var are given.  gamma/beta may be NULL (1 / 0).  pre_bias (may be
+ *                    NULL) is a per-channel bias the producing layer would have added to x: batch
+ *                    normalisation cancels it exactly, so it only shifts the running mean.
  * kdf_rowbn_apply_fwd  y = act(x*scale + shift) [+ residual]      (residual may be NULL)
  * kdf_rowbn_bwd      d x, d gamma, d beta from grad_out: dy = g*act'(x*scale+shift);
  *                    batch_stats != 0 chains through the batch mean / variance (training mode),
@@ -125,7 +130,7 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
 size_t kdf_rowbn_workspace_bytes(int C);
 size_t kdf_rowbn_bwd_workspace_bytes(int C);
 int kdf_rowbn_stats(const void *x, int dtype, int64_t M, int C, const float *gamma, const float *beta,
-                    float eps, float momentum, float *running_mean, float *running_var,
+                    const float *pre_bias, float eps, float momentum, float *running_mean, float *running_var,
                     float *mean, float *invstd, float *scale, float *shift, void *workspace, void *stream);
 int kdf_rowbn_apply_fwd(const void *x, const void *residual, int dtype, int64_t M, int C,
                         const float *scale, const float *shift, int act, void *y, void *stream);

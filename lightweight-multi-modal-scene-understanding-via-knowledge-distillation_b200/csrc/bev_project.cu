@@ -264,6 +264,194 @@ bev_bwd_kernel(const T *__restrict__ grad_grid, const T *__restrict__ feats, con
     }
 }
 
+
+// ----------------------------------------------------------------------------- reduce / backward, wide-load variants
+// Same contract as the kernels above for the common shapes where one row is LPR 16-byte lanes
+// (LPR in {8,16,32}: C = 64/128/256 bf16 or 32/64/128 fp32).  A warp owns a cell; its 32 lanes
+// are split into RPL = 32/LPR row groups so that every lane always moves 16 bytes, U row groups
+// are in flight per iteration and the point ids of the next iteration are prefetched while the
+// current rows are consumed: enough bytes in flight to hide HBM latency at 32 warps/SM.
+template <typename T> struct Raw16;
+template <> struct Raw16<float> {
+    static constexpr int VEC = 4;
+    static __device__ __forceinline__ void unpack(const uint4 &u, float *v) {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float *v) {
+        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
+};
+template <> struct Raw16<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ void unpack(const uint4 &u, float *v) {
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float *v) {
+        return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+};
+
+template <typename T, int LPR, int REDUCE>
+__global__ void __launch_bounds__(256)
+bev_reduce_wide_kernel(const T *__restrict__ feats, const int32_t *__restrict__ order,
+                       const int32_t *__restrict__ offsets, T *__restrict__ grid, int32_t *__restrict__ ties,
+                       int64_t n_cells, int64_t N, int HW) {
+    constexpr int VEC = Raw16<T>::VEC, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * VEC;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
+        const int64_t b = cid / HW;
+        const int c = (int)(cid - b * HW);
+        const int beg = __ldg(offsets + b * (HW + 1) + c);
+        const int n = __ldg(offsets + b * (HW + 1) + c + 1) - beg;
+        const int32_t *ord = order + b * N + beg;
+        const T *fb = feats + b * N * C + ch;
+        float m[VEC];
+        int k[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { m[q] = (REDUCE == KDF_REDUCE_MAX) ? -INFINITY : 0.f; k[q] = 0; }
+        int idn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+        for (int j0 = 0; j0 < n; j0 += STEP) {
+            uint4 raw[U];
+            int id[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                id[u] = idn[u];
+                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(fb + (int64_t)id[u] * C));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                      // ids of the next iteration, while the rows fly
+                const int j = j0 + STEP + u * RPL + sub;
+                idn[u] = j < n ? __ldg(ord + j) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (id[u] >= 0) {
+                    float f[VEC];
+                    Raw16<T>::unpack(raw[u], f);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        if (REDUCE == KDF_REDUCE_MAX) {
+                            if (f[q] > m[q]) { m[q] = f[q]; k[q] = 1; }
+                            else if (f[q] == m[q]) { k[q]++; }
+                        } else {
+                            m[q] += f[q];
+                        }
+                    }
+                }
+            }
+        }
+        // merge the RPL row groups (lanes that own the same channels)
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                const float om = __shfl_xor_sync(0xffffffffu, m[q], o);
+                const int ok = __shfl_xor_sync(0xffffffffu, k[q], o);
+                if (REDUCE == KDF_REDUCE_MAX) {
+                    if (om > m[q]) { m[q] = om; k[q] = ok; }
+                    else if (om == m[q]) { k[q] += ok; }
+                } else {
+                    m[q] += om;
+                }
+            }
+        }
+        if (sub == 0) {
+            float o[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q)
+                o[q] = (n == 0) ? 0.f : (REDUCE == KDF_REDUCE_MEAN ? m[q] / (float)n : m[q]);
+            *reinterpret_cast<uint4 *>(grid + cid * C + ch) = Raw16<T>::pack(o);
+            if (REDUCE == KDF_REDUCE_MAX && ties) {
+                int *tp = ties + cid * C + ch;
+#pragma unroll
+                for (int q = 0; q < VEC; q += 4)
+                    *reinterpret_cast<int4 *>(tp + q) = make_int4(n ? k[q] : 0, n ? k[q + 1] : 0, n ? k[q + 2] : 0, n ? k[q + 3] : 0);
+            }
+        }
+    }
+}
+
+// Cell-major backward: a warp loads its cell's grad / max / tie rows once, then streams the
+// cell's feature rows and writes their gradient rows.  A second, point-major sweep zeroes the
+// rows of the points that fell outside the grid (they are in no cell list).
+template <typename T, int LPR, int REDUCE>
+__global__ void __launch_bounds__(256)
+bev_bwd_wide_kernel(const T *__restrict__ grad_grid, const T *__restrict__ feats, const T *__restrict__ grid,
+                    const int32_t *__restrict__ ties, const int32_t *__restrict__ order,
+                    const int32_t *__restrict__ offsets, const int32_t *__restrict__ cell,
+                    T *__restrict__ grad_feats, int64_t n_cells, int64_t N, int HW, int64_t total) {
+    constexpr int VEC = Raw16<T>::VEC, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * VEC;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
+        const int64_t b = cid / HW;
+        const int c = (int)(cid - b * HW);
+        const int beg = __ldg(offsets + b * (HW + 1) + c);
+        const int n = __ldg(offsets + b * (HW + 1) + c + 1) - beg;
+        if (n == 0) continue;
+        const int32_t *ord = order + b * N + beg;
+        float g[VEC], mx[VEC];
+        Raw16<T>::unpack(*reinterpret_cast<const uint4 *>(grad_grid + cid * C + ch), g);
+        if (REDUCE == KDF_REDUCE_MAX) {
+            Raw16<T>::unpack(*reinterpret_cast<const uint4 *>(grid + cid * C + ch), mx);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                // ATen: N_to_distribute = (self == result) + #(src == result), self is the zero init
+                const int t = __ldg(ties + cid * C + ch + q) + (mx[q] == 0.f ? 1 : 0);
+                g[q] = g[q] / (float)t;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) g[q] = g[q] / (float)n;
+        }
+        int idn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+        for (int j0 = 0; j0 < n; j0 += STEP) {
+            uint4 raw[U];
+            int id[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                id[u] = idn[u];
+                if (REDUCE == KDF_REDUCE_MAX && id[u] >= 0)
+                    raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(feats + (b * N + id[u]) * C + ch));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + STEP + u * RPL + sub;
+                idn[u] = j < n ? __ldg(ord + j) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (id[u] >= 0) {
+                    float o[VEC];
+                    if (REDUCE == KDF_REDUCE_MAX) {
+                        float f[VEC];
+                        Raw16<T>::unpack(raw[u], f);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) o[q] = (f[q] == mx[q]) ? g[q] : 0.f;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) o[q] = g[q];
+                    }
+                    *reinterpret_cast<uint4 *>(grad_feats + (b * N + id[u]) * C + ch) = Raw16<T>::pack(o);
+                }
+            }
+        }
+    }
+    // rows of points outside the grid
+    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR), gn = ((int64_t)gridDim.x * blockDim.x) / LPR;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = g0; i < total; i += gn)
+        if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(grad_feats + i * C + ch) = zero;
+}
+
 // ----------------------------------------------------------------------------- host side
 static int check_geom(int B, int64_t N, int H, int W, float xspan, float yspan) {
     KDF_CHECK_ARG(B >= 0 && N >= 0, "bev: negative B or N");
@@ -294,14 +482,31 @@ static int launch_index(const float *points, int B, int64_t N, int stride, const
     return KDF_OK;
 }
 
+static int wide_lpr(int dtype, int C) {
+    const int lpr = C / (dtype == KDF_F32 ? 4 : 8);
+    const int rem = C % (dtype == KDF_F32 ? 4 : 8);
+    return (rem == 0 && (lpr == 8 || lpr == 16 || lpr == 32)) ? lpr : 0;
+}
+
 static int launch_reduce(const void *feats, int dtype, const int32_t *order, const int32_t *offsets,
                          int B, int64_t N, int C, int HW, int reduce, void *grid, int32_t *ties, cudaStream_t st) {
     const int64_t n_cells = (int64_t)B * HW;
     const int blocks = grid_for(n_cells * 32, 256, 64);
+    const int lpr = wide_lpr(dtype, C);
+#define KDF_RW(T, L, R)                                                                                 \
+    bev_reduce_wide_kernel<T, L, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
+                                                            reinterpret_cast<T *>(grid), ties, n_cells, N, HW)
+#define KDF_RW_L(T, R)                                                          \
+    do {                                                                        \
+        if (lpr == 8) KDF_RW(T, 8, R); else if (lpr == 16) KDF_RW(T, 16, R); else KDF_RW(T, 32, R); \
+    } while (0)
 #define KDF_REDUCE_LAUNCH(T, R)                                                                    \
     bev_reduce_kernel<T, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
                                                    reinterpret_cast<T *>(grid), ties, n_cells, N, C, HW)
-    if (dtype == KDF_F32) {
+    if (lpr) {
+        if (dtype == KDF_F32) { if (reduce == KDF_REDUCE_MAX) KDF_RW_L(float, KDF_REDUCE_MAX); else KDF_RW_L(float, KDF_REDUCE_MEAN); }
+        else { if (reduce == KDF_REDUCE_MAX) KDF_RW_L(__nv_bfloat16, KDF_REDUCE_MAX); else KDF_RW_L(__nv_bfloat16, KDF_REDUCE_MEAN); }
+    } else if (dtype == KDF_F32) {
         if (reduce == KDF_REDUCE_MAX) KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MAX);
         else                          KDF_REDUCE_LAUNCH(float, KDF_REDUCE_MEAN);
     } else {
@@ -309,6 +514,8 @@ static int launch_reduce(const void *feats, int dtype, const int32_t *order, con
         else                          KDF_REDUCE_LAUNCH(__nv_bfloat16, KDF_REDUCE_MEAN);
     }
 #undef KDF_REDUCE_LAUNCH
+#undef KDF_RW_L
+#undef KDF_RW
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }
@@ -386,6 +593,7 @@ int kdf_bev_reduce(const void *feats, int dtype, const int32_t *order, const int
 
 int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *grid,
                         const int32_t *ties, const int32_t *count, const int32_t *cell,
+                        const int32_t *order, const int32_t *offsets,
                         int dtype, int B, int64_t N, int C, int H, int W, int reduce,
                         void *grad_feats, void *stream) {
     KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_bwd: bad sizes");
@@ -397,12 +605,33 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
     KDF_CHECK_ARG(grad_grid && cell && grad_feats, "bev_bwd: null pointer");
     if (reduce == KDF_REDUCE_MAX) KDF_CHECK_ARG(feats && grid && ties, "bev_bwd(max): feats/grid/ties required");
     else KDF_CHECK_ARG(count, "bev_bwd(mean): count required");
+    KDF_CHECK_ARG((order == nullptr) == (offsets == nullptr), "bev_bwd: order and offsets come together");
     cudaStream_t st = as_stream(stream);
+    const int HW = H * W;
+    const int lpr = order ? wide_lpr(dtype, C) : 0;
+    if (lpr) {                       // cell-major: per-cell rows loaded once, feature rows streamed
+        const int64_t n_cells = (int64_t)B * HW;
+        const int blocks = grid_for(n_cells * 32, 256, 64);
+#define KDF_BW(T, L, R)                                                                                      \
+    bev_bwd_wide_kernel<T, L, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(grad_grid),              \
+        reinterpret_cast<const T *>(feats), reinterpret_cast<const T *>(grid), ties, order, offsets, cell,    \
+        reinterpret_cast<T *>(grad_feats), n_cells, N, HW, total)
+#define KDF_BW_L(T, R)                                                          \
+    do {                                                                        \
+        if (lpr == 8) KDF_BW(T, 8, R); else if (lpr == 16) KDF_BW(T, 16, R); else KDF_BW(T, 32, R); \
+    } while (0)
+        if (dtype == KDF_F32) { if (reduce == KDF_REDUCE_MAX) KDF_BW_L(float, KDF_REDUCE_MAX); else KDF_BW_L(float, KDF_REDUCE_MEAN); }
+        else { if (reduce == KDF_REDUCE_MAX) KDF_BW_L(__nv_bfloat16, KDF_REDUCE_MAX); else KDF_BW_L(__nv_bfloat16, KDF_REDUCE_MEAN); }
+#undef KDF_BW_L
+#undef KDF_BW
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
     const int blocks = grid_for((total + 3) / 4 * 32, 256, 64);
 #define KDF_BWD_LAUNCH(T, R)                                                                         \
     bev_bwd_kernel<T, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(grad_grid),             \
         reinterpret_cast<const T *>(feats), reinterpret_cast<const T *>(grid), ties, count, cell,     \
-        reinterpret_cast<T *>(grad_feats), total, N, C, H * W)
+        reinterpret_cast<T *>(grad_feats), total, N, C, HW)
     if (dtype == KDF_F32) {
         if (reduce == KDF_REDUCE_MAX) KDF_BWD_LAUNCH(float, KDF_REDUCE_MAX);
         else                          KDF_BWD_LAUNCH(float, KDF_REDUCE_MEAN);

@@ -13,8 +13,10 @@
 //                                           per-channel (A, B) of the statistics chain
 //             apply  (read g, x, write)  dx = dy*scale + B*x + A
 //
-// Both reductions are per-thread fp32 partial sums over a few hundred rows, combined in
-// fp64 in a fixed order by the last CTA (deterministic, no float atomics).  All four
+// Both reductions are per-thread fp32 partial sums over a few hundred rows, reduced per CTA
+// in shared memory and accumulated across CTAs with fp64 atomics (2C adds per CTA; in fp64 the
+// accumulation order perturbs the result far below fp32 resolution), finalised by the last
+// CTA to arrive.  All four
 // kernels are HBM-bound streaming kernels; the per-channel finalisation lives in the last
 // CTA of the reduction so no tiny host-driven launches are needed.
 #include "kdf_common.cuh"
@@ -74,20 +76,20 @@ __device__ __forceinline__ bool act_open(float y, int act) {      // derivative 
     return true;
 }
 
-struct RowBnWs {            // workspace header followed by partial[blocks][2][C]
+struct RowBnWs {            // workspace header followed by acc[2][C] (fp64)
     unsigned int ticket;
     unsigned int pad[3];
 };
 
 // Two per-channel sums over the rows; `MODE` 0: (x, x^2)   1: (dy, dy*x) with dy = g * act'(x*scale+shift).
-// The last CTA combines the partials in block order and finalises.
+// The last CTA to arrive finalises from the fp64 accumulators.
 struct ReduceArgs {
     const void *x, *g;
     int64_t M;
     int C, act;
     const float *scale, *shift;      // MODE 1
     // MODE 0 finalisation (training statistics)
-    const float *gamma, *beta;
+    const float *gamma, *beta, *pre_bias;
     float eps, momentum;
     float *mean, *invstd, *out_scale, *out_shift, *running_mean, *running_var;
     // MODE 1 finalisation
@@ -148,16 +150,18 @@ rowbn_reduce_kernel(ReduceArgs a) {
         for (int q = 0; q < VEC; ++q) { dst[q] = s0[q]; dst[VEC + q] = s1[q]; }
     }
     __syncthreads();
-    float *partial = reinterpret_cast<float *>(a.ws + 1);
+    double *acc = reinterpret_cast<double *>(a.ws + 1);
     if (m.active && m.r == 0) {
         for (int rr = 1; rr < m.rows; ++rr) {
             const float *src = sm + (rr * m.G + m.g) * 2 * VEC;
 #pragma unroll
             for (int q = 0; q < VEC; ++q) { s0[q] += src[q]; s1[q] += src[VEC + q]; }
         }
-        float *p0 = partial + (int64_t)blockIdx.x * 2 * a.C + m.g * VEC;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { p0[q] = s0[q]; p0[a.C + q] = s1[q]; }
+        for (int q = 0; q < VEC; ++q) {
+            atomicAdd(acc + m.g * VEC + q, (double)s0[q]);
+            atomicAdd(acc + a.C + m.g * VEC + q, (double)s1[q]);
+        }
     }
     __threadfence();
     __syncthreads();
@@ -167,12 +171,7 @@ rowbn_reduce_kernel(ReduceArgs a) {
     __threadfence();
     const double invM = 1.0 / (double)a.M;
     for (int c = threadIdx.x; c < a.C; c += RB_THREADS) {
-        double t0 = 0.0, t1 = 0.0;
-        const volatile float *pp = partial + c;
-        for (int b = 0; b < (int)gridDim.x; ++b) {
-            t0 += (double)pp[(int64_t)b * 2 * a.C];
-            t1 += (double)pp[(int64_t)b * 2 * a.C + a.C];
-        }
+        const double t0 = __ldcg(acc + c), t1 = __ldcg(acc + a.C + c);
         if (MODE == 0) {
             const double mean = t0 * invM;
             double var = t1 * invM - mean * mean;                 // biased variance (normalisation)
@@ -185,7 +184,8 @@ rowbn_reduce_kernel(ReduceArgs a) {
             a.out_shift[c] = (a.beta ? a.beta[c] : 0.f) - (float)mean * scl;
             if (a.running_mean) {                                 // nn.BatchNorm: unbiased variance in the running stat
                 const double unb = a.M > 1 ? var * ((double)a.M / (double)(a.M - 1)) : var;
-                a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)mean;
+                const float bias = a.pre_bias ? a.pre_bias[c] : 0.f;      // BN(x + bias): only the running mean sees it
+                a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * ((float)mean + bias);
                 a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
             }
         } else {
@@ -309,7 +309,7 @@ static int launch_reduce(const ReduceArgs &a, int dtype, cudaStream_t st) {
     const int blocks = rb_blocks(a.M, a.C, vec, 16);
     const int rows = RB_THREADS / (a.C / vec);
     const size_t smem = sizeof(float) * (size_t)rows * (a.C / vec) * 2 * vec;
-    KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs), st));
+    KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * (size_t)a.C, st));
     if (dtype == KDF_F32) rowbn_reduce_kernel<float, 4, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
     else if (vec == 8)    rowbn_reduce_kernel<__nv_bfloat16, 8, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
     else                  rowbn_reduce_kernel<__nv_bfloat16, 4, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
@@ -323,17 +323,17 @@ using namespace kdf;
 
 extern "C" {
 
-size_t kdf_rowbn_workspace_bytes(int C) { return sizeof(RowBnWs) + sizeof(float) * (size_t)RB_MAX_BLOCKS * 2 * (size_t)C; }
+size_t kdf_rowbn_workspace_bytes(int C) { return sizeof(RowBnWs) + sizeof(double) * 2 * (size_t)C; }
 
 int kdf_rowbn_stats(const void *x, int dtype, int64_t M, int C, const float *gamma, const float *beta,
-                    float eps, float momentum, float *running_mean, float *running_var,
+                    const float *pre_bias, float eps, float momentum, float *running_mean, float *running_var,
                     float *mean, float *invstd, float *scale, float *shift, void *workspace, void *stream) {
     if (int e = rb_check(dtype, M, C, "rowbn_stats")) return e;
     KDF_CHECK_ARG(M > 0, "rowbn_stats: batch statistics need at least one row");
     KDF_CHECK_ARG(x && mean && invstd && scale && shift && workspace, "rowbn_stats: null pointer");
     KDF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "rowbn_stats: running stats come in pairs");
     ReduceArgs a{};
-    a.x = x; a.M = M; a.C = C; a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum;
+    a.x = x; a.M = M; a.C = C; a.gamma = gamma; a.beta = beta; a.pre_bias = pre_bias; a.eps = eps; a.momentum = momentum;
     a.mean = mean; a.invstd = invstd; a.out_scale = scale; a.out_shift = shift;
     a.running_mean = running_mean; a.running_var = running_var;
     a.ws = reinterpret_cast<RowBnWs *>(workspace);
@@ -370,7 +370,7 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
     cudaStream_t st = as_stream(stream);
     // coefficient vectors live at the tail of the workspace
     char *ws = reinterpret_cast<char *>(workspace);
-    float *coefA = reinterpret_cast<float *>(ws + sizeof(RowBnWs) + sizeof(float) * (size_t)RB_MAX_BLOCKS * 2 * (size_t)C);
+    float *coefA = reinterpret_cast<float *>(ws + kdf_rowbn_workspace_bytes(C));
     float *coefB = coefA + C;
     ReduceArgs a{};
     a.x = x; a.g = grad_out; a.M = M; a.C = C; a.act = act; a.scale = scale; a.shift = shift;

@@ -70,7 +70,8 @@ class SpatialLiDAREncoder(nn.Module):
         x = points.reshape(B * N, D)
         for i in range(0, len(self.point_mlp), 3):
             conv, bn = self.point_mlp[i], self.point_mlp[i + 1]
-            x = ops.bn_act(F.linear(x, conv.weight.squeeze(-1), conv.bias), bn, "relu")
+            # the Conv1d bias is folded into the BatchNorm (training statistics cancel it exactly)
+            x = ops.bn_act(F.linear(x, conv.weight.squeeze(-1)), bn, "relu", pre_bias=conv.bias)
         return x.view(B, N, -1)
 
     def forward_vectorized(self, points: torch.Tensor) -> torch.Tensor:

@@ -28,10 +28,10 @@ _SIGNATURES = {
     "kdf_bev_project_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _i,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kdf_bev_reduce": (C.c_int, [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "kdf_bev_project_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "kdf_bev_project_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     "kdf_rowbn_workspace_bytes": (_sz, [_i]),
     "kdf_rowbn_bwd_workspace_bytes": (_sz, [_i]),
-    "kdf_rowbn_stats": (C.c_int, [_vp, _i, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdf_rowbn_stats": (C.c_int, [_vp, _i, _i64, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kdf_rowbn_apply_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _i, _vp, _vp]),
     "kdf_rowbn_bwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_fusion_weighted_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp, _vp, _vp]),

@@ -30,7 +30,7 @@ class _RowBNActFn(torch.autograd.Function):
     eval).  Backward = kdf_rowbn_bwd (reduce + apply, chaining through the batch statistics)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, mean, invstd, act, batch_stats, residual):
+    def forward(ctx, x, gamma, beta, scale, shift, mean, invstd, act, batch_stats, residual, pre_bias):
         M, C = x.shape
         y = torch.empty_like(x)
         call("kdf_rowbn_apply_fwd", ptr(x), ptr(residual), dtype_code(x), M, C, ptr(scale), ptr(shift), act, ptr(y),
@@ -38,7 +38,7 @@ class _RowBNActFn(torch.autograd.Function):
         ctx.save_for_backward(x, scale, shift, mean, invstd)
         ctx.act, ctx.batch_stats = act, batch_stats
         ctx.has_res = residual is not None
-        ctx.affine = (gamma is not None, beta is not None)
+        ctx.affine = (gamma is not None, beta is not None, pre_bias is not None)
         return y
 
     @staticmethod
@@ -55,13 +55,20 @@ class _RowBNActFn(torch.autograd.Function):
         ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
         call("kdf_rowbn_bwd", ptr(g), ptr(x), dtype_code(x), M, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
              ctx.act, int(ctx.batch_stats), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(ws), stream_ptr(x.device))
+        dbias = None
+        if ctx.affine[2]:
+            # BN(x + b): batch statistics cancel b exactly (zero gradient); with running statistics
+            # b acts like a shift in front of the scale
+            dbias = torch.zeros_like(dbeta) if ctx.batch_stats else dbeta * scale
         return (dx, dgamma if ctx.affine[0] else None, dbeta if ctx.affine[1] else None,
-                None, None, None, None, None, None, g if ctx.has_res else None)
+                None, None, None, None, None, None, g if ctx.has_res else None, dbias)
 
 
-def _eval_affine(bn):
-    """(scale, shift, mean, invstd) of a BatchNorm in eval mode, cached until its tensors change."""
-    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None)
+def _eval_affine(bn, pre_bias=None):
+    """(scale, shift, mean, invstd) of a BatchNorm in eval mode, cached until its tensors change.
+    ``pre_bias`` (the producing layer's bias, applied as BN(x + bias)) is folded into the shift."""
+    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, pre_bias)
+                if t is not None)
     cache = getattr(bn, "_kdf_eval_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -70,12 +77,14 @@ def _eval_affine(bn):
         invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
         scale = invstd * bn.weight.float() if bn.weight is not None else invstd.clone()
         shift = (bn.bias.float() if bn.bias is not None else torch.zeros_like(mean)) - mean * scale
+        if pre_bias is not None:
+            shift = shift + pre_bias.float() * scale
         vals = tuple(t.contiguous() for t in (scale, shift, mean, invstd))
     bn._kdf_eval_cache = (key, vals)
     return vals
 
 
-def _bn_prepare(rows: torch.Tensor, bn):
+def _bn_prepare(rows: torch.Tensor, bn, pre_bias=None):
     """fp32 per-channel (scale, shift, mean, invstd, batch_stats) for a BatchNorm module over rows [M,C]:
     batch statistics (one ``kdf_rowbn_stats`` launch, which also advances the running statistics
     exactly like nn.BatchNorm) in training, cached running-statistics affine in eval."""
@@ -83,7 +92,7 @@ def _bn_prepare(rows: torch.Tensor, bn):
     M, C = rows.shape
     use_batch = bn.training or bn.running_mean is None
     if not use_batch:
-        return (*_eval_affine(bn), False)
+        return (*_eval_affine(bn, pre_bias), False)
     f32 = dict(dtype=torch.float32, device=dev)
     mean, invstd, scale, shift = (torch.empty(C, **f32) for _ in range(4))
     track = bn.training and bn.track_running_stats and bn.running_mean is not None
@@ -93,15 +102,20 @@ def _bn_prepare(rows: torch.Tensor, bn):
         mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
     ws = torch.empty(lib.kdf_rowbn_workspace_bytes(C), dtype=torch.uint8, device=dev)
     with torch.no_grad():
-        call("kdf_rowbn_stats", ptr(rows), dtype_code(rows), M, C, ptr(bn.weight), ptr(bn.bias), float(bn.eps), float(mom),
+        call("kdf_rowbn_stats", ptr(rows), dtype_code(rows), M, C, ptr(bn.weight), ptr(bn.bias),
+             ptr(pre_bias.detach().float()) if pre_bias is not None else None, float(bn.eps), float(mom),
              ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
              ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(ws), stream_ptr(dev))
     return scale, shift, mean, invstd, True
 
 
-def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``act(bn(x)) [+ residual]`` with the BatchNorm module's parameters / buffers (updated like
-    nn.BatchNorm does in training).  ``x`` is a channels-last [B,C,H,W] tensor or rows [M,C]."""
+def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
+           pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(bn(x [+ pre_bias])) [+ residual]`` with the BatchNorm module's parameters / buffers (updated
+    like nn.BatchNorm does in training).  ``x`` is a channels-last [B,C,H,W] tensor or rows [M,C].
+    ``pre_bias`` is the bias of the layer that produced ``x``: instead of adding it to every element
+    (and reducing its gradient over all rows) it is folded into the normalisation, which in training
+    cancels it exactly."""
     dev = require_cuda(x, residual)
     four_d = x.dim() == 4
     if four_d:
@@ -116,8 +130,8 @@ def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[to
         rows = rows.contiguous()
     if res is not None and (res.dtype != rows.dtype or not res.is_contiguous()):
         res = res.to(rows.dtype).contiguous()
-    scale, shift, mean, invstd, use_batch = _bn_prepare(rows, bn)
-    y = _RowBNActFn.apply(rows, bn.weight, bn.bias, scale, shift, mean, invstd, _ACT[act], use_batch, res)
+    scale, shift, mean, invstd, use_batch = _bn_prepare(rows, bn, pre_bias)
+    y = _RowBNActFn.apply(rows, bn.weight, bn.bias, scale, shift, mean, invstd, _ACT[act], use_batch, res, pre_bias)
     return y.view(B, H, W, C).permute(0, 3, 1, 2) if four_d else y
 
 
@@ -204,18 +218,21 @@ class BevProjectFn(torch.autograd.Function):
         grid = torch.empty(B, H, W, C, dtype=feats.dtype, device=dev)
         count = torch.empty(B, H * W, dtype=torch.int32, device=dev)
         cell = torch.empty(B, N, dtype=torch.int32, device=dev)
-        need_ties = reduce == _n.REDUCE_MAX and feats.requires_grad
+        need_grad = feats.requires_grad
+        need_ties = reduce == _n.REDUCE_MAX and need_grad
         ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev) if need_ties else None
+        # the cell ordering is kept for the (cell-major) backward
+        order = torch.empty(B, N, dtype=torch.int32, device=dev) if need_grad else None
+        offsets = torch.empty(B, H * W + 1, dtype=torch.int32, device=dev) if need_grad else None
         ws_bytes = lib.kdf_bev_workspace_bytes(B, N, H, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         call("kdf_bev_project_fwd", ptr(points), D, ptr(feats), dtype_code(feats), B, N, C, *geom, H, W, reduce,
-                                      ptr(grid), ptr(count), ptr(cell), ptr(ties), None, None,
-                                      ptr(ws), ws_bytes, stream_ptr(dev))
+             ptr(grid), ptr(count), ptr(cell), ptr(ties), ptr(order), ptr(offsets), ptr(ws), ws_bytes, stream_ptr(dev))
         ctx.reduce, ctx.dims = reduce, (B, N, C, H, W)
         if reduce == _n.REDUCE_MAX:
-            ctx.save_for_backward(feats, grid, ties, cell)
+            ctx.save_for_backward(feats, grid, ties, cell, order, offsets)
         else:
-            ctx.save_for_backward(count, cell)
+            ctx.save_for_backward(count, cell, order, offsets)
         ctx.mark_non_differentiable(count, cell)
         return grid.permute(0, 3, 1, 2), count, cell      # lidar_encoder.py:99: [B,C,H,W] view of NHWC memory
 
@@ -224,16 +241,16 @@ class BevProjectFn(torch.autograd.Function):
         B, N, C, H, W = ctx.dims
         gg = grad_grid.permute(0, 2, 3, 1).contiguous()
         if ctx.reduce == _n.REDUCE_MAX:
-            feats, grid, ties, cell = ctx.saved_tensors
+            feats, grid, ties, cell, order, offsets = ctx.saved_tensors
             count = None
         else:
-            count, cell = ctx.saved_tensors
+            count, cell, order, offsets = ctx.saved_tensors
             feats = grid = ties = None
         if gg.dtype != (feats.dtype if feats is not None else gg.dtype):
             gg = gg.to(feats.dtype)
         out = torch.empty(B, N, C, dtype=gg.dtype, device=gg.device)
-        call("kdf_bev_project_bwd", ptr(gg), ptr(feats), ptr(grid), ptr(ties), ptr(count), ptr(cell),
-                                      dtype_code(gg), B, N, C, H, W, ctx.reduce, ptr(out), stream_ptr(gg.device))
+        call("kdf_bev_project_bwd", ptr(gg), ptr(feats), ptr(grid), ptr(ties), ptr(count), ptr(cell), ptr(order), ptr(offsets),
+             dtype_code(gg), B, N, C, H, W, ctx.reduce, ptr(out), stream_ptr(gg.device))
         return None, out, None, None, None
 
 
