@@ -41,19 +41,35 @@ __device__ __forceinline__ RowMap row_map(int C) {
     return m;
 }
 
+// Rows are moved as raw 16-byte (8-byte for bf16 x4) registers and converted to fp32 only when
+// consumed, so U loads in flight cost U*4 registers instead of U*VEC.
 template <typename T, int VEC> struct VecIO;
-template <typename T> struct VecIO<T, 4> {
-    static __device__ __forceinline__ void load(const T *p, float *v) {
-        const float4 a = Vec4<T>::load_stream(p);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+template <> struct VecIO<float, 4> {
+    using Raw = uint4;
+    static __device__ __forceinline__ Raw load(const float *p) { return ldg_stream_u4(reinterpret_cast<const uint4 *>(p)); }
+    static __device__ __forceinline__ void unpack(const Raw &u, float *v) {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
     }
-    static __device__ __forceinline__ void store(T *p, const float *v) {
-        Vec4<T>::store(p, make_float4(v[0], v[1], v[2], v[3]));
+    static __device__ __forceinline__ void store(float *p, const float *v) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct VecIO<__nv_bfloat16, 4> {
+    using Raw = uint2;
+    static __device__ __forceinline__ Raw load(const __nv_bfloat16 *p) { return ldg_stream_u2(reinterpret_cast<const uint2 *>(p)); }
+    static __device__ __forceinline__ void unpack(const Raw &u, float *v) {
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+        uint2 u;
+        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = u;
     }
 };
 template <> struct VecIO<__nv_bfloat16, 8> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
-        const uint4 u = ldg_stream_u4(reinterpret_cast<const uint4 *>(p));
+    using Raw = uint4;
+    static __device__ __forceinline__ Raw load(const __nv_bfloat16 *p) { return ldg_stream_u4(reinterpret_cast<const uint4 *>(p)); }
+    static __device__ __forceinline__ void unpack(const Raw &u, float *v) {
         v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
         v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
     }
@@ -100,7 +116,7 @@ struct ReduceArgs {
 };
 
 template <typename T, int VEC, int MODE>
-__global__ void __launch_bounds__(RB_THREADS)
+__global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
 rowbn_reduce_kernel(ReduceArgs a) {
     extern __shared__ float sm[];                     // [rows][G][2*VEC]
     __shared__ bool last;
@@ -118,28 +134,32 @@ rowbn_reduce_kernel(ReduceArgs a) {
         }
         const int64_t stride = (int64_t)gridDim.x * m.rows;
         constexpr int U = 4;
+        using IO = VecIO<T, VEC>;
         for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < a.M; row += stride * U) {
-            float xv[U][VEC], gv[U][VEC];
+            typename IO::Raw xr[U], gr[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t rr = row + u * stride;
                 if (rr < a.M) {
-                    VecIO<T, VEC>::load(x + rr * a.C + c, xv[u]);
-                    if (MODE == 1) VecIO<T, VEC>::load(g + rr * a.C + c, gv[u]);
+                    xr[u] = IO::load(x + rr * a.C + c);
+                    if (MODE == 1) gr[u] = IO::load(g + rr * a.C + c);
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (row + u * stride < a.M) {
+                    float xv[VEC], gv[VEC];
+                    IO::unpack(xr[u], xv);
+                    if (MODE == 1) IO::unpack(gr[u], gv);
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
                         if (MODE == 0) {
-                            s0[q] += xv[u][q];
-                            s1[q] = fmaf(xv[u][q], xv[u][q], s1[q]);
+                            s0[q] += xv[q];
+                            s1[q] = fmaf(xv[q], xv[q], s1[q]);
                         } else {
-                            const float dy = act_open(fmaf(xv[u][q], sc[q], sh[q]), a.act) ? gv[u][q] : 0.f;
+                            const float dy = act_open(fmaf(xv[q], sc[q], sh[q]), a.act) ? gv[q] : 0.f;
                             s0[q] += dy;
-                            s1[q] = fmaf(dy, xv[u][q], s1[q]);
+                            s1[q] = fmaf(dy, xv[q], s1[q]);
                         }
                     }
                 }
@@ -207,7 +227,7 @@ rowbn_reduce_kernel(ReduceArgs a) {
 
 // y = act(x*scale + shift) [+ residual]
 template <typename T, int VEC>
-__global__ void __launch_bounds__(RB_THREADS)
+__global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
 rowbn_apply_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, T *__restrict__ y, int64_t M, int C,
                        const float *__restrict__ scale, const float *__restrict__ shift, int act) {
     const RowMap m = row_map<VEC>(C);
@@ -218,27 +238,30 @@ rowbn_apply_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, T *__
     for (int q = 0; q < VEC; ++q) { sc[q] = scale[c + q]; sh[q] = shift[c + q]; }
     const int64_t stride = (int64_t)gridDim.x * m.rows;
     constexpr int U = 4;
+    using IO = VecIO<T, VEC>;
     for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < M; row += stride * U) {
-        float xv[U][VEC], rv[U][VEC];
+        typename IO::Raw xr[U], rr_[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < M) {
-                VecIO<T, VEC>::load(x + rr * C + c, xv[u]);
-                if (res) VecIO<T, VEC>::load(res + rr * C + c, rv[u]);
+                xr[u] = IO::load(x + rr * C + c);
+                if (res) rr_[u] = IO::load(res + rr * C + c);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < M) {
-                float o[VEC];
+                float xv[VEC], rv[VEC], o[VEC];
+                IO::unpack(xr[u], xv);
+                if (res) IO::unpack(rr_[u], rv);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    o[q] = act_fwd(fmaf(xv[u][q], sc[q], sh[q]), act);
-                    if (res) o[q] += rv[u][q];
+                    o[q] = act_fwd(fmaf(xv[q], sc[q], sh[q]), act);
+                    if (res) o[q] += rv[q];
                 }
-                VecIO<T, VEC>::store(y + rr * C + c, o);
+                IO::store(y + rr * C + c, o);
             }
         }
     }
@@ -246,39 +269,47 @@ rowbn_apply_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, T *__
 
 // dx = dy*scale + B*x + A,  dy = g * act'(x*scale + shift)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(RB_THREADS)
+__global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
 rowbn_apply_bwd_kernel(const T *__restrict__ g, const T *__restrict__ x, T *__restrict__ dx, int64_t M, int C,
                        const float *__restrict__ scale, const float *__restrict__ shift,
                        const float *__restrict__ coefA, const float *__restrict__ coefB, int act) {
+    // per-channel coefficients live in shared memory (4*C floats) to keep registers for loads in flight
+    extern __shared__ float coef[];
+    float *sc = coef, *sh = coef + C, *A = coef + 2 * C, *B = coef + 3 * C;
+    for (int i = threadIdx.x; i < C; i += RB_THREADS) {
+        sc[i] = scale[i]; sh[i] = shift[i]; A[i] = coefA[i]; B[i] = coefB[i];
+    }
+    __syncthreads();
     const RowMap m = row_map<VEC>(C);
     if (!m.active) return;
     const int c = m.g * VEC;
-    float sc[VEC], sh[VEC], A[VEC], B[VEC];
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) { sc[q] = scale[c + q]; sh[q] = shift[c + q]; A[q] = coefA[c + q]; B[q] = coefB[c + q]; }
+    sc += c; sh += c; A += c; B += c;
     const int64_t stride = (int64_t)gridDim.x * m.rows;
     constexpr int U = 4;
+    using IO = VecIO<T, VEC>;
     for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < M; row += stride * U) {
-        float xv[U][VEC], gv[U][VEC];
+        typename IO::Raw xr[U], gr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < M) {
-                VecIO<T, VEC>::load(x + rr * C + c, xv[u]);
-                VecIO<T, VEC>::load(g + rr * C + c, gv[u]);
+                xr[u] = IO::load(x + rr * C + c);
+                gr[u] = IO::load(g + rr * C + c);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < M) {
-                float o[VEC];
+                float xv[VEC], gv[VEC], o[VEC];
+                IO::unpack(xr[u], xv);
+                IO::unpack(gr[u], gv);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    const float dy = act_open(fmaf(xv[u][q], sc[q], sh[q]), act) ? gv[u][q] : 0.f;
-                    o[q] = fmaf(dy, sc[q], fmaf(B[q], xv[u][q], A[q]));
+                    const float dy = act_open(fmaf(xv[q], sc[q], sh[q]), act) ? gv[q] : 0.f;
+                    o[q] = fmaf(dy, sc[q], fmaf(B[q], xv[q], A[q]));
                 }
-                VecIO<T, VEC>::store(dx + rr * C + c, o);
+                IO::store(dx + rr * C + c, o);
             }
         }
     }
@@ -381,11 +412,11 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
     const int vec = rb_vec(dtype, C);
     const int blocks = rb_blocks(M, C, vec, 8);
     if (dtype == KDF_F32)
-        rowbn_apply_bwd_kernel<float, 4><<<blocks, RB_THREADS, 0, st>>>((const float *)grad_out, (const float *)x, (float *)grad_x, M, C, scale, shift, coefA, coefB, act);
+        rowbn_apply_bwd_kernel<float, 4><<<blocks, RB_THREADS, sizeof(float) * 4 * C, st>>>((const float *)grad_out, (const float *)x, (float *)grad_x, M, C, scale, shift, coefA, coefB, act);
     else if (vec == 8)
-        rowbn_apply_bwd_kernel<__nv_bfloat16, 8><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)grad_out, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)grad_x, M, C, scale, shift, coefA, coefB, act);
+        rowbn_apply_bwd_kernel<__nv_bfloat16, 8><<<blocks, RB_THREADS, sizeof(float) * 4 * C, st>>>((const __nv_bfloat16 *)grad_out, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)grad_x, M, C, scale, shift, coefA, coefB, act);
     else
-        rowbn_apply_bwd_kernel<__nv_bfloat16, 4><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)grad_out, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)grad_x, M, C, scale, shift, coefA, coefB, act);
+        rowbn_apply_bwd_kernel<__nv_bfloat16, 4><<<blocks, RB_THREADS, sizeof(float) * 4 * C, st>>>((const __nv_bfloat16 *)grad_out, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)grad_x, M, C, scale, shift, coefA, coefB, act);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -28,6 +28,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from .. import native as _native
 from .. import ops
 from .optim import FlatAdamW
 from .parallel import allreduce_gradients_, world as _world
@@ -109,7 +110,8 @@ class Trainer:
                  class_weights=None, num_epochs=20, *,
                  teacher: Optional[nn.Module] = None, kd_temperature: float = 4.0,
                  kd_alpha: float = 0.5, kd_beta: float = 1.0,
-                 amp_dtype: Optional[torch.dtype] = None, verbose: bool = True):
+                 amp_dtype: Optional[torch.dtype] = None, verbose: bool = True,
+                 use_cuda_graph: bool = False, graph_warmup_steps: int = 3):
         self.model = model
         self.train_loader = train_loader
         self.val_loader = val_loader
@@ -144,14 +146,20 @@ class Trainer:
         self.history_path = os.path.join(save_dir, "training_history.json")
         self.history = {"train_loss": [], "train_miou": [], "val_loss": [], "val_miou": [], "lr": []}
         self.last_loss_terms: Optional[torch.Tensor] = None
+        # CUDA-graph replay of the whole step (forward + loss + backward + all-reduce + AdamW): the step is
+        # ~800 launches of mostly small kernels, so at B200 speeds the host cannot issue them fast enough
+        self.use_cuda_graph = use_cuda_graph
+        self.graph_warmup_steps = graph_warmup_steps
+        self._graph = None
+        self._graph_key = None
+        self._static: Dict[str, torch.Tensor] = {}
+        self._eager_steps = 0
 
     # ------------------------------------------------------------------ one optimisation step
     def _autocast(self):
         return torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None)
 
-    def training_step(self, imgs: torch.Tensor, pts: torch.Tensor, seg: torch.Tensor):
-        """zero_grad -> forward(s) -> fused loss+grad -> backward -> (all-reduce) -> AdamW.
-        Returns (loss terms f32[8] on device, student logits).  Never syncs the host."""
+    def _step_impl(self, imgs, pts, seg, update_hyper: bool):
         self.optimizer.zero_grad()
         with self._autocast():
             if self.teacher is not None:
@@ -169,9 +177,52 @@ class Trainer:
             T=self.kd_temperature, alpha=alpha, beta=beta, ignore_index=-1)
         torch.autograd.backward([logits] + list(s_feats), [d_logits] + list(d_feats))
         allreduce_gradients_(self.optimizer.flat_grad)                  # one flat NCCL bucket (no-op at world 1)
-        self.optimizer.step(grad_scale=1.0 / self.world_size)
-        self.last_loss_terms = terms
-        return terms, logits
+        self.optimizer.step(grad_scale=1.0 / self.world_size, update_hyper=update_hyper)
+        return terms, logits.detach()
+
+    def _capture(self, imgs, pts, seg):
+        self._static = {"image": torch.empty_like(imgs), "points": torch.empty_like(pts), "seg": torch.empty_like(seg)}
+        for k, v in (("image", imgs), ("points", pts), ("seg", seg)):
+            self._static[k].copy_(v)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        k0 = _native.launch_stats["kernels"]
+        with torch.cuda.graph(graph):
+            out = self._step_impl(self._static["image"], self._static["points"], self._static["seg"], update_hyper=False)
+        self._graph_kernels = _native.launch_stats["kernels"] - k0      # our kernels inside one replay
+        _native.launch_stats["kernels"] = k0
+        self._graph, self._graph_out = graph, out
+        self._graph_key = (imgs.shape, pts.shape, seg.shape, imgs.dtype, self.model.training)
+
+    def training_step(self, imgs: torch.Tensor, pts: torch.Tensor, seg: torch.Tensor):
+        """zero_grad -> forward(s) -> fused loss+grad -> backward -> (all-reduce) -> AdamW.
+        Returns (loss terms f32[8] on device, student logits).  Never syncs the host.  With
+        ``use_cuda_graph`` the first ``graph_warmup_steps`` calls run eagerly, then the whole step is
+        captured once per input shape and replayed (outputs are then static buffers, valid until the
+        next call)."""
+        if not self.use_cuda_graph:
+            out = self._step_impl(imgs, pts, seg, update_hyper=True)
+            self.last_loss_terms = out[0]
+            return out
+        key = (imgs.shape, pts.shape, seg.shape, imgs.dtype, self.model.training)
+        if self._graph is None or key != self._graph_key:
+            if self._eager_steps < self.graph_warmup_steps:
+                self._eager_steps += 1
+                out = self._step_impl(imgs, pts, seg, update_hyper=True)
+                self.last_loss_terms = out[0]
+                return out
+            self._capture(imgs, pts, seg)
+        else:
+            self._static["image"].copy_(imgs, non_blocking=True)
+            self._static["points"].copy_(pts, non_blocking=True)
+            self._static["seg"].copy_(seg, non_blocking=True)
+        opt = self.optimizer
+        opt._step += 1
+        opt.set_hyper(opt.param_groups[0]["lr"], opt._step)      # device-side (lr, step) the captured AdamW reads
+        self._graph.replay()
+        _native.launch_stats["kernels"] += self._graph_kernels
+        self.last_loss_terms = self._graph_out[0]
+        return self._graph_out
 
     # ------------------------------------------------------------------ epochs
     def _to_device(self, batch):

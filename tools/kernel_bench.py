@@ -1,0 +1,68 @@
+"""Developer tool: launch each hand-written kernel once or a few times at the bench shapes (for ncu captures)
+and print CUDA-event timings.   python tools/kernel_bench.py [--iters 3] [--only rowbn,bev,kd,fusion]"""
+import os, sys, argparse
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "lightweight-multi-modal-scene-understanding-via-knowledge-distillation_b200"))
+import torch
+from src import native, ops
+from src.data_loading.synthetic_frames import make_frames
+ap = argparse.ArgumentParser(); ap.add_argument("--iters", type=int, default=3); ap.add_argument("--only", default="rowbn,bev,kd,fusion")
+ap.add_argument("--batch", type=int, default=32); ap.add_argument("--points", type=int, default=170000)
+a = ap.parse_args()
+dev = torch.device("cuda", 0); p = native.ptr; st = native.stream_ptr(dev)
+B, N, C, H, W = a.batch, a.points, 128, 64, 64
+dt = torch.bfloat16
+def timeit(name, fn, nbytes):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    print(f"{name:34s} {ms:8.3f} ms  {nbytes/ms/1e6:8.0f} GB/s")
+only = a.only.split(",")
+M = B * N
+if "rowbn" in only:
+    for Cc in (128, 64):
+        x = torch.randn(M, Cc, device=dev, dtype=dt); y = torch.empty_like(x); g = torch.randn_like(x)
+        f32 = dict(device=dev, dtype=torch.float32)
+        gamma, beta = torch.rand(Cc, **f32) + 0.5, torch.randn(Cc, **f32)
+        mean, invstd, scale, shift = (torch.empty(Cc, **f32) for _ in range(4))
+        ws = torch.empty(native.lib.kdf_rowbn_bwd_workspace_bytes(Cc), dtype=torch.uint8, device=dev)
+        dg, db = torch.empty(Cc, **f32), torch.empty(Cc, **f32)
+        nb = x.numel() * 2
+        timeit(f"rowbn_stats C={Cc}", lambda: native.call("kdf_rowbn_stats", p(x), 1, M, Cc, p(gamma), p(beta), None, 1e-5, 0.1, None, None, p(mean), p(invstd), p(scale), p(shift), p(ws), st), nb)
+        timeit(f"rowbn_apply_fwd C={Cc}", lambda: native.call("kdf_rowbn_apply_fwd", p(x), None, 1, M, Cc, p(scale), p(shift), 1, p(y), st), 2 * nb)
+        timeit(f"rowbn_bwd(reduce+apply) C={Cc}", lambda: native.call("kdf_rowbn_bwd", p(g), p(x), 1, M, Cc, p(scale), p(shift), p(mean), p(invstd), 1, 1, p(y), p(dg), p(db), p(ws), st), 5 * nb)
+        timeit(f"torch copy C={Cc}", lambda: y.copy_(x), 2 * nb)
+        del x, y, g
+if "bev" in only:
+    pts = make_frames(B, N, seed=1, device=dev)["points"]
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    feats = torch.rand(B, N, C, device=dev, dtype=dt)
+    grid = torch.empty(B, H, W, C, dtype=dt, device=dev); cnt = torch.empty(B, H * W, dtype=torch.int32, device=dev)
+    cel = torch.empty(B, N, dtype=torch.int32, device=dev); ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev)
+    order = torch.empty(B, N, dtype=torch.int32, device=dev); offs = torch.empty(B, H * W + 1, dtype=torch.int32, device=dev)
+    wsb = native.lib.kdf_bev_workspace_bytes(B, N, H, W); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    v = 0.622
+    timeit("bev_project_fwd", lambda: native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), 1, B, N, C, *geom, H, W, 0, p(grid), p(cnt), p(cel), p(ties), p(order), p(offs), p(ws), wsb, st), B * (16 * N + C * 2 * v * N + C * 2 * H * W))
+    timeit("bev_reduce", lambda: native.call("kdf_bev_reduce", p(feats), 1, p(order), p(offs), B, N, C, H, W, 0, p(grid), p(ties), st), B * (C * 2 * v * N + C * 2 * H * W))
+    gg = torch.rand(B, H * W, C, device=dev, dtype=dt); gf = torch.empty(B, N, C, dtype=dt, device=dev)
+    timeit("bev_bwd", lambda: native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order), p(offs), 1, B, N, C, H, W, 0, p(gf), st), B * (C * 2 * v * N + C * 2 * N))
+    timeit("bev_index", lambda: native.call("kdf_bev_index", p(pts), B, N, 4, *geom, H, W, p(cel), None, p(cnt), st), B * 20 * N)
+    del feats, gf
+if "kd" in only:
+    zs = torch.randn(B, 2, H, W, device=dev, dtype=dt); zt = torch.randn_like(zs)
+    lab = (torch.rand(B, H, W, device=dev) < 0.13).long(); cw = torch.tensor([0.4, 3.5], device=dev)
+    ts = [torch.randn(B, H, W, C, device=dev, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
+    tt = [torch.randn(B, H, W, C, device=dev, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
+    timeit("kd_loss", lambda: ops.kd_loss_fwd_bwd(zs, zt, lab, cw, ts, tt), B * H * W * (2 * 3 * C * 2))
+if "fusion" in only:
+    Mp = B * H * W
+    f32 = dict(device=dev, dtype=torch.float32)
+    cam, lid = torch.randn(Mp, C, device=dev, dtype=dt), torch.randn(Mp, C, device=dev, dtype=dt)
+    sc = [torch.rand(C, **f32) + 0.5 for _ in range(2)]; sh = [torch.randn(C, **f32) * 0.1 for _ in range(2)]
+    w1, b1 = torch.randn(C, 2 * C, **f32) * 0.05, torch.randn(C, **f32) * 0.1
+    w2, b2 = torch.randn(2, C, **f32) * 0.1, torch.randn(2, **f32) * 0.1
+    fo = torch.empty(Mp, C, dtype=dt, device=dev); attn = torch.empty(Mp, 2, **f32)
+    timeit("fusion_weighted_fwd", lambda: native.call("kdf_fusion_weighted_fwd", p(cam), p(lid), 1, Mp, C, p(sc[0]), p(sh[0]), p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(fo), p(attn), st), Mp * 3 * C * 2)
