@@ -139,6 +139,22 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
                   int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,
                   void *workspace, void *stream);
 
+/* ---------------------------------------------------------------- fused point-MLP layers (tcgen05)
+ * One tensor-core layer of the point MLP (src/models/lidar_encoder.py:25-35) as ONE kernel that keeps
+ * only the pre-BatchNorm outputs in HBM:  z_out[M,128] (bf16) = prologue(input) . W^T, plus the fp64
+ * column sums / sums of squares of the stored values (this layer's BatchNorm statistics).
+ *   mode 0: input = raw points f32 [M,4]; the prologue recomputes the whole first layer
+ *           a1[c] = relu(q[c,:].(x,y,z,i) + r[c]), q f32 [64,4] = scale1*W1, r f32 [64]; Kin = 64
+ *   mode 1: input = previous z bf16 [M,Kin]; prologue relu(z*scale + shift); pro_a = scale, pro_b = shift; Kin = 128
+ *   W_bf16 [Nout=128, Kin] row-major bf16;  stats f64 [2,128] (zeroed by the call).
+ * kdf_bn_finalize turns such sums into mean / invstd / folded scale, shift and updates running stats.
+ */
+int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a, const float *pro_b,
+                      const void *W_bf16, int Kin, int Nout, void *z_out, double *stats, void *stream);
+int kdf_bn_finalize(const double *stats, int64_t M, int C, const float *gamma, const float *beta, const float *pre_bias,
+                    float eps, float momentum, float *running_mean, float *running_var,
+                    float *mean, float *invstd, float *scale, float *shift, void *stream);
+
 /* ---------------------------------------------------------------- (2) camera-LiDAR fusion
  * Inputs are the PRE-BatchNorm outputs of the two 1x1 projection convolutions
  * in pixel-major (NHWC) layout; BatchNorm is applied as y = x*scale + shift with

@@ -1,0 +1,331 @@
+// Fused point-MLP layers on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// The reference's point MLP (src/models/lidar_encoder.py:25-35,66) is Conv1d(k=1)+BatchNorm1d+ReLU
+// three times over every point of the sweep.  Executed layer by layer it moves ~9 passes over a
+// [B*N, 128] activation per layer (GEMM out, statistics, normalise, and the same again backwards).
+// Here one layer is ONE kernel that keeps only the pre-BatchNorm outputs z in HBM:
+//
+//   prologue : global -> registers -> previous layer's BatchNorm-apply + ReLU (or, for the first
+//              tensor-core layer, the whole 4->64 first layer recomputed from the raw fp32 point)
+//              -> bf16 -> 128-byte-swizzled shared memory operand tile (128 points x K)
+//   MMA      : tcgen05.mma  D[128 x 128, fp32, TMEM] = A[128 x K] . W^T      (one elected thread)
+//   epilogue : tcgen05.ld -> bf16 -> swizzled staging tile -> coalesced 16-byte stores of z, and the
+//              per-channel sum / sum of squares of exactly the values stored (this layer's BatchNorm
+//              statistics), accumulated in registers over the CTA's tiles, fp64 atomics at the end.
+//
+// Persistent CTAs (one per SM), double-buffered operand tile and accumulator: the MMA of tile i runs
+// while the global loads of tile i+1 are in flight and tile i-1 drains through the epilogue.
+#include "kdf_common.cuh"
+#include "tc_common.cuh"
+
+namespace kdf {
+
+constexpr int PM_THREADS = 256;
+constexpr int PM_ROWS = 128;          // points per tile = MMA M
+constexpr int PM_N = 128;             // output channels of the tensor-core layers
+
+struct MlpFwdArgs {
+    const void *input;                // MODE 0: points f32 [M,4];  MODE 1: z_prev bf16 [M,KIN]
+    int64_t M;
+    const float *pro_a, *pro_b;       // MODE 0: q f32 [64,4], r f32 [64];  MODE 1: scale, shift f32 [KIN]
+    const __nv_bfloat16 *W;           // [PM_N, KIN] row-major
+    __nv_bfloat16 *z_out;             // [M, PM_N]
+    double *stats;                    // [2][PM_N]  sum, sum of squares (accumulated)
+};
+
+template <int KIN>
+struct MlpSmem {
+    static constexpr int PANELS = KIN / 64;
+    static constexpr int A_BYTES = PM_ROWS * KIN * 2;
+    static constexpr int W_BYTES = PM_N * KIN * 2;
+    static constexpr int STAGE_BYTES = PM_ROWS * PM_N * 2;
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_A0 = OFF_W + W_BYTES;
+    static constexpr int OFF_A1 = OFF_A0 + A_BYTES;
+    static constexpr int OFF_STAGE = OFF_A1 + A_BYTES;
+    static constexpr int OFF_MISC = OFF_STAGE + STAGE_BYTES;     // barriers, tmem address, coefficient tables
+    static constexpr int MISC_BYTES = 64 + 4 * (64 * 4 + 64 + 2 * 128);
+    static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;    // + slack for 1024-byte alignment
+};
+
+// MODE 0: a1[c] = relu(q[c,:] . (x,y,z,i) + r[c])  for 8 channels c0..c0+7 of one point
+__device__ __forceinline__ uint4 first_layer_chunk(const float4 &p, const float *q, const float *r) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float acc = r[j];
+        acc = fmaf(q[4 * j + 0], p.x, acc);
+        acc = fmaf(q[4 * j + 1], p.y, acc);
+        acc = fmaf(q[4 * j + 2], p.z, acc);
+        acc = fmaf(q[4 * j + 3], p.w, acc);
+        v[j] = fmaxf(acc, 0.f);
+    }
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// MODE 1: relu(z*scale + shift) on 8 bf16 values
+__device__ __forceinline__ uint4 affine_relu_chunk(const uint4 &u, const float *sc, const float *sh) {
+    float v[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+template <int MODE, int KIN>
+__global__ void __launch_bounds__(PM_THREADS, 1)
+mlp_layer_fwd_kernel(MlpFwdArgs a) {
+    using L = MlpSmem<KIN>;
+    constexpr int CHUNKS_PER_ROW = KIN / 8;                       // 16-byte chunks of one operand row
+    constexpr int ROWS_PER_PASS = PM_THREADS / CHUNKS_PER_ROW;    // 16 (KIN=128) or 32 (KIN=64)
+    constexpr int PASSES = PM_ROWS / ROWS_PER_PASS;               // 8 or 4
+    constexpr uint32_t IDESC = tc::make_idesc(PM_ROWS, PM_N, 0, 0);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sW = smem + L::OFF_W, *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1}, *sStage = smem + L::OFF_STAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
+    float *coef = reinterpret_cast<float *>(smem + L::OFF_MISC + 64);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
+
+    // ---- one-time setup: coefficient tables, weights -> swizzled smem, barriers, TMEM
+    if (MODE == 0) {
+        for (int i = tid; i < 64 * 4; i += PM_THREADS) coef[i] = a.pro_a[i];
+        for (int i = tid; i < 64; i += PM_THREADS) coef[256 + i] = a.pro_b[i];
+    } else {
+        for (int i = tid; i < KIN; i += PM_THREADS) { coef[i] = a.pro_a[i]; coef[KIN + i] = a.pro_b[i]; }
+    }
+    for (int idx = tid; idx < PM_N * CHUNKS_PER_ROW; idx += PM_THREADS) {
+        const int n = idx / CHUNKS_PER_ROW, ch = idx % CHUNKS_PER_ROW;
+        const uint4 w = *reinterpret_cast<const uint4 *>(a.W + (int64_t)n * KIN + ch * 8);
+        *reinterpret_cast<uint4 *>(sW + (ch >> 3) * (PM_N * tc::ROW_BYTES) + tc::sw128_offset(n, ch & 7)) = w;
+    }
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // fixed per-thread operand chunk (so its coefficients stay in registers for the whole kernel)
+    const int pch = tid % CHUNKS_PER_ROW, prow0 = tid / CHUNKS_PER_ROW;
+    float c0[MODE == 0 ? 32 : 8], c1[8];
+    if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) c0[j] = coef[pch * 32 + j];          // q rows of channels 8*pch..8*pch+7
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c1[j] = coef[256 + pch * 8 + j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c0[j] = coef[pch * 8 + j]; c1[j] = coef[KIN + pch * 8 + j]; }
+    }
+    // fixed per-thread output chunk for the store / statistics phase: 16 chunks per 256-byte row
+    const int och = tid & 15, orow0 = tid >> 4;
+    float s_sum[8], s_sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_sum[j] = 0.f; s_sq[j] = 0.f; }
+
+    uint4 raw[PASSES];
+    auto load_tile = [&](int64_t tile) {
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int64_t row = r0 + prow0 + p * ROWS_PER_PASS;
+            if (row < a.M) {
+                if (MODE == 0) raw[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.input) + row);
+                else raw[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + row * KIN + pch * 8));
+            }
+        }
+    };
+    auto stage_tile = [&](int64_t tile, uint8_t *dst) {
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int r = prow0 + p * ROWS_PER_PASS;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);                          // rows past M contribute exact zeros
+            if (r0 + r < a.M) {
+                if (MODE == 0) {
+                    const float4 pt = make_float4(__uint_as_float(raw[p].x), __uint_as_float(raw[p].y),
+                                                  __uint_as_float(raw[p].z), __uint_as_float(raw[p].w));
+                    v = first_layer_chunk(pt, c0, c1);
+                } else {
+                    v = affine_relu_chunk(raw[p], c0, c1);
+                }
+            }
+            *reinterpret_cast<uint4 *>(dst + (pch >> 3) * (PM_ROWS * tc::ROW_BYTES) + tc::sw128_offset(r, pch & 7)) = v;
+        }
+        tc::fence_async_smem();
+    };
+    auto issue_mma = [&](int buf) {                                        // one thread
+        const uint32_t a_base = tc::smem_u32(sA[buf]), w_base = tc::smem_u32(sW);
+        const uint32_t d = tmem_base + (uint32_t)buf * PM_N;
+#pragma unroll
+        for (int k = 0; k < KIN / 16; ++k) {
+            const uint32_t koff = (uint32_t)(k >> 2) * (PM_ROWS * tc::ROW_BYTES) + (uint32_t)(k & 3) * 32u;
+            const uint32_t woff = (uint32_t)(k >> 2) * (PM_N * tc::ROW_BYTES) + (uint32_t)(k & 3) * 32u;
+            tc::mma_bf16(d, tc::desc_kmajor(a_base + koff), tc::desc_kmajor(w_base + woff), IDESC, k > 0);
+        }
+        tc::mma_commit(&bars[buf]);
+    };
+    auto epilogue = [&](int64_t tile, int buf, uint32_t parity) {
+        tc::mbar_wait(&bars[buf], parity);
+        tc::fence_after_sync();
+        // warp w: TMEM lanes 32*(w%4).., columns 64*(w/4)..; thread = one output row
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * PM_N + (uint32_t)(warp >> 2) * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + half * 32, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = (warp >> 2) * 8 + half * 4 + j;           // 16-byte chunk of the 256-byte output row
+                const uint4 v = make_uint4(pack_bf16(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])),
+                                           pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                           pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                                           pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                *reinterpret_cast<uint4 *>(sStage + row * 256 + ((chunk ^ (row & 7)) << 4)) = v;
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        // coalesced stores + statistics of exactly the stored bf16 values
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < PM_ROWS / 16; ++p) {
+            const int r = orow0 + p * 16;
+            if (r0 + r < a.M) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4 *>(a.z_out + (r0 + r) * PM_N + och * 8) = v;
+                const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                                    bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s_sum[j] += f[j]; s_sq[j] = fmaf(f[j], f[j], s_sq[j]); }
+            }
+        }
+    };
+
+    // ---- software pipeline over this CTA's tiles
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) {
+        load_tile(tile);
+        stage_tile(tile, sA[0]);
+    }
+    __syncthreads();
+    int it = 0;
+    int64_t prev_tile = -1;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0) {
+            tc::fence_after_sync();
+            issue_mma(buf);
+        }
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) load_tile(next);                               // global loads in flight during the epilogue
+        if (it > 0) epilogue(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1));
+        if (next < n_tiles) stage_tile(next, sA[buf ^ 1]);                 // A[buf^1] was consumed by the MMA just waited on
+        __syncthreads();
+        prev_tile = tile;
+    }
+    if (it > 0) {
+        epilogue(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1));
+    }
+    __syncthreads();
+
+    // ---- statistics: reduce the 16 threads that share an output chunk, then 2*128 fp64 atomics per CTA
+    float *red = reinterpret_cast<float *>(sStage);                       // [16 row lanes][16 chunks][16]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[(orow0 * 16 + och) * 16 + j] = s_sum[j]; red[(orow0 * 16 + och) * 16 + 8 + j] = s_sq[j]; }
+    __syncthreads();
+    if (tid < 16 * 16) {
+        const int ch = tid >> 4, j = tid & 15;                             // chunk, (sum|sq, element)
+        float v = 0.f;
+        for (int r = 0; r < 16; ++r) v += red[(r * 16 + ch) * 16 + j];
+        const int col = ch * 8 + (j & 7);
+        atomicAdd(a.stats + (j >> 3) * PM_N + col, (double)v);
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+// mean / invstd / folded scale,shift / running statistics from fp64 column sums
+__global__ void bn_finalize_kernel(const double *stats, int64_t M, int C, const float *gamma, const float *beta,
+                                   const float *pre_bias, float eps, float momentum, float *running_mean,
+                                   float *running_var, float *mean, float *invstd, float *scale, float *shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double invM = 1.0 / (double)M;
+    const double mu = stats[c] * invM;
+    double var = stats[C + c] * invM - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)mu;
+    invstd[c] = is;
+    const float s = (gamma ? gamma[c] : 1.f) * is;
+    scale[c] = s;
+    shift[c] = (beta ? beta[c] : 0.f) - (float)mu * s;
+    if (running_mean) {
+        const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        const float bias = pre_bias ? pre_bias[c] : 0.f;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mu + bias);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+}  // namespace kdf
+
+using namespace kdf;
+
+extern "C" {
+
+int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a, const float *pro_b,
+                      const void *W_bf16, int Kin, int Nout, void *z_out, double *stats, void *stream) {
+    KDF_CHECK_ARG(mode == 0 || mode == 1, "mlp_layer_fwd: bad mode %d", mode);
+    KDF_CHECK_ARG(M >= 0, "mlp_layer_fwd: negative M");
+    KDF_CHECK_ARG(Nout == PM_N, "mlp_layer_fwd: Nout must be %d", PM_N);
+    KDF_CHECK_ARG((mode == 0 && Kin == 64) || (mode == 1 && Kin == 128), "mlp_layer_fwd: unsupported (mode, Kin) = (%d, %d)", mode, Kin);
+    KDF_CHECK_ARG(pro_a && pro_b && W_bf16 && stats, "mlp_layer_fwd: null pointer");
+    cudaStream_t st = as_stream(stream);
+    KDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * PM_N, st));
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(input && z_out, "mlp_layer_fwd: null pointer");
+    KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(input) | reinterpret_cast<uintptr_t>(z_out) | reinterpret_cast<uintptr_t>(W_bf16)) & 15) == 0,
+                  "mlp_layer_fwd: buffers must be 16-byte aligned");
+    MlpFwdArgs a{input, M, pro_a, pro_b, reinterpret_cast<const __nv_bfloat16 *>(W_bf16),
+                 reinterpret_cast<__nv_bfloat16 *>(z_out), stats};
+    const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
+    int blocks = sm_count();
+    if (n_tiles < blocks) blocks = (int)n_tiles;
+    if (mode == 0) {
+        const int smem = MlpSmem<64>::TOTAL;
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_fwd_kernel<0, 64><<<blocks, PM_THREADS, smem, st>>>(a);
+    } else {
+        const int smem = MlpSmem<128>::TOTAL;
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_fwd_kernel<1, 128><<<blocks, PM_THREADS, smem, st>>>(a);
+    }
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_bn_finalize(const double *stats, int64_t M, int C, const float *gamma, const float *beta, const float *pre_bias,
+                    float eps, float momentum, float *running_mean, float *running_var,
+                    float *mean, float *invstd, float *scale, float *shift, void *stream) {
+    KDF_CHECK_ARG(M > 0 && C > 0, "bn_finalize: bad sizes");
+    KDF_CHECK_ARG(stats && mean && invstd && scale && shift, "bn_finalize: null pointer");
+    KDF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats come in pairs");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, M, C, gamma, beta, pre_bias, eps, momentum,
+                                                                      running_mean, running_var, mean, invstd, scale, shift);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+}  // extern "C"

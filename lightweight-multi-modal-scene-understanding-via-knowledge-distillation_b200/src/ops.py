@@ -475,3 +475,21 @@ def adamw_flat_(param, grad, exp_avg, exp_avg_sq, hyper, beta1, beta2, eps, weig
     call("kdf_adamw_flat", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(hyper),
                              float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
                              stream_ptr(dev))
+
+
+# ----------------------------------------------------------------------------- fused point-MLP layers (tcgen05)
+def mlp_layer_fwd(mode: int, x: torch.Tensor, pro_a: torch.Tensor, pro_b: torch.Tensor, weight_bf16: torch.Tensor):
+    """One tensor-core MLP layer: z [M,128] bf16 = prologue(x) @ W^T and the fp64 column sums of z and z^2.
+    mode 0: x = raw points f32 [M,4] (first layer recomputed in the prologue, pro_a = q [64,4], pro_b = r [64]);
+    mode 1: x = previous z bf16 [M,128] (prologue relu(z*pro_a + pro_b))."""
+    dev = require_cuda(x, pro_a, pro_b, weight_bf16)
+    x = x.contiguous()
+    M = x.shape[0]
+    Nout, Kin = weight_bf16.shape
+    if weight_bf16.dtype != torch.bfloat16 or not weight_bf16.is_contiguous():
+        raise TypeError("weight must be a contiguous bf16 [Nout, Kin] tensor")
+    z = torch.empty(M, Nout, dtype=torch.bfloat16, device=dev)
+    stats = torch.empty(2, Nout, dtype=torch.float64, device=dev)
+    call("kdf_mlp_layer_fwd", mode, ptr(x), M, ptr(pro_a.float().contiguous()), ptr(pro_b.float().contiguous()),
+         ptr(weight_bf16), Kin, Nout, ptr(z), ptr(stats), stream_ptr(dev))
+    return z, stats
