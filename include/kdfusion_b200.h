@@ -87,6 +87,13 @@ int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats
                         int32_t *order, int32_t *offsets,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* The sort stage alone (index -> scan -> fill): cell ids, occupancy and the cell ordering, to be
+ * shared by several reductions over the same sweep (teacher and student project the same points). */
+int kdf_bev_build_order(const float *points, int point_stride, int B, int64_t N,
+                        float x0, float xspan, float y0, float yspan, int H, int W,
+                        int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 /* The reduce stage alone, over a cell ordering produced earlier (by
  * kdf_bev_project_fwd with order/offsets supplied, e.g. to share one sort between
  * the teacher's and the student's projection of the same sweep, or to time the
@@ -138,6 +145,24 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
                   const float *scale, const float *shift, const float *mean, const float *invstd,
                   int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,
                   void *workspace, void *stream);
+
+/* Projection of a layer whose BatchNorm+ReLU has not been applied yet (fused point-MLP path):
+ * the feature scattered is a3 = bf16(relu(z*scale + shift)), computed on the fly from the stored
+ * pre-BatchNorm rows z (bf16 [B,N,C]).  kdf_bev_reduce_affine = per-cell max / tie count of a3 over an
+ * existing cell ordering; kdf_bev_bwd_affine = gradient w.r.t. the BatchNorm OUTPUT y3 (ReLU folded in),
+ *   dy[p,c] = (a3[p,c] == max && max > 0) ? g/ties : 0,
+ * zeros for points outside, plus sums f64 [2,C] = (sum dy, sum dy*z) for BatchNorm's backward
+ * (zeroed by the call).  kdf_point_moments: sums of (x,y,z,i) and their 10 pairwise products over all
+ * points (f64 [14], zeroed by the call) -- the first MLP layer is linear in the point, so its
+ * BatchNorm statistics follow from these. */
+int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *shift,
+                          const int32_t *order, const int32_t *offsets, int B, int64_t N, int C, int H, int W,
+                          void *grid_bf16, int32_t *ties, void *stream);
+int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const float *scale, const float *shift,
+                       const void *grid_bf16, const int32_t *ties, const int32_t *order, const int32_t *offsets,
+                       const int32_t *cell, int B, int64_t N, int C, int H, int W,
+                       void *dy_bf16, double *sums, void *stream);
+int kdf_point_moments(const float *points, int64_t M, double *out14, void *stream);
 
 /* ---------------------------------------------------------------- fused point-MLP layers (tcgen05)
  * One tensor-core layer of the point MLP (src/models/lidar_encoder.py:25-35) as ONE kernel that keeps

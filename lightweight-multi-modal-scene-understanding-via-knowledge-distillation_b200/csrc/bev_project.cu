@@ -452,6 +452,182 @@ bev_bwd_wide_kernel(const T *__restrict__ grad_grid, const T *__restrict__ feats
         if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(grad_feats + i * C + ch) = zero;
 }
 
+
+// ----------------------------------------------------------------------------- projection of a BN+ReLU'd layer (fused MLP path)
+// The fused point-MLP keeps only the pre-BatchNorm output z3 of the last layer in HBM; the feature the
+// reference scatters is a3 = relu(z3*scale + shift) (lidar_encoder.py:32-34 then :85-96).  These two
+// kernels apply that affine+ReLU on the fly (rounded to bf16, the storage type of the grid) so a3 is
+// never materialised: forward = per-cell max/tie count of a3, backward = d z3-side gradient
+//   dy3[p,c] = (a3[p,c] == max[cell,c] && max > 0) ? g[cell,c] / ties : 0
+// (the ReLU derivative folded in; when the max is 0 the ReLU kills the gradient whatever ATen's
+// tie quirk says) plus the two per-channel sums BatchNorm's backward needs, S0 = sum dy3 and
+// S1 = sum dy3*z3, accumulated in registers -> shared memory -> fp64 atomics.
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+bev_reduce_affine_kernel(const __nv_bfloat16 *__restrict__ z, const float *__restrict__ scale, const float *__restrict__ shift,
+                         const int32_t *__restrict__ order, const int32_t *__restrict__ offsets,
+                         __nv_bfloat16 *__restrict__ grid, int32_t *__restrict__ ties, int64_t n_cells, int64_t N, int HW) {
+    using T = __nv_bfloat16;
+    constexpr int VEC = 8, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * VEC;
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) { sc[q] = scale[ch + q]; sh[q] = shift[ch + q]; }
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
+        const int64_t b = cid / HW;
+        const int c = (int)(cid - b * HW);
+        const int beg = __ldg(offsets + b * (HW + 1) + c);
+        const int n = __ldg(offsets + b * (HW + 1) + c + 1) - beg;
+        const int32_t *ord = order + b * N + beg;
+        const T *fb = z + b * N * C + ch;
+        float m[VEC];
+        int k[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { m[q] = -1.f; k[q] = 0; }            // a3 >= 0, so -1 is "nothing yet"
+        int idn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+        for (int j0 = 0; j0 < n; j0 += STEP) {
+            uint4 raw[U];
+            int id[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                id[u] = idn[u];
+                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(fb + (int64_t)id[u] * C));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (id[u] >= 0) {
+                    float f[VEC];
+                    Raw16<T>::unpack(raw[u], f);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        const float a = bf16_round(fmaxf(fmaf(f[q], sc[q], sh[q]), 0.f));
+                        if (a > m[q]) { m[q] = a; k[q] = 1; }
+                        else if (a == m[q]) { k[q]++; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                const float om = __shfl_xor_sync(0xffffffffu, m[q], o);
+                const int ok = __shfl_xor_sync(0xffffffffu, k[q], o);
+                if (om > m[q]) { m[q] = om; k[q] = ok; }
+                else if (om == m[q]) { k[q] += ok; }
+            }
+        }
+        if (sub == 0) {
+            float o[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o[q] = (n == 0) ? 0.f : m[q];
+            *reinterpret_cast<uint4 *>(grid + cid * C + ch) = Raw16<T>::pack(o);
+            if (ties) {
+                int *tp = ties + cid * C + ch;
+#pragma unroll
+                for (int q = 0; q < VEC; q += 4)
+                    *reinterpret_cast<int4 *>(tp + q) = make_int4(n ? k[q] : 0, n ? k[q + 1] : 0, n ? k[q + 2] : 0, n ? k[q + 3] : 0);
+            }
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bfloat16 *__restrict__ z,
+                      const float *__restrict__ scale, const float *__restrict__ shift,
+                      const __nv_bfloat16 *__restrict__ grid, const int32_t *__restrict__ ties,
+                      const int32_t *__restrict__ order, const int32_t *__restrict__ offsets, const int32_t *__restrict__ cell,
+                      __nv_bfloat16 *__restrict__ dy, double *__restrict__ sums /* [2][C] */,
+                      int64_t n_cells, int64_t N, int HW, int64_t total) {
+    using T = __nv_bfloat16;
+    constexpr int VEC = 8, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    __shared__ float red[8][2][LPR * 8];                                   // [warp][S0|S1][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, ch = (lane % LPR) * VEC;
+    float sc[VEC], sh[VEC], s0[VEC], s1[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) { sc[q] = scale[ch + q]; sh[q] = shift[ch + q]; s0[q] = 0.f; s1[q] = 0.f; }
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
+        const int64_t b = cid / HW;
+        const int c = (int)(cid - b * HW);
+        const int beg = __ldg(offsets + b * (HW + 1) + c);
+        const int n = __ldg(offsets + b * (HW + 1) + c + 1) - beg;
+        if (n == 0) continue;
+        const int32_t *ord = order + b * N + beg;
+        float g[VEC], mx[VEC];
+        Raw16<T>::unpack(*reinterpret_cast<const uint4 *>(grad_grid + cid * C + ch), g);
+        Raw16<T>::unpack(*reinterpret_cast<const uint4 *>(grid + cid * C + ch), mx);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            const int t = __ldg(ties + cid * C + ch + q);
+            g[q] = (mx[q] > 0.f) ? bf16_round(g[q] / (float)t) : 0.f;       // value every tied point receives
+        }
+        int idn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+        for (int j0 = 0; j0 < n; j0 += STEP) {
+            uint4 raw[U];
+            int id[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                id[u] = idn[u];
+                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(z + (b * N + id[u]) * C + ch));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (id[u] >= 0) {
+                    float f[VEC], o[VEC];
+                    Raw16<T>::unpack(raw[u], f);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        const float a = bf16_round(fmaxf(fmaf(f[q], sc[q], sh[q]), 0.f));
+                        o[q] = (a == mx[q]) ? g[q] : 0.f;
+                        s0[q] += o[q];
+                        s1[q] = fmaf(o[q], f[q], s1[q]);
+                    }
+                    *reinterpret_cast<uint4 *>(dy + (b * N + id[u]) * C + ch) = Raw16<T>::pack(o);
+                }
+            }
+        }
+    }
+    // rows of points outside the grid
+    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR), gn = ((int64_t)gridDim.x * blockDim.x) / LPR;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = g0; i < total; i += gn)
+        if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(dy + i * C + ch) = zero;
+    // S0 / S1: merge row groups in the warp, the 8 warps through shared memory, then fp64 atomics
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            s0[q] += __shfl_xor_sync(0xffffffffu, s0[q], o);
+            s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
+        }
+    }
+    if (sub == 0) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { red[warp][0][ch + q] = s0[q]; red[warp][1][ch + q] = s1[q]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][i / C][i % C];
+        atomicAdd(sums + i, (double)v);
+    }
+}
+
 // ----------------------------------------------------------------------------- host side
 static int check_geom(int B, int64_t N, int H, int W, float xspan, float yspan) {
     KDF_CHECK_ARG(B >= 0 && N >= 0, "bev: negative B or N");
@@ -542,6 +718,35 @@ size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W) {
     return 2 * bn + off + 256;
 }
 
+// index -> scan -> fill: cell ids, occupancy and the cell ordering (counting sort) of every frame
+static int build_order(const float *points, int point_stride, int B, int64_t N, const BevGeom &g,
+                       int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets, int32_t *rank, cudaStream_t st) {
+    const int HW = g.H * g.W;
+    const int64_t total = (int64_t)B * N;
+    if (int e = launch_index(points, B, N, point_stride, g, cell, rank, count, st)) return e;
+    bev_scan_kernel<<<B, 1024, 0, st>>>(count, offsets, HW);
+    KDF_LAUNCH_CHECK();
+    if (total > 0) {
+        bev_fill_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(cell, rank, offsets, order, total, N, HW);
+        KDF_LAUNCH_CHECK();
+    }
+    return KDF_OK;
+}
+
+int kdf_bev_build_order(const float *points, int point_stride, int B, int64_t N,
+                        float x0, float xspan, float y0, float yspan, int H, int W,
+                        int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
+    KDF_CHECK_ARG(point_stride >= 2, "bev: point_stride must be >= 2");
+    if (B == 0) return KDF_OK;
+    KDF_CHECK_ARG(((points && cell && order) || N == 0) && count && offsets && workspace, "bev_build_order: null pointer");
+    KDF_CHECK_ARG(workspace_bytes >= kdf_bev_workspace_bytes(B, N, H, W), "bev_build_order: workspace too small");
+    BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
+    return build_order(points, point_stride, B, N, g, count, cell, order, offsets, reinterpret_cast<int32_t *>(workspace),
+                       as_stream(stream));
+}
+
 int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats, int dtype,
                         int B, int64_t N, int C,
                         float x0, float xspan, float y0, float yspan, int H, int W, int reduce,
@@ -568,14 +773,7 @@ int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats
     if (!offsets) offsets = reinterpret_cast<int32_t *>(ws + 2 * bn);
     BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
     if (B == 0) return KDF_OK;
-
-    if (int e = launch_index(points, B, N, point_stride, g, cell, rank, count, st)) return e;
-    bev_scan_kernel<<<B, 1024, 0, st>>>(count, offsets, HW);
-    KDF_LAUNCH_CHECK();
-    if (total > 0) {
-        bev_fill_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(cell, rank, offsets, order, total, N, HW);
-        KDF_LAUNCH_CHECK();
-    }
+    if (int e = build_order(points, point_stride, B, N, g, count, cell, order, offsets, rank, st)) return e;
     return launch_reduce(feats, dtype, order, offsets, B, N, C, HW, reduce, grid, ties, st);
 }
 
@@ -640,6 +838,97 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
         else                          KDF_BWD_LAUNCH(__nv_bfloat16, KDF_REDUCE_MEAN);
     }
 #undef KDF_BWD_LAUNCH
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *shift,
+                          const int32_t *order, const int32_t *offsets, int B, int64_t N, int C, int H, int W,
+                          void *grid_bf16, int32_t *ties, void *stream) {
+    KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_reduce_affine: bad sizes");
+    KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_reduce_affine: C=%d not supported (64, 128, 256)", C);
+    if (B == 0) return KDF_OK;
+    KDF_CHECK_ARG((z_bf16 || N == 0) && scale && shift && order && offsets && grid_bf16, "bev_reduce_affine: null pointer");
+    const int64_t n_cells = (int64_t)B * H * W;
+    const int blocks = grid_for(n_cells * 32, 256, 64);
+    cudaStream_t st = as_stream(stream);
+    const __nv_bfloat16 *zz = reinterpret_cast<const __nv_bfloat16 *>(z_bf16);
+    __nv_bfloat16 *gg = reinterpret_cast<__nv_bfloat16 *>(grid_bf16);
+    if (C == 64)       bev_reduce_affine_kernel<8><<<blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, ties, n_cells, N, H * W);
+    else if (C == 128) bev_reduce_affine_kernel<16><<<blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, ties, n_cells, N, H * W);
+    else               bev_reduce_affine_kernel<32><<<blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, ties, n_cells, N, H * W);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const float *scale, const float *shift,
+                       const void *grid_bf16, const int32_t *ties, const int32_t *order, const int32_t *offsets,
+                       const int32_t *cell, int B, int64_t N, int C, int H, int W,
+                       void *dy_bf16, double *sums, void *stream) {
+    KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_bwd_affine: bad sizes");
+    KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_bwd_affine: C=%d not supported (64, 128, 256)", C);
+    KDF_CHECK_ARG(sums, "bev_bwd_affine: null pointer");
+    cudaStream_t st = as_stream(stream);
+    KDF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const int64_t total = (int64_t)B * N;
+    if (total == 0) return KDF_OK;
+    KDF_CHECK_ARG(grad_grid_bf16 && z_bf16 && scale && shift && grid_bf16 && ties && order && offsets && cell && dy_bf16,
+                  "bev_bwd_affine: null pointer");
+    const int64_t n_cells = (int64_t)B * H * W;
+    int64_t blocks = (n_cells + 7) / 8;
+    if (blocks > (int64_t)sm_count() * 6) blocks = (int64_t)sm_count() * 6;      // persistent: per-CTA sums -> few atomics
+    typedef const __nv_bfloat16 *cb;
+#define KDF_BA(L)                                                                                               \
+    bev_bwd_affine_kernel<L><<<(int)blocks, 256, 0, st>>>((cb)grad_grid_bf16, (cb)z_bf16, scale, shift, (cb)grid_bf16, \
+        ties, order, offsets, cell, reinterpret_cast<__nv_bfloat16 *>(dy_bf16), sums, n_cells, N, H * W, total)
+    if (C == 64) KDF_BA(8); else if (C == 128) KDF_BA(16); else KDF_BA(32);
+#undef KDF_BA
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+// Sums over all points of (x, y, z, i) and of their 10 distinct pairwise products: the first MLP layer is
+// linear in the point, so its BatchNorm statistics (and the weight gradient's z1-term) follow from these
+// 14 numbers -- no pass over a [M,64] activation is needed.  out f64 [14] (zeroed by the call):
+// [0..3] = sum x_k, then xx, xy, xz, xi, yy, yz, yi, zz, zi, ii.
+__global__ void __launch_bounds__(256)
+point_moments_kernel(const float4 *__restrict__ pts, int64_t M, double *__restrict__ out) {
+    __shared__ float red[8][14];
+    float acc[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = 0.f;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += nthreads) {
+        const float4 p = ldg_stream_f4(pts + i);
+        acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
+        acc[4] = fmaf(p.x, p.x, acc[4]); acc[5] = fmaf(p.x, p.y, acc[5]); acc[6] = fmaf(p.x, p.z, acc[6]); acc[7] = fmaf(p.x, p.w, acc[7]);
+        acc[8] = fmaf(p.y, p.y, acc[8]); acc[9] = fmaf(p.y, p.z, acc[9]); acc[10] = fmaf(p.y, p.w, acc[10]);
+        acc[11] = fmaf(p.z, p.z, acc[11]); acc[12] = fmaf(p.z, p.w, acc[12]); acc[13] = fmaf(p.w, p.w, acc[13]);
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = warp_sum(acc[i]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 14; ++i) red[warp][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 14) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        atomicAdd(out + threadIdx.x, (double)v);
+    }
+}
+
+int kdf_point_moments(const float *points, int64_t M, double *out14, void *stream) {
+    KDF_CHECK_ARG(M >= 0 && out14, "point_moments: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    KDF_CUDA(cudaMemsetAsync(out14, 0, sizeof(double) * 14, st));
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(points && (reinterpret_cast<uintptr_t>(points) & 15) == 0, "point_moments: points must be 16-byte aligned [M,4]");
+    int64_t blocks = (M + 256 * 16 - 1) / (256 * 16);
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    point_moments_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(points), M, out14);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -21,12 +21,16 @@ def test_mlp_layer_fwd_mode1_affine_relu_gemm(M):
     shift = torch.randn(128, generator=g) * 0.3
     W = (torch.randn(128, 128, generator=g) / 11.3).to(torch.bfloat16)
     z, stats = ops.mlp_layer_fwd(1, zprev.cuda(), scale.cuda(), shift.cuda(), W.cuda())
-    a = torch.relu(zprev.float() * scale + shift).to(torch.bfloat16).float()
+    a32 = torch.relu(zprev.float() * scale + shift)
+    a = a32.to(torch.bfloat16).float()
     ref = a @ W.float().t()
-    # bf16 output rounding: half an ulp = 2^-9 relative per element
     assert z.dtype == torch.bfloat16 and z.shape == (M, 128)
     err = (z.float().cpu() - ref).abs()
-    assert (err <= ref.abs() * 2 ** -8 + 1e-3).all(), err.max()
+    # output rounding (2^-9 |z|) + the kernel forms z*scale+shift with one FMA rounding instead of two, so an
+    # activation within rounding of a bf16 boundary may land one bf16 ulp away (<= 2^-8 |a| |W| per term)
+    tol = ref.abs() * 2 ** -8 + (a32.abs() @ W.float().abs().t()) * 2 ** -8 + 1e-3
+    assert (err <= tol).all(), (err / tol).max()
+    assert (err.mean() / ref.abs().mean()).item() < 2e-3
     zc = z.float().cpu().double()
     np.testing.assert_allclose(stats[0].cpu().numpy(), zc.sum(0).numpy(), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(stats[1].cpu().numpy(), (zc * zc).sum(0).numpy(), rtol=1e-5, atol=1e-3)

@@ -66,3 +66,12 @@ if "fusion" in only:
     w2, b2 = torch.randn(2, C, **f32) * 0.1, torch.randn(2, **f32) * 0.1
     fo = torch.empty(Mp, C, dtype=dt, device=dev); attn = torch.empty(Mp, 2, **f32)
     timeit("fusion_weighted_fwd", lambda: native.call("kdf_fusion_weighted_fwd", p(cam), p(lid), 1, Mp, C, p(sc[0]), p(sh[0]), p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(fo), p(attn), st), Mp * 3 * C * 2)
+if "mlp" in only:
+    zprev = torch.randn(M, 128, device=dev, dtype=dt)
+    sc, sh = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
+    W3 = (torch.randn(128, 128, device=dev) / 11).to(dt)
+    timeit("mlp_layer_fwd mode1 (L3)", lambda: ops.mlp_layer_fwd(1, zprev, sc, sh, W3), M * 512)
+    pts2 = torch.randn(M, 4, device=dev)
+    q, r = torch.randn(64, 4, device=dev) * 0.02, torch.randn(64, device=dev) * 0.1
+    W2 = (torch.randn(128, 64, device=dev) / 8).to(dt)
+    timeit("mlp_layer_fwd mode0 (L1+L2)", lambda: ops.mlp_layer_fwd(0, pts2, q, r, W2), M * 272)
