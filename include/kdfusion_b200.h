@@ -180,6 +180,20 @@ int kdf_bn_finalize(const double *stats, int64_t M, int C, const float *gamma, c
                     float eps, float momentum, float *running_mean, float *running_var,
                     float *mean, float *invstd, float *scale, float *shift, void *stream);
 
+/* The same layer backwards, ONE kernel (dgrad + wgrad on the tensor cores, BatchNorm backward in the prologue):
+ *   dz = gs*dy + ga + gb*z   (dy, z bf16 [M,128]; gs/ga/gb f32 [128]: BatchNorm backward of THIS layer, chained
+ *                             through the batch statistics by the caller from the previous kernel's column sums)
+ *   dW f32 [128,Kin] = dz^T . a_in            (a_in re-created in the prologue exactly as kdf_mlp_layer_fwd does)
+ *   mode 1 (Kin=128, input = z_prev bf16 [M,128], pro_a/pro_b = scale/shift of the previous BatchNorm):
+ *           dy_prev bf16 [M,128] = (dz . W) * (a_in > 0);  sums f64 [2,128] = (sum dy_prev, sum dy_prev*z_prev)
+ *   mode 0 (Kin=64, input = raw points f32 [M,4], pro_a = q [64,4], pro_b = r [64]): nothing per point is stored;
+ *           with dy1 = (dz . W) * (a1 > 0):  sums f64 [5,64] = (sum dy1, sum dy1*x, sum dy1*y, sum dy1*z, sum dy1*i),
+ *           from which the caller forms the first layer's BatchNorm / weight gradients (it is linear in the point).
+ * sums and dW are zeroed by the call.  Replaces autograd through Conv1d+BatchNorm1d+ReLU (lidar_encoder.py:25-35). */
+int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, const float *ga, const float *gb,
+                      const void *input, int64_t M, const float *pro_a, const float *pro_b, const void *W_bf16,
+                      int Kin, void *dy_prev, double *sums, float *dW, void *stream);
+
 /* ---------------------------------------------------------------- (2) camera-LiDAR fusion
  * Inputs are the PRE-BatchNorm outputs of the two 1x1 projection convolutions
  * in pixel-major (NHWC) layout; BatchNorm is applied as y = x*scale + shift with

@@ -255,6 +255,360 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
     if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
 }
 
+
+// ============================================================================= fused backward layer
+// One tensor-core layer of the point MLP, backwards, as ONE kernel.  For a 128-point tile it forms, from
+// the gradient dy w.r.t. this layer's BatchNorm output (ReLU already folded in) and the stored pre-BatchNorm
+// rows z, the BatchNorm backward       dz = gs*dy + ga + gb*z            (per-channel coefficients that chain
+// through the batch mean / variance, prepared by the host from the two column sums of the previous kernel),
+// re-creates the layer's INPUT activation in the prologue exactly like the forward kernel did, and runs
+//   dgrad : dA[128 pts x KIN]  = dz . W            (A = dz tile K-major, B = W tile MN-major)
+//   wgrad : dW[128 x KIN]     += dz^T . A          (both operands are the MN-major view of the same tiles;
+//                                                   the accumulator stays in TMEM for all tiles of the CTA)
+// Epilogue, MODE 1 (layer 3 -> 2): dy_prev = dA * (a_prev > 0) stored as bf16 together with its two column
+// sums (sum dy_prev, sum dy_prev * z_prev) -- the inputs of the next layer's BatchNorm backward.
+// Epilogue, MODE 0 (layer 2 -> 1): the first layer is linear in the raw point, so nothing per-point is
+// stored: only S0[c] = sum dy1[.,c] and T[c,:] = sum dy1[.,c] * point  (64 x 5 numbers) leave the kernel.
+struct MlpBwdArgs {
+    const __nv_bfloat16 *dy;          // [M,128]
+    const __nv_bfloat16 *z;           // [M,128]
+    const float *gs, *ga, *gb;        // [128]
+    const void *input;                // MODE 1: z_prev bf16 [M,128];  MODE 0: points f32 [M,4]
+    const float *pro_a, *pro_b;       // as in the forward kernel
+    const __nv_bfloat16 *W;           // [128, KIN] row-major
+    int64_t M;
+    __nv_bfloat16 *dy_prev;           // MODE 1: [M,128]
+    double *sums;                     // MODE 1: [2][128];  MODE 0: [5][64] = S0, T[:,x], T[:,y], T[:,z], T[:,i]
+    float *dW;                        // [128, KIN] fp32, accumulated with atomics (zeroed by the host wrapper)
+};
+
+template <int KIN>
+struct MlpBwdSmem {
+    static constexpr int W_BYTES = PM_N * KIN * 2;                // rows n, KIN/64 panels
+    static constexpr int D_BYTES = PM_ROWS * PM_N * 2;            // dz tile: rows = points, 2 panels (also the staging tile)
+    static constexpr int A_BYTES = PM_ROWS * KIN * 2;             // input-activation tile
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_D0 = OFF_W + W_BYTES;
+    static constexpr int OFF_D1 = OFF_D0 + D_BYTES;
+    static constexpr int OFF_A0 = OFF_D1 + D_BYTES;
+    static constexpr int OFF_A1 = OFF_A0 + A_BYTES;
+    static constexpr int OFF_PTS = OFF_A1 + A_BYTES;               // MODE 0: the tile's raw points, 2 x 128 float4
+    static constexpr int OFF_MISC = OFF_PTS + 2 * PM_ROWS * 16;
+    static constexpr int MISC_BYTES = 64 + 4 * (3 * 128 + 64 * 4 + 64 + 2 * 128);
+    static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
+};
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+template <int MODE, int KIN>
+__global__ void __launch_bounds__(PM_THREADS, 1)
+mlp_layer_bwd_kernel(MlpBwdArgs a) {
+    using L = MlpBwdSmem<KIN>;
+    constexpr int ACH = KIN / 8;                                  // 16-byte chunks per activation row
+    constexpr int A_ROWS_PER_PASS = PM_THREADS / ACH;             // 16 or 32
+    constexpr int A_PASSES = PM_ROWS / A_ROWS_PER_PASS;           // 8 or 4
+    constexpr int D_PASSES = PM_ROWS / 16;                        // dz tile: 16 chunks per row, 16 rows per pass
+    constexpr uint32_t PANEL = PM_ROWS * tc::ROW_BYTES;           // 16384: bytes between 64-column panels
+    constexpr uint32_t IDESC_D = tc::make_idesc(PM_ROWS, KIN, 0, 1);   // dgrad: A K-major, B MN-major
+    constexpr uint32_t IDESC_W = tc::make_idesc(PM_N, KIN, 1, 1);      // wgrad: both MN-major
+    constexpr uint32_t TMEM_COLS = (3 * KIN > 256) ? 512 : 256;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sW = smem + L::OFF_W;
+    uint8_t *sD[2] = {smem + L::OFF_D0, smem + L::OFF_D1};
+    uint8_t *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1};
+    float4 *sPts = reinterpret_cast<float4 *>(smem + L::OFF_PTS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
+    float *cgs = reinterpret_cast<float *>(smem + L::OFF_MISC + 64), *cga = cgs + 128, *cgb = cga + 128;
+    float *coef = cgb + 128;                                      // MODE 0: q[256], r[64];  MODE 1: scale[128], shift[128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
+
+    for (int i = tid; i < 128; i += PM_THREADS) { cgs[i] = a.gs[i]; cga[i] = a.ga[i]; cgb[i] = a.gb[i]; }
+    if (MODE == 0) {
+        for (int i = tid; i < 64 * 4; i += PM_THREADS) coef[i] = a.pro_a[i];
+        for (int i = tid; i < 64; i += PM_THREADS) coef[256 + i] = a.pro_b[i];
+    } else {
+        for (int i = tid; i < KIN; i += PM_THREADS) { coef[i] = a.pro_a[i]; coef[KIN + i] = a.pro_b[i]; }
+    }
+    for (int idx = tid; idx < PM_N * ACH; idx += PM_THREADS) {
+        const int n = idx / ACH, ch = idx % ACH;
+        const uint4 w = *reinterpret_cast<const uint4 *>(a.W + (int64_t)n * KIN + ch * 8);
+        *reinterpret_cast<uint4 *>(sW + (ch >> 3) * PANEL + tc::sw128_offset(n, ch & 7)) = w;
+    }
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // fixed per-thread chunks: dz tile (dch, rows drow0 + 16p); activation tile (ach, rows arow0 + A_ROWS_PER_PASS*p)
+    const int dch = tid & 15, drow0 = tid >> 4;
+    const int ach = tid % ACH, arow0 = tid / ACH;
+
+    uint4 raw_dy[D_PASSES], raw_z[D_PASSES], raw_in[A_PASSES];
+    auto load_tile = [&](int64_t tile) {
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < D_PASSES; ++p) {
+            const int64_t row = r0 + drow0 + p * 16;
+            if (row < a.M) {
+                raw_dy[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
+                raw_z[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < A_PASSES; ++p) {
+            const int64_t row = r0 + arow0 + p * A_ROWS_PER_PASS;
+            if (row < a.M) {
+                if (MODE == 0) raw_in[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.input) + row);
+                else raw_in[p] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + row * KIN + ach * 8);
+            }
+        }
+    };
+    auto stage_tile = [&](int64_t tile, int buf) {
+        const int64_t r0 = tile * PM_ROWS;
+        {
+            float gs[8], ga[8], gb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { gs[j] = cgs[dch * 8 + j]; ga[j] = cga[dch * 8 + j]; gb[j] = cgb[dch * 8 + j]; }
+#pragma unroll
+            for (int p = 0; p < D_PASSES; ++p) {
+                const int r = drow0 + p * 16;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (r0 + r < a.M) {
+                    float g[8], zz[8];
+                    unpack8(raw_dy[p], g);
+                    unpack8(raw_z[p], zz);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
+                    v = pack8(g);
+                }
+                *reinterpret_cast<uint4 *>(sD[buf] + (dch >> 3) * PANEL + tc::sw128_offset(r, dch & 7)) = v;
+            }
+        }
+        {
+            float c0[MODE == 0 ? 32 : 8], c1[8];
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) c0[j] = coef[ach * 32 + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c1[j] = coef[256 + ach * 8 + j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c0[j] = coef[ach * 8 + j]; c1[j] = coef[KIN + ach * 8 + j]; }
+            }
+#pragma unroll
+            for (int p = 0; p < A_PASSES; ++p) {
+                const int r = arow0 + p * A_ROWS_PER_PASS;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (r0 + r < a.M) {
+                    if (MODE == 0) {
+                        const float4 pt = make_float4(__uint_as_float(raw_in[p].x), __uint_as_float(raw_in[p].y),
+                                                      __uint_as_float(raw_in[p].z), __uint_as_float(raw_in[p].w));
+                        v = first_layer_chunk(pt, c0, c1);
+                        if (ach == 0) sPts[buf * PM_ROWS + r] = pt;
+                    } else {
+                        v = affine_relu_chunk(raw_in[p], c0, c1);
+                    }
+                }
+                *reinterpret_cast<uint4 *>(sA[buf] + (ach >> 3) * PANEL + tc::sw128_offset(r, ach & 7)) = v;
+            }
+        }
+        tc::fence_async_smem();
+    };
+    auto issue_mma = [&](int buf, bool first) {                            // one thread
+        const uint32_t d_base = tc::smem_u32(sD[buf]), a_base = tc::smem_u32(sA[buf]), w_base = tc::smem_u32(sW);
+        const uint32_t acc_d = tmem_base + (uint32_t)buf * KIN, acc_w = tmem_base + 2u * KIN;
+#pragma unroll
+        for (int k = 0; k < PM_N / 16; ++k) {                              // dgrad: K = the 128 gradient channels
+            const uint32_t koff = (uint32_t)(k >> 2) * PANEL + (uint32_t)(k & 3) * 32u;
+            tc::mma_bf16(acc_d, tc::desc_kmajor(d_base + koff), tc::desc_mnmajor(w_base + (uint32_t)k * 2048u, PANEL), IDESC_D, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < PM_ROWS / 16; ++k) {                           // wgrad: K = the 128 points of the tile
+            tc::mma_bf16(acc_w, tc::desc_mnmajor(d_base + (uint32_t)k * 2048u, PANEL), tc::desc_mnmajor(a_base + (uint32_t)k * 2048u, PANEL),
+                         IDESC_W, !(first && k == 0));
+        }
+        tc::mma_commit(&bars[buf]);
+    };
+
+    // accumulators of the column sums, fixed per thread for the whole kernel
+    constexpr int NACC = MODE == 1 ? 16 : 5;
+    float acc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+    const int och = tid & 15, orow0 = tid >> 4;                            // MODE 1 store phase
+    const int ccol = tid & 63, crq = tid >> 6;                             // MODE 0 column-owner phase
+
+    auto epilogue = [&](int64_t tile, int buf, uint32_t parity) {
+        const int64_t r0 = tile * PM_ROWS;
+        uint8_t *sStage = sD[buf];                                         // the dz tile is dead once the MMAs have completed
+        uint4 zk[MODE == 1 ? D_PASSES : 1];
+        if (MODE == 1) {                                                   // z_prev chunks of the store phase (L2 hits), issued early
+#pragma unroll
+            for (int p = 0; p < D_PASSES; ++p) {
+                const int64_t row = r0 + orow0 + p * 16;
+                zk[p] = make_uint4(0u, 0u, 0u, 0u);
+                if (row < a.M) zk[p] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + row * KIN + och * 8);
+            }
+        }
+        tc::mbar_wait(&bars[buf], parity);
+        tc::fence_after_sync();
+        const int row = (warp & 3) * 32 + lane;
+        if (MODE == 1) {
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)(warp >> 2) * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + half * 32, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int chunk = (warp >> 2) * 8 + half * 4 + j;       // 16-byte chunk of the 256-byte row
+                    const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
+                    float act[8], v[8];
+                    unpack8(av, act);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = act[e] > 0.f ? __uint_as_float(r[8 * j + e]) : 0.f;
+                    *reinterpret_cast<uint4 *>(sStage + row * 256 + ((chunk ^ (row & 7)) << 4)) = pack8(v);
+                }
+            }
+        } else {
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)(warp >> 2) * 32;
+            uint32_t r[32];
+            tc::tmem_ld32(taddr, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = (warp >> 2) * 4 + j;                      // 8 channels of the 64-channel activation row
+                const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + tc::sw128_offset(row, chunk));
+                float act[8];
+                unpack8(av, act);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                               // fp32 staging: 16 chunks of 4 floats per row
+                    const int c4 = chunk * 2 + h;
+                    float4 o;
+                    o.x = act[4 * h + 0] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 0]) : 0.f;
+                    o.y = act[4 * h + 1] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 1]) : 0.f;
+                    o.z = act[4 * h + 2] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 2]) : 0.f;
+                    o.w = act[4 * h + 3] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 3]) : 0.f;
+                    *reinterpret_cast<float4 *>(sStage + row * 256 + ((c4 ^ (row & 15)) << 4)) = o;
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        if (MODE == 1) {
+#pragma unroll
+            for (int p = 0; p < D_PASSES; ++p) {
+                const int r = orow0 + p * 16;
+                if (r0 + r < a.M) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
+                    *reinterpret_cast<uint4 *>(a.dy_prev + (r0 + r) * PM_N + och * 8) = v;
+                    float f[8], zz[8];
+                    unpack8(v, f);
+                    unpack8(zk[p], zz);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] = fmaf(f[j], zz[j], acc[8 + j]); }
+                }
+            }
+        } else {
+            const int rows = (int)((a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS);
+            const int rbeg = crq * 32, rend = (rbeg + 32 < rows) ? rbeg + 32 : rows;
+            for (int r = rbeg; r < rend; ++r) {
+                const float v = *reinterpret_cast<const float *>(sStage + r * 256 + (((ccol >> 2) ^ (r & 15)) << 4) + (ccol & 3) * 4);
+                const float4 pt = sPts[buf * PM_ROWS + r];
+                acc[0] += v;
+                acc[1] = fmaf(v, pt.x, acc[1]); acc[2] = fmaf(v, pt.y, acc[2]);
+                acc[3] = fmaf(v, pt.z, acc[3]); acc[4] = fmaf(v, pt.w, acc[4]);
+            }
+        }
+        __syncthreads();                                                   // the staging tile is the next dz tile
+    };
+
+    // ---- software pipeline over this CTA's tiles (same schedule as the forward kernel)
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) {
+        load_tile(tile);
+        stage_tile(tile, 0);
+    }
+    __syncthreads();
+    int it = 0;
+    int64_t prev_tile = -1;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0) {
+            tc::fence_after_sync();
+            issue_mma(buf, it == 0);
+        }
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) load_tile(next);
+        if (it > 0) epilogue(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1));
+        if (next < n_tiles) stage_tile(next, buf ^ 1);
+        __syncthreads();
+        prev_tile = tile;
+    }
+    if (it > 0) epilogue(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1));
+
+    // ---- column sums -> fp64 atomics
+    float *red = reinterpret_cast<float *>(sD[0]);
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) red[(orow0 * 16 + och) * 16 + j] = acc[j];
+        __syncthreads();
+        {
+            const int ch = tid >> 4, j = tid & 15;
+            float v = 0.f;
+            for (int r = 0; r < 16; ++r) v += red[(r * 16 + ch) * 16 + j];
+            atomicAdd(a.sums + (j >> 3) * PM_N + ch * 8 + (j & 7), (double)v);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) red[(crq * 64 + ccol) * 5 + j] = acc[j];
+        __syncthreads();
+        for (int i = tid; i < 64 * 5; i += PM_THREADS) {
+            const int c = i / 5, j = i % 5;
+            float v = 0.f;
+            for (int q = 0; q < 4; ++q) v += red[(q * 64 + c) * 5 + j];
+            atomicAdd(a.sums + j * 64 + c, (double)v);
+        }
+    }
+    // ---- weight gradient of this CTA's tiles: TMEM -> fp32 atomics (every MMA completed: the last epilogue waited)
+    if (it > 0) {
+        tc::fence_after_sync();
+        const int n = (warp & 3) * 32 + lane;
+        constexpr int COLS_PER_WARP = KIN / 2;
+#pragma unroll
+        for (int h = 0; h < COLS_PER_WARP / 32; ++h) {
+            const int col = (warp >> 2) * COLS_PER_WARP + h * 32;
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * KIN + (uint32_t)col, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(a.dW + n * KIN + col + j, __uint_as_float(r[j]));
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // mean / invstd / folded scale,shift / running statistics from fp64 column sums
 __global__ void bn_finalize_kernel(const double *stats, int64_t M, int C, const float *gamma, const float *beta,
                                    const float *pre_bias, float eps, float momentum, float *running_mean,
@@ -311,6 +665,40 @@ int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a
         const int smem = MlpSmem<128>::TOTAL;
         KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         mlp_layer_fwd_kernel<1, 128><<<blocks, PM_THREADS, smem, st>>>(a);
+    }
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, const float *ga, const float *gb,
+                      const void *input, int64_t M, const float *pro_a, const float *pro_b, const void *W_bf16,
+                      int Kin, void *dy_prev, double *sums, float *dW, void *stream) {
+    KDF_CHECK_ARG(mode == 0 || mode == 1, "mlp_layer_bwd: bad mode %d", mode);
+    KDF_CHECK_ARG(M >= 0, "mlp_layer_bwd: negative M");
+    KDF_CHECK_ARG((mode == 0 && Kin == 64) || (mode == 1 && Kin == 128), "mlp_layer_bwd: unsupported (mode, Kin) = (%d, %d)", mode, Kin);
+    KDF_CHECK_ARG(gs && ga && gb && pro_a && pro_b && W_bf16 && sums && dW, "mlp_layer_bwd: null pointer");
+    cudaStream_t st = as_stream(stream);
+    KDF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (mode == 1 ? 2 * PM_N : 5 * 64), st));
+    KDF_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * PM_N * Kin, st));
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(dy && z && input && (mode == 0 || dy_prev), "mlp_layer_bwd: null pointer");
+    KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(input) |
+                    reinterpret_cast<uintptr_t>(dy_prev) | reinterpret_cast<uintptr_t>(W_bf16)) & 15) == 0,
+                  "mlp_layer_bwd: buffers must be 16-byte aligned");
+    MlpBwdArgs a{reinterpret_cast<const __nv_bfloat16 *>(dy), reinterpret_cast<const __nv_bfloat16 *>(z), gs, ga, gb, input,
+                 pro_a, pro_b, reinterpret_cast<const __nv_bfloat16 *>(W_bf16), M,
+                 reinterpret_cast<__nv_bfloat16 *>(dy_prev), sums, dW};
+    const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
+    int blocks = sm_count();
+    if (n_tiles < blocks) blocks = (int)n_tiles;
+    if (mode == 0) {
+        const int smem = MlpBwdSmem<64>::TOTAL;
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_bwd_kernel<0, 64><<<blocks, PM_THREADS, smem, st>>>(a);
+    } else {
+        const int smem = MlpBwdSmem<128>::TOTAL;
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_bwd_kernel<1, 128><<<blocks, PM_THREADS, smem, st>>>(a);
     }
     KDF_LAUNCH_CHECK();
     return KDF_OK;

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import ops, point_mlp
 
 
 class SpatialLiDAREncoder(nn.Module):
@@ -33,6 +33,7 @@ class SpatialLiDAREncoder(nn.Module):
         self.feature_dim = feature_dim
         self.point_cloud_range = point_cloud_range
         self.use_vectorized = use_vectorized
+        self.fuse_point_mlp = True      # bf16-autocast fast path (src/point_mlp.py); False = layer by layer
         H, W = grid_size
 
         widths = (input_dim, 64, 128, feature_dim)
@@ -78,8 +79,14 @@ class SpatialLiDAREncoder(nn.Module):
         if not points.is_cuda:
             raise RuntimeError("SpatialLiDAREncoder runs on CUDA tensors only (no CPU fallback)")
         points = points.float()
-        feats = self.point_features(points)
-        grid, count, cell = ops.bev_project(points, feats, self._geom, tuple(self.grid_size), "max")
+        if self.fuse_point_mlp and point_mlp.fused_supported(points, self.point_mlp, self.feature_dim) and \
+                (self.training or not torch.is_grad_enabled()):
+            # bf16 autocast: MLP + projection as tcgen05 layer kernels that keep only pre-BatchNorm rows in HBM
+            grid, count, cell = point_mlp.fused_lidar_branch(points, self.point_mlp, self._geom, tuple(self.grid_size),
+                                                             self.training)
+        else:
+            feats = self.point_features(points)
+            grid, count, cell = ops.bev_project(points, feats, self._geom, tuple(self.grid_size), "max")
         self.last_occupancy, self.last_cells = count, cell
         return grid
 

@@ -493,3 +493,25 @@ def mlp_layer_fwd(mode: int, x: torch.Tensor, pro_a: torch.Tensor, pro_b: torch.
     call("kdf_mlp_layer_fwd", mode, ptr(x), M, ptr(pro_a.float().contiguous()), ptr(pro_b.float().contiguous()),
          ptr(weight_bf16), Kin, Nout, ptr(z), ptr(stats), stream_ptr(dev))
     return z, stats
+
+
+def mlp_layer_bwd(mode: int, dy: torch.Tensor, z: torch.Tensor, gs: torch.Tensor, ga: torch.Tensor, gb: torch.Tensor,
+                  x: torch.Tensor, pro_a: torch.Tensor, pro_b: torch.Tensor, weight_bf16: torch.Tensor):
+    """The same layer backwards (one kernel): dz = gs*dy + ga + gb*z, dW = dz^T @ a_in, and
+    mode 1: (dy_prev bf16 [M,128], sums f64 [2,128], dW f32 [128,128]);
+    mode 0: (None, sums f64 [5,64] = sum dy1 * (1, x, y, z, i), dW f32 [128,64])."""
+    dev = require_cuda(dy, z, gs, ga, gb, x, pro_a, pro_b, weight_bf16)
+    M = dy.shape[0]
+    Nout, Kin = weight_bf16.shape
+    if dy.dtype != torch.bfloat16 or z.dtype != torch.bfloat16 or weight_bf16.dtype != torch.bfloat16:
+        raise TypeError("dy, z and the weight must be bf16")
+    if tuple(dy.shape) != (M, Nout) or tuple(z.shape) != (M, Nout) or x.shape[0] != M:
+        raise ValueError("mlp_layer_bwd: shape mismatch")
+    dy, z, x = dy.contiguous(), z.contiguous(), x.contiguous()
+    dy_prev = torch.empty(M, Kin, dtype=torch.bfloat16, device=dev) if mode == 1 else None
+    sums = torch.empty((2, Kin) if mode == 1 else (5, Kin), dtype=torch.float64, device=dev)
+    dW = torch.empty(Nout, Kin, dtype=torch.float32, device=dev)
+    f = lambda t: t.float().contiguous()
+    call("kdf_mlp_layer_bwd", mode, ptr(dy), ptr(z), ptr(f(gs)), ptr(f(ga)), ptr(f(gb)), ptr(x), M, ptr(f(pro_a)), ptr(f(pro_b)),
+         ptr(weight_bf16.contiguous()), Kin, ptr(dy_prev), ptr(sums), ptr(dW), stream_ptr(dev))
+    return dy_prev, sums, dW

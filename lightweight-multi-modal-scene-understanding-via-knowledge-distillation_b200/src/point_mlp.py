@@ -1,0 +1,279 @@
+"""Fused LiDAR branch: point MLP + BEV projection with only pre-BatchNorm rows in HBM.
+
+The reference's branch (src/models/lidar_encoder.py:25-35, 57-99) is Conv1d+BatchNorm1d+ReLU three
+times over every point, then index math, a boolean-mask gather and ``scatter_reduce_(amax)``.  Layer by
+layer that is ~9 passes over a ``[B*N, 128]`` activation per layer (forward + backward).  Here:
+
+  forward   points --(kdf_point_moments)--> BatchNorm-1 statistics (layer 1 is linear in the point)
+            points --(kdf_mlp_layer_fwd mode 0: layer 1 recomputed in the prologue, tcgen05 GEMM)--> z2 + stats
+            z2     --(kdf_mlp_layer_fwd mode 1: BN2+ReLU in the prologue, tcgen05 GEMM)--> z3 + stats
+            z3     --(kdf_bev_reduce_affine: BN3+ReLU on the fly, per-cell max + tie count)--> grid
+  backward  grid grad --(kdf_bev_bwd_affine)--> dy3 + sums
+            --(kdf_mlp_layer_bwd mode 1: BN3 backward in the prologue, dgrad+wgrad)--> dy2 + sums, dW3
+            --(kdf_mlp_layer_bwd mode 0)--> 64x5 sums, dW2   --(closed form)--> dW1, BatchNorm-1 gradients
+
+Features are bf16 (this is the autocast path; the fp32 parity path stays layer by layer), points, index
+math and every statistic stay fp32/fp64.  The per-channel coefficient algebra between kernels is a few
+128-element torch ops on the device (no host sync; CUDA-graph capturable).
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import native as _n
+from .native import call, lib, ptr, require_cuda, stream_ptr
+
+__all__ = ["bev_build_order", "bev_reduce_affine", "bev_bwd_affine", "point_moments", "fused_lidar_branch",
+           "mlp_layer_fwd_raw", "bn_finalize"]
+
+
+# ----------------------------------------------------------------------------- thin wrappers
+def bev_build_order(points: torch.Tensor, geom, grid_size):
+    """Cell id per point, occupancy, and the cell ordering (counting sort) of every frame:
+    (cell i32 [B,N], count i32 [B,HW], order i32 [B,N], offsets i32 [B,HW+1])."""
+    dev = require_cuda(points)
+    B, N, D = points.shape
+    if points.dtype != torch.float32:
+        raise TypeError("points must stay float32 (index math is fp32 by contract)")
+    points = points.contiguous()
+    H, W = grid_size
+    i32 = dict(dtype=torch.int32, device=dev)
+    cell, order = torch.empty(B, N, **i32), torch.empty(B, N, **i32)
+    count, offsets = torch.empty(B, H * W, **i32), torch.empty(B, H * W + 1, **i32)
+    nb = lib.kdf_bev_workspace_bytes(B, N, H, W)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    call("kdf_bev_build_order", ptr(points), D, B, N, *geom, H, W, ptr(count), ptr(cell), ptr(order), ptr(offsets),
+         ptr(ws), nb, stream_ptr(dev))
+    return cell, count, order, offsets
+
+
+_order_cache = {"ref": None, "key": None, "val": None}
+
+
+def cached_build_order(points: torch.Tensor, geom, grid_size):
+    """``bev_build_order`` shared between encoders that project the SAME tensor object (the teacher and the
+    student of a distillation step see the same sweep): keyed on object identity + version counter."""
+    key = (points._version, tuple(points.shape), tuple(geom), tuple(grid_size), torch.cuda.current_stream(points.device).cuda_stream,
+           torch.cuda.is_current_stream_capturing())
+    ref = _order_cache["ref"]
+    if ref is not None and ref() is points and _order_cache["key"] == key:
+        return _order_cache["val"]
+    val = bev_build_order(points, geom, grid_size)
+    _order_cache.update(ref=weakref.ref(points), key=key, val=val)
+    return val
+
+
+def bev_reduce_affine(z, scale, shift, order, offsets, B, N, grid_size, want_ties: bool):
+    dev = require_cuda(z, scale, shift, order, offsets)
+    H, W = grid_size
+    C = z.shape[-1]
+    grid = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev)
+    ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev) if want_ties else None
+    call("kdf_bev_reduce_affine", ptr(z), ptr(scale), ptr(shift), ptr(order), ptr(offsets), B, N, C, H, W,
+         ptr(grid), ptr(ties), stream_ptr(dev))
+    return grid, ties
+
+
+def bev_bwd_affine(grad_grid, z, scale, shift, grid, ties, order, offsets, cell, B, N, grid_size):
+    dev = require_cuda(grad_grid, z, grid, ties)
+    H, W = grid_size
+    C = z.shape[-1]
+    dy = torch.empty(B * N, C, dtype=torch.bfloat16, device=dev)
+    sums = torch.empty(2, C, dtype=torch.float64, device=dev)
+    call("kdf_bev_bwd_affine", ptr(grad_grid), ptr(z), ptr(scale), ptr(shift), ptr(grid), ptr(ties), ptr(order),
+         ptr(offsets), ptr(cell), B, N, C, H, W, ptr(dy), ptr(sums), stream_ptr(dev))
+    return dy, sums
+
+
+def point_moments(points: torch.Tensor) -> torch.Tensor:
+    """f64 [14]: sums of (x,y,z,i) and of xx,xy,xz,xi,yy,yz,yi,zz,zi,ii over all points [M,4]."""
+    dev = require_cuda(points)
+    pts = points.reshape(-1, 4).contiguous()
+    out = torch.empty(14, dtype=torch.float64, device=dev)
+    call("kdf_point_moments", ptr(pts), pts.shape[0], ptr(out), stream_ptr(dev))
+    return out
+
+
+def mlp_layer_fwd_raw(mode, x, pro_a, pro_b, w_bf16):
+    dev = x.device
+    M = x.shape[0]
+    Nout, Kin = w_bf16.shape
+    z = torch.empty(M, Nout, dtype=torch.bfloat16, device=dev)
+    stats = torch.empty(2, Nout, dtype=torch.float64, device=dev)
+    call("kdf_mlp_layer_fwd", mode, ptr(x), M, ptr(pro_a), ptr(pro_b), ptr(w_bf16), Kin, Nout, ptr(z), ptr(stats),
+         stream_ptr(dev))
+    return z, stats
+
+
+def bn_finalize(stats, M, bn, pre_bias, track: bool):
+    """(mean, invstd, scale, shift) f32 [C] from fp64 column sums; advances the running statistics like
+    nn.BatchNorm1d does in training (momentum, unbiased variance, the folded conv bias added to the mean)."""
+    dev = stats.device
+    C = stats.shape[1]
+    f32 = dict(dtype=torch.float32, device=dev)
+    mean, invstd, scale, shift = (torch.empty(C, **f32) for _ in range(4))
+    mom = 0.0
+    if track:
+        bn.num_batches_tracked.add_(1)
+        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    call("kdf_bn_finalize", ptr(stats), M, C, ptr(bn.weight), ptr(bn.bias), ptr(pre_bias) if track else None,
+         float(bn.eps), float(mom), ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+         ptr(mean), ptr(invstd), ptr(scale), ptr(shift), stream_ptr(dev))
+    return mean, invstd, scale, shift
+
+
+_SYM_IDX = {}
+
+
+def _sym4(m14: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(sum p [4], sum p p^T [4,4]) from the 14 moments."""
+    idx = _SYM_IDX.get(m14.device)
+    if idx is None:      # created once per device, outside any graph capture (the first steps run eagerly)
+        idx = _SYM_IDX[m14.device] = torch.tensor([4, 5, 6, 7, 5, 8, 9, 10, 6, 9, 11, 12, 7, 10, 12, 13], device=m14.device)
+    return m14[:4], m14.index_select(0, idx).view(4, 4)
+
+
+def _bn_bwd_coeffs(S0, S1, mean, invstd, scale, M):
+    """BatchNorm backward through the batch statistics as per-channel coefficients:
+    dz = gs*dy + ga + gb*z;  also dgamma, dbeta.  All inputs [C]; S0 = sum dy, S1 = sum dy*z (fp64)."""
+    mean, invstd, scale = mean.double(), invstd.double(), scale.double()
+    dgamma = invstd * (S1 - mean * S0)
+    gb = -(scale * invstd * dgamma) / M
+    ga = -(scale * S0) / M - gb * mean
+    return scale.float(), ga.float(), gb.float(), dgamma.float(), S0.float()
+
+
+# ----------------------------------------------------------------------------- the fused branch
+class _FusedLidarFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *args):
+        with torch.autocast("cuda", enabled=False):          # statistics / coefficient algebra stay fp32/fp64
+            return _FusedLidarFn._forward(ctx, *args)
+
+    @staticmethod
+    def _forward(ctx, points, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, g3, be3, mlp, geom, grid_size, training, need_grad):
+        dev = require_cuda(points, w1, w2, w3)
+        B, N, D = points.shape
+        if D != 4:
+            raise ValueError("the fused point MLP takes (x, y, z, intensity) points")
+        if tuple(w1.shape[:2]) != (64, 4) or tuple(w2.shape[:2]) != (128, 64) or tuple(w3.shape[:2]) != (128, 128):
+            raise ValueError("the fused point MLP is built for the reference's 4->64->128->128 widths")
+        M = B * N
+        pts = points.contiguous()
+        bn1, bn2, bn3 = mlp[1], mlp[4], mlp[7]
+        W1 = w1.detach().reshape(64, 4).double()
+        w2b = w2.detach().reshape(128, 64).to(torch.bfloat16).contiguous()
+        w3b = w3.detach().reshape(128, 128).to(torch.bfloat16).contiguous()
+        batch = training or bn1.running_mean is None
+        track = training and bn1.track_running_stats and bn1.running_mean is not None
+
+        # ---- layer 1: statistics in closed form from the point moments
+        if batch:
+            m14 = point_moments(pts)
+            s, pp = _sym4(m14)
+            mu_p = s / M
+            cov = pp / M - torch.outer(mu_p, mu_p)
+            mean1 = W1 @ mu_p
+            var1 = ((W1 @ cov) * W1).sum(1).clamp_min(0.0)
+            invstd1 = torch.rsqrt(var1 + bn1.eps)
+            if track:
+                bn1.num_batches_tracked.add_(1)
+                mom = bn1.momentum if bn1.momentum is not None else 1.0 / float(bn1.num_batches_tracked)
+                bn1.running_mean.mul_(1 - mom).add_((mean1 + b1.detach().double()).float(), alpha=mom)
+                bn1.running_var.mul_(1 - mom).add_((var1 * (M / max(M - 1, 1))).float(), alpha=mom)
+            scale1 = g1.detach().double() * invstd1
+            shift1 = be1.detach().double() - mean1 * scale1
+        else:
+            m14 = None
+            invstd1 = torch.rsqrt(bn1.running_var.double() + bn1.eps)
+            mean1 = bn1.running_mean.double() - b1.detach().double()        # statistics of W1.p without the bias
+            scale1 = g1.detach().double() * invstd1
+            shift1 = be1.detach().double() - mean1 * scale1
+        q = (scale1[:, None] * W1).float().contiguous()
+        r = shift1.float().contiguous()
+
+        # ---- layers 2 and 3 on the tensor cores
+        z2, st2 = mlp_layer_fwd_raw(0, pts.view(M, 4), q, r, w2b)
+        if batch:
+            mean2, invstd2, scale2, shift2 = bn_finalize(st2, M, bn2, b2.detach().float().contiguous(), track)
+        else:
+            from .ops import _eval_affine
+            scale2, shift2, mean2, invstd2 = _eval_affine(bn2, b2.detach())
+        z3, st3 = mlp_layer_fwd_raw(1, z2, scale2, shift2, w3b)
+        if batch:
+            mean3, invstd3, scale3, shift3 = bn_finalize(st3, M, bn3, b3.detach().float().contiguous(), track)
+        else:
+            from .ops import _eval_affine
+            scale3, shift3, mean3, invstd3 = _eval_affine(bn3, b3.detach())
+
+        # ---- projection (the cell ordering is shared with any other encoder that sees this tensor)
+        cell, count, order, offsets = cached_build_order(points, geom, grid_size)
+        grid, ties = bev_reduce_affine(z3, scale3, shift3, order, offsets, B, N, grid_size, need_grad)
+        if need_grad:
+            if not batch:
+                raise RuntimeError("the fused LiDAR branch differentiates through batch statistics only "
+                                   "(train mode); use the layer-by-layer path for eval-mode gradients")
+            ctx.save_for_backward(pts, z2, z3, grid, ties, cell, order, offsets, q, r, w2b, w3b, m14,
+                                  mean1.float(), invstd1.float(), scale1.float(), mean2, invstd2, scale2, shift2,
+                                  mean3, invstd3, scale3, shift3, W1.float())
+            ctx.dims = (B, N, tuple(grid_size))
+        ctx.mark_non_differentiable(count, cell)
+        return grid.permute(0, 3, 1, 2), count, cell
+
+    @staticmethod
+    def backward(ctx, grad_grid, _gc, _gi):
+        from .ops import mlp_layer_bwd
+        (pts, z2, z3, grid, ties, cell, order, offsets, q, r, w2b, w3b, m14, mean1, invstd1, scale1,
+         mean2, invstd2, scale2, shift2, mean3, invstd3, scale3, shift3, W1) = ctx.saved_tensors
+        B, N, grid_size = ctx.dims
+        M = B * N
+        gg = grad_grid.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        # projection backward: gradient w.r.t. the BatchNorm-3 output (ReLU folded in) + its two column sums
+        dy3, s3 = bev_bwd_affine(gg, z3, scale3, shift3, grid, ties, order, offsets, cell, B, N, grid_size)
+        gs3, ga3, gb3, dg3, db3 = _bn_bwd_coeffs(s3[0], s3[1], mean3, invstd3, scale3, M)
+        dy2, s2, dW3 = mlp_layer_bwd(1, dy3, z3, gs3, ga3, gb3, z2, scale2, shift2, w3b)
+        del dy3
+        gs2, ga2, gb2, dg2, db2 = _bn_bwd_coeffs(s2[0], s2[1], mean2, invstd2, scale2, M)
+        _, s1, dW2 = mlp_layer_bwd(0, dy2, z2, gs2, ga2, gb2, pts.view(M, 4), q, r, w2b)
+        del dy2
+        # layer 1 in closed form: z1 = W1.p, so sum dy1*z1 and sum dz1 p^T follow from T = sum dy1 p^T and the moments
+        S0, T = s1[0], s1[1:5].t().contiguous()                          # [64], [64,4]
+        W1d = W1.double()
+        S1 = (W1d * T).sum(1)
+        gs1, ga1, gb1, dg1, db1 = _bn_bwd_coeffs(S0, S1, mean1, invstd1, scale1, M)
+        sp, pp = _sym4(m14)
+        dW1 = gs1.double()[:, None] * T + ga1.double()[:, None] * sp[None, :] + gb1.double()[:, None] * (W1d @ pp)
+        z64, z128 = torch.zeros_like(db1), torch.zeros_like(db2)          # conv biases cancel under batch statistics
+        return (None, dW1.float().view(64, 4, 1), z64, dg1, db1, dW2.view(128, 64, 1), z128, dg2, db2,
+                dW3.view(128, 128, 1), z128, dg3, db3, None, None, None, None, None)
+
+
+def fused_lidar_branch(points: torch.Tensor, point_mlp, geom, grid_size, training: bool):
+    """-> (grid [B,128,H,W] bf16 over NHWC memory, count i32 [B,HW], cell i32 [B,N]).  ``point_mlp`` is the
+    reference-shaped ``nn.Sequential`` (Conv1d, BatchNorm1d, ReLU) x 3 whose parameters / buffers are used
+    and (running statistics) updated in place."""
+    c1, n1, c2, n2, c3, n3 = (point_mlp[i] for i in (0, 1, 3, 4, 6, 7))
+    params = (c1.weight, c1.bias, n1.weight, n1.bias, c2.weight, c2.bias, n2.weight, n2.bias, c3.weight, c3.bias, n3.weight, n3.bias)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _FusedLidarFn.apply(points, *params, point_mlp, tuple(geom), tuple(grid_size), training, need_grad)
+
+
+def fused_supported(points: torch.Tensor, point_mlp, feature_dim: int) -> bool:
+    """The fused path serves the reference architecture (4->64->128->128, affine BatchNorm with conv biases)
+    under bf16 autocast on CUDA."""
+    if not (points.is_cuda and points.dim() == 3 and points.shape[-1] == 4 and feature_dim == 128):
+        return False
+    if not (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return False
+    try:
+        convs = [point_mlp[i] for i in (0, 3, 6)]
+        bns = [point_mlp[i] for i in (1, 4, 7)]
+    except (IndexError, TypeError):
+        return False
+    shapes = [tuple(c.weight.shape) for c in convs]
+    if shapes != [(64, 4, 1), (128, 64, 1), (128, 128, 1)]:
+        return False
+    return all(c.bias is not None for c in convs) and all(b.affine and b.weight is not None for b in bns)

@@ -1,0 +1,152 @@
+"""GPU tests of the fused LiDAR branch (src/point_mlp.py): the projection kernels that apply BatchNorm+ReLU on
+the fly, the point moments, and the whole branch (forward, parameter gradients, running statistics) against
+(a) an fp32 torch restatement of the reference's branch (lidar_encoder.py:25-35, 57-99) and (b) the
+layer-by-layer kernels of this repo under the same bf16 autocast."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _frames(seed, B, N, dev):
+    from oracle.weights import synthetic_frames
+    _, pts, _ = synthetic_frames(seed, B, N, edge_cases=True, nonfinite=False)
+    return pts.to(dev)
+
+
+def test_point_moments():
+    from src import point_mlp
+    pts = _frames(3, 3, 5000, "cuda")
+    m = point_mlp.point_moments(pts).cpu()
+    p = pts.reshape(-1, 4).double().cpu()
+    ref = [p[:, k].sum() for k in range(4)] + [(p[:, i] * p[:, j]).sum() for i in range(4) for j in range(i, 4)]
+    mag = [p[:, k].abs().sum() for k in range(4)] + [(p[:, i] * p[:, j]).abs().sum() for i in range(4) for j in range(i, 4)]
+    # fp32 partial sums per thread / warp, fp64 across CTAs: 2e-6 of the sum of magnitudes
+    assert ((m - torch.stack(ref)).abs() <= 2e-6 * torch.stack(mag)).all()
+
+
+@pytest.mark.parametrize("B,N", [(2, 4000), (3, 20000)])
+def test_bev_affine_reduce_and_backward(B, N):
+    """max / tie count of bf16(relu(z*scale+shift)) per cell, and the gradient w.r.t. the BatchNorm output."""
+    from src import ops, point_mlp
+    dev = "cuda"
+    pts = _frames(11, B, N, dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    C, H, W = 128, 64, 64
+    z = (torch.randn(B * N, C, generator=g) * 1.5).to(torch.bfloat16).to(dev)
+    scale = (torch.randn(C, generator=g)).to(dev)            # both signs
+    shift = (torch.randn(C, generator=g) * 0.5).to(dev)
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    cell, count, order, offsets = point_mlp.bev_build_order(pts, geom, (H, W))
+    grid, ties = point_mlp.bev_reduce_affine(z, scale, shift, order, offsets, B, N, (H, W), True)
+    # reference: exact affine in fp64 -> fp32 -> relu -> bf16, then scatter amax
+    a3 = torch.relu((z.double() * scale.double() + shift.double()).float()).to(torch.bfloat16).float()
+    flat = (cell.long() + torch.arange(B, device=dev)[:, None] * (H * W)).reshape(-1)
+    valid = cell.reshape(-1) >= 0
+    ref = torch.zeros(B * H * W, C, device=dev)
+    ref.scatter_reduce_(0, flat[valid][:, None].expand(-1, C), a3[valid], "amax", include_self=True)
+    assert torch.equal(grid.reshape(B * H * W, C).float(), ref)
+    is_max = (a3 == ref[flat.clamp_min(0)]) & valid[:, None]
+    ref_ties = torch.zeros(B * H * W, C, device=dev)
+    ref_ties.index_add_(0, flat[valid], is_max[valid].float())
+    occupied = (count.reshape(-1) > 0)[:, None].expand(-1, C)
+    assert torch.equal(ties.reshape(B * H * W, C)[occupied].float(), ref_ties[occupied])
+
+    gg = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(dev)
+    dy, sums = point_mlp.bev_bwd_affine(gg, z, scale, shift, grid, ties, order, offsets, cell, B, N, (H, W))
+    share = (gg.reshape(-1, C).float() / ref_ties.clamp_min(1)).to(torch.bfloat16).float()
+    ref_dy = torch.where(is_max & (ref[flat.clamp_min(0)] > 0), share[flat.clamp_min(0)], torch.zeros((), device=dev))
+    assert torch.equal(dy.float(), ref_dy)
+    np.testing.assert_allclose(sums[0].cpu().numpy(), ref_dy.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(sums[1].cpu().numpy(), (ref_dy.double() * z.double()).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
+
+
+def _reference_branch(enc, pts):
+    """fp32 torch restatement of the reference's branch on the GPU, using the module's own layers."""
+    B, N, _ = pts.shape
+    H, W = enc.grid_size
+    feats = enc.point_mlp(pts.transpose(1, 2)).transpose(1, 2)           # [B,N,C] (lidar_encoder.py:66)
+    cell, _ = enc.bev_cells(pts)
+    flat = (cell.long() + torch.arange(B, device=pts.device)[:, None] * (H * W)).reshape(-1)
+    valid = flat >= 0
+    valid &= (cell.reshape(-1) >= 0)
+    C = feats.shape[-1]
+    out = torch.zeros(B * H * W, C, device=pts.device)
+    out = out.scatter_reduce(0, flat[valid][:, None].expand(-1, C), feats.reshape(-1, C)[valid], "amax", include_self=False)
+    return out.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("B,N", [(2, 6000), (4, 30011)])
+def test_fused_branch_matches_reference_and_layerwise(B, N):
+    from src.models.lidar_encoder import SpatialLiDAREncoder
+    dev = "cuda"
+    torch.manual_seed(B * 100 + 7)
+    enc = SpatialLiDAREncoder(grid_size=(64, 64)).to(dev).train()
+    with torch.no_grad():                                        # non-trivial BatchNorm affine parameters
+        for m in enc.point_mlp:
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    ref_enc, lay_enc = copy.deepcopy(enc), copy.deepcopy(enc)
+    lay_enc.fuse_point_mlp = False
+    pts = _frames(B, B, N, dev)
+    gout = torch.randn(B, 128, 64, 64, device=dev) * (torch.rand(B, 128, 64, 64, device=dev) < 0.5)
+
+    ref = _reference_branch(ref_enc, pts)
+    ref.backward(gout)
+    outs = {}
+    for name, e in (("fused", enc), ("layerwise", lay_enc)):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = e(pts)
+        assert y.dtype == torch.bfloat16 and y.shape == (B, 128, 64, 64)
+        y.backward(gout.to(torch.bfloat16))
+        outs[name] = y
+    # forward: bf16 features through three layers
+    assert _l2(outs["fused"].float(), ref) < 1.5e-2, _l2(outs["fused"].float(), ref)
+    assert _l2(outs["fused"].float(), outs["layerwise"].float()) < 1.5e-2
+    # empty cells are exactly zero, occupancy / cell ids identical to the unfused path
+    assert torch.equal(outs["fused"] == 0, outs["fused"] == 0)
+    assert torch.equal(enc.last_cells, lay_enc.last_cells) and torch.equal(enc.last_occupancy, lay_enc.last_occupancy)
+    # parameter gradients and running statistics
+    for (n, p), (_, pr), (_, pl) in zip(enc.named_parameters(), ref_enc.named_parameters(), lay_enc.named_parameters()):
+        assert p.grad is not None, n
+        if n.endswith("0.bias") or n.endswith("3.bias") or n.endswith("6.bias"):
+            assert p.grad.abs().max().item() == 0.0              # conv biases cancel under batch statistics
+            continue
+        e_ref, e_lay = _l2(p.grad, pr.grad), _l2(pl.grad, pr.grad)
+        assert e_ref < max(4e-2, 2.0 * e_lay), (n, e_ref, e_lay)
+    for (n, b), (_, br) in zip(enc.named_buffers(), ref_enc.named_buffers()):
+        if "running" in n:
+            assert _l2(b, br) < 3e-3, (n, _l2(b, br))
+        elif "num_batches" in n:
+            assert torch.equal(b, br)
+
+
+def test_fused_branch_eval_mode_matches_layerwise():
+    """Teacher path: eval-mode BatchNorm folded into the prologues, no statistics, no gradient state."""
+    from src.models.lidar_encoder import SpatialLiDAREncoder
+    dev = "cuda"
+    torch.manual_seed(5)
+    enc = SpatialLiDAREncoder(grid_size=(64, 64)).to(dev)
+    with torch.no_grad():
+        for m in enc.point_mlp:
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.5)
+                m.running_var.uniform_(0.5, 2.0)
+                m.weight.uniform_(0.5, 1.5)
+    enc.eval()
+    pts = _frames(9, 2, 9000, dev)
+    with torch.no_grad():
+        ref = _reference_branch(enc, pts)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = enc(pts)
+    assert y.dtype == torch.bfloat16
+    assert _l2(y.float(), ref) < 1.5e-2, _l2(y.float(), ref)

@@ -54,3 +54,63 @@ def test_mlp_layer_fwd_mode0_first_layer_recomputed(M):
     assert (err <= tol).all(), (err / tol).max()
     zc = z.float().cpu().double()
     np.testing.assert_allclose(stats[0].cpu().numpy(), zc.sum(0).numpy(), rtol=1e-5, atol=1e-3)
+
+
+def _bwd_inputs(M, seed):
+    g = torch.Generator().manual_seed(seed)
+    dy = (torch.randn(M, 128, generator=g) * (torch.rand(M, 128, generator=g) < 0.1)).to(torch.bfloat16)
+    z = (torch.randn(M, 128, generator=g) * 1.5).to(torch.bfloat16)
+    gs = torch.rand(128, generator=g) + 0.5
+    ga = torch.randn(128, generator=g) * 0.01
+    gb = torch.randn(128, generator=g) * 0.01
+    return g, dy, z, gs, ga, gb
+
+
+@pytest.mark.parametrize("M", [128, 1000, 128 * 148 * 2 + 77])
+def test_mlp_layer_bwd_mode1(M):
+    """dgrad + wgrad + BatchNorm-backward prologue + ReLU-mask/column-sum epilogue of the 128->128 layer."""
+    from src import ops
+    g, dy, z, gs, ga, gb = _bwd_inputs(M, M)
+    zprev = (torch.randn(M, 128, generator=g) * 2).to(torch.bfloat16)
+    scale = torch.rand(128, generator=g) + 0.5
+    shift = torch.randn(128, generator=g) * 0.3
+    W = (torch.randn(128, 128, generator=g) / 11.3).to(torch.bfloat16)
+    c = lambda t: t.cuda()
+    dyp, sums, dW = ops.mlp_layer_bwd(1, c(dy), c(z), c(gs), c(ga), c(gb), c(zprev), c(scale), c(shift), c(W))
+    dz = (gs * dy.float() + ga + gb * z.float()).to(torch.bfloat16).double()
+    a = torch.relu(zprev.float() * scale + shift).to(torch.bfloat16).double()
+    dA = dz @ W.double()
+    ref = dA * (a > 0)
+    got = dyp.float().cpu().double()
+    # a handful of elements may differ by the one-FMA-vs-two rounding of dz / a at a bf16 boundary
+    tol = ref.abs() * 2 ** -7 + (dz.abs() @ W.double().abs()) * 2 ** -8 + 1e-3
+    assert ((got - ref).abs() <= tol).all(), ((got - ref).abs() / tol).max()
+    assert ((got - ref).abs().mean() / ref.abs().mean()).item() < 4e-3
+    np.testing.assert_allclose(sums[0].cpu().numpy(), got.sum(0).numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(sums[1].cpu().numpy(), (got * zprev.double()).sum(0).numpy(), rtol=1e-4, atol=1e-2)
+    ref_dW = dz.t() @ a
+    assert rel_err(dW.cpu(), ref_dW) < 2e-3, rel_err(dW.cpu(), ref_dW)
+
+
+@pytest.mark.parametrize("M", [64, 5000, 128 * 148 * 2 + 5])
+def test_mlp_layer_bwd_mode0(M):
+    """64->128 layer backwards with the first layer recomputed from the raw points; only 64x5 sums leave the kernel."""
+    from src import ops
+    g, dy, z, gs, ga, gb = _bwd_inputs(M, M + 7)
+    pts = torch.randn(M, 4, generator=g) * torch.tensor([40.0, 40.0, 2.0, 70.0])
+    q = torch.randn(64, 4, generator=g) * 0.02
+    r = torch.randn(64, generator=g) * 0.3
+    W = (torch.randn(128, 64, generator=g) / 8).to(torch.bfloat16)
+    c = lambda t: t.cuda()
+    none, sums, dW = ops.mlp_layer_bwd(0, c(dy), c(z), c(gs), c(ga), c(gb), c(pts), c(q), c(r), c(W))
+    assert none is None
+    dz = (gs * dy.float() + ga + gb * z.float()).to(torch.bfloat16).double()
+    a1 = torch.relu(pts @ q.t() + r).to(torch.bfloat16).double()
+    dy1 = (dz @ W.double()) * (a1 > 0)
+    ref = torch.cat([dy1.sum(0, keepdim=True), dy1.t() @ pts.double()[:, :4]]).reshape(5, 64) if False else \
+        torch.stack([dy1.sum(0)] + [(dy1 * pts.double()[:, d:d + 1]).sum(0) for d in range(4)])
+    scale = torch.stack([dy1.abs().sum(0)] + [(dy1.abs() * pts.double()[:, d:d + 1].abs()).sum(0) for d in range(4)])
+    err = (sums.cpu() - ref).abs() / (scale + 1e-6)
+    assert err.max().item() < 3e-3, err.max()
+    ref_dW = dz.t() @ a1
+    assert rel_err(dW.cpu(), ref_dW) < 2e-3, rel_err(dW.cpu(), ref_dW)
