@@ -146,22 +146,23 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
                   int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,
                   void *workspace, void *stream);
 
-/* Projection of a layer whose BatchNorm+ReLU has not been applied yet (fused point-MLP path):
- * the feature scattered is a3 = bf16(relu(z*scale + shift)), computed on the fly from the stored
- * pre-BatchNorm rows z (bf16 [B,N,C]).  kdf_bev_reduce_affine = per-cell max / tie count of a3 over an
- * existing cell ordering; kdf_bev_bwd_affine = gradient w.r.t. the BatchNorm OUTPUT y3 (ReLU folded in),
- *   dy[p,c] = (a3[p,c] == max && max > 0) ? g/ties : 0,
- * zeros for points outside, plus sums f64 [2,C] = (sum dy, sum dy*z) for BatchNorm's backward
- * (zeroed by the call).  kdf_point_moments: sums of (x,y,z,i) and their 10 pairwise products over all
- * points (f64 [14], zeroed by the call) -- the first MLP layer is linear in the point, so its
- * BatchNorm statistics follow from these. */
+/* Projection of a layer whose BatchNorm+ReLU has not been applied yet (fused point-MLP path): the feature the
+ * reference scatters (lidar_encoder.py:32-34, 85-96) is a3 = bf16(relu(z*scale + shift)), formed on the fly from
+ * the stored pre-BatchNorm rows z (bf16 [B,N,C]).  BatchNorm-apply, ReLU and rounding are monotonic, so
+ * kdf_bev_reduce_affine reduces the raw rows to the per-cell EXTREME of z (max where scale >= 0, min where
+ * scale < 0; grid_z bf16 [B,HW,C], optional) and stores its activation (grid bf16 [B,HW,C] = the per-cell max of
+ * a3; empty cells 0).  kdf_bev_bwd_affine = gradient w.r.t. the BatchNorm OUTPUT y3 (ReLU folded in): the rows
+ * whose z equals the cell's extreme share the cell's gradient evenly (k rows -> g/k each, bf16) when the
+ * activation is positive, every other row gets zeros; sums f64 [2,C] = (sum dy, sum dy*z) for BatchNorm's
+ * backward (zeroed by the call).  kdf_point_moments: sums of (x,y,z,i) and their 10 pairwise products over all
+ * points (f64 [14], zeroed by the call) -- the first MLP layer is linear in the point, so its BatchNorm
+ * statistics follow from these. */
 int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *shift,
                           const int32_t *order, const int32_t *offsets, int B, int64_t N, int C, int H, int W,
-                          void *grid_bf16, int32_t *ties, void *stream);
-int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const float *scale, const float *shift,
-                       const void *grid_bf16, const int32_t *ties, const int32_t *order, const int32_t *offsets,
-                       const int32_t *cell, int B, int64_t N, int C, int H, int W,
-                       void *dy_bf16, double *sums, void *stream);
+                          void *grid_bf16, void *grid_z_bf16, void *stream);
+int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const void *grid_bf16, const void *grid_z_bf16,
+                       const int32_t *order, const int32_t *offsets, const int32_t *cell,
+                       int B, int64_t N, int C, int H, int W, void *dy_bf16, double *sums, void *stream);
 int kdf_point_moments(const float *points, int64_t M, double *out14, void *stream);
 
 /* ---------------------------------------------------------------- fused point-MLP layers (tcgen05)

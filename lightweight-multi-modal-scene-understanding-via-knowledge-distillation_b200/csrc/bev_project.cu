@@ -20,6 +20,7 @@
 // C*s bytes per valid point + one grid write (kernel table).
 #include <float.h>
 
+#include <stdlib.h>
 #include "kdf_common.cuh"
 
 namespace kdf {
@@ -454,172 +455,245 @@ bev_bwd_wide_kernel(const T *__restrict__ grad_grid, const T *__restrict__ feats
 
 
 // ----------------------------------------------------------------------------- projection of a BN+ReLU'd layer (fused MLP path)
-// The fused point-MLP keeps only the pre-BatchNorm output z3 of the last layer in HBM; the feature the
-// reference scatters is a3 = relu(z3*scale + shift) (lidar_encoder.py:32-34 then :85-96).  These two
-// kernels apply that affine+ReLU on the fly (rounded to bf16, the storage type of the grid) so a3 is
-// never materialised: forward = per-cell max/tie count of a3, backward = d z3-side gradient
-//   dy3[p,c] = (a3[p,c] == max[cell,c] && max > 0) ? g[cell,c] / ties : 0
-// (the ReLU derivative folded in; when the max is 0 the ReLU kills the gradient whatever ATen's
-// tie quirk says) plus the two per-channel sums BatchNorm's backward needs, S0 = sum dy3 and
-// S1 = sum dy3*z3, accumulated in registers -> shared memory -> fp64 atomics.
+// The fused point-MLP keeps only the pre-BatchNorm output z3 of the last layer in HBM (bf16); the feature the
+// reference scatters is a3 = relu(z3*scale + shift) (lidar_encoder.py:32-34 then :85-96).  BatchNorm-apply,
+// ReLU and the rounding to bf16 are all monotonic, so the per-cell maximum of a3 is a3 of the per-cell
+// EXTREME of z3 (maximum where scale >= 0, minimum where scale < 0): the reduction runs on the raw packed
+// bf16 rows -- one XOR (sign flip for negative scales) and one packed max per two channels -- and the
+// affine+ReLU is applied once per cell.  Forward stores both the extreme (grid_z) and its activation (grid).
+// Backward: the gradient of a cell goes, split evenly, to the rows whose stored z equals the extreme (the
+// arg-max rows), if the activation is positive; the two column sums BatchNorm's backward needs follow per
+// CELL (S0 += k*share, S1 += k*share*z_ext), not per row.
+// Persistent warps walk cells with a one-cell-ahead prefetch of the cell's offsets and first point ids, so
+// the offsets -> ids -> rows dependency chain of one cell overlaps the row traffic of the previous one.
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-template <int LPR>
-__global__ void __launch_bounds__(256)
-bev_reduce_affine_kernel(const __nv_bfloat16 *__restrict__ z, const float *__restrict__ scale, const float *__restrict__ shift,
-                         const int32_t *__restrict__ order, const int32_t *__restrict__ offsets,
-                         __nv_bfloat16 *__restrict__ grid, int32_t *__restrict__ ties, int64_t n_cells, int64_t N, int HW) {
-    using T = __nv_bfloat16;
-    constexpr int VEC = 8, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
-    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * VEC;
-    float sc[VEC], sh[VEC];
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) { sc[q] = scale[ch + q]; sh[q] = shift[ch + q]; }
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {          // 0xFFFF per equal half
+    uint32_t d;
+    asm("set.eq.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+struct CellMeta { int beg, n; int64_t rowbase; };
+__device__ __forceinline__ CellMeta cell_meta(const int32_t *__restrict__ offsets, int64_t cid, int64_t n_cells, int64_t N, int HW) {
+    CellMeta m{0, 0, 0};
+    if (cid < n_cells) {
         const int64_t b = cid / HW;
         const int c = (int)(cid - b * HW);
-        const int beg = __ldg(offsets + b * (HW + 1) + c);
-        const int n = __ldg(offsets + b * (HW + 1) + c + 1) - beg;
-        const int32_t *ord = order + b * N + beg;
-        const T *fb = z + b * N * C + ch;
-        float m[VEC];
-        int k[VEC];
+        m.beg = __ldg(offsets + b * (HW + 1) + c);
+        m.n = __ldg(offsets + b * (HW + 1) + c + 1) - m.beg;
+        m.rowbase = b * N;
+    }
+    return m;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256, 4)
+bev_reduce_affine_kernel(const __nv_bfloat16 *__restrict__ z, const float *__restrict__ scale, const float *__restrict__ shift,
+                         const int32_t *__restrict__ order, const int32_t *__restrict__ offsets,
+                         __nv_bfloat16 *__restrict__ grid, __nv_bfloat16 *__restrict__ grid_z, int64_t n_cells, int64_t N, int HW) {
+    constexpr int C = LPR * 8, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * 8;
+    uint32_t flip[4];
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { m[q] = -1.f; k[q] = 0; }            // a3 >= 0, so -1 is "nothing yet"
-        int idn[U];
+    for (int q = 0; q < 4; ++q)
+        flip[q] = (__ldg(scale + ch + 2 * q) < 0.f ? 0x8000u : 0u) | (__ldg(scale + ch + 2 * q + 1) < 0.f ? 0x80000000u : 0u);
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+    int64_t cid = warp0;
+    CellMeta cur = cell_meta(offsets, cid, n_cells, N, HW);
+    int idn[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
-        for (int j0 = 0; j0 < n; j0 += STEP) {
+    for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < cur.n ? __ldg(order + cur.rowbase + cur.beg + j) : -1; }
+    CellMeta nxt = cell_meta(offsets, cid + nwarps, n_cells, N, HW);
+    while (cid < n_cells) {
+        // one cell ahead: first ids of the next cell (its offsets arrived during the previous cell), offsets of the one after
+        int idn2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn2[u] = j < nxt.n ? __ldg(order + nxt.rowbase + nxt.beg + j) : -1; }
+        const CellMeta nxt2 = cell_meta(offsets, cid + 2 * nwarps, n_cells, N, HW);
+
+        const int32_t *ord = order + cur.rowbase + cur.beg;
+        const __nv_bfloat16 *zb = z + cur.rowbase * C + ch;
+        uint32_t m[4] = {0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u};           // -inf, -inf
+        for (int j0 = 0; j0 < cur.n; j0 += STEP) {
             uint4 raw[U];
             int id[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 id[u] = idn[u];
-                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(fb + (int64_t)id[u] * C));
+                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(zb + (int64_t)id[u] * C));
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < cur.n ? __ldg(ord + j) : -1; }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (id[u] >= 0) {
-                    float f[VEC];
-                    Raw16<T>::unpack(raw[u], f);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        const float a = bf16_round(fmaxf(fmaf(f[q], sc[q], sh[q]), 0.f));
-                        if (a > m[q]) { m[q] = a; k[q] = 1; }
-                        else if (a == m[q]) { k[q]++; }
-                    }
+                    m[0] = bf16x2_max(m[0], raw[u].x ^ flip[0]);
+                    m[1] = bf16x2_max(m[1], raw[u].y ^ flip[1]);
+                    m[2] = bf16x2_max(m[2], raw[u].z ^ flip[2]);
+                    m[3] = bf16x2_max(m[3], raw[u].w ^ flip[3]);
                 }
             }
         }
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1) {
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) {
-                const float om = __shfl_xor_sync(0xffffffffu, m[q], o);
-                const int ok = __shfl_xor_sync(0xffffffffu, k[q], o);
-                if (om > m[q]) { m[q] = om; k[q] = ok; }
-                else if (om == m[q]) { k[q] += ok; }
-            }
+            for (int q = 0; q < 4; ++q) m[q] = bf16x2_max(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
         }
         if (sub == 0) {
-            float o[VEC];
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) o[q] = (n == 0) ? 0.f : m[q];
-            *reinterpret_cast<uint4 *>(grid + cid * C + ch) = Raw16<T>::pack(o);
-            if (ties) {
-                int *tp = ties + cid * C + ch;
-#pragma unroll
-                for (int q = 0; q < VEC; q += 4)
-                    *reinterpret_cast<int4 *>(tp + q) = make_int4(n ? k[q] : 0, n ? k[q + 1] : 0, n ? k[q + 2] : 0, n ? k[q + 3] : 0);
+            uint4 ze = make_uint4(0u, 0u, 0u, 0u), av = make_uint4(0u, 0u, 0u, 0u);
+            if (cur.n > 0) {
+                ze = make_uint4(m[0] ^ flip[0], m[1] ^ flip[1], m[2] ^ flip[2], m[3] ^ flip[3]);
+                float f[8];
+                Raw16<__nv_bfloat16>::unpack(ze, f);
+                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(scale + ch)), s1 = __ldg(reinterpret_cast<const float4 *>(scale + ch + 4));
+                const float4 t0 = __ldg(reinterpret_cast<const float4 *>(shift + ch)), t1 = __ldg(reinterpret_cast<const float4 *>(shift + ch + 4));
+                f[0] = fmaxf(fmaf(f[0], s0.x, t0.x), 0.f); f[1] = fmaxf(fmaf(f[1], s0.y, t0.y), 0.f);
+                f[2] = fmaxf(fmaf(f[2], s0.z, t0.z), 0.f); f[3] = fmaxf(fmaf(f[3], s0.w, t0.w), 0.f);
+                f[4] = fmaxf(fmaf(f[4], s1.x, t1.x), 0.f); f[5] = fmaxf(fmaf(f[5], s1.y, t1.y), 0.f);
+                f[6] = fmaxf(fmaf(f[6], s1.z, t1.z), 0.f); f[7] = fmaxf(fmaf(f[7], s1.w, t1.w), 0.f);
+                av = Raw16<__nv_bfloat16>::pack(f);
             }
+            *reinterpret_cast<uint4 *>(grid + cid * C + ch) = av;
+            if (grid_z) *reinterpret_cast<uint4 *>(grid_z + cid * C + ch) = ze;
         }
+        cid += nwarps;
+        cur = nxt;
+        nxt = nxt2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) idn[u] = idn2[u];
     }
 }
 
-template <int LPR>
-__global__ void __launch_bounds__(256)
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bfloat16 *__restrict__ z,
-                      const float *__restrict__ scale, const float *__restrict__ shift,
-                      const __nv_bfloat16 *__restrict__ grid, const int32_t *__restrict__ ties,
+                      const __nv_bfloat16 *__restrict__ grid, const __nv_bfloat16 *__restrict__ grid_z,
                       const int32_t *__restrict__ order, const int32_t *__restrict__ offsets, const int32_t *__restrict__ cell,
                       __nv_bfloat16 *__restrict__ dy, double *__restrict__ sums /* [2][C] */,
                       int64_t n_cells, int64_t N, int HW, int64_t total) {
     using T = __nv_bfloat16;
-    constexpr int VEC = 8, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    constexpr int C = LPR * 8, RPL = 32 / LPR, U = 4, STEP = RPL * U;
     __shared__ float red[8][2][LPR * 8];                                   // [warp][S0|S1][C]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, ch = (lane % LPR) * VEC;
-    float sc[VEC], sh[VEC], s0[VEC], s1[VEC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, ch = (lane % LPR) * 8;
+    // per-warp column sums live in shared memory (touched once per cell by the sub-0 lanes, each its own slots)
+    if (sub == 0) {
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) { sc[q] = scale[ch + q]; sh[q] = shift[ch + q]; s0[q] = 0.f; s1[q] = 0.f; }
+        for (int q = 0; q < 8; ++q) { red[warp][0][ch + q] = 0.f; red[warp][1][ch + q] = 0.f; }
+    }
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t cid = warp0; cid < n_cells; cid += nwarps) {
-        const int64_t b = cid / HW;
-        const int c = (int)(cid - b * HW);
-        const int beg = __ldg(offsets + b * (HW + 1) + c);
-        const int n = __ldg(offsets + b * (HW + 1) + c + 1) - beg;
-        if (n == 0) continue;
-        const int32_t *ord = order + b * N + beg;
-        float g[VEC], mx[VEC];
-        Raw16<T>::unpack(*reinterpret_cast<const uint4 *>(grad_grid + cid * C + ch), g);
-        Raw16<T>::unpack(*reinterpret_cast<const uint4 *>(grid + cid * C + ch), mx);
+
+    int64_t cid = warp0;
+    CellMeta cur = cell_meta(offsets, cid, n_cells, N, HW);
+    int idn[U];
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-            const int t = __ldg(ties + cid * C + ch + q);
-            g[q] = (mx[q] > 0.f) ? bf16_round(g[q] / (float)t) : 0.f;       // value every tied point receives
-        }
-        int idn[U];
+    for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < cur.n ? __ldg(order + cur.rowbase + cur.beg + j) : -1; }
+    CellMeta nxt = cell_meta(offsets, cid + nwarps, n_cells, N, HW);
+    while (cid < n_cells) {
+        int idn2[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
-        for (int j0 = 0; j0 < n; j0 += STEP) {
-            uint4 raw[U];
-            int id[U];
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn2[u] = j < nxt.n ? __ldg(order + nxt.rowbase + nxt.beg + j) : -1; }
+        const CellMeta nxt2 = cell_meta(offsets, cid + 2 * nwarps, n_cells, N, HW);
+        if (cur.n > 0) {
+            const int32_t *ord = order + cur.rowbase + cur.beg;
+            const T *zb = z + cur.rowbase * C + ch;
+            T *db = dy + cur.rowbase * C + ch;
+            const uint4 ze = __ldg(reinterpret_cast<const uint4 *>(grid_z + cid * C + ch));
+            const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(grad_grid + cid * C + ch));
+            const uint4 av = __ldg(reinterpret_cast<const uint4 *>(grid + cid * C + ch));
+            // pass A: how many rows sit at the extreme, per channel
+            int k[8];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                id[u] = idn[u];
-                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(z + (b * N + id[u]) * C + ch));
+            for (int q = 0; q < 8; ++q) k[q] = 0;
+            int ida[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) ida[u] = idn[u];
+            for (int j0 = 0; j0 < cur.n; j0 += STEP) {
+                uint4 raw[U];
+                int id[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    id[u] = ida[u];
+                    if (id[u] >= 0) raw[u] = __ldg(reinterpret_cast<const uint4 *>(zb + (int64_t)id[u] * C));   // L1-allocating: pass B re-reads
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; ida[u] = j < cur.n ? __ldg(ord + j) : -1; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (id[u] >= 0) {
+                        const uint32_t e0 = bf16x2_eq_mask(raw[u].x, ze.x), e1 = bf16x2_eq_mask(raw[u].y, ze.y);
+                        const uint32_t e2 = bf16x2_eq_mask(raw[u].z, ze.z), e3 = bf16x2_eq_mask(raw[u].w, ze.w);
+                        k[0] += e0 & 1; k[1] += e0 >> 31; k[2] += e1 & 1; k[3] += e1 >> 31;
+                        k[4] += e2 & 1; k[5] += e2 >> 31; k[6] += e3 & 1; k[7] += e3 >> 31;
+                    }
+                }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < n ? __ldg(ord + j) : -1; }
+            for (int o = LPR; o < 32; o <<= 1) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (id[u] >= 0) {
-                    float f[VEC], o[VEC];
-                    Raw16<T>::unpack(raw[u], f);
+                for (int q = 0; q < 8; ++q) k[q] += __shfl_xor_sync(0xffffffffu, k[q], o);
+            }
+            // the share every arg-max row receives (bf16, as stored), and this cell's contribution to the column sums
+            float g[8], a3[8], zf[8], sh[8];
+            Raw16<T>::unpack(gv, g);
+            Raw16<T>::unpack(av, a3);
+            Raw16<T>::unpack(ze, zf);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        const float a = bf16_round(fmaxf(fmaf(f[q], sc[q], sh[q]), 0.f));
-                        o[q] = (a == mx[q]) ? g[q] : 0.f;
-                        s0[q] += o[q];
-                        s1[q] = fmaf(o[q], f[q], s1[q]);
+            for (int q = 0; q < 8; ++q) {
+                sh[q] = (a3[q] > 0.f && k[q] > 0) ? bf16_round(g[q] / (float)k[q]) : 0.f;
+                if (sub == 0) {
+                    const float tot = sh[q] * (float)k[q];
+                    red[warp][0][ch + q] += tot;
+                    red[warp][1][ch + q] = fmaf(tot, zf[q], red[warp][1][ch + q]);
+                }
+            }
+            const uint4 share = Raw16<T>::pack(sh);
+            // pass B: write the gradient rows
+#pragma unroll
+            for (int u = 0; u < U; ++u) ida[u] = idn[u];
+            for (int j0 = 0; j0 < cur.n; j0 += STEP) {
+                uint4 raw[U];
+                int id[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    id[u] = ida[u];
+                    if (id[u] >= 0) raw[u] = __ldg(reinterpret_cast<const uint4 *>(zb + (int64_t)id[u] * C));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; ida[u] = j < cur.n ? __ldg(ord + j) : -1; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (id[u] >= 0) {
+                        uint4 o;
+                        o.x = share.x & bf16x2_eq_mask(raw[u].x, ze.x);
+                        o.y = share.y & bf16x2_eq_mask(raw[u].y, ze.y);
+                        o.z = share.z & bf16x2_eq_mask(raw[u].z, ze.z);
+                        o.w = share.w & bf16x2_eq_mask(raw[u].w, ze.w);
+                        *reinterpret_cast<uint4 *>(db + (int64_t)id[u] * C) = o;
                     }
-                    *reinterpret_cast<uint4 *>(dy + (b * N + id[u]) * C + ch) = Raw16<T>::pack(o);
                 }
             }
         }
+        cid += nwarps;
+        cur = nxt;
+        nxt = nxt2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) idn[u] = idn2[u];
     }
     // rows of points outside the grid
     const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR), gn = ((int64_t)gridDim.x * blockDim.x) / LPR;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     for (int64_t i = g0; i < total; i += gn)
         if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(dy + i * C + ch) = zero;
-    // S0 / S1: merge row groups in the warp, the 8 warps through shared memory, then fp64 atomics
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-            s0[q] += __shfl_xor_sync(0xffffffffu, s0[q], o);
-            s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
-        }
-    }
-    if (sub == 0) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) { red[warp][0][ch + q] = s0[q]; red[warp][1][ch + q] = s1[q]; }
-    }
+    // S0 / S1: the 8 warps through shared memory, then fp64 atomics (only sub 0 accumulated)
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
         float v = 0.f;
@@ -844,27 +918,27 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
 
 int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *shift,
                           const int32_t *order, const int32_t *offsets, int B, int64_t N, int C, int H, int W,
-                          void *grid_bf16, int32_t *ties, void *stream) {
+                          void *grid_bf16, void *grid_z_bf16, void *stream) {
     KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_reduce_affine: bad sizes");
     KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_reduce_affine: C=%d not supported (64, 128, 256)", C);
     if (B == 0) return KDF_OK;
     KDF_CHECK_ARG((z_bf16 || N == 0) && scale && shift && order && offsets && grid_bf16, "bev_reduce_affine: null pointer");
     const int64_t n_cells = (int64_t)B * H * W;
-    const int blocks = grid_for(n_cells * 32, 256, 64);
+    int64_t blocks = (n_cells + 7) / 8;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;      // persistent warps, several cells each
     cudaStream_t st = as_stream(stream);
     const __nv_bfloat16 *zz = reinterpret_cast<const __nv_bfloat16 *>(z_bf16);
-    __nv_bfloat16 *gg = reinterpret_cast<__nv_bfloat16 *>(grid_bf16);
-    if (C == 64)       bev_reduce_affine_kernel<8><<<blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, ties, n_cells, N, H * W);
-    else if (C == 128) bev_reduce_affine_kernel<16><<<blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, ties, n_cells, N, H * W);
-    else               bev_reduce_affine_kernel<32><<<blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, ties, n_cells, N, H * W);
+    __nv_bfloat16 *gg = reinterpret_cast<__nv_bfloat16 *>(grid_bf16), *gz = reinterpret_cast<__nv_bfloat16 *>(grid_z_bf16);
+    if (C == 64)       bev_reduce_affine_kernel<8><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);
+    else if (C == 128) bev_reduce_affine_kernel<16><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);
+    else               bev_reduce_affine_kernel<32><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }
 
-int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const float *scale, const float *shift,
-                       const void *grid_bf16, const int32_t *ties, const int32_t *order, const int32_t *offsets,
-                       const int32_t *cell, int B, int64_t N, int C, int H, int W,
-                       void *dy_bf16, double *sums, void *stream) {
+int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const void *grid_bf16, const void *grid_z_bf16,
+                       const int32_t *order, const int32_t *offsets, const int32_t *cell,
+                       int B, int64_t N, int C, int H, int W, void *dy_bf16, double *sums, void *stream) {
     KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_bwd_affine: bad sizes");
     KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_bwd_affine: C=%d not supported (64, 128, 256)", C);
     KDF_CHECK_ARG(sums, "bev_bwd_affine: null pointer");
@@ -872,16 +946,17 @@ int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const flo
     KDF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const int64_t total = (int64_t)B * N;
     if (total == 0) return KDF_OK;
-    KDF_CHECK_ARG(grad_grid_bf16 && z_bf16 && scale && shift && grid_bf16 && ties && order && offsets && cell && dy_bf16,
+    KDF_CHECK_ARG(grad_grid_bf16 && z_bf16 && grid_bf16 && grid_z_bf16 && order && offsets && cell && dy_bf16,
                   "bev_bwd_affine: null pointer");
     const int64_t n_cells = (int64_t)B * H * W;
     int64_t blocks = (n_cells + 7) / 8;
-    if (blocks > (int64_t)sm_count() * 6) blocks = (int64_t)sm_count() * 6;      // persistent: per-CTA sums -> few atomics
+    static const int minb = getenv("KDF_BEV_BWD_MINB") ? atoi(getenv("KDF_BEV_BWD_MINB")) : 3;   // tuning knob
+    if (blocks > (int64_t)sm_count() * minb) blocks = (int64_t)sm_count() * minb;    // persistent: per-CTA sums -> few atomics
     typedef const __nv_bfloat16 *cb;
-#define KDF_BA(L)                                                                                               \
-    bev_bwd_affine_kernel<L><<<(int)blocks, 256, 0, st>>>((cb)grad_grid_bf16, (cb)z_bf16, scale, shift, (cb)grid_bf16, \
-        ties, order, offsets, cell, reinterpret_cast<__nv_bfloat16 *>(dy_bf16), sums, n_cells, N, H * W, total)
-    if (C == 64) KDF_BA(8); else if (C == 128) KDF_BA(16); else KDF_BA(32);
+#define KDF_BA(L, MB)                                                                                           \
+    bev_bwd_affine_kernel<L, MB><<<(int)blocks, 256, 0, st>>>((cb)grad_grid_bf16, (cb)z_bf16, (cb)grid_bf16, (cb)grid_z_bf16, \
+        order, offsets, cell, reinterpret_cast<__nv_bfloat16 *>(dy_bf16), sums, n_cells, N, H * W, total)
+    if (C == 64) KDF_BA(8, 3); else if (C == 128) { if (minb == 2) KDF_BA(16, 2); else KDF_BA(16, 3); } else KDF_BA(32, 3);
 #undef KDF_BA
     KDF_LAUNCH_CHECK();
     return KDF_OK;

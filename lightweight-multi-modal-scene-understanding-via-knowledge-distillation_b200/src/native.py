@@ -36,7 +36,7 @@ _SIGNATURES = {
     "kdf_rowbn_apply_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _i, _vp, _vp]),
     "kdf_rowbn_bwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_bev_reduce_affine": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp]),
-    "kdf_bev_bwd_affine": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "kdf_bev_bwd_affine": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "kdf_point_moments": (C.c_int, [_vp, _i64, _vp, _vp]),
     "kdf_mlp_layer_fwd": (C.c_int, [_i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "kdf_mlp_layer_bwd": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

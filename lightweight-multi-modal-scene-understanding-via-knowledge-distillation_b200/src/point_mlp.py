@@ -7,7 +7,7 @@ layer that is ~9 passes over a ``[B*N, 128]`` activation per layer (forward + ba
   forward   points --(kdf_point_moments)--> BatchNorm-1 statistics (layer 1 is linear in the point)
             points --(kdf_mlp_layer_fwd mode 0: layer 1 recomputed in the prologue, tcgen05 GEMM)--> z2 + stats
             z2     --(kdf_mlp_layer_fwd mode 1: BN2+ReLU in the prologue, tcgen05 GEMM)--> z3 + stats
-            z3     --(kdf_bev_reduce_affine: BN3+ReLU on the fly, per-cell max + tie count)--> grid
+            z3     --(kdf_bev_reduce_affine: per-cell extreme of z3, BN3+ReLU applied once per cell)--> grid
   backward  grid grad --(kdf_bev_bwd_affine)--> dy3 + sums
             --(kdf_mlp_layer_bwd mode 1: BN3 backward in the prologue, dgrad+wgrad)--> dy2 + sums, dW3
             --(kdf_mlp_layer_bwd mode 0)--> 64x5 sums, dW2   --(closed form)--> dW1, BatchNorm-1 gradients
@@ -66,25 +66,28 @@ def cached_build_order(points: torch.Tensor, geom, grid_size):
     return val
 
 
-def bev_reduce_affine(z, scale, shift, order, offsets, B, N, grid_size, want_ties: bool):
+def bev_reduce_affine(z, scale, shift, order, offsets, B, N, grid_size, want_extreme: bool):
+    """Per-cell max of bf16(relu(z*scale+shift)) -> grid [B,H,W,C]; with ``want_extreme`` also the per-cell
+    extreme of z itself (what the backward compares rows against)."""
     dev = require_cuda(z, scale, shift, order, offsets)
     H, W = grid_size
     C = z.shape[-1]
     grid = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev)
-    ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev) if want_ties else None
+    grid_z = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev) if want_extreme else None
     call("kdf_bev_reduce_affine", ptr(z), ptr(scale), ptr(shift), ptr(order), ptr(offsets), B, N, C, H, W,
-         ptr(grid), ptr(ties), stream_ptr(dev))
-    return grid, ties
+         ptr(grid), ptr(grid_z), stream_ptr(dev))
+    return grid, grid_z
 
 
-def bev_bwd_affine(grad_grid, z, scale, shift, grid, ties, order, offsets, cell, B, N, grid_size):
-    dev = require_cuda(grad_grid, z, grid, ties)
+def bev_bwd_affine(grad_grid, z, grid, grid_z, order, offsets, cell, B, N, grid_size):
+    """-> (dy bf16 [B*N, C], sums f64 [2,C]): the cell gradient shared among the rows at the cell's extreme."""
+    dev = require_cuda(grad_grid, z, grid, grid_z)
     H, W = grid_size
     C = z.shape[-1]
     dy = torch.empty(B * N, C, dtype=torch.bfloat16, device=dev)
     sums = torch.empty(2, C, dtype=torch.float64, device=dev)
-    call("kdf_bev_bwd_affine", ptr(grad_grid), ptr(z), ptr(scale), ptr(shift), ptr(grid), ptr(ties), ptr(order),
-         ptr(offsets), ptr(cell), B, N, C, H, W, ptr(dy), ptr(sums), stream_ptr(dev))
+    call("kdf_bev_bwd_affine", ptr(grad_grid), ptr(z), ptr(grid), ptr(grid_z), ptr(order), ptr(offsets), ptr(cell),
+         B, N, C, H, W, ptr(dy), ptr(sums), stream_ptr(dev))
     return dy, sums
 
 
@@ -211,12 +214,12 @@ class _FusedLidarFn(torch.autograd.Function):
 
         # ---- projection (the cell ordering is shared with any other encoder that sees this tensor)
         cell, count, order, offsets = cached_build_order(points, geom, grid_size)
-        grid, ties = bev_reduce_affine(z3, scale3, shift3, order, offsets, B, N, grid_size, need_grad)
+        grid, grid_z = bev_reduce_affine(z3, scale3, shift3, order, offsets, B, N, grid_size, need_grad)
         if need_grad:
             if not batch:
                 raise RuntimeError("the fused LiDAR branch differentiates through batch statistics only "
                                    "(train mode); use the layer-by-layer path for eval-mode gradients")
-            ctx.save_for_backward(pts, z2, z3, grid, ties, cell, order, offsets, q, r, w2b, w3b, m14,
+            ctx.save_for_backward(pts, z2, z3, grid, grid_z, cell, order, offsets, q, r, w2b, w3b, m14,
                                   mean1.float(), invstd1.float(), scale1.float(), mean2, invstd2, scale2, shift2,
                                   mean3, invstd3, scale3, shift3, W1.float())
             ctx.dims = (B, N, tuple(grid_size))
@@ -226,13 +229,13 @@ class _FusedLidarFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_grid, _gc, _gi):
         from .ops import mlp_layer_bwd
-        (pts, z2, z3, grid, ties, cell, order, offsets, q, r, w2b, w3b, m14, mean1, invstd1, scale1,
+        (pts, z2, z3, grid, grid_z, cell, order, offsets, q, r, w2b, w3b, m14, mean1, invstd1, scale1,
          mean2, invstd2, scale2, shift2, mean3, invstd3, scale3, shift3, W1) = ctx.saved_tensors
         B, N, grid_size = ctx.dims
         M = B * N
         gg = grad_grid.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
         # projection backward: gradient w.r.t. the BatchNorm-3 output (ReLU folded in) + its two column sums
-        dy3, s3 = bev_bwd_affine(gg, z3, scale3, shift3, grid, ties, order, offsets, cell, B, N, grid_size)
+        dy3, s3 = bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, grid_size)
         gs3, ga3, gb3, dg3, db3 = _bn_bwd_coeffs(s3[0], s3[1], mean3, invstd3, scale3, M)
         dy2, s2, dW3 = mlp_layer_bwd(1, dy3, z3, gs3, ga3, gb3, z2, scale2, shift2, w3b)
         del dy3

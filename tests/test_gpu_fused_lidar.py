@@ -35,7 +35,8 @@ def test_point_moments():
 
 @pytest.mark.parametrize("B,N", [(2, 4000), (3, 20000)])
 def test_bev_affine_reduce_and_backward(B, N):
-    """max / tie count of bf16(relu(z*scale+shift)) per cell, and the gradient w.r.t. the BatchNorm output."""
+    """Per-cell max of bf16(relu(z*scale+shift)) via the per-cell extreme of z (max for scale >= 0, min for
+    scale < 0), and the gradient w.r.t. the BatchNorm output shared among the rows at the extreme."""
     from src import ops, point_mlp
     dev = "cuda"
     pts = _frames(11, B, N, dev)
@@ -46,27 +47,36 @@ def test_bev_affine_reduce_and_backward(B, N):
     shift = (torch.randn(C, generator=g) * 0.5).to(dev)
     geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
     cell, count, order, offsets = point_mlp.bev_build_order(pts, geom, (H, W))
-    grid, ties = point_mlp.bev_reduce_affine(z, scale, shift, order, offsets, B, N, (H, W), True)
-    # reference: exact affine in fp64 -> fp32 -> relu -> bf16, then scatter amax
+    grid, grid_z = point_mlp.bev_reduce_affine(z, scale, shift, order, offsets, B, N, (H, W), True)
+    # reference: exact affine in fp64 -> fp32 -> relu -> bf16 for every row, then scatter amax (the reference's order)
     a3 = torch.relu((z.double() * scale.double() + shift.double()).float()).to(torch.bfloat16).float()
     flat = (cell.long() + torch.arange(B, device=dev)[:, None] * (H * W)).reshape(-1)
     valid = cell.reshape(-1) >= 0
+    idx = flat[valid][:, None].expand(-1, C)
     ref = torch.zeros(B * H * W, C, device=dev)
-    ref.scatter_reduce_(0, flat[valid][:, None].expand(-1, C), a3[valid], "amax", include_self=True)
+    ref.scatter_reduce_(0, idx, a3[valid], "amax", include_self=True)
     assert torch.equal(grid.reshape(B * H * W, C).float(), ref)
-    is_max = (a3 == ref[flat.clamp_min(0)]) & valid[:, None]
-    ref_ties = torch.zeros(B * H * W, C, device=dev)
-    ref_ties.index_add_(0, flat[valid], is_max[valid].float())
+    # the extreme of z: max where scale >= 0, min where scale < 0
+    zs = torch.where(scale >= 0, z.float(), -z.float())
+    ext = torch.full((B * H * W, C), -float("inf"), device=dev)
+    ext.scatter_reduce_(0, idx, zs[valid], "amax", include_self=True)
+    ext = torch.where(scale >= 0, ext, -ext)
     occupied = (count.reshape(-1) > 0)[:, None].expand(-1, C)
-    assert torch.equal(ties.reshape(B * H * W, C)[occupied].float(), ref_ties[occupied])
+    assert torch.equal(grid_z.reshape(B * H * W, C).float()[occupied], ext[occupied])
+    assert (grid_z.reshape(B * H * W, C)[~occupied] == 0).all() and (grid.reshape(B * H * W, C)[~occupied] == 0).all()
 
     gg = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(dev)
-    dy, sums = point_mlp.bev_bwd_affine(gg, z, scale, shift, grid, ties, order, offsets, cell, B, N, (H, W))
-    share = (gg.reshape(-1, C).float() / ref_ties.clamp_min(1)).to(torch.bfloat16).float()
-    ref_dy = torch.where(is_max & (ref[flat.clamp_min(0)] > 0), share[flat.clamp_min(0)], torch.zeros((), device=dev))
+    dy, sums = point_mlp.bev_bwd_affine(gg, z, grid, grid_z, order, offsets, cell, B, N, (H, W))
+    at_ext = (z.float() == ext[flat.clamp_min(0)]) & valid[:, None]
+    k = torch.zeros(B * H * W, C, device=dev)
+    k.index_add_(0, flat[valid], at_ext[valid].float())
+    share = (gg.reshape(-1, C).float() / k.clamp_min(1)).to(torch.bfloat16).float()
+    ref_dy = torch.where(at_ext & (ref[flat.clamp_min(0)] > 0), share[flat.clamp_min(0)], torch.zeros((), device=dev))
     assert torch.equal(dy.float(), ref_dy)
     np.testing.assert_allclose(sums[0].cpu().numpy(), ref_dy.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(sums[1].cpu().numpy(), (ref_dy.double() * z.double()).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-4)
+    # the rows at the extreme are arg-max rows of the activation: the gradient lands only where a3 equals the cell max
+    assert ((ref_dy != 0) <= (a3 == ref[flat.clamp_min(0)])).all()
 
 
 def _reference_branch(enc, pts):

@@ -75,3 +75,24 @@ if "mlp" in only:
     q, r = torch.randn(64, 4, device=dev) * 0.02, torch.randn(64, device=dev) * 0.1
     W2 = (torch.randn(128, 64, device=dev) / 8).to(dt)
     timeit("mlp_layer_fwd mode0 (L1+L2)", lambda: ops.mlp_layer_fwd(0, pts2, q, r, W2), M * 272)
+    dy = (torch.randn(M, 128, device=dev) * (torch.rand(M, 128, device=dev) < 0.05)).to(dt)
+    z3 = torch.randn(M, 128, device=dev, dtype=dt)
+    gs, ga, gb = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.01, torch.randn(128, device=dev) * 0.01
+    timeit("mlp_layer_bwd mode1 (L3)", lambda: ops.mlp_layer_bwd(1, dy, z3, gs, ga, gb, zprev, sc, sh, W3), M * 1024)
+    timeit("mlp_layer_bwd mode0 (L2+L1)", lambda: ops.mlp_layer_bwd(0, dy, z3, gs, ga, gb, pts2, q, r, W2), M * 528)
+    del dy
+if "affine" in only:
+    from src import point_mlp
+    pts = make_frames(B, N, seed=1, device=dev)["points"]
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    z3 = torch.randn(M, 128, device=dev, dtype=dt)
+    sc, sh = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
+    v = 0.622
+    timeit("bev_build_order", lambda: point_mlp.bev_build_order(pts, geom, (H, W)), B * N * (16 + 4 + 4 + 4 + 4))
+    cell, count, order, offsets = point_mlp.bev_build_order(pts, geom, (H, W))
+    timeit("bev_reduce_affine (+extreme)", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True), B * (C * 2 * v * N + C * 2 * H * W))
+    timeit("bev_reduce_affine", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), False), B * (C * 2 * v * N + C * 2 * H * W))
+    grid, grid_z = point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True)
+    gg = torch.randn(B, H, W, C, device=dev, dtype=dt)
+    timeit("bev_bwd_affine", lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W)), B * (C * 2 * v * N + C * 2 * N + C * 2 * H * W))
+    timeit("point_moments", lambda: point_mlp.point_moments(pts), B * N * 16)
