@@ -9,10 +9,22 @@
 //
 // This file is the fp32-arithmetic implementation used for the 1e-5 parity bar
 // (CUDA-core FMA; every product and sum in fp32).  fusion_tc.cu holds the bf16
-// tensor-core (tcgen05 + TMA) implementation of the same contract.
+// tensor-core (tcgen05 + TMEM) implementation of the same contract, used for bf16 rows with C = 128.
 #include "kdf_common.cuh"
 
 namespace kdf {
+
+// bf16 / C=128 tensor-core implementation (fusion_tc.cu)
+bool fusion_tc_enabled();
+int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
+                           const float *csc, const float *csh, const float *lsc, const float *lsh,
+                           const float *w1, const float *b1, const float *w2, const float *b2,
+                           void *out, float *attn, cudaStream_t st);
+int fusion_weighted_bwd_tc(const void *grad_out, const void *cam_pre, const void *lid_pre, int64_t M,
+                           const float *csc, const float *csh, const float *lsc, const float *lsh,
+                           const float *w1, const float *b1, const float *w2, const float *attn,
+                           void *gcam, void *glid, float *gaff, float *gw1, float *gb1, float *gw2, float *gb2,
+                           cudaStream_t st);
 
 constexpr int FW_TM = 32;         // pixels per tile
 constexpr int FW_THREADS = 256;   // 8 warps, warp w owns pixels 4w..4w+3
@@ -523,6 +535,8 @@ int kdf_fusion_weighted_fwd(const void *cam_pre, const void *lid_pre, int dtype,
                   "fusion_weighted_fwd: null pointer");
     if (M == 0) return KDF_OK;
     cudaStream_t st = as_stream(stream);
+    if (dtype == KDF_BF16 && C == 128 && fusion_tc_enabled())
+        return fusion_weighted_fwd_tc(cam_pre, lid_pre, M, cam_scale, cam_shift, lid_scale, lid_shift, w1, b1, w2, b2, out, attn, st);
     const size_t smem = fw_fwd_smem(C);
     int64_t blocks = (M + FW_TM - 1) / FW_TM;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
@@ -564,6 +578,9 @@ int kdf_fusion_weighted_bwd(const void *grad_out, const void *cam_pre, const voi
     KDF_CUDA(cudaMemsetAsync(grad_w2, 0, sizeof(float) * 2 * C, st));
     KDF_CUDA(cudaMemsetAsync(grad_b2, 0, sizeof(float) * 2, st));
     if (M == 0) return KDF_OK;
+    if (dtype == KDF_BF16 && C == 128 && fusion_tc_enabled())
+        return fusion_weighted_bwd_tc(grad_out, cam_pre, lid_pre, M, cam_scale, cam_shift, lid_scale, lid_shift, w1, b1, w2, attn,
+                                      grad_cam_pre, grad_lid_pre, grad_affine, grad_w1, grad_b1, grad_w2, grad_b2, st);
     const size_t smem = fw_bwd_smem(C);
     int64_t blocks = (M + FW_TM - 1) / FW_TM;
     if (blocks > sm_count()) blocks = sm_count();

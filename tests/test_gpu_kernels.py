@@ -463,3 +463,54 @@ def test_rowbn_rows_bf16_and_large_m(ops):
     yc = ops.bn_act(x.cuda(), bn_cuda, "relu")
     assert yc.dtype == torch.bfloat16 and rel_err(yc.float().cpu(), y) < 1e-2
     assert rel_err(bn_cuda.running_var.cpu(), bn_ref.running_var) < 1e-4
+
+
+@pytest.mark.parametrize("M", [128 * 3, 128 * 148 + 57, 8192])
+def test_fusion_weighted_tensor_core_kernels_vs_fp32_autograd(ops, M):
+    """The tcgen05 weighted-fusion kernels (bf16 rows, C=128) through the C ABI against fp32 torch autograd of
+    fusion_module.py:126-136 on the same bf16 inputs.  bf16 operands / fp32 accumulation: stated tolerance
+    1e-2 relative L2 on outputs and gradients (2e-2 max-norm on the output)."""
+    from src import native
+    C = 128
+    g = torch.Generator().manual_seed(M)
+    dev = "cuda"
+    cam = (torch.randn(M, C, generator=g)).to(torch.bfloat16).to(dev)
+    lid = (torch.randn(M, C, generator=g) * (torch.rand(M, 1, generator=g) > 0.3)).to(torch.bfloat16).to(dev)
+    f = lambda *s, k=1.0: (torch.randn(*s, generator=g) * k).to(dev)
+    csc, csh, lsc, lsh = f(C).abs() + 0.5, f(C, k=0.3), -(f(C).abs() + 0.5), f(C, k=0.3)
+    w1, b1, w2, b2 = f(C, 2 * C, k=0.08), f(C, k=0.2), f(2, C, k=0.3), f(2, k=0.1)
+    gout = f(M, C).to(torch.bfloat16)
+    p, st = native.ptr, native.stream_ptr(torch.device(dev))
+    out = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
+    attn = torch.empty(M, 2, device=dev)
+    native.call("kdf_fusion_weighted_fwd", p(cam), p(lid), native.KDF_BF16, M, C, p(csc), p(csh), p(lsc), p(lsh),
+                p(w1), p(b1), p(w2), p(b2), p(out), p(attn), st)
+    gcam, glid = torch.empty_like(cam), torch.empty_like(lid)
+    gaff, gw1, gb1 = torch.empty(4, C, device=dev), torch.empty(C, 2 * C, device=dev), torch.empty(C, device=dev)
+    gw2, gb2 = torch.empty(2, C, device=dev), torch.empty(2, device=dev)
+    native.call("kdf_fusion_weighted_bwd", p(gout), p(cam), p(lid), native.KDF_BF16, M, C, p(csc), p(csh), p(lsc), p(lsh),
+                p(w1), p(b1), p(w2), p(b2), p(attn), p(gcam), p(glid), p(gaff), p(gw1), p(gb1), p(gw2), p(gb2), st)
+    # autograd reference in fp64 on the operands the tensor cores see: activations and W1 rounded to bf16
+    # (straight-through), so that the hidden layer's ReLU masks are the same ones (a mask that flips because
+    # of operand rounding moves the gradient by a whole unit's worth, which is not what this test measures)
+    leaves = [t.clone().double().requires_grad_(True) for t in (cam, lid, csc, csh, lsc, lsh, w1, b1, w2, b2)]
+    xc, xl, rcsc, rcsh, rlsc, rlsh, rw1, rb1, rw2, rb2 = leaves
+    ste = lambda t: t + (t.detach().float().to(torch.bfloat16).double() - t.detach())
+    yc = ste(torch.relu((xc.float() * rcsc.float() + rcsh.float()).double()))
+    yl = ste(torch.relu((xl.float() * rlsc.float() + rlsh.float()).double()))
+    hid = torch.relu(torch.cat([yc, yl], 1) @ ste(rw1).t() + rb1)
+    w = torch.softmax(hid @ rw2.t() + rb2, dim=1)
+    ref = yc * w[:, :1] + yl * w[:, 1:]
+    ref.backward(gout.double())
+
+    def l2(a, b):
+        a, b = a.double(), b.double()
+        return ((a - b).norm() / (b.norm() + 1e-30)).item()
+    assert rel_err(out.float(), ref.detach()) < 2e-2 and l2(out.float(), ref.detach()) < 5e-3
+    assert l2(attn, w.detach()) < 5e-3
+    assert l2(gcam.float(), xc.grad) < 1e-2, l2(gcam.float(), xc.grad)
+    assert l2(glid.float(), xl.grad) < 1e-2, l2(glid.float(), xl.grad)
+    ref_aff = torch.stack([rcsc.grad, rcsh.grad, rlsc.grad, rlsh.grad])
+    assert l2(gaff, ref_aff) < 1e-2, l2(gaff, ref_aff)
+    for name, got, want in (("w1", gw1, rw1.grad), ("b1", gb1, rb1.grad), ("w2", gw2, rw2.grad), ("b2", gb2, rb2.grad)):
+        assert l2(got, want) < 1e-2, (name, l2(got, want))

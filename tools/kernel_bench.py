@@ -66,6 +66,10 @@ if "fusion" in only:
     w2, b2 = torch.randn(2, C, **f32) * 0.1, torch.randn(2, **f32) * 0.1
     fo = torch.empty(Mp, C, dtype=dt, device=dev); attn = torch.empty(Mp, 2, **f32)
     timeit("fusion_weighted_fwd", lambda: native.call("kdf_fusion_weighted_fwd", p(cam), p(lid), 1, Mp, C, p(sc[0]), p(sh[0]), p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(fo), p(attn), st), Mp * 3 * C * 2)
+    go = torch.randn(Mp, C, device=dev, dtype=dt); g1, g2 = torch.empty_like(cam), torch.empty_like(lid)
+    gaff, gw1, gb1 = torch.empty(4, C, **f32), torch.empty(C, 2 * C, **f32), torch.empty(C, **f32)
+    gw2, gb2 = torch.empty(2, C, **f32), torch.empty(2, **f32)
+    timeit("fusion_weighted_bwd", lambda: native.call("kdf_fusion_weighted_bwd", p(go), p(cam), p(lid), 1, Mp, C, p(sc[0]), p(sh[0]), p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(attn), p(g1), p(g2), p(gaff), p(gw1), p(gb1), p(gw2), p(gb2), st), Mp * 5 * C * 2)
 if "mlp" in only:
     zprev = torch.randn(M, 128, device=dev, dtype=dt)
     sc, sh = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
