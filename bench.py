@@ -463,7 +463,14 @@ def run_native(args):
                 "loss_terms_last_step": dict(zip(("loss", "ce", "kl", "mse"), loss_terms))}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroying an NCCL communicator whose all-reduce sits inside
+        # a captured CUDA graph blocked for minutes on the 2-GPU box (NCCL 2.28.9).  Everything is synchronised and
+        # flushed, so a hard exit loses nothing.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -72,31 +72,63 @@ __device__ __forceinline__ void kd_normaliser(const KdWorkspace *ws, const float
     }
 }
 
+// 16 bytes of tap elements <-> floats
+template <typename TF> struct TapVec;
+template <> struct TapVec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void unpack(const uint4 &u, float *v) {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float *v) {
+        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
+};
+template <> struct TapVec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void unpack(const uint4 &u, float *v) {
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float *v) {
+        return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+};
+
+// One mimic tap: sum (s-t)^2 and d = coef*(s-t), 16-byte accesses, U independent load pairs in flight per thread.
 template <typename TF>
 __device__ __forceinline__ float kd_tap(const TF *__restrict__ s, const TF *__restrict__ t, TF *__restrict__ d,
                                         int64_t n, float coef, int64_t tid, int64_t nthreads) {
     // coef = grad_scale * beta * 2 / n
+    constexpr int V = TapVec<TF>::N, U = 4;
     float acc = 0.f;
-    const int64_t n4 = n >> 2;
-    constexpr int U = 4;
-    for (int64_t i = tid; i < n4; i += nthreads * U) {
-        float4 a[U], b[U];
+    const int64_t nv = n / V;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(s), *t4 = reinterpret_cast<const uint4 *>(t);
+    uint4 *d4 = reinterpret_cast<uint4 *>(d);
+    for (int64_t i = tid; i < nv; i += nthreads * U) {
+        uint4 a[U], b[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t j = i + (int64_t)u * nthreads;
-            if (j < n4) { a[u] = Vec4<TF>::load_stream(s + 4 * j); b[u] = Vec4<TF>::load_stream(t + 4 * j); }
+            if (j < nv) { a[u] = ldg_stream_u4(s4 + j); b[u] = ldg_stream_u4(t4 + j); }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t j = i + (int64_t)u * nthreads;
-            if (j < n4) {
-                const float4 e = make_float4(a[u].x - b[u].x, a[u].y - b[u].y, a[u].z - b[u].z, a[u].w - b[u].w);
-                acc += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
-                Vec4<TF>::store(d + 4 * j, make_float4(coef * e.x, coef * e.y, coef * e.z, coef * e.w));
+            if (j < nv) {
+                float x[V], y[V];
+                TapVec<TF>::unpack(a[u], x);
+                TapVec<TF>::unpack(b[u], y);
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    const float e = x[q] - y[q];
+                    acc = fmaf(e, e, acc);
+                    x[q] = coef * e;
+                }
+                d4[j] = TapVec<TF>::pack(x);
             }
         }
     }
-    for (int64_t j = (n4 << 2) + tid; j < n; j += nthreads) {     // tail (numel % 4)
+    for (int64_t j = nv * V + tid; j < n; j += nthreads) {        // tail (numel % V)
         const float e = to_float<TF>(s[j]) - to_float<TF>(t[j]);
         acc += e * e;
         d[j] = from_float<TF>(coef * e);
@@ -105,7 +137,7 @@ __device__ __forceinline__ float kd_tap(const TF *__restrict__ s, const TF *__re
 }
 
 template <typename TL, typename TF>
-__global__ void __launch_bounds__(KD_THREADS)
+__global__ void __launch_bounds__(KD_THREADS, 3)
 kd_loss_kernel(KdParams p) {
     __shared__ float red[KD_THREADS / 32];
     __shared__ bool is_last;
@@ -271,9 +303,9 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
     p.s1 = s_feat1; p.t1 = t_feat1; p.d1 = d_feat1; p.n1 = numel1 > 0 ? numel1 : 0;
     p.dz = d_logits; p.scalars = scalars; p.ws = ws;
 
-    // persistent grid: a multiple of the SM count, enough CTAs to cover the work
+    // persistent grid: exactly the resident CTAs (3 per SM, one wave), fewer when the work is small
     const int64_t work = npix + (p.n0 + p.n1) / 16;
-    int blocks = sm_count() * 8;
+    int blocks = sm_count() * 3;
     const int64_t need = (work + KD_THREADS - 1) / KD_THREADS;
     if (need < blocks) blocks = (int)(need < 1 ? 1 : need);
     if (blocks > KD_MAX_BLOCKS) blocks = KD_MAX_BLOCKS;
