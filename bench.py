@@ -227,73 +227,121 @@ def time_kernel(fn, iters=20, warm=3):
     return a.elapsed_time(b) / iters
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each hand-written kernel at the bench
+    shapes, from the committed `ncu --set full` captures (profiles/r01_ncu_traffic.json names the capture files)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            return json.load(f)["bytes_per_launch"]
+    except Exception:
+        return {}
+
+
 def kernel_rooflines(args, device, fp32):
-    """Each hand-written kernel alone at the step's shapes.  Algorithmic bytes follow SURVEY.md 8(d)
-    (stated again in DESIGN.md); inputs per launch are >> L2 for the projection kernels, and a 256 MB
-    buffer is rewritten between launches for the small ones."""
-    from src import native, ops
+    """Each hand-written kernel of the step alone at the step's shapes.  Algorithmic bytes follow SURVEY.md 8(d) and
+    DESIGN.md section 4 (stated per kernel in `note`); inputs per launch are >> L2 for the per-point kernels, and a
+    256 MB buffer is rewritten between launches for the small (per-pixel) ones."""
+    from src import native, ops, point_mlp
     from src.data_loading.synthetic_frames import make_frames
     B, N, C, H, W = args.batch, args.points, 128, 64, 64
     s = 4 if fp32 else 2
     dt = torch.float32 if fp32 else torch.bfloat16
     pts = make_frames(B, N, seed=123, device=device)["points"]
     geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
-    feats = torch.rand(B, N, C, device=device, dtype=dt)
     peak, peak_src = peak_gbs()
+    traffic = ncu_traffic()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     out = []
+    f32 = dict(device=device, dtype=torch.float32)
+    st = native.stream_ptr(device)
+    p = native.ptr
+    Mpts = B * N
 
-    def add(name, ms, alg_bytes, note):
+    def add(name, ms, alg_bytes, note, in_step=True):
         out.append({"kernel": name, "ms": ms, "algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms * 1e-3) / 1e9,
                     "peak": peak, "unit": "GB/s", "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "bound": "hbm",
-                    "traffic": None, "note": note})
+                    "traffic": traffic.get(name), "in_step": in_step, "note": note})
 
-    # ---- projection: whole forward call, reduce kernel alone, backward, index only
-    cell, count = ops.bev_index(pts, geom, (H, W))
+    def with_flush(fn):
+        def g():
+            flush.fill_(1)
+            fn()
+        return g
+    t_flush = time_kernel(lambda: flush.fill_(1))
+
+    cell, count, order, offsets = point_mlp.bev_build_order(pts, geom, (H, W))
     v = (cell >= 0).float().mean().item()
+
+    if not fp32:
+        # ---- fused point MLP (tcgen05): the four layer kernels of the student (the teacher runs the two forward ones)
+        q, r = torch.randn(64, 4, **f32) * 0.02, torch.randn(64, **f32) * 0.1
+        W2 = (torch.randn(128, 64, **f32) / 8).to(dt)
+        W3 = (torch.randn(128, 128, **f32) / 11).to(dt)
+        sc, sh = torch.rand(128, **f32) + 0.5, torch.randn(128, **f32) * 0.1
+        flat = pts.view(Mpts, 4)
+        z2, _ = point_mlp.mlp_layer_fwd_raw(0, flat, q, r, W2)
+        add("mlp_layer_fwd_kernel<0>", time_kernel(lambda: point_mlp.mlp_layer_fwd_raw(0, flat, q, r, W2), 10), Mpts * (16 + C * s),
+            "layers 1+2: 16 B point in, C*s pre-BatchNorm row out per point")
+        add("mlp_layer_fwd_kernel<1>", time_kernel(lambda: point_mlp.mlp_layer_fwd_raw(1, z2, sc, sh, W3), 10), Mpts * 2 * C * s,
+            "layer 3: C*s row in, C*s row out per point")
+        z3, _ = point_mlp.mlp_layer_fwd_raw(1, z2, sc, sh, W3)
+        dy = (torch.randn(Mpts, 128, device=device) * (torch.rand(Mpts, 128, device=device) < 0.05)).to(dt)
+        gs, ga, gb = torch.rand(128, **f32) + 0.5, torch.randn(128, **f32) * 0.01, torch.randn(128, **f32) * 0.01
+        add("mlp_layer_bwd_kernel<1>", time_kernel(lambda: ops.mlp_layer_bwd(1, dy, z3, gs, ga, gb, z2, sc, sh, W3), 10), Mpts * 4 * C * s,
+            "layer 3 backward: dy, z, z_prev rows in, dy_prev row out per point (dgrad + wgrad + BatchNorm backward)")
+        add("mlp_layer_bwd_kernel<0>", time_kernel(lambda: ops.mlp_layer_bwd(0, dy, z3, gs, ga, gb, flat, q, r, W2), 10), Mpts * (2 * C * s + 16),
+            "layers 2+1 backward: dy, z rows + 16 B point in per point; 64x5 sums out")
+        del dy
+        # ---- projection of the un-normalised last layer
+        add("bev_build_order (index+scan+fill)", time_kernel(lambda: point_mlp.bev_build_order(pts, geom, (H, W)), 10),
+            B * (16 * N + 4 * N + 4 * N + 4 * N + 4 * v * N + 8 * H * W),
+            "16N points in; cell ids, arrival ranks out and in again, order out; occupancy + offsets per cell")
+        add("bev_reduce_affine_kernel", time_kernel(lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True), 10),
+            B * (C * s * v * N + 4 * v * N + 2 * C * s * H * W),
+            "C*s*v*N rows of valid points read once + 4*v*N ids; grid and extreme written once (2*C*s*HW)")
+        grid, grid_z = point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True)
+        gg = torch.randn(B, H, W, C, device=device, dtype=dt)
+        add("bev_bwd_affine_kernel", time_kernel(lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W)), 10),
+            B * (3 * C * s * H * W + C * s * v * N + C * s * N + 8 * N),
+            "grad/grid/extreme rows per cell (3*C*s*HW) + rows of valid points read once (C*s*v*N; the second sweep hits "
+            "L1/L2) + a gradient row per point (C*s*N) + ids")
+        del z2, z3, gg, grid, grid_z
+
+    # ---- layer-by-layer projection path (fp32 parity path; bf16 features here): the reference's scatter as one call
+    feats = torch.rand(B, N, C, device=device, dtype=dt)
     grid = torch.empty(B, H, W, C, dtype=dt, device=device)
     cnt = torch.empty(B, H * W, dtype=torch.int32, device=device)
     cel = torch.empty(B, N, dtype=torch.int32, device=device)
     ties = torch.empty(B, H * W, C, dtype=torch.int32, device=device)
-    order = torch.empty(B, N, dtype=torch.int32, device=device)
+    order2 = torch.empty(B, N, dtype=torch.int32, device=device)
     offs = torch.empty(B, H * W + 1, dtype=torch.int32, device=device)
     wsb = native.lib.kdf_bev_workspace_bytes(B, N, H, W)
     ws = torch.empty(wsb, dtype=torch.uint8, device=device)
-    st = native.stream_ptr(device)
-    p = native.ptr
 
     def proj_fwd():
         native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), native.dtype_code(feats), B, N, C, *geom, H, W, 0,
-                    p(grid), p(cnt), p(cel), p(ties), p(order), p(offs), p(ws), wsb, st)
-    fwd_bytes = B * (16 * N + C * s * v * N + C * s * H * W + 4 * H * W)
-    add("bev_project_fwd (index+scan+fill+reduce)", time_kernel(proj_fwd), fwd_bytes,
-        "16N + C*s*v*N + C*s*HW + 4*HW per frame")
-
-    def reduce_only():
-        native.call("kdf_bev_reduce", p(feats), native.dtype_code(feats), p(order), p(offs), B, N, C, H, W, 0,
-                    p(grid), p(ties), st)
-    add("bev_reduce_kernel", time_kernel(reduce_only), B * (C * s * v * N + C * s * H * W),
-        "C*s*v*N + C*s*HW per frame (feature rows of valid points read once, grid written once)")
-
+                    p(grid), p(cnt), p(cel), p(ties), p(order2), p(offs), p(ws), wsb, st)
+    add("bev_project_fwd (index+scan+fill+reduce with tie counts)", time_kernel(proj_fwd), B * (16 * N + C * s * v * N + C * s * H * W + 4 * H * W),
+        "16N + C*s*v*N + C*s*HW + 4*HW per frame (SURVEY 8d)", in_step=fp32)
     gg = torch.rand(B, H * W, C, device=device, dtype=dt)
     gf = torch.empty(B, N, C, dtype=dt, device=device)
 
     def proj_bwd():
-        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order), p(offs),
+        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order2), p(offs),
                     native.dtype_code(feats), B, N, C, H, W, 0, p(gf), st)
-    add("bev_bwd_kernel", time_kernel(proj_bwd), B * (C * s * H * W + C * s * v * N + 4 * N),
+    add("bev_bwd_wide_kernel", time_kernel(proj_bwd), B * (C * s * H * W + C * s * v * N + 4 * N),
         "C*s*HW + C*s*v*N + 4N per frame (SURVEY 8d); actual traffic is higher: feats re-read for the exact "
-        "tie split (C*s*v*N) and zero rows written for points outside (C*s*(1-v)*N)")
+        "tie split (C*s*v*N) and zero rows written for points outside (C*s*(1-v)*N)", in_step=fp32)
 
     def index_only():
         native.call("kdf_bev_index", p(pts), B, N, 4, *geom, H, W, p(cel), None, p(cnt), st)
     add("bev_index_kernel", time_kernel(index_only), B * (16 * N + 4 * N + 4 * H * W), "16N + 4N + 4*HW per frame")
+    del feats, gf, gg, ties
 
     # ---- fusion (weighted) forward / backward on pre-BN rows
     M = B * H * W
     cam_pre = torch.randn(M, C, device=device, dtype=dt)
     lid_pre = torch.randn(M, C, device=device, dtype=dt)
-    f32 = dict(device=device, dtype=torch.float32)
     sc = [torch.rand(C, **f32) + 0.5 for _ in range(2)]
     sh = [torch.randn(C, **f32) * 0.1 for _ in range(2)]
     w1, b1 = torch.randn(C, 2 * C, **f32) * 0.05, torch.randn(C, **f32) * 0.1
@@ -301,16 +349,9 @@ def kernel_rooflines(args, device, fp32):
     fo = torch.empty(M, C, dtype=dt, device=device)
     attn = torch.empty(M, 2, **f32)
 
-    def with_flush(fn):
-        def g():
-            flush.fill_(1)
-            fn()
-        return g
-
     def fus_fwd():
         native.call("kdf_fusion_weighted_fwd", p(cam_pre), p(lid_pre), native.dtype_code(cam_pre), M, C, p(sc[0]), p(sh[0]),
                     p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(fo), p(attn), st)
-    t_flush = time_kernel(lambda: flush.fill_(1))
     add("fusion_weighted_fwd_kernel", time_kernel(with_flush(fus_fwd)) - t_flush, M * 3 * C * s,
         "3*C*s per pixel (whole block fused, single pass); L2 flushed between launches")
     go = torch.randn(M, C, device=device, dtype=dt)
@@ -332,11 +373,16 @@ def kernel_rooflines(args, device, fp32):
     taps_s = [torch.randn(B, H, W, C, device=device, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
     taps_t = [torch.randn(B, H, W, C, device=device, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
     cw = torch.tensor(CLASS_WEIGHTS, device=device)
+    d_l = [torch.empty_like(t) for t in taps_s]
+    dz, scal = torch.empty_like(zs), torch.empty(8, **f32)
+    kws = torch.empty(native.lib.kdf_kd_loss_workspace_bytes(), dtype=torch.uint8, device=device)
+    K = 2
 
     def kd():
-        ops.kd_loss_fwd_bwd(zs, zt, lab, cw, taps_s, taps_t)
-    K = 2
-    add("kd_loss_kernel (fwd+bwd)", time_kernel(with_flush(kd)) - t_flush, M * (2 * K * s + 8 + K * s + 2 * 3 * C * s),
+        native.call("kdf_kd_loss_fwd_bwd", p(zs), p(zt), p(lab), p(cw), B, K, H * W, native.dtype_code(zs), 4.0, 0.5, 1.0, -1,
+                    p(taps_s[0]), p(taps_t[0]), p(d_l[0]), taps_s[0].numel(), p(taps_s[1]), p(taps_t[1]), p(d_l[1]),
+                    taps_s[1].numel(), native.dtype_code(taps_s[0]), 1.0, p(dz), p(scal), p(kws), st)
+    add("kd_loss_kernel (label histogram + loss fwd+bwd)", time_kernel(with_flush(kd)) - t_flush, M * (2 * K * s + 8 + K * s + 2 * 3 * C * s),
         "per pixel 2K*s + 8 + K*s logits/labels + 3*C*s per mimic tap (2 taps)")
     return out, v
 
@@ -440,9 +486,9 @@ def run_native(args):
         del batches
         torch.cuda.empty_cache()
         kernels, valid_frac = kernel_rooflines(args, device, args.fp32)
-        dom = max((k for k in kernels if k["kernel"] != "bev_project_fwd (index+scan+fill+reduce)"), key=lambda k: k["ms"])
+        dom = max((k for k in kernels if k["in_step"]), key=lambda k: k["ms"])     # the longest hand-written kernel of the step
         roof = {"bound": "hbm", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "kernel": dom["kernel"], "launch_ms": dom["ms"],
+                "traffic": dom["traffic"], "kernel": dom["kernel"], "launch_ms": dom["ms"],
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "peak_source": peak_gbs()[1],
                 "valid_point_fraction": valid_frac}
     if world > 1:

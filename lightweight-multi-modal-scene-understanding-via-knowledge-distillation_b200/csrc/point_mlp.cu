@@ -20,9 +20,19 @@
 
 namespace kdf {
 
-constexpr int PM_THREADS = 256;
 constexpr int PM_ROWS = 128;          // points per tile = MMA M
 constexpr int PM_N = 128;             // output channels of the tensor-core layers
+// Threads per CTA are a template parameter NT (256 or 512): the CUDA-core prologue / epilogue work is latency-bound
+// and 16 warps hide more of it, except for the first-layer-recompute forward kernel (measured: 0.46 ms at 256
+// threads, 0.60 ms at 512).  Derived per kernel:
+//   PM_CGROUPS = NT/128   TMEM epilogue: warp w reads lanes 32*(w%4).., column group w/4
+//   PM_OROWS   = NT/16    rows per pass of the 16-chunks-per-row (256-byte row) phases
+#define KDF_PM_DERIVED(NT)                                   \
+    constexpr int PM_THREADS = NT;                           \
+    constexpr int PM_CGROUPS = PM_THREADS / 128;             \
+    constexpr int PM_OROWS = PM_THREADS / 16;                \
+    constexpr int PM_OPASSES = PM_ROWS / PM_OROWS;           \
+    (void)PM_CGROUPS; (void)PM_OROWS; (void)PM_OPASSES
 
 struct MlpFwdArgs {
     const void *input;                // MODE 0: points f32 [M,4];  MODE 1: z_prev bf16 [M,KIN]
@@ -71,9 +81,10 @@ __device__ __forceinline__ uint4 affine_relu_chunk(const uint4 &u, const float *
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-template <int MODE, int KIN>
-__global__ void __launch_bounds__(PM_THREADS, 1)
+template <int MODE, int KIN, int NT>
+__global__ void __launch_bounds__(NT, 1)
 mlp_layer_fwd_kernel(MlpFwdArgs a) {
+    KDF_PM_DERIVED(NT);
     using L = MlpSmem<KIN>;
     constexpr int CHUNKS_PER_ROW = KIN / 8;                       // 16-byte chunks of one operand row
     constexpr int ROWS_PER_PASS = PM_THREADS / CHUNKS_PER_ROW;    // 16 (KIN=128) or 32 (KIN=64)
@@ -177,16 +188,17 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
         tc::mbar_wait(&bars[buf], parity);
         tc::fence_after_sync();
         // warp w: TMEM lanes 32*(w%4).., columns 64*(w/4)..; thread = one output row
+        constexpr int COLS_W = PM_N / PM_CGROUPS;                           // columns per warp
         const int row = (warp & 3) * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * PM_N + (uint32_t)(warp >> 2) * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * PM_N + (uint32_t)(warp >> 2) * COLS_W;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < COLS_W / 32; ++half) {
             uint32_t r[32];
             tc::tmem_ld32(taddr + half * 32, r);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int chunk = (warp >> 2) * 8 + half * 4 + j;           // 16-byte chunk of the 256-byte output row
+                const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j; // 16-byte chunk of the 256-byte output row
                 const uint4 v = make_uint4(pack_bf16(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])),
                                            pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
                                            pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
@@ -199,8 +211,8 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
         // coalesced stores + statistics of exactly the stored bf16 values
         const int64_t r0 = tile * PM_ROWS;
 #pragma unroll
-        for (int p = 0; p < PM_ROWS / 16; ++p) {
-            const int r = orow0 + p * 16;
+        for (int p = 0; p < PM_OPASSES; ++p) {
+            const int r = orow0 + p * PM_OROWS;
             if (r0 + r < a.M) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
                 *reinterpret_cast<uint4 *>(a.z_out + (r0 + r) * PM_N + och * 8) = v;
@@ -240,14 +252,14 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
     __syncthreads();
 
     // ---- statistics: reduce the 16 threads that share an output chunk, then 2*128 fp64 atomics per CTA
-    float *red = reinterpret_cast<float *>(sStage);                       // [16 row lanes][16 chunks][16]
+    float *red = reinterpret_cast<float *>(sStage);                       // [PM_OROWS row lanes][16 chunks][16]
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[(orow0 * 16 + och) * 16 + j] = s_sum[j]; red[(orow0 * 16 + och) * 16 + 8 + j] = s_sq[j]; }
     __syncthreads();
     if (tid < 16 * 16) {
         const int ch = tid >> 4, j = tid & 15;                             // chunk, (sum|sq, element)
         float v = 0.f;
-        for (int r = 0; r < 16; ++r) v += red[(r * 16 + ch) * 16 + j];
+        for (int r = 0; r < PM_OROWS; ++r) v += red[(r * 16 + ch) * 16 + j];
         const int col = ch * 8 + (j & 7);
         atomicAdd(a.stats + (j >> 3) * PM_N + col, (double)v);
     }
@@ -306,14 +318,15 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-template <int MODE, int KIN>
-__global__ void __launch_bounds__(PM_THREADS, 1)
+template <int MODE, int KIN, int NT>
+__global__ void __launch_bounds__(NT, 1)
 mlp_layer_bwd_kernel(MlpBwdArgs a) {
+    KDF_PM_DERIVED(NT);
     using L = MlpBwdSmem<KIN>;
     constexpr int ACH = KIN / 8;                                  // 16-byte chunks per activation row
     constexpr int A_ROWS_PER_PASS = PM_THREADS / ACH;             // 16 or 32
     constexpr int A_PASSES = PM_ROWS / A_ROWS_PER_PASS;           // 8 or 4
-    constexpr int D_PASSES = PM_ROWS / 16;                        // dz tile: 16 chunks per row, 16 rows per pass
+    constexpr int D_PASSES = PM_OPASSES;                          // dz tile: 16 chunks per row, PM_OROWS rows per pass
     constexpr uint32_t PANEL = PM_ROWS * tc::ROW_BYTES;           // 16384: bytes between 64-column panels
     constexpr uint32_t IDESC_D = tc::make_idesc(PM_ROWS, KIN, 0, 1);   // dgrad: A K-major, B MN-major
     constexpr uint32_t IDESC_W = tc::make_idesc(PM_N, KIN, 1, 1);      // wgrad: both MN-major
@@ -334,9 +347,9 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
 
     for (int i = tid; i < 128; i += PM_THREADS) { cgs[i] = a.gs[i]; cga[i] = a.ga[i]; cgb[i] = a.gb[i]; }
-    if (MODE == 0) {
-        for (int i = tid; i < 64 * 4; i += PM_THREADS) coef[i] = a.pro_a[i];
-        for (int i = tid; i < 64; i += PM_THREADS) coef[256 + i] = a.pro_b[i];
+    if (MODE == 0) {                                              // q rows padded to 36 floats per 8-channel chunk: conflict-free LDS.128
+        for (int i = tid; i < 64 * 4; i += PM_THREADS) coef[(i >> 5) * 36 + (i & 31)] = a.pro_a[i];
+        for (int i = tid; i < 64; i += PM_THREADS) coef[288 + i] = a.pro_b[i];
     } else {
         for (int i = tid; i < KIN; i += PM_THREADS) { coef[i] = a.pro_a[i]; coef[KIN + i] = a.pro_b[i]; }
     }
@@ -366,7 +379,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         const int64_t r0 = tile * PM_ROWS;
 #pragma unroll
         for (int p = 0; p < D_PASSES; ++p) {
-            const int64_t row = r0 + drow0 + p * 16;
+            const int64_t row = r0 + drow0 + p * PM_OROWS;
             if (row < a.M) {
                 raw_dy[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
                 raw_z[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
@@ -389,7 +402,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
             for (int j = 0; j < 8; ++j) { gs[j] = cgs[dch * 8 + j]; ga[j] = cga[dch * 8 + j]; gb[j] = cgb[dch * 8 + j]; }
 #pragma unroll
             for (int p = 0; p < D_PASSES; ++p) {
-                const int r = drow0 + p * 16;
+                const int r = drow0 + p * PM_OROWS;
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (r0 + r < a.M) {
                     float g[8], zz[8];
@@ -406,9 +419,9 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
             float c0[MODE == 0 ? 32 : 8], c1[8];
             if (MODE == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) c0[j] = coef[ach * 32 + j];
+                for (int j = 0; j < 32; ++j) c0[j] = coef[ach * 36 + j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) c1[j] = coef[256 + ach * 8 + j];
+                for (int j = 0; j < 8; ++j) c1[j] = coef[288 + ach * 8 + j];
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { c0[j] = coef[ach * 8 + j]; c1[j] = coef[KIN + ach * 8 + j]; }
@@ -455,6 +468,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
     const int och = tid & 15, orow0 = tid >> 4;                            // MODE 1 store phase
     const int ccol = tid & 63, crq = tid >> 6;                             // MODE 0 column-owner phase
+    constexpr int CRQ_ROWS = PM_ROWS / (PM_THREADS / 64);                  // rows per column-owner group
 
     auto epilogue = [&](int64_t tile, int buf, uint32_t parity) {
         const int64_t r0 = tile * PM_ROWS;
@@ -463,7 +477,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         if (MODE == 1) {                                                   // z_prev chunks of the store phase (L2 hits), issued early
 #pragma unroll
             for (int p = 0; p < D_PASSES; ++p) {
-                const int64_t row = r0 + orow0 + p * 16;
+                const int64_t row = r0 + orow0 + p * PM_OROWS;
                 zk[p] = make_uint4(0u, 0u, 0u, 0u);
                 if (row < a.M) zk[p] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + row * KIN + och * 8);
             }
@@ -472,15 +486,16 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         tc::fence_after_sync();
         const int row = (warp & 3) * 32 + lane;
         if (MODE == 1) {
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)(warp >> 2) * 64;
+            constexpr int COLS_W = KIN / PM_CGROUPS;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)(warp >> 2) * COLS_W;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < COLS_W / 32; ++half) {
                 uint32_t r[32];
                 tc::tmem_ld32(taddr + half * 32, r);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int chunk = (warp >> 2) * 8 + half * 4 + j;       // 16-byte chunk of the 256-byte row
+                    const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j;   // 16-byte chunk of the 256-byte row
                     const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
                     float act[8], v[8];
                     unpack8(av, act);
@@ -490,13 +505,14 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                 }
             }
         } else {
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)(warp >> 2) * 32;
-            uint32_t r[32];
-            tc::tmem_ld32(taddr, r);
+            constexpr int COLS_W = KIN / PM_CGROUPS;                        // 16 with 16 warps, 32 with 8
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)(warp >> 2) * COLS_W;
+            uint32_t r[COLS_W];
+            tc::tmem_ld<COLS_W>(taddr, r);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int chunk = (warp >> 2) * 4 + j;                      // 8 channels of the 64-channel activation row
+            for (int j = 0; j < COLS_W / 8; ++j) {
+                const int chunk = (warp >> 2) * (COLS_W / 8) + j;           // 8 channels of the 64-channel activation row
                 const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + tc::sw128_offset(row, chunk));
                 float act[8];
                 unpack8(av, act);
@@ -517,7 +533,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         if (MODE == 1) {
 #pragma unroll
             for (int p = 0; p < D_PASSES; ++p) {
-                const int r = orow0 + p * 16;
+                const int r = orow0 + p * PM_OROWS;
                 if (r0 + r < a.M) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
                     *reinterpret_cast<uint4 *>(a.dy_prev + (r0 + r) * PM_N + och * 8) = v;
@@ -530,7 +546,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
             }
         } else {
             const int rows = (int)((a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS);
-            const int rbeg = crq * 32, rend = (rbeg + 32 < rows) ? rbeg + 32 : rows;
+            const int rbeg = crq * CRQ_ROWS, rend = (rbeg + CRQ_ROWS < rows) ? rbeg + CRQ_ROWS : rows;
             for (int r = rbeg; r < rend; ++r) {
                 const float v = *reinterpret_cast<const float *>(sStage + r * 256 + (((ccol >> 2) ^ (r & 15)) << 4) + (ccol & 3) * 4);
                 const float4 pt = sPts[buf * PM_ROWS + r];
@@ -572,10 +588,10 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) red[(orow0 * 16 + och) * 16 + j] = acc[j];
         __syncthreads();
-        {
+        if (tid < 16 * 16) {
             const int ch = tid >> 4, j = tid & 15;
             float v = 0.f;
-            for (int r = 0; r < 16; ++r) v += red[(r * 16 + ch) * 16 + j];
+            for (int r = 0; r < PM_OROWS; ++r) v += red[(r * 16 + ch) * 16 + j];
             atomicAdd(a.sums + (j >> 3) * PM_N + ch * 8 + (j & 7), (double)v);
         }
     } else {
@@ -585,7 +601,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         for (int i = tid; i < 64 * 5; i += PM_THREADS) {
             const int c = i / 5, j = i % 5;
             float v = 0.f;
-            for (int q = 0; q < 4; ++q) v += red[(q * 64 + c) * 5 + j];
+            for (int q = 0; q < PM_THREADS / 64; ++q) v += red[(q * 64 + c) * 5 + j];
             atomicAdd(a.sums + j * 64 + c, (double)v);
         }
     }
@@ -593,15 +609,15 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     if (it > 0) {
         tc::fence_after_sync();
         const int n = (warp & 3) * 32 + lane;
-        constexpr int COLS_PER_WARP = KIN / 2;
+        constexpr int COLS_PER_WARP = KIN / PM_CGROUPS, LDW = COLS_PER_WARP < 32 ? COLS_PER_WARP : 32;
 #pragma unroll
-        for (int h = 0; h < COLS_PER_WARP / 32; ++h) {
-            const int col = (warp >> 2) * COLS_PER_WARP + h * 32;
-            uint32_t r[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * KIN + (uint32_t)col, r);
+        for (int h = 0; h < COLS_PER_WARP / LDW; ++h) {
+            const int col = (warp >> 2) * COLS_PER_WARP + h * LDW;
+            uint32_t r[LDW];
+            tc::tmem_ld<LDW>(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * KIN + (uint32_t)col, r);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(a.dW + n * KIN + col + j, __uint_as_float(r[j]));
+            for (int j = 0; j < LDW; ++j) atomicAdd(a.dW + n * KIN + col + j, __uint_as_float(r[j]));
         }
     }
     tc::fence_before_sync();
@@ -659,12 +675,12 @@ int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a
     if (n_tiles < blocks) blocks = (int)n_tiles;
     if (mode == 0) {
         const int smem = MlpSmem<64>::TOTAL;
-        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_layer_fwd_kernel<0, 64><<<blocks, PM_THREADS, smem, st>>>(a);
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_fwd_kernel<0, 64, 256><<<blocks, 256, smem, st>>>(a);
     } else {
         const int smem = MlpSmem<128>::TOTAL;
-        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_layer_fwd_kernel<1, 128><<<blocks, PM_THREADS, smem, st>>>(a);
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_fwd_kernel<1, 128, 512><<<blocks, 512, smem, st>>>(a);
     }
     KDF_LAUNCH_CHECK();
     return KDF_OK;
@@ -693,12 +709,12 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
     if (n_tiles < blocks) blocks = (int)n_tiles;
     if (mode == 0) {
         const int smem = MlpBwdSmem<64>::TOTAL;
-        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_layer_bwd_kernel<0, 64><<<blocks, PM_THREADS, smem, st>>>(a);
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<0, 64, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_bwd_kernel<0, 64, 512><<<blocks, 512, smem, st>>>(a);
     } else {
         const int smem = MlpBwdSmem<128>::TOTAL;
-        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_layer_bwd_kernel<1, 128><<<blocks, PM_THREADS, smem, st>>>(a);
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<1, 128, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_bwd_kernel<1, 128, 512><<<blocks, 512, smem, st>>>(a);
     }
     KDF_LAUNCH_CHECK();
     return KDF_OK;
