@@ -274,6 +274,17 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
                         int dtype_feat, float grad_scale,
                         void *d_logits, float *scalars, void *workspace, void *stream);
 
+/* ---------------------------------------------------------------- FPN-lite merge
+ * CameraFPNLite.forward (fusion_module.py:51-64): every lateral is resized to the largest map with
+ * F.interpolate(mode="bilinear", align_corners=False) (:61-62) and summed (:63).  One pass here:
+ *   out[B,H,W,C] = base[B,H,W,C] + bilinear(lo_a[B,h,w,C]) (+ bilinear(lo_b[B,h,w,C]) if non-null)
+ * pixel-major rows, f32 or bf16 storage (fp32 arithmetic), ATen's source-index rule for any (h,w)->(H,W).
+ * kdf_fpn_up2_bwd is the adjoint of the resize for the exact 2x case (H=2h, W=2w; what the model uses):
+ *   grad_lo[B,h,w,C] = resize^T(grad_out[B,2h,2w,C]); the gradient w.r.t. base is grad_out itself. */
+int kdf_fpn_merge_fwd(const void *base, const void *lo_a, const void *lo_b, int dtype,
+                      int B, int H, int W, int h, int w, int C, void *out, void *stream);
+int kdf_fpn_up2_bwd(const void *grad_out, int dtype, int B, int h, int w, int C, void *grad_lo, void *stream);
+
 /* ---------------------------------------------------------------- training-step helpers
  * Confusion matrix of SegmentationMetrics.update (trainer.py:18-26):
  *   conf[t,p] += 1 over pixels with label t != ignore, 0 <= t < K, p = argmax_k logits.

@@ -65,9 +65,15 @@ class CameraFPNLite(nn.Module):
             size = tuple(self.target_size)
         else:
             size = tuple(max((feats[s].shape[-2:] for s in self.stages_to_use), key=lambda hw: hw[0] * hw[1]))
+        lats = [self.laterals[s](feats[s]) for s in self.stages_to_use]
+        # one streaming pass when the pyramid is "one full-resolution map + one or two maps at half resolution,
+        # in that order" (the reference configuration: stage3 @64x64, stage4/5 @32x32)
+        if len(lats) >= 2 and tuple(lats[0].shape[-2:]) == size:
+            merged = ops.fpn_merge(lats[0], lats[1:])
+            if merged is not None:
+                return self.post(merged)
         total = None
-        for s in self.stages_to_use:
-            lat = self.laterals[s](feats[s])
+        for lat in lats:
             if tuple(lat.shape[-2:]) != size:
                 lat = F.interpolate(lat, size=size, mode="bilinear", align_corners=False)
             total = lat if total is None else total + lat

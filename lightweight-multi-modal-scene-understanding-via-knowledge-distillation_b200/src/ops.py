@@ -14,7 +14,7 @@ from . import native as _n
 from .native import call, dtype_code, lib, ptr, require_cuda, stream_ptr
 
 __all__ = [
-    "bn_act", "run_fused",
+    "bn_act", "run_fused", "fpn_merge",
     "bev_range_constants", "bev_index", "bev_project", "BevProjectFn",
     "fused_fusion", "kd_loss_fwd_bwd", "KDLossFn", "confusion_matrix_", "adamw_flat_",
 ]
@@ -363,6 +363,62 @@ def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None):
     return _FusedFusionFn.apply(cam_pre, lid_pre, cam_bn.weight, cam_bn.bias, lid_bn.weight, lid_bn.bias,
                                 cs[0], cs[1], cs[2], cs[3], ls[0], ls[1], ls[2], ls[3], cs[4], _MODES[mode],
                                 w1, b1, w2, b2)
+
+
+# ----------------------------------------------------------------------------- FPN-lite merge
+def _nhwc_rows(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """[B,C,H,W] -> its [B,H,W,C] memory if x is dense channels-last (no copy), else None."""
+    if x.dim() != 4:
+        return None
+    y = x.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else None
+
+
+class _FpnMergeFn(torch.autograd.Function):
+    """out = base + bilinear(lo_a) [+ bilinear(lo_b)] (align_corners=False), NHWC; backward = the incoming
+    gradient for ``base`` and ONE adjoint resize shared by the low-resolution inputs (exact 2x)."""
+
+    @staticmethod
+    def forward(ctx, base, lo_a, lo_b):
+        B, C, H, W = base.shape
+        h, w = lo_a.shape[-2:]
+        out = torch.empty(B, H, W, C, dtype=base.dtype, device=base.device)
+        call("kdf_fpn_merge_fwd", ptr(_nhwc_rows(base)), ptr(_nhwc_rows(lo_a)), ptr(_nhwc_rows(lo_b)) if lo_b is not None else None,
+             dtype_code(base), B, H, W, h, w, C, ptr(out), stream_ptr(base.device))
+        ctx.dims = (B, C, h, w)
+        ctx.two = lo_b is not None
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, h, w = ctx.dims
+        gr = _nhwc_rows(g)
+        if gr is None:
+            g = g.contiguous(memory_format=torch.channels_last)
+            gr = g.permute(0, 2, 3, 1)
+        glo = torch.empty(B, h, w, C, dtype=g.dtype, device=g.device)
+        call("kdf_fpn_up2_bwd", ptr(gr), dtype_code(g), B, h, w, C, ptr(glo), stream_ptr(g.device))
+        glo = glo.permute(0, 3, 1, 2)
+        return g, glo, (glo if ctx.two else None)
+
+
+def fpn_merge(base: torch.Tensor, lows: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Fused FPN-lite merge when the layout allows it (dense channels-last CUDA maps of one dtype, one or two
+    low-resolution maps at exactly half the base resolution, C a multiple of 8); None otherwise (the caller
+    then composes F.interpolate + adds)."""
+    if not (1 <= len(lows) <= 2) or not base.is_cuda:
+        return None
+    B, C, H, W = base.shape
+    for t in lows:
+        if t.dtype != base.dtype or t.shape[0] != B or t.shape[1] != C or tuple(t.shape[-2:]) != (H // 2, W // 2):
+            return None
+    if H % 2 or W % 2 or C % 8 or base.dtype not in (torch.float32, torch.bfloat16):
+        return None
+    if any(_nhwc_rows(t) is None for t in (base, *lows)):
+        return None
+    if len(lows) == 2 and tuple(lows[0].shape) != tuple(lows[1].shape):
+        return None
+    return _FpnMergeFn.apply(base, lows[0], lows[1] if len(lows) == 2 else None)
 
 
 # ----------------------------------------------------------------------------- (3) distillation loss

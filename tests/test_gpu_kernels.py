@@ -514,3 +514,31 @@ def test_fusion_weighted_tensor_core_kernels_vs_fp32_autograd(ops, M):
     assert l2(gaff, ref_aff) < 1e-2, l2(gaff, ref_aff)
     for name, got, want in (("w1", gw1, rw1.grad), ("b1", gb1, rb1.grad), ("w2", gw2, rw2.grad), ("b2", gb2, rb2.grad)):
         assert l2(got, want) < 1e-2, (name, l2(got, want))
+
+
+@pytest.mark.parametrize("dtype,two", [(torch.float32, True), (torch.float32, False), (torch.bfloat16, True)])
+def test_fpn_merge_vs_interpolate(ops, dtype, two):
+    """out = base + bilinear(lo_a) (+ bilinear(lo_b)) against F.interpolate(align_corners=False) + adds
+    (fusion_module.py:61-63), forward and the three input gradients: 1e-5 relative in fp32, 1e-2 in bf16."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W = 2, 128, 64, 48
+    mk = lambda *s: torch.randn(*s, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    base, lo_a, lo_b = mk(B, C, H, W), mk(B, C, H // 2, W // 2), mk(B, C, H // 2, W // 2)
+    lows = [lo_a, lo_b] if two else [lo_a]
+    leaves = [t.clone().requires_grad_(True) for t in [base] + lows]
+    out = ops.fpn_merge(leaves[0], leaves[1:])
+    assert out is not None and out.shape == (B, C, H, W) and out.dtype == dtype
+    gout = torch.randn(B, C, H, W, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    out.backward(gout)
+    ref_leaves = [t.clone().float().requires_grad_(True) for t in [base] + lows]
+    ref = ref_leaves[0]
+    for t in ref_leaves[1:]:
+        ref = ref + F.interpolate(t, size=(H, W), mode="bilinear", align_corners=False)
+    ref.backward(gout.float())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(out.float().cpu(), ref.detach().cpu()) < tol
+    for a, b in zip(leaves, ref_leaves):
+        assert rel_err(a.grad.float().cpu(), b.grad.cpu()) < tol
+    # layouts the fused path does not serve are declined (the module then composes torch ops)
+    assert ops.fpn_merge(base, [mk(B, C, H // 4, W // 4)]) is None
