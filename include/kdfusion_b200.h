@@ -274,6 +274,11 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
                         int dtype_feat, float grad_scale,
                         void *d_logits, float *scalars, void *workspace, void *stream);
 
+/* g[m,c] += bc[c]*x[m,c] + ac[c] over rows [M,C] (in place): the batch-statistics part of a BatchNorm backward
+ * (nn.BatchNorm2d inside Conv1x1, fusion_module.py:11-15) whose per-row part and column sums came out of the fused
+ * fusion backward; bc / ac f32 [C] are formed by the caller from those sums. */
+int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const float *bc, const float *ac, void *stream);
+
 /* ---------------------------------------------------------------- FPN-lite merge
  * CameraFPNLite.forward (fusion_module.py:51-64): every lateral is resized to the largest map with
  * F.interpolate(mode="bilinear", align_corners=False) (:61-62) and summed (:63).  One pass here:

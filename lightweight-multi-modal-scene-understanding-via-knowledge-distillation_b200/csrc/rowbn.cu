@@ -348,6 +348,38 @@ static int launch_reduce(const ReduceArgs &a, int dtype, cudaStream_t st) {
     return KDF_OK;
 }
 
+
+// g[m,c] += bc[c]*x[m,c] + ac[c] over rows [M,C]: the second half of a BatchNorm backward whose first half (the
+// per-row part and the two column sums) was produced by another kernel (the fused fusion backward).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rows_axpb_kernel(T *__restrict__ g, const T *__restrict__ x, const float *__restrict__ bc, const float *__restrict__ ac,
+                 int64_t M, int C) {
+    constexpr int V = 16 / sizeof(T);
+    const int cg = C / V;
+    const int64_t total = M * cg, nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+        const int c = (int)(i % cg) * V;
+        uint4 gv = *(reinterpret_cast<const uint4 *>(g) + i);
+        const uint4 xv = ldg_stream_u4(reinterpret_cast<const uint4 *>(x) + i);
+        float gf[V], xf[V];
+        if (sizeof(T) == 2) {
+            gf[0] = bf16_lo(gv.x); gf[1] = bf16_hi(gv.x); gf[2] = bf16_lo(gv.y); gf[3] = bf16_hi(gv.y);
+            gf[4 % V] = bf16_lo(gv.z); gf[5 % V] = bf16_hi(gv.z); gf[6 % V] = bf16_lo(gv.w); gf[7 % V] = bf16_hi(gv.w);
+            xf[0] = bf16_lo(xv.x); xf[1] = bf16_hi(xv.x); xf[2] = bf16_lo(xv.y); xf[3] = bf16_hi(xv.y);
+            xf[4 % V] = bf16_lo(xv.z); xf[5 % V] = bf16_hi(xv.z); xf[6 % V] = bf16_lo(xv.w); xf[7 % V] = bf16_hi(xv.w);
+        } else {
+            gf[0] = __uint_as_float(gv.x); gf[1] = __uint_as_float(gv.y); gf[2] = __uint_as_float(gv.z); gf[3] = __uint_as_float(gv.w);
+            xf[0] = __uint_as_float(xv.x); xf[1] = __uint_as_float(xv.y); xf[2] = __uint_as_float(xv.z); xf[3] = __uint_as_float(xv.w);
+        }
+#pragma unroll
+        for (int q = 0; q < V; ++q) gf[q] = fmaf(__ldg(bc + c + q), xf[q], gf[q]) + __ldg(ac + c + q);
+        if (sizeof(T) == 2) gv = make_uint4(pack_bf16(gf[0], gf[1]), pack_bf16(gf[2], gf[3]), pack_bf16(gf[4 % V], gf[5 % V]), pack_bf16(gf[6 % V], gf[7 % V]));
+        else gv = make_uint4(__float_as_uint(gf[0]), __float_as_uint(gf[1]), __float_as_uint(gf[2]), __float_as_uint(gf[3]));
+        *(reinterpret_cast<uint4 *>(g) + i) = gv;
+    }
+}
+
 }  // namespace kdf
 
 using namespace kdf;
@@ -422,5 +454,22 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
 }
 
 size_t kdf_rowbn_bwd_workspace_bytes(int C) { return kdf_rowbn_workspace_bytes(C) + sizeof(float) * 2 * (size_t)C; }
+
+int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const float *bc, const float *ac, void *stream) {
+    KDF_CHECK_ARG(M >= 0 && C > 0, "rows_axpb: bad sizes");
+    KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "rows_axpb: bad dtype %d", dtype);
+    KDF_CHECK_ARG(C % (dtype == KDF_F32 ? 4 : 8) == 0, "rows_axpb: C=%d must fill 16-byte groups", C);
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(g && x && bc && ac, "rows_axpb: null pointer");
+    KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "rows_axpb: rows must be 16-byte aligned");
+    const int64_t total = M * (C / (dtype == KDF_F32 ? 4 : 8));
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == KDF_F32) rows_axpb_kernel<float><<<(int)blocks, 256, 0, st>>>((float *)g, (const float *)x, bc, ac, M, C);
+    else rows_axpb_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((__nv_bfloat16 *)g, (const __nv_bfloat16 *)x, bc, ac, M, C);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
 
 }  // extern "C"

@@ -337,9 +337,9 @@ class _FusedFusionFn(torch.autograd.Function):
             dgamma = invstd * (s1 - mean * s0)          # sum dy * xhat
             dbeta = s0
             if ctx.batch_stats:                         # chain through the batch mean / variance
-                bc = -(scale * invstd * dgamma) / M
-                ac = -(scale * s0) / M - bc * mean
-                g.addcmul_(x, bc.to(f32)).add_(ac)
+                bc = (-(scale * invstd * dgamma) / M).to(f32).contiguous()
+                ac = (-(scale * s0) / M - bc * mean).to(f32).contiguous()
+                call("kdf_rows_axpb", ptr(g), ptr(x), dt, M, C, ptr(bc), ptr(ac), st)      # g += bc*x + ac, one pass
             grads_gb.append((dgamma, dbeta))
         pd = ctx.param_dtypes[0]
         return (g_cam, g_lid, grads_gb[0][0].to(pd), grads_gb[0][1].to(pd), grads_gb[1][0].to(pd), grads_gb[1][1].to(pd),
