@@ -279,6 +279,21 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
  * fusion backward; bc / ac f32 [C] are formed by the caller from those sums. */
 int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const float *bc, const float *ac, void *stream);
 
+/* ---------------------------------------------------------------- depthwise 3x3 convolution
+ * nn.Conv2d(C, C, 3, stride, padding=1, groups=C, bias=False) of the inverted-residual blocks
+ * (camera_encoder.py:27-33), DWSeparableConv (fusion_module.py:24-27) and the concat fusion (:80-82), over
+ * pixel-major maps: in [B,H,W,C], out [B,OH,OW,C] with OH = (H-1)/stride + 1; f32 or bf16 storage, fp32
+ * arithmetic; weight f32 [C,9] (= the contiguous [C,1,3,3] parameter).  stride 1 or 2.
+ *   kdf_dwconv3x3_fwd        out = conv(in, weight); flip=1 (stride 1 only) uses the taps reversed
+ *   kdf_dwconv3x3_bwd_data   grad_in [B,H,W,C] from grad_out [B,OH,OW,C]
+ *   kdf_dwconv3x3_bwd_weight grad_weight f32 [C,9] (zeroed by the call) from in and grad_out */
+int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
+                      int flip, void *out, void *stream);
+int kdf_dwconv3x3_bwd_data(const void *grad_out, const float *weight, int dtype, int B, int H, int W, int C, int stride,
+                           void *grad_in, void *stream);
+int kdf_dwconv3x3_bwd_weight(const void *in, const void *grad_out, int dtype, int B, int H, int W, int C, int stride,
+                             float *grad_weight, void *stream);
+
 /* ---------------------------------------------------------------- FPN-lite merge
  * CameraFPNLite.forward (fusion_module.py:51-64): every lateral is resized to the largest map with
  * F.interpolate(mode="bilinear", align_corners=False) (:61-62) and summed (:63).  One pass here:

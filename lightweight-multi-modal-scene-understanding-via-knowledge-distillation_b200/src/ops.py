@@ -135,6 +135,70 @@ def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[to
     return y.view(B, H, W, C).permute(0, 3, 1, 2) if four_d else y
 
 
+# ----------------------------------------------------------------------------- depthwise 3x3 convolution
+def _nhwc_rows(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """[B,C,H,W] -> its [B,H,W,C] memory if x is dense channels-last (no copy), else None."""
+    if x.dim() != 4:
+        return None
+    y = x.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else None
+
+
+class _DwConv3x3Fn(torch.autograd.Function):
+    """nn.Conv2d(C, C, 3, stride, padding=1, groups=C, bias=False) over a dense channels-last map."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        B, C, H, W = x.shape
+        OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+        w = weight.detach().reshape(C, 9).float().contiguous()
+        out = torch.empty(B, OH, OW, C, dtype=x.dtype, device=x.device)
+        call("kdf_dwconv3x3_fwd", ptr(_nhwc_rows(x)), ptr(w), dtype_code(x), B, H, W, C, stride, 0, ptr(out), stream_ptr(x.device))
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.wshape, ctx.wdtype = stride, weight.shape, weight.dtype
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, C, H, W = x.shape
+        if g.dtype != x.dtype:
+            g = g.to(x.dtype)
+        gr = _nhwc_rows(g)
+        if gr is None:
+            g = g.contiguous(memory_format=torch.channels_last)
+            gr = g.permute(0, 2, 3, 1)
+        dev, st = x.device, stream_ptr(x.device)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(B, H, W, C, dtype=x.dtype, device=dev)
+            call("kdf_dwconv3x3_bwd_data", ptr(gr), ptr(w), dtype_code(x), B, H, W, C, ctx.stride, ptr(gx), st)
+            gx = gx.permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty(C, 9, dtype=torch.float32, device=dev)
+            call("kdf_dwconv3x3_bwd_weight", ptr(_nhwc_rows(x)), ptr(gr), dtype_code(x), B, H, W, C, ctx.stride, ptr(gw), st)
+            gw = gw.view(ctx.wshape).to(ctx.wdtype)
+        return gx, gw, None
+
+
+def dwconv3x3(conv, x: torch.Tensor) -> Optional[torch.Tensor]:
+    """Depthwise 3x3 ``nn.Conv2d`` on the hand-written kernels when it is one (3x3, padding 1, stride 1|2, no bias,
+    groups == channels) and ``x`` is a dense channels-last CUDA map; None otherwise (the caller runs the module)."""
+    import torch.nn as nn
+    if not (isinstance(conv, nn.Conv2d) and x.is_cuda and x.dim() == 4):
+        return None
+    C = conv.in_channels
+    if not (conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.stride in ((1, 1), (2, 2)) and conv.bias is None
+            and conv.padding_mode == "zeros"):
+        return None
+    if torch.is_autocast_enabled() and x.dtype == torch.float32:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    if x.dtype not in (torch.float32, torch.bfloat16) or C % 8 or C > 1024 or _nhwc_rows(x) is None:
+        return None
+    return _DwConv3x3Fn.apply(x, conv.weight, conv.stride[0])
+
+
 def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run an ``nn.Sequential`` of conv / BatchNorm / ReLU(6) layers with every BatchNorm(+activation)
     group executed by the fused row kernels; ``residual`` is added after the LAST BatchNorm group.
@@ -152,7 +216,8 @@ def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> 
             x = bn_act(x, m, act, residual if i == last_bn else None)
             i += step
         else:
-            x = m(x)
+            y = dwconv3x3(m, x)                  # depthwise 3x3 on the stencil kernels, everything else on the library
+            x = m(x) if y is None else y
             i += 1
     if residual is not None and last_bn < 0:
         x = x + residual
@@ -366,14 +431,6 @@ def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None):
 
 
 # ----------------------------------------------------------------------------- FPN-lite merge
-def _nhwc_rows(x: torch.Tensor) -> Optional[torch.Tensor]:
-    """[B,C,H,W] -> its [B,H,W,C] memory if x is dense channels-last (no copy), else None."""
-    if x.dim() != 4:
-        return None
-    y = x.permute(0, 2, 3, 1)
-    return y if y.is_contiguous() else None
-
-
 class _FpnMergeFn(torch.autograd.Function):
     """out = base + bilinear(lo_a) [+ bilinear(lo_b)] (align_corners=False), NHWC; backward = the incoming
     gradient for ``base`` and ONE adjoint resize shared by the low-resolution inputs (exact 2x)."""

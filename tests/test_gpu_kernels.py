@@ -542,3 +542,36 @@ def test_fpn_merge_vs_interpolate(ops, dtype, two):
         assert rel_err(a.grad.float().cpu(), b.grad.cpu()) < tol
     # layouts the fused path does not serve are declined (the module then composes torch ops)
     assert ops.fpn_merge(base, [mk(B, C, H // 4, W // 4)]) is None
+
+
+@pytest.mark.parametrize("C,H,W,stride,dtype", [(32, 20, 28, 1, torch.float32), (192, 17, 23, 2, torch.float32),
+                                                (384, 16, 16, 1, torch.float32), (64, 9, 31, 2, torch.float32),
+                                                (768, 8, 8, 1, torch.bfloat16), (192, 32, 32, 2, torch.bfloat16),
+                                                (128, 64, 64, 1, torch.bfloat16)])
+def test_dwconv3x3_vs_torch_conv2d(ops, C, H, W, stride, dtype):
+    """Depthwise 3x3 (padding 1, stride 1|2, no bias) against nn.Conv2d(groups=C) as the reference builds it
+    (camera_encoder.py:27-33, fusion_module.py:24-27): output, d input, d weight.  fp32: 1e-5 relative;
+    bf16 storage with fp32 accumulation: 1e-2 against the fp32 convolution of the same bf16 values."""
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(C + H)
+    conv = nn.Conv2d(C, C, 3, stride=stride, padding=1, groups=C, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(C, 1, 3, 3, generator=g) * 0.3)
+    x = torch.randn(3, C, H, W, generator=g).to(dtype)
+    ref_x = x.float().clone().requires_grad_(True)
+    ref = conv(ref_x)
+    gout = torch.randn(ref.shape, generator=g).to(dtype)
+    ref.backward(gout.float())
+    ref_gw = conv.weight.grad.clone()
+    conv.weight.grad = None
+    conv.cuda()
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = ops.dwconv3x3(conv, xc)
+    assert out is not None and out.dtype == dtype and tuple(out.shape) == tuple(ref.shape)
+    out.backward(gout.cuda())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(out.float().cpu(), ref.detach()) < tol
+    assert rel_err(xc.grad.float().cpu(), ref_x.grad) < tol
+    assert rel_err(conv.weight.grad.cpu(), ref_gw) < (2e-5 if dtype == torch.float32 else 1e-2)
+    # not a depthwise 3x3: declined
+    assert ops.dwconv3x3(nn.Conv2d(C, C, 1).cuda(), xc) is None
