@@ -284,11 +284,13 @@ int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const flo
  * (camera_encoder.py:27-33), DWSeparableConv (fusion_module.py:24-27) and the concat fusion (:80-82), over
  * pixel-major maps: in [B,H,W,C], out [B,OH,OW,C] with OH = (H-1)/stride + 1; f32 or bf16 storage, fp32
  * arithmetic; weight f32 [C,9] (= the contiguous [C,1,3,3] parameter).  stride 1 or 2.
- *   kdf_dwconv3x3_fwd        out = conv(in, weight); flip=1 (stride 1 only) uses the taps reversed
+ *   kdf_dwconv3x3_fwd        out = conv(in, weight); flip=1 (stride 1 only) uses the taps reversed; stats (nullable,
+ *                            f64 [2,C], zeroed by the call) receives the per-channel sum / sum of squares of the
+ *                            stored outputs -- the batch statistics of the BatchNorm that follows (kdf_bn_finalize)
  *   kdf_dwconv3x3_bwd_data   grad_in [B,H,W,C] from grad_out [B,OH,OW,C]
  *   kdf_dwconv3x3_bwd_weight grad_weight f32 [C,9] (zeroed by the call) from in and grad_out */
 int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
-                      int flip, void *out, void *stream);
+                      int flip, void *out, double *stats, void *stream);
 int kdf_dwconv3x3_bwd_data(const void *grad_out, const float *weight, int dtype, int B, int H, int W, int C, int stride,
                            void *grad_in, void *stream);
 int kdf_dwconv3x3_bwd_weight(const void *in, const void *grad_out, int dtype, int B, int H, int W, int C, int stride,

@@ -55,20 +55,24 @@ __device__ __forceinline__ void dw_load_taps(const float *__restrict__ w, int c0
 template <typename T, int STRIDE, bool FLIP>
 __global__ void __launch_bounds__(256, 2)
 dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C][9] */, T *__restrict__ out,
-                     int B, int H, int W, int C, int OH, int OW) {
+                     int B, int H, int W, int C, int OH, int OW, double *__restrict__ stats /* nullable [2][C] */) {
     typedef DwChunk<T> K;
+    __shared__ float sred[256 * 2 * DW_V];              // BatchNorm statistics of the stored outputs (only when asked for)
     constexpr int IN_ROWS = (DW_R - 1) * STRIDE + 3;
     // grid.x * blockDim.x covers one output row of (ox, channel group); grid.y strides over (frame, row block):
     // all index arithmetic is 32-bit and the thread keeps its channel group (taps in registers)
     const int cg = C / DW_V;
     const int oyb_n = (OH + DW_R - 1) / DW_R;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= OW * cg) return;
-    const int ox = idx / cg, g = idx - ox * cg;
+    const bool live = idx < OW * cg;
+    const int ox = live ? idx / cg : 0, g = live ? idx - ox * cg : 0;
     float wr[9][DW_V];
     dw_load_taps<FLIP>(w, g * DW_V, wr);
+    float s_sum[DW_V], s_sq[DW_V];
+#pragma unroll
+    for (int q = 0; q < DW_V; ++q) { s_sum[q] = 0.f; s_sq[q] = 0.f; }
     const int ix0 = ox * STRIDE - 1;
-    for (int rb = blockIdx.y; rb < B * oyb_n; rb += gridDim.y) {
+    for (int rb = blockIdx.y; live && rb < B * oyb_n; rb += gridDim.y) {
         const int b = rb / oyb_n, oyb = rb - b * oyb_n;
         const int oy0 = oyb * DW_R;
         const int iy0 = oy0 * STRIDE - 1;
@@ -108,7 +112,33 @@ dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C
 #pragma unroll
         for (int r = 0; r < DW_R; ++r) {
             const int oy = oy0 + r;
-            if (oy < OH) K::st(out + (((int64_t)b * OH + oy) * OW + ox) * C + g * DW_V, acc[r]);
+            if (oy < OH) {
+                K::st(out + (((int64_t)b * OH + oy) * OW + ox) * C + g * DW_V, acc[r]);
+                if (stats) {
+#pragma unroll
+                    for (int q = 0; q < DW_V; ++q) {
+                        const float v = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(acc[r][q])) : acc[r][q];   // the value stored
+                        s_sum[q] += v;
+                        s_sq[q] = fmaf(v, v, s_sq[q]);
+                    }
+                }
+            }
+        }
+    }
+    if (stats) {                                         // threads tid = g (mod cg) share a channel group
+#pragma unroll
+        for (int q = 0; q < DW_V; ++q) { sred[threadIdx.x * 2 * DW_V + q] = s_sum[q]; sred[threadIdx.x * 2 * DW_V + DW_V + q] = s_sq[q]; }
+        __syncthreads();
+        const int g0 = (blockIdx.x * blockDim.x) % cg;   // channel group of thread 0 of this CTA
+        for (int i = threadIdx.x; i < cg * 2 * DW_V; i += blockDim.x) {
+            const int gg = i / (2 * DW_V), e = i - gg * 2 * DW_V;
+            // first thread of the CTA whose channel group is gg, then every cg-th
+            int t0 = gg - g0;
+            if (t0 < 0) t0 += cg;
+            float v = 0.f;
+            for (int t = t0; t < (int)blockDim.x; t += cg) v += sred[t * 2 * DW_V + e];
+            const int which = e / DW_V, q = e - which * DW_V;
+            if (v != 0.f) atomicAdd(stats + which * C + gg * DW_V + q, (double)v);
         }
     }
 }
@@ -255,10 +285,13 @@ using namespace kdf;
 extern "C" {
 
 int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
-                      int flip, void *out, void *stream) {
+                      int flip, void *out, double *stats, void *stream) {
     if (int e = dw_check("dwconv3x3_fwd", dtype, B, H, W, C, stride)) return e;
     KDF_CHECK_ARG(!(flip && stride != 1), "dwconv3x3_fwd: flipped taps are the stride-1 data gradient only");
-    if (B == 0) return KDF_OK;
+    if (B == 0) {
+        if (stats) KDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, as_stream(stream)));
+        return KDF_OK;
+    }
     KDF_CHECK_ARG(in && weight && out, "dwconv3x3_fwd: null pointer");
     KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "dwconv3x3_fwd: maps must be 16-byte aligned");
     const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
@@ -270,7 +303,8 @@ int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int
     if (gy > row_blocks) gy = row_blocks;
     const dim3 grid((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy));
     cudaStream_t st = as_stream(stream);
-#define KDF_DW(T, S, F) dwconv3x3_fwd_kernel<T, S, F><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW)
+    if (stats) KDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
+#define KDF_DW(T, S, F) dwconv3x3_fwd_kernel<T, S, F><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats)
     if (dtype == KDF_F32) { if (stride == 2) KDF_DW(float, 2, false); else if (flip) KDF_DW(float, 1, true); else KDF_DW(float, 1, false); }
     else { if (stride == 2) KDF_DW(__nv_bfloat16, 2, false); else if (flip) KDF_DW(__nv_bfloat16, 1, true); else KDF_DW(__nv_bfloat16, 1, false); }
 #undef KDF_DW
@@ -280,7 +314,7 @@ int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int
 
 int kdf_dwconv3x3_bwd_data(const void *grad_out, const float *weight, int dtype, int B, int H, int W, int C, int stride,
                            void *grad_in, void *stream) {
-    if (stride == 1) return kdf_dwconv3x3_fwd(grad_out, weight, dtype, B, H, W, C, 1, 1, grad_in, stream);
+    if (stride == 1) return kdf_dwconv3x3_fwd(grad_out, weight, dtype, B, H, W, C, 1, 1, grad_in, nullptr, stream);
     if (int e = dw_check("dwconv3x3_bwd_data", dtype, B, H, W, C, stride)) return e;
     if (B == 0) return KDF_OK;
     KDF_CHECK_ARG(grad_out && weight && grad_in, "dwconv3x3_bwd_data: null pointer");

@@ -39,7 +39,7 @@ _SIGNATURES = {
     "kdf_bev_bwd_affine": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "kdf_point_moments": (C.c_int, [_vp, _i64, _vp, _vp]),
     "kdf_mlp_layer_fwd": (C.c_int, [_i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "kdf_dwconv3x3_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "kdf_dwconv3x3_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kdf_dwconv3x3_bwd_data": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "kdf_dwconv3x3_bwd_weight": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "kdf_rows_axpb": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),

@@ -110,7 +110,7 @@ def _bn_prepare(rows: torch.Tensor, bn, pre_bias=None):
 
 
 def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
-           pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+           pre_bias: Optional[torch.Tensor] = None, col_sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(bn(x [+ pre_bias])) [+ residual]`` with the BatchNorm module's parameters / buffers (updated
     like nn.BatchNorm does in training).  ``x`` is a channels-last [B,C,H,W] tensor or rows [M,C].
     ``pre_bias`` is the bias of the layer that produced ``x``: instead of adding it to every element
@@ -130,7 +130,16 @@ def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[to
         rows = rows.contiguous()
     if res is not None and (res.dtype != rows.dtype or not res.is_contiguous()):
         res = res.to(rows.dtype).contiguous()
-    scale, shift, mean, invstd, use_batch = _bn_prepare(rows, bn, pre_bias)
+    if col_sums is not None and (bn.training or bn.running_mean is None):
+        # the producing kernel already reduced sum / sum of squares of these rows: finalise only (no statistics pass)
+        from .point_mlp import bn_finalize
+        track = bn.training and bn.track_running_stats and bn.running_mean is not None
+        with torch.no_grad():
+            mean, invstd, scale, shift = bn_finalize(col_sums, rows.shape[0], bn,
+                                                     pre_bias.detach().float().contiguous() if pre_bias is not None else None, track)
+        use_batch = True
+    else:
+        scale, shift, mean, invstd, use_batch = _bn_prepare(rows, bn, pre_bias)
     y = _RowBNActFn.apply(rows, bn.weight, bn.bias, scale, shift, mean, invstd, _ACT[act], use_batch, res, pre_bias)
     return y.view(B, H, W, C).permute(0, 3, 1, 2) if four_d else y
 
@@ -148,18 +157,22 @@ class _DwConv3x3Fn(torch.autograd.Function):
     """nn.Conv2d(C, C, 3, stride, padding=1, groups=C, bias=False) over a dense channels-last map."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride):
+    def forward(ctx, x, weight, stride, want_stats):
         B, C, H, W = x.shape
         OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
         w = weight.detach().reshape(C, 9).float().contiguous()
         out = torch.empty(B, OH, OW, C, dtype=x.dtype, device=x.device)
-        call("kdf_dwconv3x3_fwd", ptr(_nhwc_rows(x)), ptr(w), dtype_code(x), B, H, W, C, stride, 0, ptr(out), stream_ptr(x.device))
+        stats = torch.empty(2, C, dtype=torch.float64, device=x.device) if want_stats else None
+        call("kdf_dwconv3x3_fwd", ptr(_nhwc_rows(x)), ptr(w), dtype_code(x), B, H, W, C, stride, 0, ptr(out), ptr(stats),
+             stream_ptr(x.device))
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.wshape, ctx.wdtype = stride, weight.shape, weight.dtype
-        return out.permute(0, 3, 1, 2)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+        return out.permute(0, 3, 1, 2), stats
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gs=None):
         x, w = ctx.saved_tensors
         B, C, H, W = x.shape
         if g.dtype != x.dtype:
@@ -178,12 +191,13 @@ class _DwConv3x3Fn(torch.autograd.Function):
             gw = torch.empty(C, 9, dtype=torch.float32, device=dev)
             call("kdf_dwconv3x3_bwd_weight", ptr(_nhwc_rows(x)), ptr(gr), dtype_code(x), B, H, W, C, ctx.stride, ptr(gw), st)
             gw = gw.view(ctx.wshape).to(ctx.wdtype)
-        return gx, gw, None
+        return gx, gw, None, None
 
 
-def dwconv3x3(conv, x: torch.Tensor) -> Optional[torch.Tensor]:
+def dwconv3x3(conv, x: torch.Tensor, want_stats: bool = False):
     """Depthwise 3x3 ``nn.Conv2d`` on the hand-written kernels when it is one (3x3, padding 1, stride 1|2, no bias,
-    groups == channels) and ``x`` is a dense channels-last CUDA map; None otherwise (the caller runs the module)."""
+    groups == channels) and ``x`` is a dense channels-last CUDA map; None otherwise (the caller runs the module).
+    With ``want_stats`` returns (out, stats f64 [2,C]): the column sums the BatchNorm that follows needs."""
     import torch.nn as nn
     if not (isinstance(conv, nn.Conv2d) and x.is_cuda and x.dim() == 4):
         return None
@@ -196,7 +210,8 @@ def dwconv3x3(conv, x: torch.Tensor) -> Optional[torch.Tensor]:
         x = x.to(torch.get_autocast_dtype("cuda"))
     if x.dtype not in (torch.float32, torch.bfloat16) or C % 8 or C > 1024 or _nhwc_rows(x) is None:
         return None
-    return _DwConv3x3Fn.apply(x, conv.weight, conv.stride[0])
+    out, stats = _DwConv3x3Fn.apply(x, conv.weight, conv.stride[0], want_stats)
+    return (out, stats) if want_stats else out
 
 
 def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -206,18 +221,28 @@ def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> 
     import torch.nn as nn
     mods = list(seq)
     last_bn = max((i for i, m in enumerate(mods) if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d))), default=-1)
-    i = 0
+    i, col_sums = 0, None
     while i < len(mods):
         m = mods[i]
         if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
             act, step = None, 1
             if i + 1 < len(mods) and isinstance(mods[i + 1], (nn.ReLU, nn.ReLU6)):
                 act, step = ("relu6" if isinstance(mods[i + 1], nn.ReLU6) else "relu"), 2
-            x = bn_act(x, m, act, residual if i == last_bn else None)
+            x = bn_act(x, m, act, residual if i == last_bn else None, col_sums=col_sums)
+            col_sums = None
             i += step
         else:
-            y = dwconv3x3(m, x)                  # depthwise 3x3 on the stencil kernels, everything else on the library
-            x = m(x) if y is None else y
+            # depthwise 3x3 on the stencil kernels (which also reduce the statistics of a train-mode BatchNorm that
+            # follows), everything else on the library
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            fuse_stats = isinstance(nxt, nn.BatchNorm2d) and (nxt.training or nxt.running_mean is None)
+            y = dwconv3x3(m, x, want_stats=fuse_stats)
+            if y is None:
+                x = m(x)
+            elif fuse_stats:
+                x, col_sums = y
+            else:
+                x = y
             i += 1
     if residual is not None and last_bn < 0:
         x = x + residual
