@@ -64,6 +64,29 @@ class FlatAdamW(torch.optim.Optimizer):
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
                 p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
 
+    def detach_grads(self):
+        """Drop the ``.grad`` views so that the next backward hands each gradient over as a fresh tensor instead of
+        adding it into the view with one tiny kernel per parameter (96 launches for the weighted student);
+        ``gather_grads_`` then moves all of them into ``flat_grad`` with one multi-tensor copy."""
+        for p in self._params:
+            p.grad = None
+
+    @torch.no_grad()
+    def gather_grads_(self):
+        """flat_grad <- the gradients autograd produced since ``detach_grads`` (zeros where a parameter got none);
+        ``p.grad`` are views of ``flat_grad`` again afterwards."""
+        srcs, dsts = [], []
+        for p, off in zip(self._params, self._offsets):
+            view = self.flat_grad[off:off + p.numel()].view(p.shape)
+            if p.grad is None:
+                view.zero_()
+            else:
+                srcs.append(p.grad if p.grad.dtype == torch.float32 else p.grad.float())
+                dsts.append(view)
+            p.grad = view
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
+
     def set_hyper(self, lr: float, step: int):
         """Device-side (lr, step); called by step(), or by the caller before replaying a captured graph."""
         self._hyper.copy_(torch.tensor([lr, float(step)], dtype=torch.float32), non_blocking=True)

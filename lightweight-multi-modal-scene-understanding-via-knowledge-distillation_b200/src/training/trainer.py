@@ -160,7 +160,7 @@ class Trainer:
         return torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None)
 
     def _step_impl(self, imgs, pts, seg, update_hyper: bool):
-        self.optimizer.zero_grad()
+        self.optimizer.detach_grads()                    # gradients arrive as fresh tensors, gathered below in one copy
         with self._autocast():
             if self.teacher is not None:
                 with torch.no_grad():
@@ -176,6 +176,7 @@ class Trainer:
             logits, t_logits, seg, self.class_weights, s_feats, t_feats,
             T=self.kd_temperature, alpha=alpha, beta=beta, ignore_index=-1)
         torch.autograd.backward([logits] + list(s_feats), [d_logits] + list(d_feats))
+        self.optimizer.gather_grads_()                                  # one multi-tensor copy into the flat bucket
         allreduce_gradients_(self.optimizer.flat_grad)                  # one flat NCCL bucket (no-op at world 1)
         self.optimizer.step(grad_scale=1.0 / self.world_size, update_hyper=update_hyper)
         return terms, logits.detach()
