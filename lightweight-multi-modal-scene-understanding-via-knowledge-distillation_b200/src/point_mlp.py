@@ -56,8 +56,9 @@ _order_cache = {"ref": None, "key": None, "val": None}
 def cached_build_order(points: torch.Tensor, geom, grid_size):
     """``bev_build_order`` shared between encoders that project the SAME tensor object (the teacher and the
     student of a distillation step see the same sweep): keyed on object identity + version counter."""
-    key = (points._version, tuple(points.shape), tuple(geom), tuple(grid_size), torch.cuda.current_stream(points.device).cuda_stream,
-           torch.cuda.is_current_stream_capturing())
+    # keyed on the tensor object and its version, not on the stream: callers that project the same sweep from two
+    # streams build the ordering before forking (Trainer._prepare_shared), which orders both consumers after it
+    key = (points._version, tuple(points.shape), tuple(geom), tuple(grid_size), torch.cuda.is_current_stream_capturing())
     ref = _order_cache["ref"]
     if ref is not None and ref() is points and _order_cache["key"] == key:
         return _order_cache["val"]

@@ -111,7 +111,7 @@ class Trainer:
                  teacher: Optional[nn.Module] = None, kd_temperature: float = 4.0,
                  kd_alpha: float = 0.5, kd_beta: float = 1.0,
                  amp_dtype: Optional[torch.dtype] = None, verbose: bool = True,
-                 use_cuda_graph: bool = False, graph_warmup_steps: int = 3):
+                 use_cuda_graph: bool = False, graph_warmup_steps: int = 3, overlap_teacher: bool = True):
         self.model = model
         self.train_loader = train_loader
         self.val_loader = val_loader
@@ -148,6 +148,8 @@ class Trainer:
         self.last_loss_terms: Optional[torch.Tensor] = None
         # CUDA-graph replay of the whole step (forward + loss + backward + all-reduce + AdamW): the step is
         # ~800 launches of mostly small kernels, so at B200 speeds the host cannot issue them fast enough
+        self.overlap_teacher = overlap_teacher and teacher is not None
+        self._side = None
         self.use_cuda_graph = use_cuda_graph
         self.graph_warmup_steps = graph_warmup_steps
         self._graph = None
@@ -163,9 +165,25 @@ class Trainer:
         self.optimizer.detach_grads()                    # gradients arrive as fresh tensors, gathered below in one copy
         with self._autocast():
             if self.teacher is not None:
-                with torch.no_grad():
-                    t_logits, t_mid = self.teacher(imgs, pts, return_intermediates=True)
+                # The frozen teacher's forward does not depend on the student's: it runs on a side stream (a parallel
+                # branch of the captured graph), so that the two camera branches -- chains of small kernels that leave
+                # most SMs idle at their heads and tails -- fill each other's gaps.  The cell ordering both LiDAR
+                # encoders share is built first, on the main stream.
+                side = self._side_stream()
+                main = torch.cuda.current_stream(self.device)
+                if side is not None:
+                    self._prepare_shared(pts)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side), torch.no_grad():
+                        t_logits, t_mid = self.teacher(imgs, pts, return_intermediates=True)
+                else:
+                    with torch.no_grad():
+                        t_logits, t_mid = self.teacher(imgs, pts, return_intermediates=True)
                 logits, mid = self.model(imgs, pts, return_intermediates=True)
+                if side is not None:
+                    main.wait_stream(side)
+                    for t in [t_logits] + [t_mid[k] for k in MIMIC_TAPS]:
+                        t.record_stream(main)
                 s_feats = [mid[k] for k in MIMIC_TAPS]
                 t_feats = [t_mid[k] for k in MIMIC_TAPS]
                 alpha, beta = self.kd_alpha, self.kd_beta
@@ -180,6 +198,21 @@ class Trainer:
         allreduce_gradients_(self.optimizer.flat_grad)                  # one flat NCCL bucket (no-op at world 1)
         self.optimizer.step(grad_scale=1.0 / self.world_size, update_hyper=update_hyper)
         return terms, logits.detach()
+
+    def _side_stream(self):
+        if not self.overlap_teacher:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def _prepare_shared(self, pts):
+        """Cell ordering of the sweep, built once on the current stream before the teacher forks off (both LiDAR
+        encoders then hit the cache)."""
+        enc = getattr(getattr(self.model, "lidar_encoder", None), "encoder", None)
+        if enc is not None and hasattr(enc, "_geom") and pts.is_cuda and pts.dtype == torch.float32:
+            from .. import point_mlp
+            point_mlp.cached_build_order(pts, enc._geom, tuple(enc.grid_size))
 
     def _capture(self, imgs, pts, seg):
         self._static = {"image": torch.empty_like(imgs), "points": torch.empty_like(pts), "seg": torch.empty_like(seg)}
