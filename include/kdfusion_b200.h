@@ -195,6 +195,22 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
                       const void *input, int64_t M, const float *pro_a, const float *pro_b, const void *W_bf16,
                       int Kin, void *dy_prev, double *sums, float *dW, void *stream);
 
+/* Per-channel algebra between the layer kernels, one tiny launch each (BatchNorm1d of lidar_encoder.py:27,30,33):
+ *   kdf_mlp_l1_stats   batch statistics of layer 1 in closed form from the 14 point moments (it is linear in the point):
+ *                      q f32 [64,4] = scale1*W1, r f32 [64] = shift1 (the folded first layer of the mode-0 prologues),
+ *                      mean / invstd / scale f32 [64]; running statistics advanced when given (b1 joins the mean)
+ *   kdf_bn_bwd_coeffs  BatchNorm backward through the batch statistics as coefficients dz = gs*dy + ga + gb*z, and
+ *                      dgamma / dbeta, from sums f64 [2,C] = (sum dy, sum dy*z)
+ *   kdf_mlp_l1_bwd     layer 1 backward in closed form from kdf_mlp_layer_bwd(mode 0)'s sums f64 [5,64] and the moments:
+ *                      dW1 f32 [64,4], dgamma, dbeta f32 [64] */
+int kdf_mlp_l1_stats(const double *moments14, int64_t M, const float *W1, const float *b1, const float *gamma,
+                     const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                     float *q, float *r, float *mean, float *invstd, float *scale, void *stream);
+int kdf_bn_bwd_coeffs(const double *sums, int C, int64_t M, const float *mean, const float *invstd, const float *scale,
+                      float *gs, float *ga, float *gb, float *dgamma, float *dbeta, void *stream);
+int kdf_mlp_l1_bwd(const double *sums5x64, const double *moments14, int64_t M, const float *W1, const float *mean,
+                   const float *invstd, const float *scale, float *dW1, float *dgamma, float *dbeta, void *stream);
+
 /* ---------------------------------------------------------------- (2) camera-LiDAR fusion
  * Inputs are the PRE-BatchNorm outputs of the two 1x1 projection convolutions
  * in pixel-major (NHWC) layout; BatchNorm is applied as y = x*scale + shift with

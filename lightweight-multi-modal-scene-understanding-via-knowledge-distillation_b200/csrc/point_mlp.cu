@@ -1014,6 +1014,94 @@ __global__ void bn_finalize_kernel(const double *stats, int64_t M, int C, const 
     }
 }
 
+
+// ----------------------------------------------------------------------------- per-channel algebra between the layer kernels
+// (one tiny launch each instead of dozens of 64/128-element torch ops)
+
+// Layer 1 is linear in the raw point, z1 = W1.p (+b1, cancelled by the batch statistics): its BatchNorm statistics
+// follow from the 14 point moments.  Outputs the folded first layer q = scale1*W1, r = shift1 the prologues use, and
+// mean / invstd / scale for the backward; advances the running statistics like nn.BatchNorm1d.
+__global__ void mlp_l1_stats_kernel(const double *__restrict__ m14, int64_t M, const float *__restrict__ W1 /* [64,4] */,
+                                    const float *__restrict__ b1, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                    float eps, float momentum, float *running_mean, float *running_var,
+                                    float *__restrict__ q, float *__restrict__ r, float *__restrict__ mean,
+                                    float *__restrict__ invstd, float *__restrict__ scale) {
+    const int c = threadIdx.x;
+    if (c >= 64) return;
+    const double invM = 1.0 / (double)M;
+    double mu[4], cov[4][4];
+    const int idx[4][4] = {{4, 5, 6, 7}, {5, 8, 9, 10}, {6, 9, 11, 12}, {7, 10, 12, 13}};
+    for (int i = 0; i < 4; ++i) mu[i] = m14[i] * invM;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) cov[i][j] = m14[idx[i][j]] * invM - mu[i] * mu[j];
+    double w[4];
+    for (int i = 0; i < 4; ++i) w[i] = (double)W1[c * 4 + i];
+    double mn = 0.0, var = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        mn += w[i] * mu[i];
+        double t = 0.0;
+        for (int j = 0; j < 4; ++j) t += cov[i][j] * w[j];
+        var += w[i] * t;
+    }
+    if (var < 0.0) var = 0.0;
+    const double is = 1.0 / sqrt(var + (double)eps);
+    const double sc = (double)gamma[c] * is;
+    const double sh = (double)beta[c] - mn * sc;
+    mean[c] = (float)mn;
+    invstd[c] = (float)is;
+    scale[c] = (float)sc;
+    r[c] = (float)sh;
+    for (int i = 0; i < 4; ++i) q[c * 4 + i] = (float)(sc * w[i]);
+    if (running_mean) {
+        const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)(mn + (double)b1[c]);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// BatchNorm backward through the batch statistics as per-channel coefficients: dz = gs*dy + ga + gb*z, plus
+// dgamma / dbeta, from S0 = sum dy and S1 = sum dy*z.
+__global__ void bn_bwd_coeffs_kernel(const double *__restrict__ sums /* [2][C] */, int C, int64_t M,
+                                     const float *__restrict__ mean, const float *__restrict__ invstd,
+                                     const float *__restrict__ scale, float *__restrict__ gs, float *__restrict__ ga,
+                                     float *__restrict__ gb, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double S0 = sums[c], S1 = sums[C + c], mn = mean[c], is = invstd[c], sc = scale[c];
+    const double dg = is * (S1 - mn * S0);
+    const double b = -(sc * is * dg) / (double)M;
+    const double a = -(sc * S0) / (double)M - b * mn;
+    gs[c] = (float)sc; ga[c] = (float)a; gb[c] = (float)b;
+    dgamma[c] = (float)dg; dbeta[c] = (float)S0;
+}
+
+// Layer 1 backward in closed form from S0 = sum dy1, T = sum dy1 p^T (sums [5][64]) and the point moments:
+// sum dy1*z1 = W1[c,:].T[c,:];  dW1 = gs*T + ga*sum p^T + gb*W1.(sum p p^T).
+__global__ void mlp_l1_bwd_kernel(const double *__restrict__ sums /* [5][64] */, const double *__restrict__ m14, int64_t M,
+                                  const float *__restrict__ W1, const float *__restrict__ mean, const float *__restrict__ invstd,
+                                  const float *__restrict__ scale, float *__restrict__ dW1 /* [64,4] */,
+                                  float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int c = threadIdx.x;
+    if (c >= 64) return;
+    const int idx[4][4] = {{4, 5, 6, 7}, {5, 8, 9, 10}, {6, 9, 11, 12}, {7, 10, 12, 13}};
+    double w[4], T[4];
+    for (int i = 0; i < 4; ++i) { w[i] = (double)W1[c * 4 + i]; T[i] = sums[(1 + i) * 64 + c]; }
+    const double S0 = sums[c];
+    double S1 = 0.0;
+    for (int i = 0; i < 4; ++i) S1 += w[i] * T[i];
+    const double mn = mean[c], is = invstd[c], sc = scale[c];
+    const double dg = is * (S1 - mn * S0);
+    const double b = -(sc * is * dg) / (double)M;
+    const double a = -(sc * S0) / (double)M - b * mn;
+    for (int j = 0; j < 4; ++j) {
+        double wpp = 0.0;
+        for (int i = 0; i < 4; ++i) wpp += w[i] * m14[idx[i][j]];
+        dW1[c * 4 + j] = (float)(sc * T[j] + a * m14[j] + b * wpp);
+    }
+    dgamma[c] = (float)dg;
+    dbeta[c] = (float)S0;
+}
+
 }  // namespace kdf
 
 using namespace kdf;
@@ -1107,6 +1195,37 @@ int kdf_bn_finalize(const double *stats, int64_t M, int C, const float *gamma, c
     KDF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats come in pairs");
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, M, C, gamma, beta, pre_bias, eps, momentum,
                                                                       running_mean, running_var, mean, invstd, scale, shift);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_mlp_l1_stats(const double *moments14, int64_t M, const float *W1, const float *b1, const float *gamma,
+                     const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                     float *q, float *r, float *mean, float *invstd, float *scale, void *stream) {
+    KDF_CHECK_ARG(M > 0, "mlp_l1_stats: M must be positive");
+    KDF_CHECK_ARG(moments14 && W1 && gamma && beta && q && r && mean && invstd && scale, "mlp_l1_stats: null pointer");
+    KDF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr) && (running_mean == nullptr || b1 != nullptr),
+                  "mlp_l1_stats: running statistics come in pairs and need the conv bias");
+    mlp_l1_stats_kernel<<<1, 64, 0, as_stream(stream)>>>(moments14, M, W1, b1, gamma, beta, eps, momentum, running_mean,
+                                                          running_var, q, r, mean, invstd, scale);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_bn_bwd_coeffs(const double *sums, int C, int64_t M, const float *mean, const float *invstd, const float *scale,
+                      float *gs, float *ga, float *gb, float *dgamma, float *dbeta, void *stream) {
+    KDF_CHECK_ARG(M > 0 && C > 0, "bn_bwd_coeffs: bad sizes");
+    KDF_CHECK_ARG(sums && mean && invstd && scale && gs && ga && gb && dgamma && dbeta, "bn_bwd_coeffs: null pointer");
+    bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sums, C, M, mean, invstd, scale, gs, ga, gb, dgamma, dbeta);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_mlp_l1_bwd(const double *sums5x64, const double *moments14, int64_t M, const float *W1, const float *mean,
+                   const float *invstd, const float *scale, float *dW1, float *dgamma, float *dbeta, void *stream) {
+    KDF_CHECK_ARG(M > 0, "mlp_l1_bwd: M must be positive");
+    KDF_CHECK_ARG(sums5x64 && moments14 && W1 && mean && invstd && scale && dW1 && dgamma && dbeta, "mlp_l1_bwd: null pointer");
+    mlp_l1_bwd_kernel<<<1, 64, 0, as_stream(stream)>>>(sums5x64, moments14, M, W1, mean, invstd, scale, dW1, dgamma, dbeta);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -129,25 +129,32 @@ def bn_finalize(stats, M, bn, pre_bias, track: bool):
     return mean, invstd, scale, shift
 
 
-_SYM_IDX = {}
+def _bn_bwd_coeffs(sums, mean, invstd, scale, M):
+    """BatchNorm backward through the batch statistics as per-channel coefficients (one tiny kernel):
+    dz = gs*dy + ga + gb*z;  also dgamma, dbeta.  sums f64 [2,C] = (sum dy, sum dy*z)."""
+    C = sums.shape[1]
+    f32 = dict(dtype=torch.float32, device=sums.device)
+    gs, ga, gb, dgamma, dbeta = (torch.empty(C, **f32) for _ in range(5))
+    call("kdf_bn_bwd_coeffs", ptr(sums), C, M, ptr(mean), ptr(invstd), ptr(scale), ptr(gs), ptr(ga), ptr(gb), ptr(dgamma),
+         ptr(dbeta), stream_ptr(sums.device))
+    return gs, ga, gb, dgamma, dbeta
 
 
-def _sym4(m14: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(sum p [4], sum p p^T [4,4]) from the 14 moments."""
-    idx = _SYM_IDX.get(m14.device)
-    if idx is None:      # created once per device, outside any graph capture (the first steps run eagerly)
-        idx = _SYM_IDX[m14.device] = torch.tensor([4, 5, 6, 7, 5, 8, 9, 10, 6, 9, 11, 12, 7, 10, 12, 13], device=m14.device)
-    return m14[:4], m14.index_select(0, idx).view(4, 4)
-
-
-def _bn_bwd_coeffs(S0, S1, mean, invstd, scale, M):
-    """BatchNorm backward through the batch statistics as per-channel coefficients:
-    dz = gs*dy + ga + gb*z;  also dgamma, dbeta.  All inputs [C]; S0 = sum dy, S1 = sum dy*z (fp64)."""
-    mean, invstd, scale = mean.double(), invstd.double(), scale.double()
-    dgamma = invstd * (S1 - mean * S0)
-    gb = -(scale * invstd * dgamma) / M
-    ga = -(scale * S0) / M - gb * mean
-    return scale.float(), ga.float(), gb.float(), dgamma.float(), S0.float()
+def _eval_first_layer(bn1, w1, b1):
+    """(q, r) of the folded first layer with running statistics, cached until the tensors involved change."""
+    key = tuple((t.data_ptr(), t._version) for t in (bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, w1, b1))
+    cache = getattr(bn1, "_kdf_l1_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    with torch.no_grad():
+        W1 = w1.detach().reshape(64, 4).double()
+        invstd1 = torch.rsqrt(bn1.running_var.double() + bn1.eps)
+        mean1 = bn1.running_mean.double() - b1.detach().double()        # statistics of W1.p without the bias
+        scale1 = bn1.weight.detach().double() * invstd1
+        shift1 = bn1.bias.detach().double() - mean1 * scale1
+        val = ((scale1[:, None] * W1).float().contiguous(), shift1.float().contiguous())
+    bn1._kdf_l1_cache = (key, val)
+    return val
 
 
 # ----------------------------------------------------------------------------- the fused branch
@@ -168,36 +175,28 @@ class _FusedLidarFn(torch.autograd.Function):
         M = B * N
         pts = points.contiguous()
         bn1, bn2, bn3 = mlp[1], mlp[4], mlp[7]
-        W1 = w1.detach().reshape(64, 4).double()
         w2b = w2.detach().reshape(128, 64).to(torch.bfloat16).contiguous()
         w3b = w3.detach().reshape(128, 128).to(torch.bfloat16).contiguous()
         batch = training or bn1.running_mean is None
         track = training and bn1.track_running_stats and bn1.running_mean is not None
 
-        # ---- layer 1: statistics in closed form from the point moments
+        # ---- layer 1: statistics in closed form from the point moments (one tiny kernel), or the cached eval affine
+        f32 = dict(dtype=torch.float32, device=dev)
+        W1f = w1.detach().reshape(64, 4).float().contiguous()
         if batch:
             m14 = point_moments(pts)
-            s, pp = _sym4(m14)
-            mu_p = s / M
-            cov = pp / M - torch.outer(mu_p, mu_p)
-            mean1 = W1 @ mu_p
-            var1 = ((W1 @ cov) * W1).sum(1).clamp_min(0.0)
-            invstd1 = torch.rsqrt(var1 + bn1.eps)
+            q, r = torch.empty(64, 4, **f32), torch.empty(64, **f32)
+            mean1, invstd1, scale1 = (torch.empty(64, **f32) for _ in range(3))
+            mom = 0.0
             if track:
                 bn1.num_batches_tracked.add_(1)
                 mom = bn1.momentum if bn1.momentum is not None else 1.0 / float(bn1.num_batches_tracked)
-                bn1.running_mean.mul_(1 - mom).add_((mean1 + b1.detach().double()).float(), alpha=mom)
-                bn1.running_var.mul_(1 - mom).add_((var1 * (M / max(M - 1, 1))).float(), alpha=mom)
-            scale1 = g1.detach().double() * invstd1
-            shift1 = be1.detach().double() - mean1 * scale1
+            call("kdf_mlp_l1_stats", ptr(m14), M, ptr(W1f), ptr(b1.detach().float().contiguous()), ptr(g1.detach()), ptr(be1.detach()),
+                 float(bn1.eps), float(mom), ptr(bn1.running_mean) if track else None, ptr(bn1.running_var) if track else None,
+                 ptr(q), ptr(r), ptr(mean1), ptr(invstd1), ptr(scale1), stream_ptr(dev))
         else:
-            m14 = None
-            invstd1 = torch.rsqrt(bn1.running_var.double() + bn1.eps)
-            mean1 = bn1.running_mean.double() - b1.detach().double()        # statistics of W1.p without the bias
-            scale1 = g1.detach().double() * invstd1
-            shift1 = be1.detach().double() - mean1 * scale1
-        q = (scale1[:, None] * W1).float().contiguous()
-        r = shift1.float().contiguous()
+            m14 = mean1 = invstd1 = scale1 = None
+            q, r = _eval_first_layer(bn1, w1, b1)
 
         # ---- layers 2 and 3 on the tensor cores
         z2, st2 = mlp_layer_fwd_raw(0, pts.view(M, 4), q, r, w2b)
@@ -221,8 +220,8 @@ class _FusedLidarFn(torch.autograd.Function):
                 raise RuntimeError("the fused LiDAR branch differentiates through batch statistics only "
                                    "(train mode); use the layer-by-layer path for eval-mode gradients")
             ctx.save_for_backward(pts, z2, z3, grid, grid_z, cell, order, offsets, q, r, w2b, w3b, m14,
-                                  mean1.float(), invstd1.float(), scale1.float(), mean2, invstd2, scale2, shift2,
-                                  mean3, invstd3, scale3, shift3, W1.float())
+                                  mean1, invstd1, scale1, mean2, invstd2, scale2, shift2,
+                                  mean3, invstd3, scale3, shift3, W1f)
             ctx.dims = (B, N, tuple(grid_size))
         ctx.mark_non_differentiable(count, cell)
         return grid.permute(0, 3, 1, 2), count, cell
@@ -237,21 +236,19 @@ class _FusedLidarFn(torch.autograd.Function):
         gg = grad_grid.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
         # projection backward: gradient w.r.t. the BatchNorm-3 output (ReLU folded in) + its two column sums
         dy3, s3 = bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, grid_size)
-        gs3, ga3, gb3, dg3, db3 = _bn_bwd_coeffs(s3[0], s3[1], mean3, invstd3, scale3, M)
+        gs3, ga3, gb3, dg3, db3 = _bn_bwd_coeffs(s3, mean3, invstd3, scale3, M)
         dy2, s2, dW3 = mlp_layer_bwd(1, dy3, z3, gs3, ga3, gb3, z2, scale2, shift2, w3b)
         del dy3
-        gs2, ga2, gb2, dg2, db2 = _bn_bwd_coeffs(s2[0], s2[1], mean2, invstd2, scale2, M)
+        gs2, ga2, gb2, dg2, db2 = _bn_bwd_coeffs(s2, mean2, invstd2, scale2, M)
         _, s1, dW2 = mlp_layer_bwd(0, dy2, z2, gs2, ga2, gb2, pts.view(M, 4), q, r, w2b)
         del dy2
         # layer 1 in closed form: z1 = W1.p, so sum dy1*z1 and sum dz1 p^T follow from T = sum dy1 p^T and the moments
-        S0, T = s1[0], s1[1:5].t().contiguous()                          # [64], [64,4]
-        W1d = W1.double()
-        S1 = (W1d * T).sum(1)
-        gs1, ga1, gb1, dg1, db1 = _bn_bwd_coeffs(S0, S1, mean1, invstd1, scale1, M)
-        sp, pp = _sym4(m14)
-        dW1 = gs1.double()[:, None] * T + ga1.double()[:, None] * sp[None, :] + gb1.double()[:, None] * (W1d @ pp)
+        f32 = dict(dtype=torch.float32, device=pts.device)
+        dW1, dg1, db1 = torch.empty(64, 4, **f32), torch.empty(64, **f32), torch.empty(64, **f32)
+        call("kdf_mlp_l1_bwd", ptr(s1), ptr(m14), M, ptr(W1), ptr(mean1), ptr(invstd1), ptr(scale1), ptr(dW1), ptr(dg1), ptr(db1),
+             stream_ptr(pts.device))
         z64, z128 = torch.zeros_like(db1), torch.zeros_like(db2)          # conv biases cancel under batch statistics
-        return (None, dW1.float().view(64, 4, 1), z64, dg1, db1, dW2.view(128, 64, 1), z128, dg2, db2,
+        return (None, dW1.view(64, 4, 1), z64, dg1, db1, dW2.view(128, 64, 1), z128, dg2, db2,
                 dW3.view(128, 128, 1), z128, dg3, db3, None, None, None, None, None)
 
 
