@@ -153,8 +153,9 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
  * scale < 0; grid_z bf16 [B,HW,C], optional) and stores its activation (grid bf16 [B,HW,C] = the per-cell max of
  * a3; empty cells 0).  kdf_bev_bwd_affine = gradient w.r.t. the BatchNorm OUTPUT y3 (ReLU folded in): the rows
  * whose z equals the cell's extreme share the cell's gradient evenly (k rows -> g/k each, bf16) when the
- * activation is positive, every other row gets zeros; sums f64 [2,C] = (sum dy, sum dy*z) for BatchNorm's
- * backward (zeroed by the call).  kdf_point_moments: sums of (x,y,z,i) and their 10 pairwise products over all
+ * activation is positive, every other row of a point inside the grid gets zeros, and so do the rows of points
+ * outside when `cell` is given (cell = NULL leaves those rows unwritten: the consumer masks them, see
+ * kdf_mlp_layer_bwd's row_cell); sums f64 [2,C] = (sum dy, sum dy*z) for BatchNorm's backward (zeroed by the call).  kdf_point_moments: sums of (x,y,z,i) and their 10 pairwise products over all
  * points (f64 [14], zeroed by the call) -- the first MLP layer is linear in the point, so its BatchNorm
  * statistics follow from these. */
 int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *shift,
@@ -190,10 +191,12 @@ int kdf_bn_finalize(const double *stats, int64_t M, int C, const float *gamma, c
  *   mode 0 (Kin=64, input = raw points f32 [M,4], pro_a = q [64,4], pro_b = r [64]): nothing per point is stored;
  *           with dy1 = (dz . W) * (a1 > 0):  sums f64 [5,64] = (sum dy1, sum dy1*x, sum dy1*y, sum dy1*z, sum dy1*i),
  *           from which the caller forms the first layer's BatchNorm / weight gradients (it is linear in the point).
- * sums and dW are zeroed by the call.  Replaces autograd through Conv1d+BatchNorm1d+ReLU (lidar_encoder.py:25-35). */
+ * sums and dW are zeroed by the call.  row_cell (nullable, i32 [M]): rows with row_cell < 0 are points outside the
+ * grid, whose dy is zero by construction -- their dy rows are ignored (kdf_bev_bwd_affine called with cell = NULL
+ * leaves them unwritten).  Replaces autograd through Conv1d+BatchNorm1d+ReLU (lidar_encoder.py:25-35). */
 int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, const float *ga, const float *gb,
                       const void *input, int64_t M, const float *pro_a, const float *pro_b, const void *W_bf16,
-                      int Kin, void *dy_prev, double *sums, float *dW, void *stream);
+                      int Kin, void *dy_prev, double *sums, float *dW, const int32_t *row_cell, void *stream);
 
 /* Per-channel algebra between the layer kernels, one tiny launch each (BatchNorm1d of lidar_encoder.py:27,30,33):
  *   kdf_mlp_l1_stats   batch statistics of layer 1 in closed form from the 14 point moments (it is linear in the point):

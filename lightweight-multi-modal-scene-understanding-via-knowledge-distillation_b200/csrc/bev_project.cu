@@ -688,11 +688,13 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
 #pragma unroll
         for (int u = 0; u < U; ++u) idn[u] = idn2[u];
     }
-    // rows of points outside the grid
-    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR), gn = ((int64_t)gridDim.x * blockDim.x) / LPR;
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    for (int64_t i = g0; i < total; i += gn)
-        if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(dy + i * C + ch) = zero;
+    // rows of points outside the grid (skipped when the consumer masks them by cell id itself)
+    if (cell != nullptr) {
+        const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR), gn = ((int64_t)gridDim.x * blockDim.x) / LPR;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t i = g0; i < total; i += gn)
+            if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(dy + i * C + ch) = zero;
+    }
     // S0 / S1: the 8 warps through shared memory, then fp64 atomics (only sub 0 accumulated)
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
@@ -946,7 +948,7 @@ int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const voi
     KDF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const int64_t total = (int64_t)B * N;
     if (total == 0) return KDF_OK;
-    KDF_CHECK_ARG(grad_grid_bf16 && z_bf16 && grid_bf16 && grid_z_bf16 && order && offsets && cell && dy_bf16,
+    KDF_CHECK_ARG(grad_grid_bf16 && z_bf16 && grid_bf16 && grid_z_bf16 && order && offsets && dy_bf16,
                   "bev_bwd_affine: null pointer");
     const int64_t n_cells = (int64_t)B * H * W;
     int64_t blocks = (n_cells + 7) / 8;

@@ -304,6 +304,8 @@ struct MlpBwdArgs {
     __nv_bfloat16 *dy_prev;           // MODE 1: [M,128]
     double *sums;                     // MODE 1: [2][128];  MODE 0: [5][64] = S0, T[:,x], T[:,y], T[:,z], T[:,i]
     float *dW;                        // [128, KIN] fp32, accumulated with atomics (zeroed by the host wrapper)
+    const int32_t *row_cell;          // nullable [M]: rows with row_cell < 0 have dy == 0 by contract and their dy rows are
+                                      // not read as data (the producer kdf_bev_bwd_affine may then skip writing them)
 };
 
 template <int KIN>
@@ -387,12 +389,15 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     const int ach = tid % ACH, arow0 = tid / ACH;
 
     uint4 raw_dy[D_PASSES], raw_z[D_PASSES], raw_in[A_PASSES];
+    int raw_cell[D_PASSES];
     auto load_tile = [&](int64_t tile) {
         const int64_t r0 = tile * PM_ROWS;
 #pragma unroll
         for (int p = 0; p < D_PASSES; ++p) {
             const int64_t row = r0 + drow0 + p * PM_OROWS;
+            raw_cell[p] = 0;
             if (row < a.M) {
+                if (a.row_cell) raw_cell[p] = __ldg(a.row_cell + row);
                 raw_dy[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
                 raw_z[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
             }
@@ -427,7 +432,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (r0 + r < a.M) {
                     float g[8], zz[8];
-                    unpack8(raw_dy[p], g);
+                    unpack8(raw_cell[p] >= 0 ? raw_dy[p] : make_uint4(0u, 0u, 0u, 0u), g);
                     unpack8(raw_z[p], zz);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
@@ -766,12 +771,15 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
         const int dch = tid & 15, drow0 = tid >> 4;
         const int ach = tid % ACH, arow0 = tid / ACH;
         uint4 rdy[PF], rz[PF], rin[MODE == 1 ? PF : 1], rpt[MODE == 0 ? A_PASSES : 1];
+        int rcell[PF];
         float gs[8], ga[8], gb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { gs[j] = cgs[dch * 8 + j]; ga[j] = cga[dch * 8 + j]; gb[j] = cgb[dch * 8 + j]; }
         auto issue = [&](int64_t tile, int p, int slot) {
             const int64_t row = tile * PM_ROWS + drow0 + p * 16;
+            rcell[slot] = 0;
             if (tile < n_tiles && row < a.M) {
+                if (a.row_cell) rcell[slot] = __ldg(a.row_cell + row);
                 rdy[slot] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
                 rz[slot] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
                 if (MODE == 1) rin[slot] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + row * KIN + dch * 8);
@@ -812,7 +820,7 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u), av = v;
                 if (r0 + r < a.M) {
                     float g[8], zz[8];
-                    unpack8(rdy[slot], g);
+                    unpack8(rcell[slot] >= 0 ? rdy[slot] : make_uint4(0u, 0u, 0u, 0u), g);
                     unpack8(rz[slot], zz);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
@@ -1141,7 +1149,7 @@ int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a
 
 int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, const float *ga, const float *gb,
                       const void *input, int64_t M, const float *pro_a, const float *pro_b, const void *W_bf16,
-                      int Kin, void *dy_prev, double *sums, float *dW, void *stream) {
+                      int Kin, void *dy_prev, double *sums, float *dW, const int32_t *row_cell, void *stream) {
     KDF_CHECK_ARG(mode == 0 || mode == 1, "mlp_layer_bwd: bad mode %d", mode);
     KDF_CHECK_ARG(M >= 0, "mlp_layer_bwd: negative M");
     KDF_CHECK_ARG((mode == 0 && Kin == 64) || (mode == 1 && Kin == 128), "mlp_layer_bwd: unsupported (mode, Kin) = (%d, %d)", mode, Kin);
@@ -1156,7 +1164,7 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
                   "mlp_layer_bwd: buffers must be 16-byte aligned");
     MlpBwdArgs a{reinterpret_cast<const __nv_bfloat16 *>(dy), reinterpret_cast<const __nv_bfloat16 *>(z), gs, ga, gb, input,
                  pro_a, pro_b, reinterpret_cast<const __nv_bfloat16 *>(W_bf16), M,
-                 reinterpret_cast<__nv_bfloat16 *>(dy_prev), sums, dW};
+                 reinterpret_cast<__nv_bfloat16 *>(dy_prev), sums, dW, row_cell};
     const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
     int blocks = sm_count();
     if (n_tiles < blocks) blocks = (int)n_tiles;

@@ -45,7 +45,7 @@ _SIGNATURES = {
     "kdf_rows_axpb": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),
     "kdf_fpn_merge_fwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "kdf_fpn_up2_bwd": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "kdf_mlp_layer_bwd": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "kdf_mlp_layer_bwd": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_mlp_l1_stats": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kdf_bn_bwd_coeffs": (C.c_int, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kdf_mlp_l1_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

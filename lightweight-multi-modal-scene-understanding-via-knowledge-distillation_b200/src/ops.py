@@ -634,10 +634,12 @@ def mlp_layer_fwd(mode: int, x: torch.Tensor, pro_a: torch.Tensor, pro_b: torch.
 
 
 def mlp_layer_bwd(mode: int, dy: torch.Tensor, z: torch.Tensor, gs: torch.Tensor, ga: torch.Tensor, gb: torch.Tensor,
-                  x: torch.Tensor, pro_a: torch.Tensor, pro_b: torch.Tensor, weight_bf16: torch.Tensor):
+                  x: torch.Tensor, pro_a: torch.Tensor, pro_b: torch.Tensor, weight_bf16: torch.Tensor,
+                  row_cell: Optional[torch.Tensor] = None):
     """The same layer backwards (one kernel): dz = gs*dy + ga + gb*z, dW = dz^T @ a_in, and
     mode 1: (dy_prev bf16 [M,128], sums f64 [2,128], dW f32 [128,128]);
-    mode 0: (None, sums f64 [5,64] = sum dy1 * (1, x, y, z, i), dW f32 [128,64])."""
+    mode 0: (None, sums f64 [5,64] = sum dy1 * (1, x, y, z, i), dW f32 [128,64]).
+    ``row_cell`` (i32 [M]): rows with a negative entry are treated as dy == 0 without trusting their contents."""
     dev = require_cuda(dy, z, gs, ga, gb, x, pro_a, pro_b, weight_bf16)
     M = dy.shape[0]
     Nout, Kin = weight_bf16.shape
@@ -651,5 +653,5 @@ def mlp_layer_bwd(mode: int, dy: torch.Tensor, z: torch.Tensor, gs: torch.Tensor
     dW = torch.empty(Nout, Kin, dtype=torch.float32, device=dev)
     f = lambda t: t.float().contiguous()
     call("kdf_mlp_layer_bwd", mode, ptr(dy), ptr(z), ptr(f(gs)), ptr(f(ga)), ptr(f(gb)), ptr(x), M, ptr(f(pro_a)), ptr(f(pro_b)),
-         ptr(weight_bf16.contiguous()), Kin, ptr(dy_prev), ptr(sums), ptr(dW), stream_ptr(dev))
+         ptr(weight_bf16.contiguous()), Kin, ptr(dy_prev), ptr(sums), ptr(dW), ptr(row_cell), stream_ptr(dev))
     return dy_prev, sums, dW

@@ -80,14 +80,15 @@ def bev_reduce_affine(z, scale, shift, order, offsets, B, N, grid_size, want_ext
     return grid, grid_z
 
 
-def bev_bwd_affine(grad_grid, z, grid, grid_z, order, offsets, cell, B, N, grid_size):
+def bev_bwd_affine(grad_grid, z, grid, grid_z, order, offsets, cell, B, N, grid_size, zero_outside: bool = True):
     """-> (dy bf16 [B*N, C], sums f64 [2,C]): the cell gradient shared among the rows at the cell's extreme."""
     dev = require_cuda(grad_grid, z, grid, grid_z)
     H, W = grid_size
     C = z.shape[-1]
     dy = torch.empty(B * N, C, dtype=torch.bfloat16, device=dev)
     sums = torch.empty(2, C, dtype=torch.float64, device=dev)
-    call("kdf_bev_bwd_affine", ptr(grad_grid), ptr(z), ptr(grid), ptr(grid_z), ptr(order), ptr(offsets), ptr(cell),
+    call("kdf_bev_bwd_affine", ptr(grad_grid), ptr(z), ptr(grid), ptr(grid_z), ptr(order), ptr(offsets),
+         ptr(cell) if zero_outside else None,
          B, N, C, H, W, ptr(dy), ptr(sums), stream_ptr(dev))
     return dy, sums
 
@@ -235,9 +236,10 @@ class _FusedLidarFn(torch.autograd.Function):
         M = B * N
         gg = grad_grid.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
         # projection backward: gradient w.r.t. the BatchNorm-3 output (ReLU folded in) + its two column sums
-        dy3, s3 = bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, grid_size)
+        # (rows of points outside the grid are left unwritten: the layer kernel masks them by cell id)
+        dy3, s3 = bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, grid_size, zero_outside=False)
         gs3, ga3, gb3, dg3, db3 = _bn_bwd_coeffs(s3, mean3, invstd3, scale3, M)
-        dy2, s2, dW3 = mlp_layer_bwd(1, dy3, z3, gs3, ga3, gb3, z2, scale2, shift2, w3b)
+        dy2, s2, dW3 = mlp_layer_bwd(1, dy3, z3, gs3, ga3, gb3, z2, scale2, shift2, w3b, row_cell=cell.view(-1))
         del dy3
         gs2, ga2, gb2, dg2, db2 = _bn_bwd_coeffs(s2, mean2, invstd2, scale2, M)
         _, s1, dW2 = mlp_layer_bwd(0, dy2, z2, gs2, ga2, gb2, pts.view(M, 4), q, r, w2b)

@@ -114,3 +114,23 @@ def test_mlp_layer_bwd_mode0(M):
     assert err.max().item() < 3e-3, err.max()
     ref_dW = dz.t() @ a1
     assert rel_err(dW.cpu(), ref_dW) < 2e-3, rel_err(dW.cpu(), ref_dW)
+
+
+def test_mlp_layer_bwd_row_mask_ignores_unwritten_rows():
+    """Rows flagged by row_cell < 0 (points outside the grid) count as dy == 0 whatever their memory holds
+    (kdf_bev_bwd_affine with cell = NULL leaves them unwritten)."""
+    from src import ops
+    M = 128 * 5 + 9
+    g, dy, z, gs, ga, gb = _bwd_inputs(M, 77)
+    zprev = (torch.randn(M, 128, generator=g) * 2).to(torch.bfloat16)
+    scale, shift = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.3
+    W = (torch.randn(128, 128, generator=g) / 11.3).to(torch.bfloat16)
+    cell = torch.randint(-1, 5, (M,), generator=g).to(torch.int32)
+    dy_clean = torch.where((cell >= 0)[:, None], dy, torch.zeros((), dtype=dy.dtype))
+    dy_dirty = torch.where((cell >= 0)[:, None], dy, torch.full((), float("nan"), dtype=dy.dtype))
+    c = lambda t: t.cuda()
+    ref = ops.mlp_layer_bwd(1, c(dy_clean), c(z), c(gs), c(ga), c(gb), c(zprev), c(scale), c(shift), c(W))
+    got = ops.mlp_layer_bwd(1, c(dy_dirty), c(z), c(gs), c(ga), c(gb), c(zprev), c(scale), c(shift), c(W), row_cell=c(cell))
+    assert torch.equal(got[0], ref[0])
+    np.testing.assert_allclose(got[1].cpu().numpy(), ref[1].cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert rel_err(got[2].cpu(), ref[2].cpu()) < 1e-5
