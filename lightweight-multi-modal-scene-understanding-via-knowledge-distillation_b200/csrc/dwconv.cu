@@ -83,15 +83,16 @@ dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C
 #pragma unroll
             for (int q = 0; q < DW_V; ++q) acc[r][q] = 0.f;
         typename K::raw_t raw[IN_ROWS][3];                             // all input chunks of the item in flight at once
+        // one 64-bit base per item, 32-bit offsets per tap (a frame's map is < 2^31 elements: checked by the host)
+        const T *ibase = ib + ((int64_t)iy0 * W + ix0) * C;
+        const int rs = W * C;
+        const bool xok0 = ix0 >= 0, xok2 = ix0 + 2 < W;
 #pragma unroll
         for (int j = 0; j < IN_ROWS; ++j) {
-            const int iy = iy0 + j;
-            const bool yok = iy >= 0 && iy < H;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ix0 + kx;
-                raw[j][kx] = (yok && ix >= 0 && ix < W) ? K::ld(ib + ((int64_t)iy * W + ix) * C) : K::zero();
-            }
+            const bool yok = (unsigned)(iy0 + j) < (unsigned)H;
+            raw[j][0] = (yok && xok0) ? K::ld(ibase + j * rs) : K::zero();
+            raw[j][1] = yok ? K::ld(ibase + j * rs + C) : K::zero();
+            raw[j][2] = (yok && xok2) ? K::ld(ibase + j * rs + 2 * C) : K::zero();
         }
 #pragma unroll
         for (int j = 0; j < IN_ROWS; ++j) {
@@ -296,7 +297,8 @@ int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int
     KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "dwconv3x3_fwd: maps must be 16-byte aligned");
     const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
     const int cg = C / DW_V, nt = dw_block(cg);
-    KDF_CHECK_ARG((int64_t)OW * cg < (1ll << 30) && (int64_t)B * OH < (1ll << 30), "dwconv3x3_fwd: map too large for 32-bit indexing");
+    KDF_CHECK_ARG((int64_t)OW * cg < (1ll << 30) && (int64_t)B * OH < (1ll << 30) && (int64_t)H * W * C < (1ll << 31),
+                  "dwconv3x3_fwd: map too large for 32-bit indexing");
     const int row_blocks = B * ((OH + DW_R - 1) / DW_R);
     const int gx = (OW * cg + nt - 1) / nt;
     int gy = (sm_count() * 8 + gx - 1) / gx;                 // ~8 CTAs per SM in total; a thread then walks several row blocks
