@@ -924,7 +924,7 @@ int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *s
     KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_reduce_affine: bad sizes");
     KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_reduce_affine: C=%d not supported (64, 128, 256)", C);
     if (B == 0) return KDF_OK;
-    KDF_CHECK_ARG((z_bf16 || N == 0) && scale && shift && order && offsets && grid_bf16, "bev_reduce_affine: null pointer");
+    KDF_CHECK_ARG(((z_bf16 && order) || N == 0) && scale && shift && offsets && grid_bf16, "bev_reduce_affine: null pointer");
     const int64_t n_cells = (int64_t)B * H * W;
     int64_t blocks = (n_cells + 7) / 8;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;      // persistent warps, several cells each

@@ -160,3 +160,52 @@ def test_fused_branch_eval_mode_matches_layerwise():
             y = enc(pts)
     assert y.dtype == torch.bfloat16
     assert _l2(y.float(), ref) < 1.5e-2, _l2(y.float(), ref)
+
+
+def test_fused_kernels_accept_empty_inputs():
+    """M = 0 / B = 0 / N = 0 are no-ops that still define their reduction outputs (zeros)."""
+    from src import ops, point_mlp
+    dev = "cuda"
+    f32 = dict(device=dev, dtype=torch.float32)
+    W3 = torch.zeros(128, 128, device=dev, dtype=torch.bfloat16)
+    z, st = point_mlp.mlp_layer_fwd_raw(1, torch.empty(0, 128, device=dev, dtype=torch.bfloat16), torch.ones(128, **f32),
+                                        torch.zeros(128, **f32), W3)
+    assert z.shape == (0, 128) and (st == 0).all()
+    e = torch.empty(0, 128, device=dev, dtype=torch.bfloat16)
+    dyp, sums, dW = ops.mlp_layer_bwd(1, e, e, torch.ones(128, **f32), torch.zeros(128, **f32), torch.zeros(128, **f32), e,
+                                      torch.ones(128, **f32), torch.zeros(128, **f32), W3)
+    assert dyp.shape == (0, 128) and (sums == 0).all() and (dW == 0).all()
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    pts = torch.empty(2, 0, 4, **f32)
+    cell, count, order, offsets = point_mlp.bev_build_order(pts, geom, (64, 64))
+    assert (count == 0).all() and (offsets == 0).all()
+    grid, grid_z = point_mlp.bev_reduce_affine(e, torch.ones(128, **f32), torch.zeros(128, **f32), order, offsets, 2, 0, (64, 64), True)
+    assert (grid == 0).all() and (grid_z == 0).all()
+    assert (point_mlp.point_moments(pts) == 0).all()
+
+
+def test_trainer_side_stream_teacher_matches_single_stream():
+    """The teacher's forward on a side stream (Trainer(overlap_teacher=True)) is a scheduling change only."""
+    from oracle.weights import make_state_dict, synthetic_frames
+    from src.models.camera_encoder import TwinLiteEncoder
+    from src.models.fusion_module import CompleteSegmentationModel
+    from src.models.lidar_encoder import LiDAREncoder
+    from src.training.trainer import Trainer
+
+    def make(ft, oc):
+        return CompleteSegmentationModel(TwinLiteEncoder(return_multiscale=True), LiDAREncoder("spatial", grid_size=(64, 64)),
+                                         num_classes=2, fusion_type=ft, fusion_out_channels=oc,
+                                         camera_fpn_stages=["stage3", "stage4", "stage5"], camera_fpn_channels=128, output_mode="same")
+    img, pts, lab = synthetic_frames(4, 2, 3000, edge_cases=True, nonfinite=False)
+    outs = []
+    for overlap in (False, True):
+        s, t = make("weighted", 128), make("concat", 256)
+        s.load_state_dict(make_state_dict(5, fusion_type="weighted"))
+        t.load_state_dict(make_state_dict(6, fusion_type="concat", random_running_stats=True))
+        tr = Trainer(s.cuda().train(), [], [], "cuda", class_weights=[0.4, 3.5], teacher=t.cuda().eval(), verbose=False,
+                     amp_dtype=torch.bfloat16, overlap_teacher=overlap, save_dir="gpurun_out/test_ckpt")
+        terms, logits = tr.training_step(img.cuda(), pts.cuda(), lab.cuda())
+        outs.append((terms[:4].cpu(), logits.float().cpu()))
+    # fp64 atomics in the statistics make runs differ in the last bits at most
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-4, atol=1e-5)
+    assert _l2(outs[0][1], outs[1][1]) < 1e-2

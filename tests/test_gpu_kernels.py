@@ -575,3 +575,15 @@ def test_dwconv3x3_vs_torch_conv2d(ops, C, H, W, stride, dtype):
     assert rel_err(conv.weight.grad.cpu(), ref_gw) < (2e-5 if dtype == torch.float32 else 1e-2)
     # not a depthwise 3x3: declined
     assert ops.dwconv3x3(nn.Conv2d(C, C, 1).cuda(), xc) is None
+
+
+def test_camera_side_kernels_accept_empty_batches(ops):
+    import torch.nn as nn
+    conv = nn.Conv2d(64, 64, 3, padding=1, groups=64, bias=False).cuda()
+    x = torch.empty(0, 64, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = ops.dwconv3x3(conv, x)
+    assert y is not None and tuple(y.shape) == (0, 64, 8, 8)
+    base = torch.empty(0, 64, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last)
+    lo = torch.empty(0, 64, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)
+    out = ops.fpn_merge(base, [lo])
+    assert out is not None and tuple(out.shape) == (0, 64, 8, 8)

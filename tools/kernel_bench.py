@@ -100,3 +100,21 @@ if "affine" in only:
     gg = torch.randn(B, H, W, C, device=dev, dtype=dt)
     timeit("bev_bwd_affine", lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W)), B * (C * 2 * v * N + C * 2 * N + C * 2 * H * W))
     timeit("point_moments", lambda: point_mlp.point_moments(pts), B * N * 16)
+if "dw" in only:
+    import torch.nn as nn
+    for (Cc, Hh, st_) in ((384, 64, 1), (192, 128, 2), (32, 128, 1), (768, 32, 1)):
+        conv = nn.Conv2d(Cc, Cc, 3, stride=st_, padding=1, groups=Cc, bias=False).to(dev)
+        x = torch.randn(B, Cc, Hh, Hh, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = ops.dwconv3x3(conv, x)
+        g = torch.randn_like(y)
+        nb_in, nb_out = x.numel() * 2, y.numel() * 2
+        with torch.no_grad():
+            timeit(f"dwconv fwd C={Cc} {Hh}x{Hh} s{st_}", lambda: ops.dwconv3x3(conv, x), nb_in + nb_out)
+        w9 = conv.weight.detach().reshape(Cc, 9).float().contiguous()
+        gx = torch.empty(B, Hh, Hh, Cc, device=dev, dtype=dt); gw = torch.empty(Cc, 9, device=dev)
+        xr, gr = x.detach().permute(0, 2, 3, 1), g.permute(0, 2, 3, 1)
+        timeit(f"dwconv dgrad C={Cc} s{st_}", lambda: native.call("kdf_dwconv3x3_bwd_data", p(gr), p(w9), 1, B, Hh, Hh, Cc, st_, p(gx), st), nb_in + nb_out)
+        timeit(f"dwconv wgrad C={Cc} s{st_}", lambda: native.call("kdf_dwconv3x3_bwd_weight", p(xr), p(gr), 1, B, Hh, Hh, Cc, st_, p(gw), st), nb_in + nb_out)
+        wb = conv.weight.detach().to(dt)
+        timeit(f"cudnn fwd C={Cc} s{st_}", lambda: torch.nn.functional.conv2d(x.detach(), wb, None, st_, 1, 1, Cc), nb_in + nb_out)
+        del x, y, g, gx
