@@ -18,6 +18,7 @@
 //   tcgen05.mma   dY[128 x 256]  = dH . W1          (A K-major, B = the MN-major view of the resident W1 tile)
 //   tcgen05.mma   dW1[128 x 256] += dH^T . Y        (both MN-major views; accumulates in TMEM across tiles)
 //   epilogue 2    ReLU mask + blend path, BN-affine backward, bf16 gradient rows, d scale / d shift sums.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "kdf_common.cuh"
@@ -227,6 +228,171 @@ fusion_weighted_fwd_tc_kernel(FusionTcArgs a) {
             }
         }
         __syncthreads();                                                   // the Y tile is rewritten next iteration
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
+}
+
+// ============================================================================= forward, TMA-staged tiles
+// Same arithmetic as fusion_weighted_fwd_tc_kernel; the pre-BatchNorm rows of a tile arrive by TMA
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps over the [M,128] row tensors, 4 boxes of 64 columns x 128
+// rows) DIRECTLY in the panel layout the tensor cores read, are BatchNorm-applied + ReLU'd in place, and two
+// operand tiles are kept in flight: the loads of tile i+1 land while tile i is transformed, multiplied and
+// blended -- no registers hold data in flight, so the CUDA-core phases run 16 warps wide.
+constexpr int FTM_THREADS = 512;
+
+struct FtTmaSmem {
+    static constexpr int OFF_W1 = 0;
+    static constexpr int OFF_Y0 = OFF_W1 + 4 * FT_PANEL;
+    static constexpr int OFF_Y1 = OFF_Y0 + 4 * FT_PANEL;
+    static constexpr int OFF_MISC = OFF_Y1 + 4 * FT_PANEL;
+    // 3 mbarriers + tmem slot, then float tables b1[128] w2[256] aff[512] rowS[256] part[1024]
+    static constexpr int MISC_BYTES = 64 + 4 * (128 + 256 + 512 + 256 + 1024);
+    static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(tmap), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(FTM_THREADS, 1)
+fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorMap tm_cam, const __grid_constant__ CUtensorMap tm_lid) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sW1 = smem + FtTmaSmem::OFF_W1;
+    uint8_t *sY[2] = {smem + FtTmaSmem::OFF_Y0, smem + FtTmaSmem::OFF_Y1};
+    uint8_t *misc = smem + FtTmaSmem::OFF_MISC;
+    uint64_t *bar_raw = reinterpret_cast<uint64_t *>(misc);           // [2]
+    uint64_t *bar_mma = bar_raw + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(misc + 32);
+    float *tb1 = reinterpret_cast<float *>(misc + 64), *tw2 = tb1 + 128, *taff = tw2 + 256, *rowS = taff + 512, *part = rowS + 256;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.M + FT_ROWS - 1) / FT_ROWS;
+    auto issue_tile = [&](int64_t tile, int buf) {                     // one thread: 4 boxes of 64 columns x 128 rows
+        mbar_expect_tx(&bar_raw[buf], 4 * FT_PANEL);
+        const int r0 = (int)(tile * FT_ROWS);
+        tma_load_2d(sY[buf] + 0 * FT_PANEL, &tm_cam, 0, r0, &bar_raw[buf]);
+        tma_load_2d(sY[buf] + 1 * FT_PANEL, &tm_cam, 64, r0, &bar_raw[buf]);
+        tma_load_2d(sY[buf] + 2 * FT_PANEL, &tm_lid, 0, r0, &bar_raw[buf]);
+        tma_load_2d(sY[buf] + 3 * FT_PANEL, &tm_lid, 64, r0, &bar_raw[buf]);
+    };
+    // barriers first, so that the first two tiles are already in flight during the rest of the setup
+    if (tid == 0) {
+        tc::mbar_init(&bar_raw[0], 1);
+        tc::mbar_init(&bar_raw[1], 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_fence_init();
+        tc::fence_async_smem();
+        if ((int64_t)blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
+        if ((int64_t)blockIdx.x + gridDim.x < n_tiles) issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+    for (int i = tid; i < 128; i += FTM_THREADS) {
+        tb1[i] = a.b1[i];
+        taff[i] = a.csc[i]; taff[128 + i] = a.csh[i]; taff[256 + i] = a.lsc[i]; taff[384 + i] = a.lsh[i];
+    }
+    for (int i = tid; i < 256; i += FTM_THREADS) tw2[i] = a.w2[i];
+    for (int idx = tid; idx < FT_C * (FT_K2 / 8); idx += FTM_THREADS) {
+        const int j = idx >> 5, ch = idx & 31;
+        const float4 lo = __ldg(reinterpret_cast<const float4 *>(a.w1 + (int64_t)j * FT_K2 + ch * 8));
+        const float4 hi = __ldg(reinterpret_cast<const float4 *>(a.w1 + (int64_t)j * FT_K2 + ch * 8 + 4));
+        const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        *reinterpret_cast<uint4 *>(sW1 + (ch >> 3) * FT_PANEL + tc::sw128_offset(j, ch & 7)) = ft_pack8(v);
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 128);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const float bb0 = __ldg(a.b2), bb1 = __ldg(a.b2 + 1);
+    // transform mapping: 32 chunks per pixel row (16 camera + 16 LiDAR), 16 rows per pass
+    const int tch = tid & 31, trow0 = tid >> 5;
+    const int tpanel = tch >> 3, tc8 = tch & 7;                        // panel 0,1 camera; 2,3 LiDAR
+    const float *t_sc = taff + (tpanel < 2 ? 0 : 256) + (tpanel & 1) * 64 + tc8 * 8;
+    const float *t_sh = t_sc + 128;
+    const int och = tid & 15, orow0 = tid >> 4;                        // blend mapping: 16 chunks per output row, 32 rows per pass
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int64_t r0 = tile * FT_ROWS;
+        uint8_t *y = sY[buf];
+        tc::mbar_wait(&bar_raw[buf], (uint32_t)((it >> 1) & 1));
+        // ---- BatchNorm-apply + ReLU in place (rows past M are forced to zero: TMA zero-fills them, relu(shift) would not be zero)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int r = trow0 + p * 16;
+            uint4 *ptr4 = reinterpret_cast<uint4 *>(y + tpanel * FT_PANEL + tc::sw128_offset(r, tc8));
+            *ptr4 = (r0 + r < a.M) ? ft_affine_relu(*ptr4, t_sc, t_sh) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            ft_mma_hidden(tc::smem_u32(y), tc::smem_u32(sW1), tmem_base, bar_mma);
+        }
+        // ---- epilogue A: attention logits per pixel (four threads share a pixel: 32 hidden units each)
+        tc::mbar_wait(bar_mma, (uint32_t)(it & 1));
+        tc::fence_after_sync();
+        const int row = (warp & 3) * 32 + lane, cgp = warp >> 2;
+        {
+            float p0 = 0.f, p1 = 0.f;
+            uint32_t r[32];
+            const int col0 = cgp * 32;
+            tc::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(tb1 + col0 + j);
+                const float4 u4 = *reinterpret_cast<const float4 *>(tw2 + col0 + j), v4 = *reinterpret_cast<const float4 *>(tw2 + 128 + col0 + j);
+                const float h0 = fmaxf(__uint_as_float(r[j]) + b4.x, 0.f), h1 = fmaxf(__uint_as_float(r[j + 1]) + b4.y, 0.f);
+                const float h2 = fmaxf(__uint_as_float(r[j + 2]) + b4.z, 0.f), h3 = fmaxf(__uint_as_float(r[j + 3]) + b4.w, 0.f);
+                p0 = fmaf(h0, u4.x, p0); p0 = fmaf(h1, u4.y, p0); p0 = fmaf(h2, u4.z, p0); p0 = fmaf(h3, u4.w, p0);
+                p1 = fmaf(h0, v4.x, p1); p1 = fmaf(h1, v4.y, p1); p1 = fmaf(h2, v4.z, p1); p1 = fmaf(h3, v4.w, p1);
+            }
+            part[(row * 4 + cgp) * 2] = p0;
+            part[(row * 4 + cgp) * 2 + 1] = p1;
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid < FT_ROWS) {
+            const float4 pa = *reinterpret_cast<const float4 *>(part + tid * 8), pb = *reinterpret_cast<const float4 *>(part + tid * 8 + 4);
+            const float s0 = ((pa.x + pa.z) + (pb.x + pb.z)) + bb0, s1 = ((pa.y + pa.w) + (pb.y + pb.w)) + bb1;
+            const float mx = fmaxf(s0, s1);
+            const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
+            const float inv = 1.f / (e0 + e1);
+            rowS[2 * tid] = e0 * inv;
+            rowS[2 * tid + 1] = e1 * inv;
+            if (r0 + tid < a.M) *reinterpret_cast<float2 *>(a.attn + 2 * (r0 + tid)) = make_float2(e0 * inv, e1 * inv);
+        }
+        __syncthreads();
+        // ---- epilogue B: blend, coalesced 16-byte stores
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int r = orow0 + p * 32;
+            if (r0 + r < a.M) {
+                const uint32_t off = (och >> 3) * FT_PANEL + tc::sw128_offset(r, och & 7);
+                float yc[8], yl[8], o[8];
+                ft_unpack8(*reinterpret_cast<const uint4 *>(y + off), yc);
+                ft_unpack8(*reinterpret_cast<const uint4 *>(y + 2 * FT_PANEL + off), yl);
+                const float w0 = rowS[2 * r], w1 = rowS[2 * r + 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = yc[j] * w0 + yl[j] * w1;
+                *reinterpret_cast<uint4 *>(a.out + (r0 + r) * FT_C + och * 8) = ft_pack8(o);
+            }
+        }
+        __syncthreads();                                                  // every read of this operand tile is done
+        if (tid == 0 && tile + 2 * (int64_t)gridDim.x < n_tiles) {
+            tc::fence_async_smem();                                        // generic-proxy accesses before the async-proxy refill
+            issue_tile(tile + 2 * (int64_t)gridDim.x, buf);
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -476,6 +642,32 @@ bool fusion_tc_enabled() {
     return !off;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// [M,128] bf16 rows, boxes of 64 columns (one 128-byte swizzle span) x 128 rows
+static bool make_row_map(CUtensorMap *tm, const void *base, int64_t M) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)FT_C, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)FT_C * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)FT_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
                            const float *csc, const float *csh, const float *lsc, const float *lsh,
                            const float *w1, const float *b1, const float *w2, const float *b2,
@@ -489,6 +681,14 @@ int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
     a.out = reinterpret_cast<__nv_bfloat16 *>(out); a.attn = attn;
     const int64_t n_tiles = (M + FT_ROWS - 1) / FT_ROWS;
     const int blocks = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    static const bool no_tma = getenv("KDF_FUSION_NO_TMA") != nullptr;      // experiment knob: register-staged tiles
+    CUtensorMap tm_cam, tm_lid;
+    if (!no_tma && M < (1ll << 31) && make_row_map(&tm_cam, cam_pre, M) && make_row_map(&tm_lid, lid_pre, M)) {
+        KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtTmaSmem::TOTAL));
+        fusion_weighted_fwd_tma_kernel<<<blocks, FTM_THREADS, FtTmaSmem::TOTAL, st>>>(a, tm_cam, tm_lid);
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
     KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_FWD));
     fusion_weighted_fwd_tc_kernel<<<blocks, FT_THREADS, FtSmem::TOTAL_FWD, st>>>(a);
     KDF_LAUNCH_CHECK();
