@@ -301,10 +301,11 @@ def kernel_rooflines(args, device, fp32):
             "C*s*v*N rows of valid points read once + 4*v*N ids; grid and extreme written once (2*C*s*HW)")
         grid, grid_z = point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True)
         gg = torch.randn(B, H, W, C, device=device, dtype=dt)
-        add("bev_bwd_affine_kernel", time_kernel(lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W)), 10),
-            B * (3 * C * s * H * W + C * s * v * N + C * s * N + 8 * N),
+        add("bev_bwd_affine_kernel",
+            time_kernel(lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W), zero_outside=False), 10),
+            B * (3 * C * s * H * W + 2 * C * s * v * N + 8 * v * N),
             "grad/grid/extreme rows per cell (3*C*s*HW) + rows of valid points read once (C*s*v*N; the second sweep hits "
-            "L1/L2) + a gradient row per point (C*s*N) + ids")
+            "L1/L2) + a gradient row per valid point (C*s*v*N; rows of points outside are masked by the consumer) + ids")
         del z2, z3, gg, grid, grid_z
 
     # ---- layer-by-layer projection path (fp32 parity path; bf16 features here): the reference's scatter as one call

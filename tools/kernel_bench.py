@@ -98,7 +98,7 @@ if "affine" in only:
     timeit("bev_reduce_affine", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), False), B * (C * 2 * v * N + C * 2 * H * W))
     grid, grid_z = point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True)
     gg = torch.randn(B, H, W, C, device=dev, dtype=dt)
-    timeit("bev_bwd_affine", lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W)), B * (C * 2 * v * N + C * 2 * N + C * 2 * H * W))
+    timeit("bev_bwd_affine", lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W), zero_outside=False), B * (2 * C * 2 * v * N + 3 * C * 2 * H * W))
     timeit("point_moments", lambda: point_mlp.point_moments(pts), B * N * 16)
 if "dw" in only:
     import torch.nn as nn
