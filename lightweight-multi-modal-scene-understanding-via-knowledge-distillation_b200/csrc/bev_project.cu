@@ -123,6 +123,106 @@ bev_scan_kernel(const int32_t *__restrict__ count, int32_t *__restrict__ offsets
     if (t == 0) off[HW] = carry_s;
 }
 
+// ----------------------------------------------------------------------------- counting sort without global atomics
+// The warp-aggregated global atomics of bev_index_kernel are bound by the L2 atomic rate (~50 G adds/s: 67 us for
+// 5.4 M points).  For the cell ORDERING a frame is cut into chunks of BEV_CHUNK points, one CTA per chunk:
+//   count : cell id per point + arrival rank inside the chunk from SHARED-memory atomics on a per-chunk histogram,
+//           which is then written out [B][chunk][HW]
+//   scan  : per frame, per cell: running sum over the chunks (in place: histogram -> chunk base), occupancy, offsets
+//   fill  : order[offsets[cell] + chunk_base[cell] + rank] = point id, bases staged in shared memory
+// No global atomic is left; cell ids, occupancy and offsets are identical to the atomic path, the order inside a cell
+// differs (both are valid: every reduction over a cell is order-independent).
+constexpr int BEV_CHUNK = 8192;
+
+__global__ void __launch_bounds__(256)
+bev_chunk_count_kernel(const float4 *__restrict__ points, int64_t N, BevGeom g, int32_t *__restrict__ cell_out,
+                       int32_t *__restrict__ rank_out, int32_t *__restrict__ chist, int nchunk) {
+    extern __shared__ int hist[];
+    const int HW = g.H * g.W;
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    for (int i = threadIdx.x; i < HW; i += 256) hist[i] = 0;
+    __syncthreads();
+    const int64_t beg = (int64_t)chunk * BEV_CHUNK, end = (beg + BEV_CHUNK < N) ? beg + BEV_CHUNK : N;
+    const float4 *pb = points + (int64_t)b * N;
+    int32_t *cb = cell_out + (int64_t)b * N, *rb = rank_out + (int64_t)b * N;
+    for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
+        const float4 p = ldg_stream_f4(pb + i);
+        const int cell = bev_cell_of(p.x, p.y, g);
+        cb[i] = cell;
+        if (cell >= 0) rb[i] = atomicAdd(&hist[cell], 1);
+    }
+    __syncthreads();
+    int32_t *out = chist + ((int64_t)b * nchunk + chunk) * HW;
+    for (int i = threadIdx.x; i < HW; i += 256) out[i] = hist[i];
+}
+
+__global__ void __launch_bounds__(1024)
+bev_chunk_scan_kernel(int32_t *__restrict__ chist /* in: histograms, out: chunk bases */, int32_t *__restrict__ count,
+                      int32_t *__restrict__ offsets, int HW, int nchunk) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    int32_t *cnt = count + (int64_t)b * HW;
+    int32_t *off = offsets + (int64_t)b * (HW + 1);
+    int32_t *hb = chist + (int64_t)b * nchunk * HW;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < HW; c0 += 1024) {
+        const int c = c0 + t;
+        int v = 0;
+        if (c < HW) {
+            for (int k = 0; k < nchunk; ++k) {
+                const int h = hb[(int64_t)k * HW + c];
+                hb[(int64_t)k * HW + c] = v;
+                v += h;
+            }
+            cnt[c] = v;
+        }
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_tot[lane] = wi - w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + warp_tot[wid] + incl - v;
+        if (c < HW) off[c] = excl;
+        __syncthreads();
+        if (t == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (t == 0) off[HW] = carry_s;
+}
+
+__global__ void __launch_bounds__(256)
+bev_chunk_fill_kernel(const int32_t *__restrict__ cell, const int32_t *__restrict__ rank, const int32_t *__restrict__ cbase,
+                      const int32_t *__restrict__ offsets, int32_t *__restrict__ order, int64_t N, int HW, int nchunk) {
+    extern __shared__ int base[];
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int32_t *cbp = cbase + ((int64_t)b * nchunk + chunk) * HW, *off = offsets + (int64_t)b * (HW + 1);
+    for (int i = threadIdx.x; i < HW; i += 256) base[i] = cbp[i] + off[i];
+    __syncthreads();
+    const int64_t beg = (int64_t)chunk * BEV_CHUNK, end = (beg + BEV_CHUNK < N) ? beg + BEV_CHUNK : N;
+    const int32_t *cb = cell + (int64_t)b * N, *rb = rank + (int64_t)b * N;
+    int32_t *ob = order + (int64_t)b * N;
+    for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
+        const int c = __ldg(cb + i);
+        if (c >= 0) ob[base[c] + __ldg(rb + i)] = (int32_t)i;
+    }
+}
+
 // ----------------------------------------------------------------------------- fill
 __global__ void __launch_bounds__(256)
 bev_fill_kernel(const int32_t *__restrict__ cell, const int32_t *__restrict__ rank,
@@ -791,7 +891,9 @@ int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
 size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W) {
     const size_t bn = align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256);
     const size_t off = align_up(sizeof(int32_t) * (size_t)B * ((size_t)H * W + 1), 256);
-    return 2 * bn + off + 256;
+    const size_t nchunk = (size_t)((N + BEV_CHUNK - 1) / BEV_CHUNK);
+    const size_t hist = align_up(sizeof(int32_t) * (size_t)B * nchunk * (size_t)H * W, 256);    // per-chunk histograms
+    return 2 * bn + off + hist + 256;
 }
 
 // index -> scan -> fill: cell ids, occupancy and the cell ordering (counting sort) of every frame
@@ -799,6 +901,28 @@ static int build_order(const float *points, int point_stride, int B, int64_t N, 
                        int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets, int32_t *rank, cudaStream_t st) {
     const int HW = g.H * g.W;
     const int64_t total = (int64_t)B * N;
+    static const bool atomic_path = getenv("KDF_BEV_ATOMIC_SORT") != nullptr;         // experiment knob
+    const int64_t nchunk = (N + BEV_CHUNK - 1) / BEV_CHUNK;
+    if (!atomic_path && point_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0 && HW * sizeof(int) <= 96 * 1024 &&
+        N > 0 && nchunk <= 65535 && B <= 65535) {
+        // the histograms live behind rank / (unused second [B,N] block) / offsets in the workspace
+        const size_t bn = align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256);
+        const size_t off = align_up(sizeof(int32_t) * (size_t)B * ((size_t)HW + 1), 256);
+        int32_t *chist = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(rank) + 2 * bn + off);
+        const size_t smem = sizeof(int) * (size_t)HW;
+        if (smem > 48 * 1024) {
+            KDF_CUDA(cudaFuncSetAttribute(bev_chunk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KDF_CUDA(cudaFuncSetAttribute(bev_chunk_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        const dim3 grid((unsigned)nchunk, (unsigned)B);
+        bev_chunk_count_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(points), N, g, cell, rank, chist, (int)nchunk);
+        KDF_LAUNCH_CHECK();
+        bev_chunk_scan_kernel<<<B, 1024, 0, st>>>(chist, count, offsets, HW, (int)nchunk);
+        KDF_LAUNCH_CHECK();
+        bev_chunk_fill_kernel<<<grid, 256, smem, st>>>(cell, rank, chist, offsets, order, N, HW, (int)nchunk);
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
     if (int e = launch_index(points, B, N, point_stride, g, cell, rank, count, st)) return e;
     bev_scan_kernel<<<B, 1024, 0, st>>>(count, offsets, HW);
     KDF_LAUNCH_CHECK();

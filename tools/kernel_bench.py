@@ -93,6 +93,9 @@ if "affine" in only:
     sc, sh = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
     v = 0.622
     timeit("bev_build_order", lambda: point_mlp.bev_build_order(pts, geom, (H, W)), B * N * (16 + 4 + 4 + 4 + 4))
+    _c, _k, _o, _f = point_mlp.bev_build_order(pts, geom, (H, W))
+    _nb = native.lib.kdf_bev_workspace_bytes(B, N, H, W); _ws = torch.empty(_nb, dtype=torch.uint8, device=dev)
+    timeit("bev_build_order (preallocated)", lambda: native.call("kdf_bev_build_order", p(pts), 4, B, N, *geom, H, W, p(_k), p(_c), p(_o), p(_f), p(_ws), _nb, st), B * N * (16 + 4 + 4 + 4 + 4))
     cell, count, order, offsets = point_mlp.bev_build_order(pts, geom, (H, W))
     timeit("bev_reduce_affine (+extreme)", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), True), B * (C * 2 * v * N + C * 2 * H * W))
     timeit("bev_reduce_affine", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order, offsets, B, N, (H, W), False), B * (C * 2 * v * N + C * 2 * H * W))

@@ -18,7 +18,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         tr.training_step(b["image"], b["points"], b["segmentation"])
     torch.cuda.synchronize()
-txt = prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90)
+txt = prof.key_averages().table(sort_by="cuda_time_total", row_limit=140, max_name_column_width=90)
 open(a.out, "w").write(txt)
 print(txt[:200])
 print("peak mem GB", torch.cuda.max_memory_allocated() / 2**30)
