@@ -145,11 +145,22 @@ bev_chunk_count_kernel(const float4 *__restrict__ points, int64_t N, BevGeom g, 
     const int64_t beg = (int64_t)chunk * BEV_CHUNK, end = (beg + BEV_CHUNK < N) ? beg + BEV_CHUNK : N;
     const float4 *pb = points + (int64_t)b * N;
     int32_t *cb = cell_out + (int64_t)b * N, *rb = rank_out + (int64_t)b * N;
-    for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
-        const float4 p = ldg_stream_f4(pb + i);
-        const int cell = bev_cell_of(p.x, p.y, g);
-        cb[i] = cell;
-        if (cell >= 0) rb[i] = atomicAdd(&hist[cell], 1);
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += 4 * 256) {           // 4 independent points in flight per thread
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 256;
+            if (i < end) p[u] = ldg_stream_f4(pb + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 256;
+            if (i < end) {
+                const int cell = bev_cell_of(p[u].x, p[u].y, g);
+                cb[i] = cell;
+                if (cell >= 0) rb[i] = atomicAdd(&hist[cell], 1);
+            }
+        }
     }
     __syncthreads();
     int32_t *out = chist + ((int64_t)b * nchunk + chunk) * HW;
@@ -171,10 +182,15 @@ bev_chunk_scan_kernel(int32_t *__restrict__ chist /* in: histograms, out: chunk 
         const int c = c0 + t;
         int v = 0;
         if (c < HW) {
-            for (int k = 0; k < nchunk; ++k) {
-                const int h = hb[(int64_t)k * HW + c];
-                hb[(int64_t)k * HW + c] = v;
-                v += h;
+            for (int k0 = 0; k0 < nchunk; k0 += 8) {                           // 8 independent loads, then the running sum
+                int h[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) h[u] = (k0 + u < nchunk) ? hb[(int64_t)(k0 + u) * HW + c] : 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (k0 + u < nchunk) hb[(int64_t)(k0 + u) * HW + c] = v;
+                    v += h[u];
+                }
             }
             cnt[c] = v;
         }
@@ -217,9 +233,18 @@ bev_chunk_fill_kernel(const int32_t *__restrict__ cell, const int32_t *__restric
     const int64_t beg = (int64_t)chunk * BEV_CHUNK, end = (beg + BEV_CHUNK < N) ? beg + BEV_CHUNK : N;
     const int32_t *cb = cell + (int64_t)b * N, *rb = rank + (int64_t)b * N;
     int32_t *ob = order + (int64_t)b * N;
-    for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
-        const int c = __ldg(cb + i);
-        if (c >= 0) ob[base[c] + __ldg(rb + i)] = (int32_t)i;
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += 4 * 256) {
+        int c[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 256;
+            c[u] = (i < end) ? __ldg(cb + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = (c[u] >= 0) ? __ldg(rb + i0 + u * 256) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c[u] >= 0) ob[base[c[u]] + r[u]] = (int32_t)(i0 + u * 256);
     }
 }
 
