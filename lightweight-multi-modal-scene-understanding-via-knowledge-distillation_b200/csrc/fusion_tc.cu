@@ -18,11 +18,11 @@
 //   tcgen05.mma   dY[128 x 256]  = dH . W1          (A K-major, B = the MN-major view of the resident W1 tile)
 //   tcgen05.mma   dW1[128 x 256] += dH^T . Y        (both MN-major views; accumulates in TMEM across tiles)
 //   epilogue 2    ReLU mask + blend path, BN-affine backward, bf16 gradient rows, d scale / d shift sums.
-#include <cuda.h>
 #include <stdlib.h>
 
 #include "kdf_common.cuh"
 #include "tc_common.cuh"
+#include "tma_common.cuh"
 
 namespace kdf {
 
@@ -252,15 +252,6 @@ struct FtTmaSmem {
     static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(tc::smem_u32(smem_dst)), "l"(tmap), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-
 __global__ void __launch_bounds__(FTM_THREADS, 1)
 fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorMap tm_cam, const __grid_constant__ CUtensorMap tm_lid) {
     extern __shared__ uint8_t smem_raw[];
@@ -276,12 +267,12 @@ fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorM
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (a.M + FT_ROWS - 1) / FT_ROWS;
     auto issue_tile = [&](int64_t tile, int buf) {                     // one thread: 4 boxes of 64 columns x 128 rows
-        mbar_expect_tx(&bar_raw[buf], 4 * FT_PANEL);
+        tma::mbar_expect_tx(&bar_raw[buf], 4 * FT_PANEL);
         const int r0 = (int)(tile * FT_ROWS);
-        tma_load_2d(sY[buf] + 0 * FT_PANEL, &tm_cam, 0, r0, &bar_raw[buf]);
-        tma_load_2d(sY[buf] + 1 * FT_PANEL, &tm_cam, 64, r0, &bar_raw[buf]);
-        tma_load_2d(sY[buf] + 2 * FT_PANEL, &tm_lid, 0, r0, &bar_raw[buf]);
-        tma_load_2d(sY[buf] + 3 * FT_PANEL, &tm_lid, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sY[buf] + 0 * FT_PANEL, &tm_cam, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sY[buf] + 1 * FT_PANEL, &tm_cam, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sY[buf] + 2 * FT_PANEL, &tm_lid, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sY[buf] + 3 * FT_PANEL, &tm_lid, 64, r0, &bar_raw[buf]);
     };
     // barriers first, so that the first two tiles are already in flight during the rest of the setup
     if (tid == 0) {
@@ -642,32 +633,6 @@ bool fusion_tc_enabled() {
     return !off;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-// [M,128] bf16 rows, boxes of 64 columns (one 128-byte swizzle span) x 128 rows
-static bool make_row_map(CUtensorMap *tm, const void *base, int64_t M) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)FT_C, (cuuint64_t)M};
-    const cuuint64_t strides[1] = {(cuuint64_t)FT_C * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)FT_ROWS};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
                            const float *csc, const float *csh, const float *lsc, const float *lsh,
                            const float *w1, const float *b1, const float *w2, const float *b2,
@@ -683,7 +648,7 @@ int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
     const int blocks = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     static const bool no_tma = getenv("KDF_FUSION_NO_TMA") != nullptr;      // experiment knob: register-staged tiles
     CUtensorMap tm_cam, tm_lid;
-    if (!no_tma && M < (1ll << 31) && make_row_map(&tm_cam, cam_pre, M) && make_row_map(&tm_lid, lid_pre, M)) {
+    if (!no_tma && M < (1ll << 31) && tma::make_row_map(&tm_cam, cam_pre, M, FT_C) && tma::make_row_map(&tm_lid, lid_pre, M, FT_C)) {
         KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtTmaSmem::TOTAL));
         fusion_weighted_fwd_tma_kernel<<<blocks, FTM_THREADS, FtTmaSmem::TOTAL, st>>>(a, tm_cam, tm_lid);
         KDF_LAUNCH_CHECK();

@@ -19,6 +19,7 @@
 
 #include "kdf_common.cuh"
 #include "tc_common.cuh"
+#include "tma_common.cuh"
 
 namespace kdf {
 
@@ -998,6 +999,273 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
     if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ============================================================================= layers 2+1 backward, TMA-staged
+// mlp_layer_bwd_kernel<0> spends a third of its instructions forming dz = gs*dy + ga + gb*z element by element before
+// the GEMMs.  The GEMMs are linear and gs/ga/gb are per-channel, so the BatchNorm backward folds into the WEIGHTS:
+//   dgrad : dA = dy.(diag(gs) W) + z.(diag(gb) W) + ga.W                        (two GEMMs + a constant row)
+//   wgrad : dW = diag(gs).(dy^T a1) + diag(gb).(z^T a1) + ga (x) sum_rows(a1)   (two accumulators, combined at the end)
+// and the raw bf16 dy / z tiles become tensor-core operands as they are: they arrive by TMA (SWIZZLE_128B boxes, two
+// tiles in flight, no registers, no instructions), nothing is re-rounded, and the only prologue work left is the
+// recompute of the first layer from the raw point.  Epilogue as before (ReLU mask, sum dy1, sum dy1 p^T), staged in bf16.
+struct MlpBwd0TmaSmem {
+    static constexpr int PANEL = PM_ROWS * 128;                      // 16384
+    static constexpr int OFF_WS = 0;                                 // diag(gs) W2  [128 n x 64 k] bf16
+    static constexpr int OFF_WB = OFF_WS + PANEL;                    // diag(gb) W2
+    static constexpr int OFF_DY0 = OFF_WB + PANEL;                   // dy tile, 2 panels, x 2 stages
+    static constexpr int OFF_DY1 = OFF_DY0 + 2 * PANEL;
+    static constexpr int OFF_Z0 = OFF_DY1 + 2 * PANEL;               // z tile, 2 panels, x 2 stages
+    static constexpr int OFF_Z1 = OFF_Z0 + 2 * PANEL;
+    static constexpr int OFF_A0 = OFF_Z1 + 2 * PANEL;                // a1 tile, 1 panel, x 2 stages
+    static constexpr int OFF_A1 = OFF_A0 + PANEL;
+    static constexpr int OFF_STAGE = OFF_A1 + PANEL;                 // dy1 staging, bf16 [128 x 64]
+    static constexpr int OFF_PTS = OFF_STAGE + PANEL;                // raw points, 2 x 128 float4
+    static constexpr int OFF_MISC = OFF_PTS + 2 * PM_ROWS * 16;
+    // 4 mbarriers + tmem slot, then floats: ga[128] gs[128] gb[128] q[8*36] r[64] cvec[64] asum[64]
+    static constexpr int MISC_BYTES = 64 + 4 * (3 * 128 + 8 * 36 + 64 + 64 + 64);
+    static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
+};
+
+constexpr int B0T_THREADS = 512;
+
+__global__ void __launch_bounds__(B0T_THREADS, 1)
+mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_z) {
+    using L = MlpBwd0TmaSmem;
+    constexpr int KIN = 64;
+    constexpr uint32_t PANEL = L::PANEL;
+    constexpr uint32_t IDESC_D = tc::make_idesc(PM_ROWS, KIN, 0, 1);       // dgrad: A K-major, B MN-major
+    constexpr uint32_t IDESC_W = tc::make_idesc(PM_N, KIN, 1, 1);          // wgrad: both MN-major
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sWs = smem + L::OFF_WS, *sWb = smem + L::OFF_WB;
+    uint8_t *sDy[2] = {smem + L::OFF_DY0, smem + L::OFF_DY1};
+    uint8_t *sZ[2] = {smem + L::OFF_Z0, smem + L::OFF_Z1};
+    uint8_t *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1};
+    uint8_t *sStage = smem + L::OFF_STAGE;
+    float4 *sPts = reinterpret_cast<float4 *>(smem + L::OFF_PTS);
+    uint64_t *bar_raw = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);            // [2]
+    uint64_t *bar_mma = bar_raw + 2;                                                 // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 48);
+    float *cga = reinterpret_cast<float *>(smem + L::OFF_MISC + 64), *cgs = cga + 128, *cgb = cgs + 128;
+    float *coef = cgb + 128;                                         // q: 8 chunks x 36, r at 288
+    float *cvec = coef + 8 * 36 + 64, *asum = cvec + 64;
+    float *red = reinterpret_cast<float *>(sStage);                  // end-of-kernel reductions reuse the staging tile (4096 floats)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
+    auto issue_tile = [&](int64_t tile, int buf) {                   // one thread: dy and z tiles, 2 boxes each
+        tma::mbar_expect_tx(&bar_raw[buf], 4 * PANEL);
+        const int r0 = (int)(tile * PM_ROWS);
+        tma::load_2d(sDy[buf], &tm_dy, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sDy[buf] + PANEL, &tm_dy, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sZ[buf], &tm_z, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sZ[buf] + PANEL, &tm_z, 64, r0, &bar_raw[buf]);
+    };
+    if (tid == 0) {
+        tc::mbar_init(&bar_raw[0], 1); tc::mbar_init(&bar_raw[1], 1);
+        tc::mbar_init(&bar_mma[0], 1); tc::mbar_init(&bar_mma[1], 1);
+        tc::mbar_fence_init();
+        tc::fence_async_smem();
+        if ((int64_t)blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
+        if ((int64_t)blockIdx.x + gridDim.x < n_tiles) issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+    for (int i = tid; i < 128; i += B0T_THREADS) { cgs[i] = a.gs[i]; cga[i] = a.ga[i]; cgb[i] = a.gb[i]; }
+    for (int i = tid; i < 64 * 4; i += B0T_THREADS) coef[(i >> 5) * 36 + (i & 31)] = a.pro_a[i];
+    for (int i = tid; i < 64; i += B0T_THREADS) coef[288 + i] = a.pro_b[i];
+    // the two scaled copies of W2 (rounded once, from the bf16 weight the forward used)
+    for (int idx = tid; idx < PM_N * 8; idx += B0T_THREADS) {
+        const int n = idx >> 3, ch = idx & 7;
+        float w[8], ws[8], wb[8];
+        unpack8(*reinterpret_cast<const uint4 *>(a.W + (int64_t)n * KIN + ch * 8), w);
+        const float s = __ldg(a.gs + n), b = __ldg(a.gb + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ws[j] = s * w[j]; wb[j] = b * w[j]; }
+        *reinterpret_cast<uint4 *>(sWs + tc::sw128_offset(n, ch)) = pack8(ws);
+        *reinterpret_cast<uint4 *>(sWb + tc::sw128_offset(n, ch)) = pack8(wb);
+    }
+    if (tid < 64) {                                                  // the constant row of the data gradient: ga . W2
+        float v = 0.f;
+        for (int n = 0; n < PM_N; ++n) v = fmaf(__ldg(a.ga + n), __bfloat162float(a.W[(int64_t)n * KIN + tid]), v);
+        cvec[tid] = v;
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // activation tile: 8 chunks per row, 64 rows per pass, 2 passes
+    const int ach = tid & 7, arow0 = tid >> 3;
+    float c0[32], c1[8];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) c0[j] = coef[ach * 36 + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c1[j] = coef[288 + ach * 8 + j];
+    float a_sum[8];                                                  // column sums of a1 over this CTA's rows (for ga (x) sum a1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a_sum[j] = 0.f;
+    uint4 rpt[2];
+    auto load_pts = [&](int64_t tile) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int64_t row = tile * PM_ROWS + arow0 + p * 64;
+            if (tile < n_tiles && row < a.M) rpt[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.input) + row);
+        }
+    };
+    auto stage_a = [&](int64_t tile, int buf) {
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int r = arow0 + p * 64;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r0 + r < a.M) {
+                const float4 pt = make_float4(__uint_as_float(rpt[p].x), __uint_as_float(rpt[p].y),
+                                              __uint_as_float(rpt[p].z), __uint_as_float(rpt[p].w));
+                v = first_layer_chunk(pt, c0, c1);
+                float f[8];
+                unpack8(v, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a_sum[j] += f[j];
+                if (ach == 0) sPts[buf * PM_ROWS + r] = pt;
+            }
+            *reinterpret_cast<uint4 *>(sA[buf] + tc::sw128_offset(r, ach)) = v;
+        }
+        tc::fence_async_smem();
+    };
+    auto issue_mma = [&](int buf, bool first, uint32_t raw_parity) {     // one thread
+        tc::mbar_wait(&bar_raw[buf], raw_parity);                        // dy / z of this tile have landed
+        tc::fence_after_sync();
+        const uint32_t dy = tc::smem_u32(sDy[buf]), z = tc::smem_u32(sZ[buf]), act = tc::smem_u32(sA[buf]);
+        const uint32_t ws = tc::smem_u32(sWs), wb = tc::smem_u32(sWb);
+        const uint32_t acc_d = tmem_base + (uint32_t)buf * KIN, acc_ws = tmem_base + 2u * KIN, acc_wb = tmem_base + 3u * KIN;
+#pragma unroll
+        for (int k = 0; k < PM_N / 16; ++k) {                            // dgrad: K = the 128 gradient channels, twice
+            const uint32_t koff = (uint32_t)(k >> 2) * PANEL + (uint32_t)(k & 3) * 32u;
+            tc::mma_bf16(acc_d, tc::desc_kmajor(dy + koff), tc::desc_mnmajor(ws + (uint32_t)k * 2048u, PANEL), IDESC_D, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < PM_N / 16; ++k) {
+            const uint32_t koff = (uint32_t)(k >> 2) * PANEL + (uint32_t)(k & 3) * 32u;
+            tc::mma_bf16(acc_d, tc::desc_kmajor(z + koff), tc::desc_mnmajor(wb + (uint32_t)k * 2048u, PANEL), IDESC_D, true);
+        }
+#pragma unroll
+        for (int k = 0; k < PM_ROWS / 16; ++k) {                         // wgrad: K = the 128 points of the tile, two accumulators
+            tc::mma_bf16(acc_ws, tc::desc_mnmajor(dy + (uint32_t)k * 2048u, PANEL), tc::desc_mnmajor(act + (uint32_t)k * 2048u, PANEL),
+                         IDESC_W, !(first && k == 0));
+        }
+#pragma unroll
+        for (int k = 0; k < PM_ROWS / 16; ++k) {
+            tc::mma_bf16(acc_wb, tc::desc_mnmajor(z + (uint32_t)k * 2048u, PANEL), tc::desc_mnmajor(act + (uint32_t)k * 2048u, PANEL),
+                         IDESC_W, !(first && k == 0));
+        }
+        tc::mma_commit(&bar_mma[buf]);
+    };
+
+    float acc[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) acc[j] = 0.f;
+    const int ccol = tid & 63, crq = tid >> 6;                           // column-owner phase: 8 groups x 16 rows
+    auto epilogue = [&](int64_t tile, int buf, uint32_t parity, int64_t refill_tile) {
+        const int64_t r0 = tile * PM_ROWS;
+        tc::mbar_wait(&bar_mma[buf], parity);
+        tc::fence_after_sync();
+        // the tensor cores are done with this stage's dy / z tiles: refill them right away
+        if (tid == 0 && refill_tile < n_tiles) issue_tile(refill_tile, buf);
+        const int row = (warp & 3) * 32 + lane;
+        {
+            const int col0 = (warp >> 2) * 16;                           // 16 warps: 4 column groups of 16
+            uint32_t r[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * KIN + (uint32_t)col0, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int chunk = (col0 >> 3) + j;
+                float act[8], v[8];
+                unpack8(*reinterpret_cast<const uint4 *>(sA[buf] + tc::sw128_offset(row, chunk)), act);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = act[e] > 0.f ? __uint_as_float(r[8 * j + e]) + cvec[chunk * 8 + e] : 0.f;
+                *reinterpret_cast<uint4 *>(sStage + tc::sw128_offset(row, chunk)) = pack8(v);
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        {
+            const int rows = (int)((a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS);
+            const int rbeg = crq * 16, rend = (rbeg + 16 < rows) ? rbeg + 16 : rows;
+            for (int r = rbeg; r < rend; ++r) {
+                const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16 *>(sStage + tc::sw128_offset(r, ccol >> 3) + (ccol & 7) * 2);
+                const float v = __bfloat162float(hv);
+                const float4 pt = sPts[buf * PM_ROWS + r];
+                acc[0] += v;
+                acc[1] = fmaf(v, pt.x, acc[1]); acc[2] = fmaf(v, pt.y, acc[2]);
+                acc[3] = fmaf(v, pt.z, acc[3]); acc[4] = fmaf(v, pt.w, acc[4]);
+            }
+        }
+        __syncthreads();                                                 // staging tile, a1 tile and points of this stage are free again
+    };
+
+    // ---- pipeline: MMA(i) | points(i+1) in flight | epilogue(i-1) + TMA refill | a1(i+1)
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) {
+        load_pts(tile);
+        stage_a(tile, 0);
+    }
+    __syncthreads();
+    int it = 0;
+    int64_t prev_tile = -1;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0) issue_mma(buf, it == 0, (uint32_t)((it >> 1) & 1));
+        const int64_t next = tile + gridDim.x;
+        load_pts(next);
+        if (it > 0) epilogue(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1), next);   // refills stage buf^1 with tile i+1
+        if (next < n_tiles) stage_a(next, buf ^ 1);
+        __syncthreads();
+        prev_tile = tile;
+    }
+    if (it > 0) epilogue(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1), n_tiles);
+
+    // ---- column sums -> fp64 atomics
+#pragma unroll
+    for (int j = 0; j < 5; ++j) red[tid * 5 + j] = acc[j];
+    __syncthreads();
+    for (int i = tid; i < 64 * 5; i += B0T_THREADS) {
+        const int c = i / 5, j = i % 5;
+        float v = 0.f;
+        for (int q = 0; q < B0T_THREADS / 64; ++q) v += red[(q * 64 + c) * 5 + j];
+        atomicAdd(a.sums + j * 64 + c, (double)v);
+    }
+    __syncthreads();
+    // ---- sum_rows a1 of this CTA (threads sharing a chunk: tid & 7), then the weight gradient
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[tid * 8 + j] = a_sum[j];
+    __syncthreads();
+    if (tid < 64) {
+        const int ch = tid >> 3, j = tid & 7;
+        float v = 0.f;
+        for (int t = ch; t < B0T_THREADS; t += 8) v += red[t * 8 + j];
+        asum[tid] = v;
+    }
+    __syncthreads();
+    if (it > 0) {
+        tc::fence_after_sync();
+        const int n = (warp & 3) * 32 + lane;
+        const int col0 = (warp >> 2) * 16;
+        uint32_t rs[16], rb[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * KIN + (uint32_t)col0, rs);
+        tc::tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 3u * KIN + (uint32_t)col0, rb);
+        tc::tmem_ld_wait();
+        const float gs = cgs[n], gb = cgb[n], ga = cga[n];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            atomicAdd(a.dW + n * KIN + col0 + j, fmaf(gs, __uint_as_float(rs[j]), fmaf(gb, __uint_as_float(rb[j]), ga * asum[col0 + j])));
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
 // mean / invstd / folded scale,shift / running statistics from fp64 column sums
 __global__ void bn_finalize_kernel(const double *stats, int64_t M, int C, const float *gamma, const float *beta,
                                    const float *pre_bias, float eps, float momentum, float *running_mean,
@@ -1168,6 +1436,14 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
     const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
     int blocks = sm_count();
     if (n_tiles < blocks) blocks = (int)n_tiles;
+    static const bool no_tma = getenv("KDF_MLP_NO_TMA") != nullptr;                  // experiment knob: register-staged mode-0 backward
+    CUtensorMap tm_dy, tm_z;
+    if (mode == 0 && !no_tma && row_cell == nullptr && tma::make_row_map(&tm_dy, dy, M, PM_N) && tma::make_row_map(&tm_z, z, M, PM_N)) {
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd0_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpBwd0TmaSmem::TOTAL));
+        mlp_layer_bwd0_tma_kernel<<<blocks, B0T_THREADS, MlpBwd0TmaSmem::TOTAL, st>>>(a, tm_dy, tm_z);
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
     static const bool warp_spec = getenv("KDF_MLP_WARP_SPECIALISED") != nullptr;   // experiment knob (measured slower: 1.64 / 1.90 ms
     if (warp_spec) {                                                                 // against 1.48 / 1.38 ms)
         if (mode == 0) {
