@@ -313,7 +313,6 @@ def kernel_rooflines(args, device, fp32):
     grid = torch.empty(B, H, W, C, dtype=dt, device=device)
     cnt = torch.empty(B, H * W, dtype=torch.int32, device=device)
     cel = torch.empty(B, N, dtype=torch.int32, device=device)
-    ties = torch.empty(B, H * W, C, dtype=torch.int32, device=device)
     order2 = torch.empty(B, N, dtype=torch.int32, device=device)
     offs = torch.empty(B, H * W + 1, dtype=torch.int32, device=device)
     wsb = native.lib.kdf_bev_workspace_bytes(B, N, H, W)
@@ -321,23 +320,23 @@ def kernel_rooflines(args, device, fp32):
 
     def proj_fwd():
         native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), native.dtype_code(feats), B, N, C, *geom, H, W, 0,
-                    p(grid), p(cnt), p(cel), p(ties), p(order2), p(offs), p(ws), wsb, st)
-    add("bev_project_fwd (index+scan+fill+reduce with tie counts)", time_kernel(proj_fwd), B * (16 * N + C * s * v * N + C * s * H * W + 4 * H * W),
+                    p(grid), p(cnt), p(cel), None, p(order2), p(offs), p(ws), wsb, st)
+    add("bev_project_fwd (index+scan+fill+max)", time_kernel(proj_fwd), B * (16 * N + C * s * v * N + C * s * H * W + 4 * H * W),
         "16N + C*s*v*N + C*s*HW + 4*HW per frame (SURVEY 8d)", in_step=fp32)
     gg = torch.rand(B, H * W, C, device=device, dtype=dt)
     gf = torch.empty(B, N, C, dtype=dt, device=device)
 
     def proj_bwd():
-        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order2), p(offs),
+        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), None, None, p(cel), p(order2), p(offs),
                     native.dtype_code(feats), B, N, C, H, W, 0, p(gf), st)
-    add("bev_bwd_wide_kernel", time_kernel(proj_bwd), B * (C * s * H * W + C * s * v * N + 4 * N),
-        "C*s*HW + C*s*v*N + 4N per frame (SURVEY 8d); actual traffic is higher: feats re-read for the exact "
-        "tie split (C*s*v*N) and zero rows written for points outside (C*s*(1-v)*N)", in_step=fp32)
+    add("bev_bwd_max_kernel", time_kernel(proj_bwd), B * (2 * C * s * H * W + 2 * C * s * v * N + C * s * (1 - v) * N + 4 * N + 4 * v * N),
+        "grad/max rows per cell (2*C*s*HW) + rows of valid points read once for the exact tie split (C*s*v*N; the second "
+        "sweep hits L1/L2) + a gradient row per point (C*s*N, zeros for points outside) + cell ids and order", in_step=fp32)
 
     def index_only():
         native.call("kdf_bev_index", p(pts), B, N, 4, *geom, H, W, p(cel), None, p(cnt), st)
     add("bev_index_kernel", time_kernel(index_only), B * (16 * N + 4 * N + 4 * H * W), "16N + 4N + 4*HW per frame")
-    del feats, gf, gg, ties
+    del feats, gf, gg
 
     # ---- fusion (weighted) forward / backward on pre-BN rows
     M = B * H * W

@@ -75,7 +75,10 @@ size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W);
  *                                     reference returns (lidar_encoder.py:99)
  *   count     i32 [B,H*W] out
  *   cell      i32 [B,N]   out
- *   ties      i32 [B,H*W,C] out, max only, may be NULL: sources equal to the max
+ *   ties      i32 [B,H*W,C] out, max only, may be NULL: sources equal to the max.  Pass NULL when
+ *                          one row is 8/16/32 16-byte lanes (C = 64/128/256 bf16, 32/64/128 fp32): the
+ *                          forward is then a pure packed maximum and kdf_bev_project_bwd counts the ties
+ *                          itself from feats/grid (faster both ways); other C need it for the backward
  *   order     i32 [B,N]   out, may be NULL (then taken from workspace): point ids
  *                          grouped by cell (counting sort), offsets in `offsets`
  *   offsets   i32 [B,H*W+1] out, may be NULL (then taken from workspace)
@@ -106,7 +109,8 @@ int kdf_bev_reduce(const void *feats, int dtype, const int32_t *order, const int
  * evenly among the sources equal to the max (ATen ScatterReduceBackward), with
  * ATen's quirk that a max of exactly 0.0 counts the zero-initialised output as
  * one more tie.  mean: grad / count.  Points outside the grid get 0.
- *   grad_grid dtype [B,H*W,C]; grid/ties from the forward (max only);
+ *   grad_grid dtype [B,H*W,C]; grid/ties from the forward (max only; ties may be NULL when the forward
+ *   was run without them, see kdf_bev_project_fwd -- needs order/offsets);
  *   order/offsets: the forward's cell ordering (both or neither); with it the gradient is
  *   computed cell-major (per-cell rows read once), without it point-major;
  *   grad_feats dtype [B,N,C] out (every row written).

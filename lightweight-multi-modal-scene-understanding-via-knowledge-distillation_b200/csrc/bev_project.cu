@@ -81,6 +81,46 @@ bev_index_kernel(const float *__restrict__ points, int64_t total, int64_t N, int
     }
 }
 
+// Cell ids + occupancy only (no arrival ranks): a CTA walks a slice of one frame, counts into a SHARED-memory
+// histogram with non-returning atomics and flushes its non-empty bins with one global add each -- HW adds per
+// CTA instead of one per (warp, distinct cell).  The slice length is chosen by the host so that the grid still
+// fills the SMs (launch_index).
+__global__ void __launch_bounds__(512)
+bev_index_hist_kernel(const float4 *__restrict__ points, int64_t N, int64_t slice, BevGeom g,
+                      int32_t *__restrict__ cell_out, int32_t *__restrict__ count) {
+    extern __shared__ int hist[];
+    const int HW = g.H * g.W;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < HW; i += 512) hist[i] = 0;
+    __syncthreads();
+    const int64_t beg = (int64_t)blockIdx.x * slice, end = (beg + slice < N) ? beg + slice : N;
+    const float4 *pb = points + (int64_t)b * N;
+    int32_t *cb = cell_out + (int64_t)b * N;
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += 4 * 512) {           // 4 independent points in flight per thread
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 512;
+            if (i < end) p[u] = ldg_stream_f4(pb + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 512;
+            if (i < end) {
+                const int cell = bev_cell_of(p[u].x, p[u].y, g);
+                cb[i] = cell;
+                if (cell >= 0) atomicAdd(&hist[cell], 1);
+            }
+        }
+    }
+    __syncthreads();
+    int32_t *cnt = count + (int64_t)b * HW;
+    for (int i = threadIdx.x; i < HW; i += 512) {
+        const int h = hist[i];
+        if (h) atomicAdd(cnt + i, h);
+    }
+}
+
 // ----------------------------------------------------------------------------- scan
 // One CTA per frame: offsets[b, 0..HW] = exclusive prefix of count[b, :].
 __global__ void __launch_bounds__(1024)
@@ -829,6 +869,207 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
     }
 }
 
+// ----------------------------------------------------------------------------- the reference op without tie counts in the forward
+// `scatter_reduce_(amax, include_self=False)` (lidar_encoder.py:85-96) for rows of LPR 16-byte lanes, built like the
+// two kernels above: the forward is a pure maximum (one `max.bf16x2` per two bf16 channels / one FMNMX per fp32
+// channel -- the tie counts ATen's backward needs are NOT formed here, which is what made `bev_reduce_wide_kernel`
+// ALU-bound), and the backward counts the rows at the maximum in a first sweep and writes the shares in a second
+// one that is served by L1/L2.  Persistent warps with the one-cell-ahead prefetch of offsets and first point ids.
+template <typename T> struct MaxAcc;
+template <> struct MaxAcc<__nv_bfloat16> {
+    uint32_t m[4];
+    __device__ __forceinline__ void init() { m[0] = m[1] = m[2] = m[3] = 0xFF80FF80u; }
+    __device__ __forceinline__ void take(const uint4 &r) {
+        m[0] = bf16x2_max(m[0], r.x); m[1] = bf16x2_max(m[1], r.y); m[2] = bf16x2_max(m[2], r.z); m[3] = bf16x2_max(m[3], r.w);
+    }
+    __device__ __forceinline__ void merge(int o) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = bf16x2_max(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
+    }
+    __device__ __forceinline__ uint4 raw() const { return make_uint4(m[0], m[1], m[2], m[3]); }
+};
+template <> struct MaxAcc<float> {
+    float m[4];
+    __device__ __forceinline__ void init() { m[0] = m[1] = m[2] = m[3] = -INFINITY; }
+    __device__ __forceinline__ void take(const uint4 &r) {
+        m[0] = fmaxf(m[0], __uint_as_float(r.x)); m[1] = fmaxf(m[1], __uint_as_float(r.y));
+        m[2] = fmaxf(m[2], __uint_as_float(r.z)); m[3] = fmaxf(m[3], __uint_as_float(r.w));
+    }
+    __device__ __forceinline__ void merge(int o) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
+    }
+    __device__ __forceinline__ uint4 raw() const {
+        return make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), __float_as_uint(m[3]));
+    }
+};
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256, 4)
+bev_reduce_max_kernel(const T *__restrict__ feats, const int32_t *__restrict__ order, const int32_t *__restrict__ offsets,
+                      T *__restrict__ grid, int64_t n_cells, int64_t N, int HW) {
+    constexpr int VEC = Raw16<T>::VEC, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * VEC;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+    int64_t cid = warp0;
+    CellMeta cur = cell_meta(offsets, cid, n_cells, N, HW);
+    int idn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < cur.n ? __ldg(order + cur.rowbase + cur.beg + j) : -1; }
+    CellMeta nxt = cell_meta(offsets, cid + nwarps, n_cells, N, HW);
+    while (cid < n_cells) {
+        int idn2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn2[u] = j < nxt.n ? __ldg(order + nxt.rowbase + nxt.beg + j) : -1; }
+        const CellMeta nxt2 = cell_meta(offsets, cid + 2 * nwarps, n_cells, N, HW);
+
+        const int32_t *ord = order + cur.rowbase + cur.beg;
+        const T *fb = feats + cur.rowbase * C + ch;
+        MaxAcc<T> acc;
+        acc.init();
+        for (int j0 = 0; j0 < cur.n; j0 += STEP) {
+            uint4 raw[U];
+            int id[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                id[u] = idn[u];
+                if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(fb + (int64_t)id[u] * C));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < cur.n ? __ldg(ord + j) : -1; }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (id[u] >= 0) acc.take(raw[u]);
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) acc.merge(o);
+        if (sub == 0)
+            *reinterpret_cast<uint4 *>(grid + cid * C + ch) = cur.n > 0 ? acc.raw() : make_uint4(0u, 0u, 0u, 0u);   // empty cells are 0
+        cid += nwarps;
+        cur = nxt;
+        nxt = nxt2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) idn[u] = idn2[u];
+    }
+}
+
+template <typename T> struct EqRows;
+template <> struct EqRows<__nv_bfloat16> {
+    static __device__ __forceinline__ void count(const uint4 &r, const uint4 &mx, int *k) {
+        const uint32_t e0 = bf16x2_eq_mask(r.x, mx.x), e1 = bf16x2_eq_mask(r.y, mx.y);
+        const uint32_t e2 = bf16x2_eq_mask(r.z, mx.z), e3 = bf16x2_eq_mask(r.w, mx.w);
+        k[0] += e0 & 1; k[1] += e0 >> 31; k[2] += e1 & 1; k[3] += e1 >> 31;
+        k[4] += e2 & 1; k[5] += e2 >> 31; k[6] += e3 & 1; k[7] += e3 >> 31;
+    }
+    static __device__ __forceinline__ uint4 select(const uint4 &r, const uint4 &mx, const uint4 &share) {
+        return make_uint4(share.x & bf16x2_eq_mask(r.x, mx.x), share.y & bf16x2_eq_mask(r.y, mx.y),
+                          share.z & bf16x2_eq_mask(r.z, mx.z), share.w & bf16x2_eq_mask(r.w, mx.w));
+    }
+};
+template <> struct EqRows<float> {
+    static __device__ __forceinline__ void count(const uint4 &r, const uint4 &mx, int *k) {
+        k[0] += __uint_as_float(r.x) == __uint_as_float(mx.x); k[1] += __uint_as_float(r.y) == __uint_as_float(mx.y);
+        k[2] += __uint_as_float(r.z) == __uint_as_float(mx.z); k[3] += __uint_as_float(r.w) == __uint_as_float(mx.w);
+    }
+    static __device__ __forceinline__ uint4 select(const uint4 &r, const uint4 &mx, const uint4 &share) {
+        return make_uint4(__uint_as_float(r.x) == __uint_as_float(mx.x) ? share.x : 0u, __uint_as_float(r.y) == __uint_as_float(mx.y) ? share.y : 0u,
+                          __uint_as_float(r.z) == __uint_as_float(mx.z) ? share.z : 0u, __uint_as_float(r.w) == __uint_as_float(mx.w) ? share.w : 0u);
+    }
+};
+
+template <typename T, int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bev_bwd_max_kernel(const T *__restrict__ grad_grid, const T *__restrict__ feats, const T *__restrict__ grid,
+                   const int32_t *__restrict__ order, const int32_t *__restrict__ offsets, const int32_t *__restrict__ cell,
+                   T *__restrict__ grad_feats, int64_t n_cells, int64_t N, int HW, int64_t total) {
+    constexpr int VEC = Raw16<T>::VEC, C = LPR * VEC, RPL = 32 / LPR, U = 4, STEP = RPL * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, ch = (lane % LPR) * VEC;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+    int64_t cid = warp0;
+    CellMeta cur = cell_meta(offsets, cid, n_cells, N, HW);
+    int idn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < cur.n ? __ldg(order + cur.rowbase + cur.beg + j) : -1; }
+    CellMeta nxt = cell_meta(offsets, cid + nwarps, n_cells, N, HW);
+    while (cid < n_cells) {
+        int idn2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn2[u] = j < nxt.n ? __ldg(order + nxt.rowbase + nxt.beg + j) : -1; }
+        const CellMeta nxt2 = cell_meta(offsets, cid + 2 * nwarps, n_cells, N, HW);
+        if (cur.n > 0) {
+            const int32_t *ord = order + cur.rowbase + cur.beg;
+            const T *fb = feats + cur.rowbase * C + ch;
+            T *db = grad_feats + cur.rowbase * C + ch;
+            const uint4 mx = __ldg(reinterpret_cast<const uint4 *>(grid + cid * C + ch));
+            const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(grad_grid + cid * C + ch));
+            // sweep A: rows at the maximum, per channel
+            int k[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) k[q] = 0;
+            int ida[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) ida[u] = idn[u];
+            for (int j0 = 0; j0 < cur.n; j0 += STEP) {
+                uint4 raw[U];
+                int id[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    id[u] = ida[u];
+                    if (id[u] >= 0) raw[u] = __ldg(reinterpret_cast<const uint4 *>(fb + (int64_t)id[u] * C));     // L1-allocating: sweep B re-reads
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; ida[u] = j < cur.n ? __ldg(ord + j) : -1; }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (id[u] >= 0) EqRows<T>::count(raw[u], mx, k);
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) k[q] += __shfl_xor_sync(0xffffffffu, k[q], o);
+            }
+            // ATen: N_to_distribute = (self == result) + #(src == result), self being the zero-initialised output
+            float g[VEC], m[VEC];
+            Raw16<T>::unpack(gv, g);
+            Raw16<T>::unpack(mx, m);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) g[q] = g[q] / (float)(k[q] + (m[q] == 0.f ? 1 : 0));
+            const uint4 share = Raw16<T>::pack(g);
+            // sweep B: the gradient rows
+#pragma unroll
+            for (int u = 0; u < U; ++u) ida[u] = idn[u];
+            for (int j0 = 0; j0 < cur.n; j0 += STEP) {
+                uint4 raw[U];
+                int id[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    id[u] = ida[u];
+                    if (id[u] >= 0) raw[u] = __ldg(reinterpret_cast<const uint4 *>(fb + (int64_t)id[u] * C));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; ida[u] = j < cur.n ? __ldg(ord + j) : -1; }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (id[u] >= 0) *reinterpret_cast<uint4 *>(db + (int64_t)id[u] * C) = EqRows<T>::select(raw[u], mx, share);
+            }
+        }
+        cid += nwarps;
+        cur = nxt;
+        nxt = nxt2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) idn[u] = idn2[u];
+    }
+    // rows of points outside the grid
+    const int64_t g0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR), gn = ((int64_t)gridDim.x * blockDim.x) / LPR;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = g0; i < total; i += gn)
+        if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(grad_feats + i * C + ch) = zero;
+}
+
 // ----------------------------------------------------------------------------- host side
 static int check_geom(int B, int64_t N, int H, int W, float xspan, float yspan) {
     KDF_CHECK_ARG(B >= 0 && N >= 0, "bev: negative B or N");
@@ -852,6 +1093,24 @@ static int launch_index(const float *points, int B, int64_t N, int stride, const
     KDF_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)B * g.H * g.W, st));
     if (total == 0) return KDF_OK;
     const bool vec4 = (stride == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    static const bool warp_atomics = getenv("KDF_BEV_INDEX_WARP_ATOMICS") != nullptr;             // experiment knob
+    const size_t hist_bytes = sizeof(int) * (size_t)g.H * g.W;
+    if (vec4 && rank == nullptr && !warp_atomics && hist_bytes <= 96 * 1024 && B <= 65535) {
+        // slices of >= 8192 points, about four 512-thread CTAs per SM over the whole batch
+        static const int per_sm = getenv("KDF_BEV_INDEX_CTAS_PER_SM") ? atoi(getenv("KDF_BEV_INDEX_CTAS_PER_SM")) : 4;
+        int64_t slice = (total + (int64_t)sm_count() * per_sm - 1) / ((int64_t)sm_count() * per_sm);
+        if (slice < 8192) slice = 8192;
+        slice = (slice + 2047) / 2048 * 2048;
+        const int64_t nslice = (N + slice - 1) / slice;
+        if (nslice <= 65535) {
+            if (hist_bytes > 48 * 1024)
+                KDF_CUDA(cudaFuncSetAttribute(bev_index_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+            bev_index_hist_kernel<<<dim3((unsigned)nslice, (unsigned)B), 512, hist_bytes, st>>>(
+                reinterpret_cast<const float4 *>(points), N, slice, g, cell, count);
+            KDF_LAUNCH_CHECK();
+            return KDF_OK;
+        }
+    }
     const int blocks = grid_for(total, 256, 4);
     if (vec4) bev_index_kernel<true><<<blocks, 256, 0, st>>>(points, total, N, stride, g, cell, rank, count);
     else      bev_index_kernel<false><<<blocks, 256, 0, st>>>(points, total, N, stride, g, cell, rank, count);
@@ -870,6 +1129,17 @@ static int launch_reduce(const void *feats, int dtype, const int32_t *order, con
     const int64_t n_cells = (int64_t)B * HW;
     const int blocks = grid_for(n_cells * 32, 256, 64);
     const int lpr = wide_lpr(dtype, C);
+    if (lpr && reduce == KDF_REDUCE_MAX && ties == nullptr) {        // pure maximum: persistent warps, several cells each
+        int64_t pb = (n_cells + 7) / 8;
+        if (pb > (int64_t)sm_count() * 8) pb = (int64_t)sm_count() * 8;
+#define KDF_RM(T, L) bev_reduce_max_kernel<T, L><<<(int)pb, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
+                                                                         reinterpret_cast<T *>(grid), n_cells, N, HW)
+        if (dtype == KDF_F32) { if (lpr == 8) KDF_RM(float, 8); else if (lpr == 16) KDF_RM(float, 16); else KDF_RM(float, 32); }
+        else { if (lpr == 8) KDF_RM(__nv_bfloat16, 8); else if (lpr == 16) KDF_RM(__nv_bfloat16, 16); else KDF_RM(__nv_bfloat16, 32); }
+#undef KDF_RM
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
 #define KDF_RW(T, L, R)                                                                                 \
     bev_reduce_wide_kernel<T, L, R><<<blocks, 256, 0, st>>>(reinterpret_cast<const T *>(feats), order, offsets, \
                                                             reinterpret_cast<T *>(grid), ties, n_cells, N, HW)
@@ -1026,12 +1296,26 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
     KDF_CHECK_ARG(reduce == KDF_REDUCE_MAX || reduce == KDF_REDUCE_MEAN, "bev_bwd: bad reduce %d", reduce);
     if (total == 0) return KDF_OK;
     KDF_CHECK_ARG(grad_grid && cell && grad_feats, "bev_bwd: null pointer");
-    if (reduce == KDF_REDUCE_MAX) KDF_CHECK_ARG(feats && grid && ties, "bev_bwd(max): feats/grid/ties required");
+    if (reduce == KDF_REDUCE_MAX) KDF_CHECK_ARG(feats && grid, "bev_bwd(max): feats/grid required");
     else KDF_CHECK_ARG(count, "bev_bwd(mean): count required");
     KDF_CHECK_ARG((order == nullptr) == (offsets == nullptr), "bev_bwd: order and offsets come together");
     cudaStream_t st = as_stream(stream);
     const int HW = H * W;
     const int lpr = order ? wide_lpr(dtype, C) : 0;
+    if (reduce == KDF_REDUCE_MAX) KDF_CHECK_ARG(ties || lpr, "bev_bwd(max): tie counts are required for this C / without the cell ordering");
+    if (lpr && reduce == KDF_REDUCE_MAX && ties == nullptr) {       // tie counts formed here (sweep A), shares written in sweep B
+        const int64_t n_cells = (int64_t)B * HW;
+        int64_t pb = (n_cells + 7) / 8;
+        if (pb > (int64_t)sm_count() * 3) pb = (int64_t)sm_count() * 3;
+#define KDF_BM(T, L) bev_bwd_max_kernel<T, L, 3><<<(int)pb, 256, 0, st>>>(reinterpret_cast<const T *>(grad_grid),          \
+        reinterpret_cast<const T *>(feats), reinterpret_cast<const T *>(grid), order, offsets, cell,                     \
+        reinterpret_cast<T *>(grad_feats), n_cells, N, HW, total)
+        if (dtype == KDF_F32) { if (lpr == 8) KDF_BM(float, 8); else if (lpr == 16) KDF_BM(float, 16); else KDF_BM(float, 32); }
+        else { if (lpr == 8) KDF_BM(__nv_bfloat16, 8); else if (lpr == 16) KDF_BM(__nv_bfloat16, 16); else KDF_BM(__nv_bfloat16, 32); }
+#undef KDF_BM
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
     if (lpr) {                       // cell-major: per-cell rows loaded once, feature rows streamed
         const int64_t n_cells = (int64_t)B * HW;
         const int blocks = grid_for(n_cells * 32, 256, 64);

@@ -309,7 +309,9 @@ class BevProjectFn(torch.autograd.Function):
         count = torch.empty(B, H * W, dtype=torch.int32, device=dev)
         cell = torch.empty(B, N, dtype=torch.int32, device=dev)
         need_grad = feats.requires_grad
-        need_ties = reduce == _n.REDUCE_MAX and need_grad
+        # rows of 8/16/32 16-byte lanes: pure-maximum forward, the backward counts the ties itself
+        lanes, rem = divmod(C * feats.element_size(), 16)
+        need_ties = reduce == _n.REDUCE_MAX and need_grad and not (rem == 0 and lanes in (8, 16, 32))
         ties = torch.empty(B, H * W, C, dtype=torch.int32, device=dev) if need_ties else None
         # the cell ordering is kept for the (cell-major) backward
         order = torch.empty(B, N, dtype=torch.int32, device=dev) if need_grad else None

@@ -180,6 +180,39 @@ def test_bev_project_bf16_features_exact_max(ops):
     np.testing.assert_array_equal(grid.float().permute(0, 2, 3, 1).reshape(B, 4096, C).cpu().numpy(), ref_grid)
 
 
+@pytest.mark.parametrize("dtype,C", [(torch.float32, 128), (torch.float32, 32), (torch.bfloat16, 128), (torch.bfloat16, 64)])
+def test_bev_project_tie_free_forward_equals_tie_counting_path(ops, dtype, C):
+    """The pure-maximum forward + tie-counting backward (ties = NULL through the C ABI) against the forward that
+    stores tie counts (the earlier kernels, still what other channel counts use): identical grids and gradients,
+    bit for bit, including ties, zero maxima (ATen's extra tie) and points outside the grid."""
+    from src import native
+    B, N, H, W = 3, 7000, 64, 64
+    pts, feats = _proj_inputs(B, N, C, seed=31)
+    pts, feats = pts.cuda(), feats.to(dtype).cuda()
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    gg = torch.randn(B, H * W, C, device="cuda").to(dtype)
+    p, st = native.ptr, native.stream_ptr(pts.device)
+    wsb = native.lib.kdf_bev_workspace_bytes(B, N, H, W)
+    outs = []
+    for with_ties in (True, False):
+        grid = torch.empty(B, H, W, C, dtype=dtype, device="cuda")
+        cnt = torch.empty(B, H * W, dtype=torch.int32, device="cuda")
+        cel = torch.empty(B, N, dtype=torch.int32, device="cuda")
+        ties = torch.empty(B, H * W, C, dtype=torch.int32, device="cuda") if with_ties else None
+        order = torch.empty(B, N, dtype=torch.int32, device="cuda")
+        offs = torch.empty(B, H * W + 1, dtype=torch.int32, device="cuda")
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        gf = torch.full((B, N, C), 7.0, dtype=dtype, device="cuda")
+        native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), native.dtype_code(feats), B, N, C, *geom, H, W, 0,
+                    p(grid), p(cnt), p(cel), p(ties), p(order), p(offs), p(ws), wsb, st)
+        native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order), p(offs),
+                    native.dtype_code(feats), B, N, C, H, W, 0, p(gf), st)
+        outs.append((grid, gf))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert (outs[1][1] != 0).any()
+
+
 def test_bev_project_mean(ops):
     """per-cell mean (north star; not in the reference -> parity unpinned, torch scatter_reduce as oracle)."""
     B, N, C = 2, 5000, 64
