@@ -182,6 +182,13 @@ int kdf_point_moments(const float *points, int64_t M, double *out14, void *strea
  */
 int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a, const float *pro_b,
                       const void *W_bf16, int Kin, int Nout, void *z_out, double *stats, void *stream);
+/* All three layers in ONE kernel when the BatchNorms use running statistics (eval mode -- the frozen teacher of the
+ * distillation step): points f32 [M,4] -> z3 bf16 [M,128] (pre-BatchNorm-3 rows, what kdf_bev_reduce_affine takes).
+ * q/r: folded first layer as in mode 0 above; scale2/shift2 f32 [128]: BatchNorm-2 with running statistics;
+ * W2 bf16 [128,64], W3 bf16 [128,128].  z2 never exists in HBM (16 + 256 B per point instead of 16 + 768).
+ * Bit-identical to kdf_mlp_layer_fwd(mode 0) followed by kdf_mlp_layer_fwd(mode 1). */
+int kdf_mlp_eval3_fwd(const float *points, int64_t M, const float *q, const float *r, const void *W2_bf16,
+                      const float *scale2, const float *shift2, const void *W3_bf16, void *z3_out, void *stream);
 int kdf_bn_finalize(const double *stats, int64_t M, int C, const float *gamma, const float *beta, const float *pre_bias,
                     float eps, float momentum, float *running_mean, float *running_var,
                     float *mean, float *invstd, float *scale, float *shift, void *stream);

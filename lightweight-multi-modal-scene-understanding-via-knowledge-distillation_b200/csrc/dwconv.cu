@@ -11,6 +11,8 @@
 //   dgrad2  : stride-2 data gradient in gather form, one 2x2 input patch per thread (no parity divergence).
 //   wgrad   : per-thread [9][4] partial sums over strips of 8 output pixels with a sliding 3x3 input window,
 //             block reduction, fp32 atomics.
+#include <stdlib.h>
+
 #include "kdf_common.cuh"
 
 namespace kdf {
@@ -301,7 +303,9 @@ int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int
                   "dwconv3x3_fwd: map too large for 32-bit indexing");
     const int row_blocks = B * ((OH + DW_R - 1) / DW_R);
     const int gx = (OW * cg + nt - 1) / nt;
-    int gy = (sm_count() * 8 + gx - 1) / gx;                 // ~8 CTAs per SM in total; a thread then walks several row blocks
+    static const int per_sm_stats = getenv("KDF_DW_STATS_CTAS_PER_SM") ? atoi(getenv("KDF_DW_STATS_CTAS_PER_SM")) : 8;   // tuning knob
+    const int per_sm = stats ? per_sm_stats : 8;             // with statistics every CTA ends with 2C fp64 atomics
+    int gy = (sm_count() * per_sm + gx - 1) / gx;            // ~8 CTAs per SM in total; a thread then walks several row blocks
     if (gy > row_blocks) gy = row_blocks;
     const dim3 grid((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy));
     cudaStream_t st = as_stream(stream);
@@ -353,7 +357,8 @@ int kdf_dwconv3x3_bwd_weight(const void *in, const void *grad_out, int dtype, in
     const int64_t nitems = (int64_t)B * OH * ((OW + DW_L - 1) / DW_L);
     KDF_CHECK_ARG(nitems < (1ll << 30), "dwconv3x3_bwd_weight: map too large for 32-bit indexing");
     int64_t blocks = (nitems + rows - 1) / rows;
-    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+    static const int wg_per_sm = getenv("KDF_DW_WGRAD_CTAS_PER_SM") ? atoi(getenv("KDF_DW_WGRAD_CTAS_PER_SM")) : 4;      // tuning knob
+    if (blocks > (int64_t)sm_count() * wg_per_sm) blocks = (int64_t)sm_count() * wg_per_sm;
     const size_t smem = sizeof(float) * (size_t)nt * 36;
 #define KDF_DWW(T, S)                                                                                          \
     do {                                                                                                       \

@@ -281,6 +281,233 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
 }
 
 
+// ============================================================================= all three layers, running statistics
+// With running statistics (eval mode: the frozen teacher of the distillation step) no batch statistic separates
+// the layers, so the whole point MLP is ONE kernel per 128-point tile:
+//   prologue  : fp32 point -> layer 1 (folded BatchNorm) + ReLU -> bf16 operand tile A1 [128 x 64]
+//   MMA 1     : z2 = A1 . W2^T                     (TMEM columns 0..127)
+//   epilogue 1: tcgen05.ld -> round to bf16 (what the layer-by-layer kernels store) -> BatchNorm-2 apply + ReLU
+//               -> bf16 -> operand tile A2 [128 x 128] in shared memory: z2 never exists in HBM
+//   MMA 2     : z3 = A2 . W3^T                     (TMEM columns 128..255)
+//   epilogue 2: tcgen05.ld -> bf16 -> staging -> coalesced 16-byte stores of z3 (no statistics in eval mode)
+// 16 B in, C*2 B out per point instead of 16 + 3*C*2.  The arithmetic is that of mlp_layer_fwd_kernel<0> followed
+// by <1>, operation for operation, so z3 is bit-identical to the two-kernel path.
+// Pipeline: MMA 1 of tile i runs while the points of tile i+1 are loaded and tile i-1 drains through epilogue 2.
+struct MlpEvalArgs {
+    const void *points;               // f32 [M,4]
+    int64_t M;
+    const float *q, *r;               // folded first layer: a1 = relu(q . p + r), q f32 [64,4], r f32 [64]
+    const __nv_bfloat16 *W2;          // [128, 64]
+    const float *sc2, *sh2;           // BatchNorm-2 (running statistics) as scale / shift f32 [128]
+    const __nv_bfloat16 *W3;          // [128, 128]
+    __nv_bfloat16 *z_out;             // [M, 128] pre-BatchNorm-3 rows
+};
+
+struct MlpEvalSmem {
+    static constexpr int OFF_W2 = 0;                                   // 1 panel  [128 n][64 k]
+    static constexpr int OFF_W3 = OFF_W2 + PM_N * 64 * 2;              // 2 panels [128 n][128 k]
+    static constexpr int OFF_A1_0 = OFF_W3 + PM_N * 128 * 2;
+    static constexpr int OFF_A1_1 = OFF_A1_0 + PM_ROWS * 64 * 2;
+    static constexpr int OFF_A2 = OFF_A1_1 + PM_ROWS * 64 * 2;
+    static constexpr int OFF_STAGE = OFF_A2 + PM_ROWS * 128 * 2;
+    static constexpr int OFF_MISC = OFF_STAGE + PM_ROWS * PM_N * 2;
+    static constexpr int MISC_BYTES = 64 + 4 * (64 * 4 + 64 + 2 * 128);
+    static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+mlp_eval3_kernel(MlpEvalArgs a) {
+    KDF_PM_DERIVED(NT);
+    using L = MlpEvalSmem;
+    constexpr int ROWS_PER_PASS = PM_THREADS / 8;                 // 8 chunks per 64-wide A1 row
+    constexpr int PASSES = PM_ROWS / ROWS_PER_PASS;
+    constexpr uint32_t IDESC = tc::make_idesc(PM_ROWS, PM_N, 0, 0);
+    constexpr uint32_t PANEL = PM_ROWS * tc::ROW_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sW2 = smem + L::OFF_W2, *sW3 = smem + L::OFF_W3, *sA1[2] = {smem + L::OFF_A1_0, smem + L::OFF_A1_1};
+    uint8_t *sA2 = smem + L::OFF_A2, *sStage = smem + L::OFF_STAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [0] MMA 1 done, [1] MMA 2 done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
+    float *coef = reinterpret_cast<float *>(smem + L::OFF_MISC + 64);           // q[256] r[64] sc2[128] sh2[128]
+    const float *tsc = coef + 320, *tsh = coef + 448;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
+
+    for (int i = tid; i < 64 * 4; i += PM_THREADS) coef[i] = a.q[i];
+    for (int i = tid; i < 64; i += PM_THREADS) coef[256 + i] = a.r[i];
+    for (int i = tid; i < 128; i += PM_THREADS) { coef[320 + i] = a.sc2[i]; coef[448 + i] = a.sh2[i]; }
+    for (int idx = tid; idx < PM_N * 8; idx += PM_THREADS) {
+        const int n = idx >> 3, ch = idx & 7;
+        *reinterpret_cast<uint4 *>(sW2 + tc::sw128_offset(n, ch)) = *reinterpret_cast<const uint4 *>(a.W2 + (int64_t)n * 64 + ch * 8);
+    }
+    for (int idx = tid; idx < PM_N * 16; idx += PM_THREADS) {
+        const int n = idx >> 4, ch = idx & 15;
+        *reinterpret_cast<uint4 *>(sW3 + (ch >> 3) * (PM_N * tc::ROW_BYTES) + tc::sw128_offset(n, ch & 7)) =
+            *reinterpret_cast<const uint4 *>(a.W3 + (int64_t)n * 128 + ch * 8);
+    }
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pch = tid & 7, prow0 = tid >> 3;
+    float c0[32], c1[8];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) c0[j] = coef[pch * 32 + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c1[j] = coef[256 + pch * 8 + j];
+    const int och = tid & 15, orow0 = tid >> 4;
+
+    uint4 raw[PASSES];
+    auto load_tile = [&](int64_t tile) {
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int64_t row = r0 + prow0 + p * ROWS_PER_PASS;
+            if (row < a.M) raw[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.points) + row);
+        }
+    };
+    auto l2_prefetch = [&](int64_t tile) {
+        if (tile >= n_tiles) return;
+        const int64_t r0 = tile * PM_ROWS;
+        const int64_t rows = (a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS;
+        tc::prefetch_l2(reinterpret_cast<const uint4 *>(a.points) + r0, (uint32_t)(rows * 16));
+    };
+    auto stage_tile = [&](int64_t tile, uint8_t *dst) {
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int r = prow0 + p * ROWS_PER_PASS;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r0 + r < a.M) {
+                const float4 pt = make_float4(__uint_as_float(raw[p].x), __uint_as_float(raw[p].y),
+                                              __uint_as_float(raw[p].z), __uint_as_float(raw[p].w));
+                v = first_layer_chunk(pt, c0, c1);
+            }
+            *reinterpret_cast<uint4 *>(dst + tc::sw128_offset(r, pch)) = v;
+        }
+        tc::fence_async_smem();
+    };
+    auto issue_mma1 = [&](int buf) {                                       // one thread
+        const uint32_t a_base = tc::smem_u32(sA1[buf]), w_base = tc::smem_u32(sW2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            tc::mma_bf16(tmem_base, tc::desc_kmajor(a_base + (uint32_t)k * 32u), tc::desc_kmajor(w_base + (uint32_t)k * 32u), IDESC, k > 0);
+        tc::mma_commit(&bars[0]);
+    };
+    auto issue_mma2 = [&]() {                                              // one thread
+        const uint32_t a_base = tc::smem_u32(sA2), w_base = tc::smem_u32(sW3);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t koff = (uint32_t)(k >> 2) * PANEL + (uint32_t)(k & 3) * 32u;
+            tc::mma_bf16(tmem_base + PM_N, tc::desc_kmajor(a_base + koff), tc::desc_kmajor(w_base + koff), IDESC, k > 0);
+        }
+        tc::mma_commit(&bars[1]);
+    };
+    constexpr int COLS_W = PM_N / PM_CGROUPS;                              // accumulator columns per warp
+    const int erow = (warp & 3) * 32 + lane;                               // this thread's accumulator row
+    const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
+    auto epilogue1 = [&](uint32_t parity) {                                // z2 -> BatchNorm-2 + ReLU -> A2
+        tc::mbar_wait(&bars[0], parity);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int half = 0; half < COLS_W / 32; ++half) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_base + lane_bits + (uint32_t)(warp >> 2) * COLS_W + half * 32, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j;
+                const int col = chunk * 8;
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t zz = pack_bf16(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));   // z2 as stored
+                    const float v0 = fmaxf(fmaf(bf16_lo(zz), tsc[col + 2 * e], tsh[col + 2 * e]), 0.f);
+                    const float v1 = fmaxf(fmaf(bf16_hi(zz), tsc[col + 2 * e + 1], tsh[col + 2 * e + 1]), 0.f);
+                    o[e] = pack_bf16(v0, v1);
+                }
+                *reinterpret_cast<uint4 *>(sA2 + (uint32_t)(chunk >> 3) * PANEL + tc::sw128_offset(erow, chunk & 7)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+    };
+    auto epilogue2 = [&](int64_t tile, uint32_t parity) {                  // z3 -> bf16 rows
+        tc::mbar_wait(&bars[1], parity);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int half = 0; half < COLS_W / 32; ++half) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_base + lane_bits + PM_N + (uint32_t)(warp >> 2) * COLS_W + half * 32, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j;
+                const uint4 v = make_uint4(pack_bf16(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])),
+                                           pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                           pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                                           pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                *reinterpret_cast<uint4 *>(sStage + erow * 256 + ((chunk ^ (erow & 7)) << 4)) = v;
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        const int64_t r0 = tile * PM_ROWS;
+#pragma unroll
+        for (int p = 0; p < PM_OPASSES; ++p) {
+            const int r = orow0 + p * PM_OROWS;
+            if (r0 + r < a.M)
+                *reinterpret_cast<uint4 *>(a.z_out + (r0 + r) * PM_N + och * 8) =
+                    *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) {
+        load_tile(tile);
+        stage_tile(tile, sA1[0]);
+    }
+    __syncthreads();
+    int it = 0;
+    int64_t prev_tile = -1;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0) {
+            tc::fence_after_sync();
+            issue_mma1(buf);
+        }
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) load_tile(next);
+        if (tid == 32) l2_prefetch(next + gridDim.x);
+        if (it > 0) epilogue2(prev_tile, (uint32_t)((it - 1) & 1));        // also: MMA 2 of the previous tile has consumed A2
+        if (next < n_tiles) stage_tile(next, sA1[buf ^ 1]);
+        epilogue1((uint32_t)(it & 1));
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            issue_mma2();
+        }
+        prev_tile = tile;
+    }
+    if (it > 0) epilogue2(prev_tile, (uint32_t)((it - 1) & 1));
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+
 // ============================================================================= fused backward layer
 // One tensor-core layer of the point MLP, backwards, as ONE kernel.  For a 128-point tile it forms, from
 // the gradient dy w.r.t. this layer's BatchNorm output (ReLU already folded in) and the stored pre-BatchNorm
@@ -1410,6 +1637,33 @@ int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a
         const int smem = MlpSmem<128>::TOTAL;
         KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         mlp_layer_fwd_kernel<1, 128, 512><<<blocks, 512, smem, st>>>(a);
+    }
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+int kdf_mlp_eval3_fwd(const float *points, int64_t M, const float *q, const float *r, const void *W2_bf16,
+                      const float *scale2, const float *shift2, const void *W3_bf16, void *z3_out, void *stream) {
+    KDF_CHECK_ARG(M >= 0, "mlp_eval3_fwd: negative M");
+    KDF_CHECK_ARG(q && r && W2_bf16 && scale2 && shift2 && W3_bf16, "mlp_eval3_fwd: null pointer");
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(points && z3_out, "mlp_eval3_fwd: null pointer");
+    KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(points) | reinterpret_cast<uintptr_t>(z3_out) | reinterpret_cast<uintptr_t>(W2_bf16) |
+                    reinterpret_cast<uintptr_t>(W3_bf16)) & 15) == 0, "mlp_eval3_fwd: buffers must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    MlpEvalArgs a{points, M, q, r, reinterpret_cast<const __nv_bfloat16 *>(W2_bf16), scale2, shift2,
+                  reinterpret_cast<const __nv_bfloat16 *>(W3_bf16), reinterpret_cast<__nv_bfloat16 *>(z3_out)};
+    const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
+    int blocks = sm_count();
+    if (n_tiles < blocks) blocks = (int)n_tiles;
+    static const int nt = getenv("KDF_MLP_EVAL_THREADS") ? atoi(getenv("KDF_MLP_EVAL_THREADS")) : 256;    // tuning knob
+    const int smem = MlpEvalSmem::TOTAL;
+    if (nt == 256) {
+        KDF_CUDA(cudaFuncSetAttribute(mlp_eval3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_eval3_kernel<256><<<blocks, 256, smem, st>>>(a);
+    } else {
+        KDF_CUDA(cudaFuncSetAttribute(mlp_eval3_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_eval3_kernel<512><<<blocks, 512, smem, st>>>(a);
     }
     KDF_LAUNCH_CHECK();
     return KDF_OK;

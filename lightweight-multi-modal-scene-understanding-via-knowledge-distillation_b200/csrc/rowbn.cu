@@ -19,12 +19,15 @@
 // CTA to arrive.  All four
 // kernels are HBM-bound streaming kernels; the per-channel finalisation lives in the last
 // CTA of the reduction so no tiny host-driven launches are needed.
+#include <stdlib.h>
+
 #include "kdf_common.cuh"
 
 namespace kdf {
 
 constexpr int RB_THREADS = 256;
 constexpr int RB_MAX_BLOCKS = 1184;          // 148 SMs x 8 CTAs
+constexpr int RB_COPIES = 8;                 // accumulator sets of the column reductions
 
 struct RowMap {           // thread -> (row lane r, column group g) for rows of C = G*VEC channels
     int G, rows, r, g;
@@ -92,7 +95,7 @@ __device__ __forceinline__ bool act_open(float y, int act) {      // derivative 
     return true;
 }
 
-struct RowBnWs {            // workspace header followed by acc[2][C] (fp64)
+struct RowBnWs {            // workspace header followed by acc[RB_COPIES][2][C] (fp64)
     unsigned int ticket;
     unsigned int pad[3];
 };
@@ -170,7 +173,9 @@ rowbn_reduce_kernel(ReduceArgs a) {
         for (int q = 0; q < VEC; ++q) { dst[q] = s0[q]; dst[VEC + q] = s1[q]; }
     }
     __syncthreads();
-    double *acc = reinterpret_cast<double *>(a.ws + 1);
+    // RB_COPIES accumulator sets spread the same-address fp64 atomics (they serialise in L2); the last CTA adds them up
+    double *acc0 = reinterpret_cast<double *>(a.ws + 1);
+    double *acc = acc0 + (size_t)(blockIdx.x % RB_COPIES) * 2 * a.C;
     if (m.active && m.r == 0) {
         for (int rr = 1; rr < m.rows; ++rr) {
             const float *src = sm + (rr * m.G + m.g) * 2 * VEC;
@@ -191,7 +196,12 @@ rowbn_reduce_kernel(ReduceArgs a) {
     __threadfence();
     const double invM = 1.0 / (double)a.M;
     for (int c = threadIdx.x; c < a.C; c += RB_THREADS) {
-        const double t0 = __ldcg(acc + c), t1 = __ldcg(acc + a.C + c);
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < RB_COPIES; ++k) {
+            t0 += __ldcg(acc0 + (size_t)k * 2 * a.C + c);
+            t1 += __ldcg(acc0 + (size_t)k * 2 * a.C + a.C + c);
+        }
         if (MODE == 0) {
             const double mean = t0 * invM;
             double var = t1 * invM - mean * mean;                 // biased variance (normalisation)
@@ -325,10 +335,12 @@ static int rb_check(int dtype, int64_t M, int C, const char *who) {
     return KDF_OK;
 }
 
-static int rb_blocks(int64_t M, int C, int vec, int per_thread_rows) {
+static int rb_blocks(int64_t M, int C, int vec, int per_thread_rows, int max_blocks = 0) {
     const int rows = RB_THREADS / (C / vec);
+
     int64_t b = (M + (int64_t)rows * per_thread_rows - 1) / ((int64_t)rows * per_thread_rows);
-    const int cap = sm_count() * 8 < RB_MAX_BLOCKS ? sm_count() * 8 : RB_MAX_BLOCKS;
+    int cap = sm_count() * 8 < RB_MAX_BLOCKS ? sm_count() * 8 : RB_MAX_BLOCKS;
+    if (max_blocks > 0 && max_blocks < cap) cap = max_blocks;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -337,10 +349,14 @@ static int rb_blocks(int64_t M, int C, int vec, int per_thread_rows) {
 template <int MODE>
 static int launch_reduce(const ReduceArgs &a, int dtype, cudaStream_t st) {
     const int vec = rb_vec(dtype, a.C);
-    const int blocks = rb_blocks(a.M, a.C, vec, 16);
+    // every CTA ends with 2C fp64 atomics on the same 2C addresses: the grid is capped (measured: more, smaller CTAs
+    // lose more to the serialised atomics than they gain in latency hiding)
+    static const int cap = getenv("KDF_ROWBN_REDUCE_CAP") ? atoi(getenv("KDF_ROWBN_REDUCE_CAP")) : 2 * sm_count();      // tuning knob
+    static const int ptr_ = getenv("KDF_ROWBN_REDUCE_ROWS") ? atoi(getenv("KDF_ROWBN_REDUCE_ROWS")) : 16;
+    const int blocks = rb_blocks(a.M, a.C, vec, ptr_, cap);
     const int rows = RB_THREADS / (a.C / vec);
     const size_t smem = sizeof(float) * (size_t)rows * (a.C / vec) * 2 * vec;
-    KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * (size_t)a.C, st));
+    KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * RB_COPIES * (size_t)a.C, st));
     if (dtype == KDF_F32) rowbn_reduce_kernel<float, 4, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
     else if (vec == 8)    rowbn_reduce_kernel<__nv_bfloat16, 8, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
     else                  rowbn_reduce_kernel<__nv_bfloat16, 4, MODE><<<blocks, RB_THREADS, smem, st>>>(a);
@@ -386,7 +402,7 @@ using namespace kdf;
 
 extern "C" {
 
-size_t kdf_rowbn_workspace_bytes(int C) { return sizeof(RowBnWs) + sizeof(double) * 2 * (size_t)C; }
+size_t kdf_rowbn_workspace_bytes(int C) { return sizeof(RowBnWs) + sizeof(double) * 2 * RB_COPIES * (size_t)C; }
 
 int kdf_rowbn_stats(const void *x, int dtype, int64_t M, int C, const float *gamma, const float *beta,
                     const float *pre_bias, float eps, float momentum, float *running_mean, float *running_var,

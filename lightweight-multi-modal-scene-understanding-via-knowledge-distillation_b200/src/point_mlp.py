@@ -18,6 +18,8 @@ math and every statistic stay fp32/fp64.  The per-channel coefficient algebra be
 """
 from __future__ import annotations
 
+import os
+
 import weakref
 from typing import Optional, Tuple
 
@@ -113,6 +115,16 @@ def mlp_layer_fwd_raw(mode, x, pro_a, pro_b, w_bf16):
     return z, stats
 
 
+def mlp_eval3_fwd(points, q, r, w2_bf16, scale2, shift2, w3_bf16):
+    """z3 bf16 [M,128] of the whole point MLP under running statistics (one kernel; see kdf_mlp_eval3_fwd)."""
+    dev = points.device
+    M = points.shape[0]
+    z3 = torch.empty(M, 128, dtype=torch.bfloat16, device=dev)
+    call("kdf_mlp_eval3_fwd", ptr(points), M, ptr(q), ptr(r), ptr(w2_bf16), ptr(scale2), ptr(shift2), ptr(w3_bf16), ptr(z3),
+         stream_ptr(dev))
+    return z3
+
+
 def bn_finalize(stats, M, bn, pre_bias, track: bool):
     """(mean, invstd, scale, shift) f32 [C] from fp64 column sums; advances the running statistics like
     nn.BatchNorm1d does in training (momentum, unbiased variance, the folded conv bias added to the mean)."""
@@ -200,6 +212,16 @@ class _FusedLidarFn(torch.autograd.Function):
             q, r = _eval_first_layer(bn1, w1, b1)
 
         # ---- layers 2 and 3 on the tensor cores
+        if not batch and not need_grad and os.environ.get("KDF_MLP_NO_EVAL3") is None:
+            # running statistics: nothing separates the layers -> one kernel, z2 never leaves the SM
+            from .ops import _eval_affine
+            scale2, shift2, _, _ = _eval_affine(bn2, b2.detach())
+            scale3, shift3, _, _ = _eval_affine(bn3, b3.detach())
+            z3 = mlp_eval3_fwd(pts.view(M, 4), q, r, w2b, scale2, shift2, w3b)
+            cell, count, order, offsets = cached_build_order(points, geom, grid_size)
+            grid, _ = bev_reduce_affine(z3, scale3, shift3, order, offsets, B, N, grid_size, False)
+            ctx.mark_non_differentiable(count, cell)
+            return grid.permute(0, 3, 1, 2), count, cell
         z2, st2 = mlp_layer_fwd_raw(0, pts.view(M, 4), q, r, w2b)
         if batch:
             mean2, invstd2, scale2, shift2 = bn_finalize(st2, M, bn2, b2.detach().float().contiguous(), track)

@@ -56,6 +56,41 @@ def test_mlp_layer_fwd_mode0_first_layer_recomputed(M):
     np.testing.assert_allclose(stats[0].cpu().numpy(), zc.sum(0).numpy(), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("M", [1, 129, 5000, 128 * 148 * 3 + 17, 32 * 170_000])
+@pytest.mark.parametrize("threads", ["256", "512"])
+def test_mlp_eval3_bit_identical_to_layer_kernels(M, threads, monkeypatch):
+    """The one-kernel eval-mode MLP (running statistics; z2 stays on the SM) against kdf_mlp_layer_fwd mode 0
+    followed by mode 1: the same operations in the same order, so the pre-BatchNorm-3 rows must be bit-identical."""
+    import subprocess, sys, os, textwrap
+    # the thread count is read once per process: run each variant in its own interpreter
+    code = textwrap.dedent(f"""
+        import sys, torch
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        sys.path.insert(0, {os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lightweight-multi-modal-scene-understanding-via-knowledge-distillation_b200")!r})
+        from src import point_mlp
+        M = {M}
+        g = torch.Generator(device="cuda").manual_seed(M % 1000)
+        pts = torch.randn(M, 4, generator=g, device="cuda") * torch.tensor([40.0, 40.0, 2.0, 70.0], device="cuda")
+        q = torch.randn(64, 4, generator=g, device="cuda") * 0.02
+        r = torch.randn(64, generator=g, device="cuda") * 0.3
+        W2 = (torch.randn(128, 64, generator=g, device="cuda") / 8).to(torch.bfloat16)
+        W3 = (torch.randn(128, 128, generator=g, device="cuda") / 11.3).to(torch.bfloat16)
+        sc = torch.rand(128, generator=g, device="cuda") + 0.5
+        sc[::7] *= -1
+        sh = torch.randn(128, generator=g, device="cuda") * 0.3
+        z2, _ = point_mlp.mlp_layer_fwd_raw(0, pts, q, r, W2)
+        z3, _ = point_mlp.mlp_layer_fwd_raw(1, z2, sc, sh, W3)
+        got = point_mlp.mlp_eval3_fwd(pts, q, r, W2, sc, sh, W3)
+        torch.cuda.synchronize()
+        assert got.shape == z3.shape and torch.equal(got.view(torch.int16), z3.view(torch.int16)), (got.float() - z3.float()).abs().max()
+        assert z3.float().abs().max() > 0
+        print("ok")
+    """)
+    env = dict(os.environ, KDF_MLP_EVAL_THREADS=threads)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def _bwd_inputs(M, seed):
     g = torch.Generator().manual_seed(seed)
     dy = (torch.randn(M, 128, generator=g) * (torch.rand(M, 128, generator=g) < 0.1)).to(torch.bfloat16)
