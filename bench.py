@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU (weak scaling)")
     ap.add_argument("--points", type=int, default=170_000)
     ap.add_argument("--fp32", action="store_true", help="fp32 activations instead of bf16")
+    ap.add_argument("--student", default="weighted", choices=("weighted", "concat", "minimal"),
+                    help="student fusion ablation (BASELINE.json configs[2] sweeps all three at --batch 64)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="frames per CPU-baseline step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -61,7 +63,8 @@ def parse_args():
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "teacher(concat/256, eval) -> student(weighted/128, train) KD training step, 2-class, "
+    width = 256 if args.student == "concat" else 128
+    return {"workload": f"teacher(concat/256, eval) -> student({args.student}/{width}, train) KD training step, 2-class, "
                         f"{'fp32' if args.fp32 else 'bf16'} activations, {args.batch} frames/GPU, "
                         f"{args.points}-pt sweeps, 256x256 images, 64x64 BEV",
             "global_batch": args.batch * n_gpus, "frames_per_gpu": args.batch, "points_per_frame": args.points,
@@ -72,13 +75,13 @@ def workload_config(args, n_gpus):
 
 
 # ============================================================================= CPU arm (oracle port)
-def cpu_step_runner(batch, points, seed=0):
+def cpu_step_runner(batch, points, seed=0, fusion="weighted"):
     """The reference's CPU path, restated by the oracle: teacher fwd (eval) + student fwd/bwd (train) +
     KD loss + torch AdamW, eager fp32 on all host threads."""
     from oracle import kd_oracle, model_oracle
     from oracle.weights import make_state_dict, synthetic_frames
     torch.set_num_threads(os.cpu_count() or 1)
-    sd_s = model_oracle.clone_state(make_state_dict(5, fusion_type="weighted"), requires_grad=True)
+    sd_s = model_oracle.clone_state(make_state_dict(5, fusion_type=fusion), requires_grad=True)
     sd_t = model_oracle.clone_state(make_state_dict(6, fusion_type="concat", random_running_stats=True))
     params = [v for v in sd_s.values() if v.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-3)
@@ -89,7 +92,7 @@ def cpu_step_runner(batch, points, seed=0):
         opt.zero_grad()
         with torch.no_grad():
             tl, tm = model_oracle.model_forward(img, pts, sd_t, fusion_type="concat", train=False)
-        sl, sm = model_oracle.model_forward(img, pts, sd_s, fusion_type="weighted", train=True)
+        sl, sm = model_oracle.model_forward(img, pts, sd_s, fusion_type=fusion, train=True)
         out = kd_oracle.kd_loss(sl, tl, lab, w, [sm[k] for k in kd_oracle.MIMIC_TAPS], [tm[k] for k in kd_oracle.MIMIC_TAPS])
         out["loss"].backward()
         opt.step()
@@ -97,8 +100,8 @@ def cpu_step_runner(batch, points, seed=0):
     return step
 
 
-def time_cpu(batch, points, steps, warmup):
-    step = cpu_step_runner(batch, points)
+def time_cpu(batch, points, steps, warmup, fusion="weighted"):
+    step = cpu_step_runner(batch, points, fusion=fusion)
     for _ in range(warmup):
         step()
     ts = []
@@ -118,7 +121,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cb = time_cpu(args.cpu_batch, args.points, max(1, args.steps), max(0, args.warmup))
+    cb = time_cpu(args.cpu_batch, args.points, max(1, args.steps), max(0, args.warmup), args.student)
     cfg = workload_config(args, args.gpus)
     cfg["sample"] = f"each step is a bounded sample of {args.cpu_batch} frames of the same workload"
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -184,7 +187,7 @@ class ClockSampler:
 
 
 # ============================================================================= native arm
-def build_models(device, fp32, use_graph=False):
+def build_models(device, fp32, use_graph=False, student_fusion="weighted"):
     from src.models.camera_encoder import TwinLiteEncoder
     from src.models.fusion_module import CompleteSegmentationModel
     from src.models.lidar_encoder import LiDAREncoder
@@ -197,7 +200,7 @@ def build_models(device, fp32, use_graph=False):
                                          camera_fpn_stages=["stage3", "stage4", "stage5"], camera_fpn_channels=128,
                                          output_mode="same").to(device)
     torch.manual_seed(0)                                  # identical replicas on every rank
-    student, teacher = make("weighted", 128), make("concat", 256)
+    student, teacher = make(student_fusion, 256 if student_fusion == "concat" else 128), make("concat", 256)
     trainer = Trainer(student, [], [], device, lr=1e-3, weight_decay=1e-3, class_weights=CLASS_WEIGHTS,
                       save_dir=os.path.join(ROOT, "gpurun_out", "bench_ckpt"), teacher=teacher,
                       amp_dtype=None if fp32 else torch.bfloat16, verbose=False, use_cuda_graph=use_graph)
@@ -402,7 +405,7 @@ def run_native(args):
     from src.data_loading.synthetic_frames import make_frames
     from src.training.parallel import frame_seed, reduce_max
 
-    trainer = build_models(device, args.fp32, use_graph=not args.no_graph)
+    trainer = build_models(device, args.fp32, use_graph=not args.no_graph, student_fusion=args.student)
     B, N = args.batch, args.points
     n_data = 3
     batches = [make_frames(B, N, seed=frame_seed(rank, i), device=device) for i in range(n_data)]
@@ -497,7 +500,7 @@ def run_native(args):
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        cb = time_cpu(args.cpu_batch, args.points, args.cpu_steps, 1)
+        cb = time_cpu(args.cpu_batch, args.points, args.cpu_steps, 1, args.student)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:

@@ -321,6 +321,12 @@ int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const flo
  *   kdf_dwconv3x3_bwd_weight grad_weight f32 [C,9] (zeroed by the call) from in and grad_out */
 int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
                       int flip, void *out, double *stats, void *stream);
+/* The same convolution followed, in the same kernel, by the BatchNorm (running statistics, given as per-channel
+ * scale/shift f32 [C]) and activation (0 none, 1 ReLU, 2 ReLU6) that come after it in eval mode
+ * (camera_encoder.py:26-33 with the module in eval()): out = act(round(conv(in)) * scale + shift), where round() is the
+ * storage rounding the two-kernel sequence would have applied -- bit-identical to kdf_dwconv3x3_fwd + kdf_rowbn_apply_fwd. */
+int kdf_dwconv3x3_affine_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
+                             const float *post_scale, const float *post_shift, int act, void *out, void *stream);
 int kdf_dwconv3x3_bwd_data(const void *grad_out, const float *weight, int dtype, int B, int H, int W, int C, int stride,
                            void *grad_in, void *stream);
 int kdf_dwconv3x3_bwd_weight(const void *in, const void *grad_out, int dtype, int B, int H, int W, int C, int stride,

@@ -57,7 +57,8 @@ __device__ __forceinline__ void dw_load_taps(const float *__restrict__ w, int c0
 template <typename T, int STRIDE, bool FLIP>
 __global__ void __launch_bounds__(256, 2)
 dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C][9] */, T *__restrict__ out,
-                     int B, int H, int W, int C, int OH, int OW, double *__restrict__ stats /* nullable [2][C] */) {
+                     int B, int H, int W, int C, int OH, int OW, double *__restrict__ stats /* nullable [2][C] */,
+                     const float *__restrict__ post_scale /* nullable [C] */, const float *__restrict__ post_shift, int post_act) {
     typedef DwChunk<T> K;
     __shared__ float sred[256 * 2 * DW_V];              // BatchNorm statistics of the stored outputs (only when asked for)
     constexpr int IN_ROWS = (DW_R - 1) * STRIDE + 3;
@@ -73,6 +74,14 @@ dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C
     float s_sum[DW_V], s_sq[DW_V];
 #pragma unroll
     for (int q = 0; q < DW_V; ++q) { s_sum[q] = 0.f; s_sq[q] = 0.f; }
+    // optional epilogue: the BatchNorm (running statistics) + activation that follows, applied to the value as it
+    // would have been stored (same rounding as the two-kernel sequence)
+    float psc[DW_V], psh[DW_V];
+#pragma unroll
+    for (int q = 0; q < DW_V; ++q) {
+        psc[q] = post_scale ? __ldg(post_scale + g * DW_V + q) : 1.f;
+        psh[q] = post_scale ? __ldg(post_shift + g * DW_V + q) : 0.f;
+    }
     const int ix0 = ox * STRIDE - 1;
     for (int rb = blockIdx.y; live && rb < B * oyb_n; rb += gridDim.y) {
         const int b = rb / oyb_n, oyb = rb - b * oyb_n;
@@ -116,6 +125,16 @@ dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C
         for (int r = 0; r < DW_R; ++r) {
             const int oy = oy0 + r;
             if (oy < OH) {
+                if (post_scale) {
+#pragma unroll
+                    for (int q = 0; q < DW_V; ++q) {
+                        const float z = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(acc[r][q])) : acc[r][q];
+                        float y = fmaf(z, psc[q], psh[q]);
+                        if (post_act == 1) y = fmaxf(y, 0.f);
+                        else if (post_act == 2) y = fminf(fmaxf(y, 0.f), 6.f);
+                        acc[r][q] = y;
+                    }
+                }
                 K::st(out + (((int64_t)b * OH + oy) * OW + ox) * C + g * DW_V, acc[r]);
                 if (stats) {
 #pragma unroll
@@ -287,8 +306,9 @@ using namespace kdf;
 
 extern "C" {
 
-int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
-                      int flip, void *out, double *stats, void *stream) {
+static int dwconv_fwd_impl(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
+                           int flip, void *out, double *stats, const float *post_scale, const float *post_shift, int post_act,
+                           void *stream) {
     if (int e = dw_check("dwconv3x3_fwd", dtype, B, H, W, C, stride)) return e;
     KDF_CHECK_ARG(!(flip && stride != 1), "dwconv3x3_fwd: flipped taps are the stride-1 data gradient only");
     if (B == 0) {
@@ -310,12 +330,24 @@ int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int
     const dim3 grid((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy));
     cudaStream_t st = as_stream(stream);
     if (stats) KDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-#define KDF_DW(T, S, F) dwconv3x3_fwd_kernel<T, S, F><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats)
+#define KDF_DW(T, S, F) dwconv3x3_fwd_kernel<T, S, F><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats, post_scale, post_shift, post_act)
     if (dtype == KDF_F32) { if (stride == 2) KDF_DW(float, 2, false); else if (flip) KDF_DW(float, 1, true); else KDF_DW(float, 1, false); }
     else { if (stride == 2) KDF_DW(__nv_bfloat16, 2, false); else if (flip) KDF_DW(__nv_bfloat16, 1, true); else KDF_DW(__nv_bfloat16, 1, false); }
 #undef KDF_DW
     KDF_LAUNCH_CHECK();
     return KDF_OK;
+}
+
+int kdf_dwconv3x3_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
+                      int flip, void *out, double *stats, void *stream) {
+    return dwconv_fwd_impl(in, weight, dtype, B, H, W, C, stride, flip, out, stats, nullptr, nullptr, 0, stream);
+}
+
+int kdf_dwconv3x3_affine_fwd(const void *in, const float *weight, int dtype, int B, int H, int W, int C, int stride,
+                             const float *post_scale, const float *post_shift, int act, void *out, void *stream) {
+    KDF_CHECK_ARG(post_scale && post_shift, "dwconv3x3_affine_fwd: null pointer");
+    KDF_CHECK_ARG(act >= 0 && act <= 2, "dwconv3x3_affine_fwd: bad activation %d", act);
+    return dwconv_fwd_impl(in, weight, dtype, B, H, W, C, stride, 0, out, nullptr, post_scale, post_shift, act, stream);
 }
 
 int kdf_dwconv3x3_bwd_data(const void *grad_out, const float *weight, int dtype, int B, int H, int W, int C, int stride,

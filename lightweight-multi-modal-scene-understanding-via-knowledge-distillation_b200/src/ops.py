@@ -194,10 +194,12 @@ class _DwConv3x3Fn(torch.autograd.Function):
         return gx, gw, None, None
 
 
-def dwconv3x3(conv, x: torch.Tensor, want_stats: bool = False):
+def dwconv3x3(conv, x: torch.Tensor, want_stats: bool = False, post=None):
     """Depthwise 3x3 ``nn.Conv2d`` on the hand-written kernels when it is one (3x3, padding 1, stride 1|2, no bias,
     groups == channels) and ``x`` is a dense channels-last CUDA map; None otherwise (the caller runs the module).
-    With ``want_stats`` returns (out, stats f64 [2,C]): the column sums the BatchNorm that follows needs."""
+    With ``want_stats`` returns (out, stats f64 [2,C]): the column sums the BatchNorm that follows needs.
+    ``post`` = (scale, shift, act code): the eval-mode BatchNorm + activation that follow, applied in the same kernel
+    (inference only: no autograd through it)."""
     import torch.nn as nn
     if not (isinstance(conv, nn.Conv2d) and x.is_cuda and x.dim() == 4):
         return None
@@ -210,6 +212,16 @@ def dwconv3x3(conv, x: torch.Tensor, want_stats: bool = False):
         x = x.to(torch.get_autocast_dtype("cuda"))
     if x.dtype not in (torch.float32, torch.bfloat16) or C % 8 or C > 1024 or _nhwc_rows(x) is None:
         return None
+    if post is not None:
+        scale, shift, act = post
+        B, _, H, W = x.shape
+        stride = conv.stride[0]
+        OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+        w = conv.weight.detach().reshape(C, 9).float().contiguous()
+        out = torch.empty(B, OH, OW, C, dtype=x.dtype, device=x.device)
+        call("kdf_dwconv3x3_affine_fwd", ptr(_nhwc_rows(x)), ptr(w), dtype_code(x), B, H, W, C, stride, ptr(scale), ptr(shift),
+             act, ptr(out), stream_ptr(x.device))
+        return out.permute(0, 3, 1, 2)
     out, stats = _DwConv3x3Fn.apply(x, conv.weight, conv.stride[0], want_stats)
     return (out, stats) if want_stats else out
 
@@ -236,6 +248,18 @@ def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> 
             # follows), everything else on the library
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             fuse_stats = isinstance(nxt, nn.BatchNorm2d) and (nxt.training or nxt.running_mean is None)
+            if (isinstance(nxt, nn.BatchNorm2d) and not fuse_stats and not torch.is_grad_enabled()
+                    and not (residual is not None and i + 1 == last_bn)):
+                # inference: the running-statistics BatchNorm (+ activation) rides in the stencil kernel's epilogue
+                act, step = None, 2
+                if i + 2 < len(mods) and isinstance(mods[i + 2], (nn.ReLU, nn.ReLU6)):
+                    act, step = ("relu6" if isinstance(mods[i + 2], nn.ReLU6) else "relu"), 3
+                scale, shift, _, _ = _eval_affine(nxt)
+                y = dwconv3x3(m, x, post=(scale, shift, _ACT[act]))
+                if y is not None:
+                    x = y
+                    i += step
+                    continue
             y = dwconv3x3(m, x, want_stats=fuse_stats)
             if y is None:
                 x = m(x)

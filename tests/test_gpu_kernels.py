@@ -610,6 +610,41 @@ def test_dwconv3x3_vs_torch_conv2d(ops, C, H, W, stride, dtype):
     assert ops.dwconv3x3(nn.Conv2d(C, C, 1).cuda(), xc) is None
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stride,act", [(1, "relu6"), (2, "relu6"), (1, "relu"), (2, None)])
+def test_dwconv3x3_eval_batchnorm_epilogue_bit_identical(ops, dtype, stride, act):
+    """Inference: depthwise conv + running-statistics BatchNorm + activation in one kernel (run_fused under no_grad)
+    against the two-kernel sequence (stencil kernel, then the row BatchNorm kernel): bit-identical."""
+    import torch.nn as nn
+    C, H, W = 96, 20, 24
+    g = torch.Generator().manual_seed(7 + stride)
+    layers = [nn.Conv2d(C, C, 3, stride=stride, padding=1, groups=C, bias=False), nn.BatchNorm2d(C)]
+    if act:
+        layers.append(nn.ReLU6() if act == "relu6" else nn.ReLU())
+    seq = nn.Sequential(*layers)
+    with torch.no_grad():
+        seq[0].weight.copy_(torch.randn(C, 1, 3, 3, generator=g) * 0.5)
+        seq[1].weight.copy_(torch.rand(C, generator=g) + 0.5)
+        seq[1].bias.copy_(torch.randn(C, generator=g))
+        seq[1].running_mean.copy_(torch.randn(C, generator=g) * 0.2)
+        seq[1].running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    seq.cuda().eval()
+    x = (torch.randn(2, C, H, W, generator=g) * 3).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        fused = ops.run_fused(seq, x)
+    with torch.enable_grad():                                   # the epilogue is an inference-only path
+        two = ops.run_fused(seq, x).detach()
+    assert fused.dtype == dtype and fused.shape == two.shape
+    assert torch.equal(fused, two)
+    ref = seq(x.float())
+    assert rel_err(fused.float().cpu(), ref.cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
+    # a shortcut added after this BatchNorm keeps the separate kernel (and still agrees)
+    with torch.no_grad():
+        res = ops.run_fused(nn.Sequential(*list(seq)[:2]), x, residual=x) if stride == 1 else None
+    if res is not None:
+        assert rel_err(res.float().cpu(), (nn.Sequential(*list(seq)[:2])(x.float()) + x.float()).cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
 def test_camera_side_kernels_accept_empty_batches(ops):
     import torch.nn as nn
     conv = nn.Conv2d(64, 64, 3, padding=1, groups=64, bias=False).cuda()
