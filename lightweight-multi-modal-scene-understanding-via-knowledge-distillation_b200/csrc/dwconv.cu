@@ -281,11 +281,19 @@ dwconv3x3_wgrad_kernel(const T *__restrict__ in, const T *__restrict__ gout, flo
 #pragma unroll
         for (int q = 0; q < DW_V; ++q) red[(lane_row * cg + g) * 36 + k * DW_V + q] = acc[k][q];
     __syncthreads();
-    for (int i = threadIdx.x; i < cg * 36; i += blockDim.x) {
-        const int gg = i / 36, e = i - gg * 36, k = e / DW_V, q = e - k * DW_V;
-        float v = 0.f;
-        for (int r = 0; r < rows_per_cta; ++r) v += red[(r * cg + gg) * 36 + e];
-        atomicAdd(dw + (gg * DW_V + q) * 9 + k, v);
+    // a channel group's 4 x 9 gradients are 36 consecutive floats of dw: 9 16-byte vector reductions per group
+    for (int i = threadIdx.x; i < cg * 9; i += blockDim.x) {
+        const int gg = i / 9, j = i - gg * 9;
+        float v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int o = j * 4 + t, q = o / 9, k = o - q * 9;              // dw[(gg*4 + q)*9 + k]
+            float acc_ = 0.f;
+            for (int r = 0; r < rows_per_cta; ++r) acc_ += red[(r * cg + gg) * 36 + k * DW_V + q];
+            v[t] = acc_;
+        }
+        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(dw + gg * 36 + j * 4), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     }
 }
 

@@ -91,13 +91,13 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // One-time setup shared by both kernels: coefficient tables, W1 -> bf16 swizzled panels, barriers, TMEM.
 __device__ __forceinline__ void ft_setup(const FusionTcArgs &a, uint8_t *sW1, float *tb1, float *tw2, float *taff,
                                          uint64_t *bars, uint32_t *tmem_slot, uint32_t tmem_cols) {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 128; i += FT_THREADS) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int i = tid; i < 128; i += nthr) {
         tb1[i] = a.b1[i];
         taff[i] = a.csc[i]; taff[128 + i] = a.csh[i]; taff[256 + i] = a.lsc[i]; taff[384 + i] = a.lsh[i];
     }
-    for (int i = tid; i < 256; i += FT_THREADS) tw2[i] = a.w2[i];
-    for (int idx = tid; idx < FT_C * (FT_K2 / 8); idx += FT_THREADS) {
+    for (int i = tid; i < 256; i += nthr) tw2[i] = a.w2[i];
+    for (int idx = tid; idx < FT_C * (FT_K2 / 8); idx += nthr) {
         const int j = idx >> 5, ch = idx & 31;
         const float4 lo = __ldg(reinterpret_cast<const float4 *>(a.w1 + (int64_t)j * FT_K2 + ch * 8));
         const float4 hi = __ldg(reinterpret_cast<const float4 *>(a.w1 + (int64_t)j * FT_K2 + ch * 8 + 4));
@@ -391,8 +391,15 @@ fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorM
 }
 
 // ============================================================================= backward
-__global__ void __launch_bounds__(FT_THREADS, 1)
+// NT = 256 or 512 threads: the CUDA-core phases (staging, the two epilogues, the coalesced store phase) are latency-bound,
+// 16 warps hide more of it; per-thread tile state halves with NT = 512 (4 row passes, 32 accumulator columns per phase).
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
+    constexpr int RG = NT / 16;                   // row groups of the 16-chunks-per-row phases
+    constexpr int RP = FT_ROWS / RG;              // row passes per tile
+    constexpr int CG = NT / 128;                  // accumulator column groups (warp >> 2)
+    constexpr int E1_COLS = FT_C / CG;            // hidden columns per warp in epilogue 1 (64 or 32)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sW1 = smem + FtSmem::OFF_W1, *sY = smem + FtSmem::OFF_Y, *sG = smem + FtSmem::OFF_G, *sDH = smem + FtSmem::OFF_DH;
@@ -414,19 +421,31 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
     float g_sc[16], g_sh[16];                    // d scale / d shift of (cam | lid) channels och*8 .. +8
 #pragma unroll
     for (int j = 0; j < 16; ++j) { g_sc[j] = 0.f; g_sh[j] = 0.f; }
-    float g_b1[2] = {0.f, 0.f}, g_w2a[2] = {0.f, 0.f}, g_w2b[2] = {0.f, 0.f};   // column = (warp>>2)*64 + chunk*32 + lane
+    float g_b1[E1_COLS / 32], g_w2a[E1_COLS / 32], g_w2b[E1_COLS / 32];       // column = (warp>>2)*E1_COLS + half*32 + lane
+#pragma unroll
+    for (int h = 0; h < E1_COLS / 32; ++h) { g_b1[h] = 0.f; g_w2a[h] = 0.f; g_w2b[h] = 0.f; }
     float g_b2a = 0.f, g_b2b = 0.f;
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int64_t r0 = tile * FT_ROWS;
         // ---- loads + staging: Y (4 panels), G (2 panels); per-pixel dots d0 = G.Ycam, d1 = G.Ylid
-        uint4 raw_c[8], raw_l[8];
+        if (tid == 64) {                                                   // the next tile on its way into L2
+            const int64_t nt_ = tile + gridDim.x;
+            if (nt_ < n_tiles) {
+                const int64_t nr0 = nt_ * FT_ROWS;
+                const uint32_t bytes = (uint32_t)(((a.M - nr0 < FT_ROWS) ? (a.M - nr0) : FT_ROWS) * FT_C * 2);
+                tc::prefetch_l2(a.cam + nr0 * FT_C, bytes);
+                tc::prefetch_l2(a.lid + nr0 * FT_C, bytes);
+                tc::prefetch_l2(a.gout + nr0 * FT_C, bytes);
+            }
+        }
+        uint4 raw_c[RP], raw_l[RP];
         {
-            uint4 raw_g[8];
+            uint4 raw_g[RP];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int64_t row = r0 + orow0 + p * 16;
+            for (int p = 0; p < RP; ++p) {
+                const int64_t row = r0 + orow0 + p * RG;
                 if (row < a.M) {
                     raw_c[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.cam + row * FT_C + och * 8));
                     raw_l[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.lid + row * FT_C + och * 8));
@@ -434,8 +453,8 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
                 }
             }
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int r = orow0 + p * 16;
+            for (int p = 0; p < RP; ++p) {
+                const int r = orow0 + p * RG;
                 uint4 yc = make_uint4(0u, 0u, 0u, 0u), yl = yc, gv = yc;
                 if (r0 + r < a.M) {
                     yc = ft_affine_relu(raw_c[p], taff + och * 8, taff + 128 + och * 8);
@@ -482,8 +501,8 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
         tc::mbar_wait(&bars[0], (uint32_t)(it & 1));
         tc::fence_after_sync();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int col0 = (warp >> 2) * 64 + half * 32;
+        for (int half = 0; half < E1_COLS / 32; ++half) {
+            const int col0 = (warp >> 2) * E1_COLS + half * 32;
             uint32_t r[32];
             tc::tmem_ld32(tmem_base + lane_bits + (uint32_t)col0, r);
             tc::tmem_ld_wait();
@@ -530,12 +549,14 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
         }
         tc::mbar_wait(&bars[1], (uint32_t)(it & 1));
         tc::fence_after_sync();
-        // ---- epilogue 2 (thread = pixel; warps 0-3 the camera half, 4-7 the LiDAR half): dY + blend path, ReLU mask
+        // ---- epilogue 2 (thread = pixel; the first half of the warps the camera half, the rest the LiDAR half): dY + blend path, ReLU mask
         {
-            const int half = warp >> 2;
+            constexpr int E2_WG = CG / 2;                                   // warp groups per half (1 or 2)
+            const int half = (warp >> 2) / E2_WG, cq = (warp >> 2) % E2_WG;
             const float wsel = half ? rowS[4 * row + 1] : rowS[4 * row];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int cc = 0; cc < 4 / E2_WG; ++cc) {
+                const int c4 = cq * (4 / E2_WG) + cc;
                 uint32_t r[32];
                 tc::tmem_ld32(tmem_base + lane_bits + (uint32_t)(half * 128 + c4 * 32), r);
                 tc::tmem_ld_wait();
@@ -557,8 +578,8 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
         __syncthreads();
         // ---- coalesced phase: BN-affine backward, gradient rows, d scale / d shift
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = orow0 + p * 16;
+        for (int p = 0; p < RP; ++p) {
+            const int r = orow0 + p * RG;
             if (r0 + r < a.M) {
                 const uint32_t off = (och >> 3) * FT_PANEL + tc::sw128_offset(r, och & 7);
                 float gy[8], x[8], o[8];
@@ -586,21 +607,21 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
     }
 
     // ---- flush: per-thread sums -> shared-memory reduction over the 16 row groups -> atomics
-    float *red = reinterpret_cast<float *>(sY);                            // [16 row groups][16 chunks][32]
+    float *red = reinterpret_cast<float *>(sY);                            // [RG row groups][16 chunks][32]
 #pragma unroll
     for (int j = 0; j < 16; ++j) { red[(orow0 * 16 + och) * 32 + j] = g_sc[j]; red[(orow0 * 16 + och) * 32 + 16 + j] = g_sh[j]; }
     __syncthreads();
-    for (int i = tid; i < 16 * 32; i += FT_THREADS) {
+    for (int i = tid; i < 16 * 32; i += NT) {
         const int ch = i >> 5, j = i & 31;
         float v = 0.f;
-        for (int g = 0; g < 16; ++g) v += red[(g * 16 + ch) * 32 + j];
+        for (int g = 0; g < RG; ++g) v += red[(g * 16 + ch) * 32 + j];
         // j: 0-7 d cam scale, 8-15 d lid scale, 16-23 d cam shift, 24-31 d lid shift of channel ch*8 + (j & 7)
         const int which = (j < 8) ? 0 : (j < 16) ? 2 : (j < 24) ? 1 : 3;
         atomicAdd(a.gaff + which * FT_C + ch * 8 + (j & 7), v);
     }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int col = (warp >> 2) * 64 + half * 32 + lane;
+    for (int half = 0; half < E1_COLS / 32; ++half) {
+        const int col = (warp >> 2) * E1_COLS + half * 32 + lane;
         atomicAdd(a.gb1 + col, g_b1[half]);
         atomicAdd(a.gw2 + col, g_w2a[half]);
         atomicAdd(a.gw2 + FT_C + col, g_w2b[half]);
@@ -613,13 +634,14 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
         tc::fence_after_sync();
         const int j = (warp & 3) * 32 + lane;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const int col = (warp >> 2) * 128 + c4 * 32;
+        for (int c4 = 0; c4 < 8 / CG; ++c4) {
+            const int col = (warp >> 2) * (FT_K2 / CG) + c4 * 32;
             uint32_t r[32];
             tc::tmem_ld32(tmem_base + lane_bits + 256u + (uint32_t)col, r);
             tc::tmem_ld_wait();
+            float *dst = a.gw1 + (int64_t)j * FT_K2 + col;                 // 32 consecutive floats of row j: 8 vector reductions
 #pragma unroll
-            for (int e = 0; e < 32; ++e) atomicAdd(a.gw1 + (int64_t)j * FT_K2 + col + e, __uint_as_float(r[e]));
+            for (int e = 0; e < 32; e += 4) tc::red_add_v4(dst + e, __uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
         }
     }
     tc::fence_before_sync();
@@ -678,8 +700,14 @@ int fusion_weighted_bwd_tc(const void *grad_out, const void *cam_pre, const void
     a.gaff = gaff; a.gw1 = gw1; a.gb1 = gb1; a.gw2 = gw2; a.gb2 = gb2;
     const int64_t n_tiles = (M + FT_ROWS - 1) / FT_ROWS;
     const int blocks = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_BWD));
-    fusion_weighted_bwd_tc_kernel<<<blocks, FT_THREADS, FtSmem::TOTAL_BWD, st>>>(a);
+    static const int nt = getenv("KDF_FUSION_BWD_THREADS") ? atoi(getenv("KDF_FUSION_BWD_THREADS")) : 512;     // tuning knob
+    if (nt == 256) {
+        KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_bwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_BWD));
+        fusion_weighted_bwd_tc_kernel<256><<<blocks, 256, FtSmem::TOTAL_BWD, st>>>(a);
+    } else {
+        KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_bwd_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_BWD));
+        fusion_weighted_bwd_tc_kernel<512><<<blocks, 512, FtSmem::TOTAL_BWD, st>>>(a);
+    }
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -872,7 +872,8 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
             tc::tmem_ld<LDW>(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2u * KIN + (uint32_t)col, r);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < LDW; ++j) atomicAdd(a.dW + n * KIN + col + j, __uint_as_float(r[j]));
+            for (int j = 0; j < LDW; j += 4)                                // 16-byte vector reductions: 4x fewer L2 atomic operations
+                tc::red_add_v4(a.dW + n * KIN + col + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
     }
     tc::fence_before_sync();
@@ -1217,7 +1218,8 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
                 tc::tmem_ld32(tmem_base + lane_bits + 2u * KIN + (uint32_t)col, r);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(a.dW + n * KIN + col + j, __uint_as_float(r[j]));
+                for (int j = 0; j < 32; j += 4)
+                    tc::red_add_v4(a.dW + n * KIN + col + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             }
         }
     }
@@ -1484,9 +1486,11 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
         tc::tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 3u * KIN + (uint32_t)col0, rb);
         tc::tmem_ld_wait();
         const float gs = cgs[n], gb = cgb[n], ga = cga[n];
+        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            atomicAdd(a.dW + n * KIN + col0 + j, fmaf(gs, __uint_as_float(rs[j]), fmaf(gb, __uint_as_float(rb[j]), ga * asum[col0 + j])));
+        for (int j = 0; j < 16; ++j) o[j] = fmaf(gs, __uint_as_float(rs[j]), fmaf(gb, __uint_as_float(rb[j]), ga * asum[col0 + j]));
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) tc::red_add_v4(a.dW + n * KIN + col0 + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
     }
     tc::fence_before_sync();
     __syncthreads();

@@ -82,6 +82,12 @@ __device__ __forceinline__ void prefetch_l2(const void *gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
+// One 16-byte vector reduction into global memory (sm_90+; addr 16-byte aligned): a flush of an accumulator tile
+// costs 4x fewer L2 atomic operations than scalar adds (they, not the bytes, bound such a flush).
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ----------------------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {      // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
