@@ -84,8 +84,10 @@ __device__ __forceinline__ uint4 affine_relu_chunk(const uint4 &u, const float *
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-template <int MODE, int KIN, int NT>
-__global__ void __launch_bounds__(NT, 1)
+// MINB = 2: two co-resident CTAs per SM (layers 1+2: 85 KB of shared memory, 256 TMEM columns and <= 128 registers each),
+// so that one CTA's barrier / TMEM round trips overlap the other's CUDA-core phases.
+template <int MODE, int KIN, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB)
 mlp_layer_fwd_kernel(MlpFwdArgs a) {
     KDF_PM_DERIVED(NT);
     using L = MlpSmem<KIN>;
@@ -1635,8 +1637,16 @@ int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a
     if (n_tiles < blocks) blocks = (int)n_tiles;
     if (mode == 0) {
         const int smem = MlpSmem<64>::TOTAL;
-        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_layer_fwd_kernel<0, 64, 256><<<blocks, 256, smem, st>>>(a);
+        static const int per_sm = getenv("KDF_MLP_FWD0_CTAS_PER_SM") ? atoi(getenv("KDF_MLP_FWD0_CTAS_PER_SM")) : 2;    // tuning knob
+        if (per_sm == 2) {
+            blocks = 2 * sm_count();
+            if (n_tiles < blocks) blocks = (int)n_tiles;
+            KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            mlp_layer_fwd_kernel<0, 64, 256, 2><<<blocks, 256, smem, st>>>(a);
+        } else {
+            KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            mlp_layer_fwd_kernel<0, 64, 256><<<blocks, 256, smem, st>>>(a);
+        }
     } else {
         const int smem = MlpSmem<128>::TOTAL;
         KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
