@@ -19,6 +19,7 @@
 // CTA to arrive.  All four
 // kernels are HBM-bound streaming kernels; the per-channel finalisation lives in the last
 // CTA of the reduction so no tiny host-driven launches are needed.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "kdf_common.cuh"
@@ -325,6 +326,141 @@ rowbn_apply_bwd_kernel(const T *__restrict__ g, const T *__restrict__ x, T *__re
     }
 }
 
+// BatchNorm backward as ONE cooperative kernel for tensors that stay in L2 between the two passes: column reduction,
+// grid-wide barrier, per-channel coefficients (every CTA, from the accumulator sets), apply.  Same arithmetic as
+// rowbn_reduce_kernel<MODE 1> + rowbn_apply_bwd_kernel; what it saves is a launch, the last-CTA finalisation round
+// trip and the second kernel's ramp -- ~10 us of the ~40 us such a pair costs on a 30 MB tensor.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
+rowbn_bwd_coop_kernel(ReduceArgs a, T *__restrict__ dx) {
+    extern __shared__ float sm[];                     // phase 1: [rows][G][2*VEC]; phase 2: scale, shift, A, B [4][C]
+    const RowMap m = row_map<VEC>(a.C);
+    const T *x = reinterpret_cast<const T *>(a.x);
+    const T *g = reinterpret_cast<const T *>(a.g);
+    const int c = m.g * VEC;
+    const int64_t stride = (int64_t)gridDim.x * m.rows;
+    constexpr int U = 4;
+    using IO = VecIO<T, VEC>;
+    {
+        float s0[VEC], s1[VEC], sc[VEC], sh[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { s0[q] = 0.f; s1[q] = 0.f; sc[q] = 1.f; sh[q] = 0.f; }
+        if (m.active) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { sc[q] = a.scale[c + q]; sh[q] = a.shift[c + q]; }
+            for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < a.M; row += stride * U) {
+                typename IO::Raw xr[U], gr[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t rr = row + u * stride;
+                    if (rr < a.M) {                              // L2-allocating loads: phase 2 reads the same rows again
+                        xr[u] = *reinterpret_cast<const typename IO::Raw *>(x + rr * a.C + c);
+                        gr[u] = *reinterpret_cast<const typename IO::Raw *>(g + rr * a.C + c);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (row + u * stride < a.M) {
+                        float xv[VEC], gv[VEC];
+                        IO::unpack(xr[u], xv);
+                        IO::unpack(gr[u], gv);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            const float dy = act_open(fmaf(xv[q], sc[q], sh[q]), a.act) ? gv[q] : 0.f;
+                            s0[q] += dy;
+                            s1[q] = fmaf(dy, xv[q], s1[q]);
+                        }
+                    }
+                }
+            }
+            float *dst = sm + (m.r * m.G + m.g) * 2 * VEC;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { dst[q] = s0[q]; dst[VEC + q] = s1[q]; }
+        }
+        __syncthreads();
+        double *acc0 = reinterpret_cast<double *>(a.ws + 1);
+        double *acc = acc0 + (size_t)(blockIdx.x % RB_COPIES) * 2 * a.C;
+        if (m.active && m.r == 0) {
+            for (int rr = 1; rr < m.rows; ++rr) {
+                const float *src = sm + (rr * m.G + m.g) * 2 * VEC;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) { s0[q] += src[q]; s1[q] += src[VEC + q]; }
+            }
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                atomicAdd(acc + m.g * VEC + q, (double)s0[q]);
+                atomicAdd(acc + a.C + m.g * VEC + q, (double)s1[q]);
+            }
+        }
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    // ---- per-channel coefficients (every CTA computes them; CTA 0 also publishes d gamma / d beta)
+    float *csc = sm, *csh = sm + a.C, *cA = sm + 2 * a.C, *cB = sm + 3 * a.C;
+    {
+        const double *acc0 = reinterpret_cast<const double *>(a.ws + 1);
+        const double invM = 1.0 / (double)a.M;
+        for (int ch = threadIdx.x; ch < a.C; ch += RB_THREADS) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < RB_COPIES; ++k) {
+                t0 += __ldcg(acc0 + (size_t)k * 2 * a.C + ch);
+                t1 += __ldcg(acc0 + (size_t)k * 2 * a.C + a.C + ch);
+            }
+            const float mean = a.in_mean[ch], invstd = a.in_invstd[ch], scl = a.scale[ch];
+            const float S0 = (float)t0, S1 = (float)t1;
+            const float dgamma = invstd * (S1 - mean * S0);
+            float A = 0.f, B = 0.f;
+            if (a.batch_stats) {
+                B = -(scl * invstd * dgamma) * (float)invM;
+                A = -(scl * S0) * (float)invM - B * mean;
+            }
+            csc[ch] = scl; csh[ch] = a.shift[ch]; cA[ch] = A; cB[ch] = B;
+            if (blockIdx.x == 0) {
+                if (a.dgamma) a.dgamma[ch] = dgamma;
+                if (a.dbeta) a.dbeta[ch] = S0;
+            }
+        }
+    }
+    __syncthreads();
+    if (!m.active) return;
+    for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < a.M; row += stride * U) {
+        typename IO::Raw xr[U], gr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < a.M) {
+                xr[u] = IO::load(x + rr * a.C + c);
+                gr[u] = IO::load(g + rr * a.C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < a.M) {
+                float xv[VEC], gv[VEC], o[VEC];
+                IO::unpack(xr[u], xv);
+                IO::unpack(gr[u], gv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const float dy = act_open(fmaf(xv[q], csc[c + q], csh[c + q]), a.act) ? gv[q] : 0.f;
+                    o[q] = fmaf(dy, csc[c + q], fmaf(cB[c + q], xv[q], cA[c + q]));
+                }
+                IO::store(dx + rr * a.C + c, o);
+            }
+        }
+    }
+}
+
+template <typename T, int VEC>
+static int launch_bwd_coop(ReduceArgs a, void *dx, int blocks, size_t smem, cudaStream_t st) {
+    T *dxp = reinterpret_cast<T *>(dx);
+    void *args[] = {&a, &dxp};
+    KDF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&rowbn_bwd_coop_kernel<T, VEC>), dim3(blocks), dim3(RB_THREADS),
+                                         args, smem, st));
+    return KDF_OK;
+}
+
 static int rb_vec(int dtype, int C) { return (dtype == KDF_BF16 && C % 8 == 0) ? 8 : 4; }
 
 static int rb_check(int dtype, int64_t M, int C, const char *who) {
@@ -456,8 +592,22 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
     a.in_mean = mean; a.in_invstd = invstd; a.batch_stats = batch_stats;
     a.dgamma = dgamma; a.dbeta = dbeta; a.coefA = coefA; a.coefB = coefB;
     a.ws = reinterpret_cast<RowBnWs *>(workspace);
-    if (int e = launch_reduce<1>(a, dtype, st)) return e;
     const int vec = rb_vec(dtype, C);
+    // one cooperative kernel (reduce, grid barrier, apply) up to KDF_ROWBN_COOP_MB of input; measured in the step
+    // (B=32): 0 MB 12.02 ms, 72 MB 12.00 ms, 250 MB 11.88 ms (all but the 2 x 201 MB expand BatchNorm of stage 2)
+    static const long coop_mb = getenv("KDF_ROWBN_COOP_MB") ? atol(getenv("KDF_ROWBN_COOP_MB")) : 250;       // 0 disables
+    const size_t in_bytes = 2 * (size_t)M * C * (dtype == KDF_F32 ? 4 : 2);
+    if (coop_mb > 0 && in_bytes <= (size_t)coop_mb << 20) {
+        const int rows = RB_THREADS / (C / vec);
+        size_t smem = sizeof(float) * (size_t)rows * (C / vec) * 2 * vec;
+        if (smem < sizeof(float) * 4 * (size_t)C) smem = sizeof(float) * 4 * (size_t)C;
+        const int cblocks = rb_blocks(M, C, vec, 4, 2 * sm_count());                    // co-resident by construction (<= 2 CTAs/SM)
+        KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * RB_COPIES * (size_t)a.C, st));
+        if (dtype == KDF_F32) return launch_bwd_coop<float, 4>(a, grad_x, cblocks, smem, st);
+        if (vec == 8) return launch_bwd_coop<__nv_bfloat16, 8>(a, grad_x, cblocks, smem, st);
+        return launch_bwd_coop<__nv_bfloat16, 4>(a, grad_x, cblocks, smem, st);
+    }
+    if (int e = launch_reduce<1>(a, dtype, st)) return e;
     const int blocks = rb_blocks(M, C, vec, 8);
     if (dtype == KDF_F32)
         rowbn_apply_bwd_kernel<float, 4><<<blocks, RB_THREADS, sizeof(float) * 4 * C, st>>>((const float *)grad_out, (const float *)x, (float *)grad_x, M, C, scale, shift, coefA, coefB, act);
