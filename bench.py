@@ -287,6 +287,8 @@ def kernel_rooflines(args, device, fp32):
             "layers 1+2: 16 B point in, C*s pre-BatchNorm row out per point")
         add("mlp_layer_fwd_kernel<1>", time_kernel(lambda: point_mlp.mlp_layer_fwd_raw(1, z2, sc, sh, W3), 10), Mpts * 2 * C * s,
             "layer 3: C*s row in, C*s row out per point")
+        add("mlp_eval3_kernel", time_kernel(lambda: point_mlp.mlp_eval3_fwd(flat, q, r, W2, sc, sh, W3), 10), Mpts * (16 + C * s),
+            "the teacher's whole point MLP (running statistics) in one kernel: 16 B point in, C*s pre-BatchNorm-3 row out per point")
         z3, _ = point_mlp.mlp_layer_fwd_raw(1, z2, sc, sh, W3)
         dy = (torch.randn(Mpts, 128, device=device) * (torch.rand(Mpts, 128, device=device) < 0.05)).to(dt)
         gs, ga, gb = torch.rand(128, **f32) + 0.5, torch.randn(128, **f32) * 0.01, torch.randn(128, **f32) * 0.01

@@ -45,10 +45,12 @@ if "bev" in only:
     order = torch.empty(B, N, dtype=torch.int32, device=dev); offs = torch.empty(B, H * W + 1, dtype=torch.int32, device=dev)
     wsb = native.lib.kdf_bev_workspace_bytes(B, N, H, W); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     v = 0.622
-    timeit("bev_project_fwd", lambda: native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), 1, B, N, C, *geom, H, W, 0, p(grid), p(cnt), p(cel), p(ties), p(order), p(offs), p(ws), wsb, st), B * (16 * N + C * 2 * v * N + C * 2 * H * W))
-    timeit("bev_reduce", lambda: native.call("kdf_bev_reduce", p(feats), 1, p(order), p(offs), B, N, C, H, W, 0, p(grid), p(ties), st), B * (C * 2 * v * N + C * 2 * H * W))
+    timeit("bev_project_fwd (tie counts)", lambda: native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), 1, B, N, C, *geom, H, W, 0, p(grid), p(cnt), p(cel), p(ties), p(order), p(offs), p(ws), wsb, st), B * (16 * N + C * 2 * v * N + C * 2 * H * W))
+    timeit("bev_bwd (tie counts)", lambda: native.call("kdf_bev_project_bwd", p(torch.rand(B, H * W, C, device=dev, dtype=dt)), p(feats), p(grid), p(ties), None, p(cel), p(order), p(offs), 1, B, N, C, H, W, 0, p(torch.empty(B, N, C, dtype=dt, device=dev)), st), B * (C * 2 * v * N + C * 2 * N))
+    timeit("bev_project_fwd", lambda: native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), 1, B, N, C, *geom, H, W, 0, p(grid), p(cnt), p(cel), None, p(order), p(offs), p(ws), wsb, st), B * (16 * N + C * 2 * v * N + C * 2 * H * W))
+    timeit("bev_reduce (max)", lambda: native.call("kdf_bev_reduce", p(feats), 1, p(order), p(offs), B, N, C, H, W, 0, p(grid), None, st), B * (C * 2 * v * N + C * 2 * H * W))
     gg = torch.rand(B, H * W, C, device=dev, dtype=dt); gf = torch.empty(B, N, C, dtype=dt, device=dev)
-    timeit("bev_bwd", lambda: native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), p(ties), None, p(cel), p(order), p(offs), 1, B, N, C, H, W, 0, p(gf), st), B * (C * 2 * v * N + C * 2 * N))
+    timeit("bev_bwd (max)", lambda: native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), None, None, p(cel), p(order), p(offs), 1, B, N, C, H, W, 0, p(gf), st), B * (2 * C * 2 * v * N + C * 2 * (1 - v) * N + 2 * C * 2 * H * W + 8 * N))
     timeit("bev_index", lambda: native.call("kdf_bev_index", p(pts), B, N, 4, *geom, H, W, p(cel), None, p(cnt), st), B * 20 * N)
     del feats, gf
 if "kd" in only:
@@ -79,6 +81,8 @@ if "mlp" in only:
     q, r = torch.randn(64, 4, device=dev) * 0.02, torch.randn(64, device=dev) * 0.1
     W2 = (torch.randn(128, 64, device=dev) / 8).to(dt)
     timeit("mlp_layer_fwd mode0 (L1+L2)", lambda: ops.mlp_layer_fwd(0, pts2, q, r, W2), M * 272)
+    from src import point_mlp as _pm
+    timeit("mlp_eval3 (L1+L2+L3, eval)", lambda: _pm.mlp_eval3_fwd(pts2, q, r, W2, sc, sh, W3), M * 272)
     dy = (torch.randn(M, 128, device=dev) * (torch.rand(M, 128, device=dev) < 0.05)).to(dt)
     z3 = torch.randn(M, 128, device=dev, dtype=dt)
     gs, ga, gb = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.01, torch.randn(128, device=dev) * 0.01
