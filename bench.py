@@ -401,6 +401,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
     n_gpus = world
     from src import native

@@ -140,3 +140,36 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# ----------------------------------------------------------------------------- BatchNorm batch counters
+# nn.BatchNorm increments num_batches_tracked once per training forward: 29 one-element kernels per student step.  Inside
+# ``deferred_batch_counters()`` (the Trainer's step) the increments are collected and issued as ONE multi-tensor add.
+_pending_counters = None
+
+
+def bump_batch_counter(bn) -> float:
+    """Advance bn.num_batches_tracked like nn.BatchNorm does and return the momentum of this update."""
+    global _pending_counters
+    if bn.momentum is not None and _pending_counters is not None:
+        _pending_counters.append(bn.num_batches_tracked)
+        return float(bn.momentum)
+    bn.num_batches_tracked.add_(1)
+    return float(bn.momentum) if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+
+
+class deferred_batch_counters:
+    def __enter__(self):
+        global _pending_counters
+        self._outer = _pending_counters
+        _pending_counters = []
+        return self
+
+    def __exit__(self, *exc):
+        global _pending_counters
+        pending, _pending_counters = _pending_counters, self._outer
+        if pending:
+            import torch
+            with torch.no_grad():
+                torch._foreach_add_(pending, 1)
+        return False

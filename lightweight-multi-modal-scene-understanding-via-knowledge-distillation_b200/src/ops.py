@@ -112,8 +112,7 @@ def _bn_prepare(rows: torch.Tensor, bn, pre_bias=None):
     track = bn.training and bn.track_running_stats and bn.running_mean is not None
     mom = 0.0
     if track:
-        bn.num_batches_tracked.add_(1)
-        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        mom = _n.bump_batch_counter(bn)
     ws = torch.empty(lib.kdf_rowbn_workspace_bytes(C), dtype=torch.uint8, device=dev)
     with torch.no_grad():
         call("kdf_rowbn_stats", ptr(rows), dtype_code(rows), M, C, ptr(bn.weight), ptr(bn.bias),
@@ -160,8 +159,7 @@ def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[to
         track = bn.training and bn.track_running_stats and bn.running_mean is not None
         mom = 0.0
         if track:
-            bn.num_batches_tracked.add_(1)
-            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            mom = _n.bump_batch_counter(bn)
         train = (float(bn.eps), float(mom), bn.running_mean if track else None, bn.running_var if track else None,
                  pre_bias.detach().float().contiguous() if pre_bias is not None else None)
         use_batch = True
@@ -255,6 +253,24 @@ def dwconv3x3(conv, x: torch.Tensor, want_stats: bool = False, post=None):
     return (out, stats) if want_stats else out
 
 
+def _conv_frozen(m, x: torch.Tensor) -> torch.Tensor:
+    """``m(x)``; for a convolution run without autograd under bf16 autocast (the frozen teacher) the bf16 copy of its
+    weight is cached until the weight changes, instead of being re-cast by autocast on every step."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    if not (isinstance(m, nn.Conv2d) and x.is_cuda and not torch.is_grad_enabled() and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16 and m.weight.dtype == torch.float32
+            and m.padding_mode == "zeros" and not isinstance(m.padding, str)):
+        return m(x)
+    key = (m.weight.data_ptr(), m.weight._version, None if m.bias is None else m.bias._version)
+    cache = getattr(m, "_kdf_w16", None)
+    if cache is None or cache[0] != key:
+        cache = (key, m.weight.detach().to(torch.bfloat16), None if m.bias is None else m.bias.detach().to(torch.bfloat16))
+        m._kdf_w16 = cache
+    return F.conv2d(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), cache[1], cache[2], m.stride, m.padding,
+                    m.dilation, m.groups)
+
+
 def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run an ``nn.Sequential`` of conv / BatchNorm / ReLU(6) layers with every BatchNorm(+activation)
     group executed by the fused row kernels; ``residual`` is added after the LAST BatchNorm group.
@@ -291,7 +307,7 @@ def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> 
                     continue
             y = dwconv3x3(m, x, want_stats=fuse_stats)
             if y is None:
-                x = m(x)
+                x = _conv_frozen(m, x)
             elif fuse_stats:
                 x, col_sums = y
             else:

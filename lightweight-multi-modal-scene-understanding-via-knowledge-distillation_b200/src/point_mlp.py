@@ -134,8 +134,7 @@ def bn_finalize(stats, M, bn, pre_bias, track: bool):
     mean, invstd, scale, shift = (torch.empty(C, **f32) for _ in range(4))
     mom = 0.0
     if track:
-        bn.num_batches_tracked.add_(1)
-        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        mom = _n.bump_batch_counter(bn)
     call("kdf_bn_finalize", ptr(stats), M, C, ptr(bn.weight), ptr(bn.bias), ptr(pre_bias) if track else None,
          float(bn.eps), float(mom), ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
          ptr(mean), ptr(invstd), ptr(scale), ptr(shift), stream_ptr(dev))
@@ -202,8 +201,7 @@ class _FusedLidarFn(torch.autograd.Function):
             mean1, invstd1, scale1 = (torch.empty(64, **f32) for _ in range(3))
             mom = 0.0
             if track:
-                bn1.num_batches_tracked.add_(1)
-                mom = bn1.momentum if bn1.momentum is not None else 1.0 / float(bn1.num_batches_tracked)
+                mom = _n.bump_batch_counter(bn1)
             call("kdf_mlp_l1_stats", ptr(m14), M, ptr(W1f), ptr(b1.detach().float().contiguous()), ptr(g1.detach()), ptr(be1.detach()),
                  float(bn1.eps), float(mom), ptr(bn1.running_mean) if track else None, ptr(bn1.running_var) if track else None,
                  ptr(q), ptr(r), ptr(mean1), ptr(invstd1), ptr(scale1), stream_ptr(dev))

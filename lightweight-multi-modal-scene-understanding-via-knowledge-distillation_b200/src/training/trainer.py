@@ -172,7 +172,7 @@ class Trainer:
 
     def _step_impl(self, imgs, pts, seg, update_hyper: bool):
         self.optimizer.detach_grads()                    # gradients arrive as fresh tensors, gathered below in one copy
-        with self._autocast():
+        with self._autocast(), _native.deferred_batch_counters():
             if self.teacher is not None:
                 # The frozen teacher's forward does not depend on the student's: it runs on a side stream (a parallel
                 # branch of the captured graph), so that the two camera branches -- chains of small kernels that leave

@@ -83,6 +83,7 @@ def main():
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     from src import native, ops
     from src.data_loading.synthetic_frames import make_frames
