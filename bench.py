@@ -130,23 +130,28 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ============================================================================= clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms` on this rank's GPU, started before the warm-up steps (the tool needs a few hundred ms to start,
+    longer on an 8-GPU box) and bracketed by mark_begin()/mark_end() around the timed region: the clocks reported are
+    the samples whose timestamps fall inside the bracket; when the timed region is shorter than the sampling
+    period they are the samples under load around it (warm-up + timed), and `window` says which."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, device):
         self.proc = None
+        self.t_begin = self.t_end = None
         try:
             uuid = str(torch.cuda.get_device_properties(device).uuid)
             if not uuid.startswith("GPU-"):
                 uuid = "GPU-" + uuid
-            self.cmd = ["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"]
+            self.cmd = ["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"]
         except Exception:
             self.cmd = None
 
@@ -158,32 +163,47 @@ class ClockSampler:
                 self.proc = None
         return self
 
+    def mark_begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
+
     def __exit__(self, *exc):
-        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": None}
         if not self.proc:
             return
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in out.splitlines():
             parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(parts[1]), float(parts[2]), parts[4:8]))
             except ValueError:
                 continue
-            for name, val in zip(self.NAMES, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                           "samples": len(sm)}
+        inside = [r for r in rows if self.t_begin and self.t_end and self.t_begin <= r[0] <= self.t_end]
+        near = [r for r in rows if self.t_begin and r[0] >= self.t_begin - datetime.timedelta(seconds=0.3)]
+        use, window = (inside, "timed region") if inside else (near, "warm-up + timed region (timed region shorter than the sampling period)")
+        if use:
+            reasons = set()
+            for _, _, _, flags in use:
+                for name, val in zip(self.NAMES, flags):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            self.result = {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": max(r[2] for r in use),
+                           "reasons": sorted(reasons), "samples": len(use), "window": window}
 
 
 # ============================================================================= native arm
@@ -424,21 +444,23 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---------------- value: inputs resident in HBM
-    if not args.no_graph:                 # untimed: eager steps + one-off capture of the step graph
-        for i in range(trainer.graph_warmup_steps + 1):
+    with ClockSampler(device) as clk:     # started early: nvidia-smi needs a few hundred ms before its first sample
+        if not args.no_graph:             # untimed: eager steps + one-off capture of the step graph
+            for i in range(trainer.graph_warmup_steps + 1):
+                step(i)
+        for i in range(args.warmup):
             step(i)
-    for i in range(args.warmup):
-        step(i)
-    fence()
-    k0 = native.launch_stats["kernels"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(device) as clk:
+        fence()
+        k0 = native.launch_stats["kernels"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk.mark_begin()
         e0.record()
         for i in range(args.steps):
             terms, _ = step(args.warmup + i)
         e1.record()
         fence()
-    launches = native.launch_stats["kernels"] - k0
+        clk.mark_end()
+        launches = native.launch_stats["kernels"] - k0
     ms = reduce_max(e0.elapsed_time(e1) / args.steps, device)
     value = B * n_gpus / (ms * 1e-3)
     loss_terms = [float(x) for x in terms[:4].float().cpu()]
@@ -513,7 +535,7 @@ def run_native(args):
                 "config": workload_config(args, n_gpus), "clocks": clk.result, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
                 "loss_terms_last_step": dict(zip(("loss", "ce", "kl", "mse"), loss_terms))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Leave without tearing the communicator down: destroying an NCCL communicator whose all-reduce sits inside
         # a captured CUDA graph blocked for minutes on the 2-GPU box (NCCL 2.28.9).  Everything is synchronised and
@@ -525,8 +547,27 @@ def run_native(args):
         os._exit(0)
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
+    # Libraries print on stdout too (NCCL's version banner when the box sets NCCL_DEBUG): file descriptor 1 is pointed at
+    # stderr for the duration of the run and the JSON line goes to a duplicate of the original stdout.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -746,12 +746,13 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
                       int64_t n_cells, int64_t N, int HW, int64_t total) {
     using T = __nv_bfloat16;
     constexpr int C = LPR * 8, RPL = 32 / LPR, U = 4, STEP = RPL * U;
-    __shared__ float red[8][2][LPR * 8];                                   // [warp][S0|S1][C]
+    __shared__ float red[8][2][LPR * 8];                                   // [warp][S0|S1][q * LPR + lane]: channel 8*lane + q (lanes hit distinct banks)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, ch = (lane % LPR) * 8;
     // per-warp column sums live in shared memory (touched once per cell by the sub-0 lanes, each its own slots)
+    const int rl = lane % LPR;                                             // this lane's column of the per-warp sums
     if (sub == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { red[warp][0][ch + q] = 0.f; red[warp][1][ch + q] = 0.f; }
+        for (int q = 0; q < 8; ++q) { red[warp][0][q * LPR + rl] = 0.f; red[warp][1][q * LPR + rl] = 0.f; }
     }
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -816,8 +817,8 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
                 sh[q] = (a3[q] > 0.f && k[q] > 0) ? bf16_round(g[q] / (float)k[q]) : 0.f;
                 if (sub == 0) {
                     const float tot = sh[q] * (float)k[q];
-                    red[warp][0][ch + q] += tot;
-                    red[warp][1][ch + q] = fmaf(tot, zf[q], red[warp][1][ch + q]);
+                    red[warp][0][q * LPR + rl] += tot;
+                    red[warp][1][q * LPR + rl] = fmaf(tot, zf[q], red[warp][1][q * LPR + rl]);
                 }
             }
             const uint4 share = Raw16<T>::pack(sh);
@@ -863,8 +864,9 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
     // S0 / S1: the 8 warps through shared memory, then fp64 atomics (only sub 0 accumulated)
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        const int c = i % C, idx = (c & 7) * LPR + (c >> 3);
         float v = 0.f;
-        for (int w = 0; w < 8; ++w) v += red[w][i / C][i % C];
+        for (int w = 0; w < 8; ++w) v += red[w][i / C][idx];
         atomicAdd(sums + i, (double)v);
     }
 }
