@@ -673,6 +673,27 @@ def test_dwconv3x3_eval_batchnorm_epilogue_bit_identical(ops, dtype, stride, act
         assert rel_err(res.float().cpu(), (nn.Sequential(*list(seq)[:2])(x.float()) + x.float()).cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
 
 
+def test_frozen_conv_bf16_weight_cache(ops):
+    """Inference under bf16 autocast: run_fused keeps the bf16 copy of a frozen convolution's weight (the teacher) instead
+    of letting autocast re-cast it every step; same output as the module, and the copy follows weight updates."""
+    import torch.nn as nn
+    conv = nn.Conv2d(32, 48, 1, bias=True).cuda()
+    seq = nn.Sequential(conv)
+    x = torch.randn(2, 32, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last)
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        a = ops.run_fused(seq, x)
+        b = conv(x)
+        assert a.dtype == torch.bfloat16 and torch.equal(a, b)
+        w16 = conv._kdf_w16[1]
+        assert ops.run_fused(seq, x).data_ptr() != a.data_ptr() and conv._kdf_w16[1] is w16      # cached
+        conv.weight.mul_(2.0)                                                                   # in-place update: new version
+        c = ops.run_fused(seq, x)
+        assert conv._kdf_w16[1] is not w16 and torch.equal(c, conv(x))
+    with torch.autocast("cuda", dtype=torch.bfloat16):                                          # training: the module itself
+        y = ops.run_fused(seq, x)
+        assert y.requires_grad
+
+
 def test_camera_side_kernels_accept_empty_batches(ops):
     import torch.nn as nn
     conv = nn.Conv2d(64, 64, 3, padding=1, groups=64, bias=False).cuda()

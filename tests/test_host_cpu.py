@@ -164,6 +164,27 @@ def test_host_rasterizer_matches_reference_semantics():
     np.testing.assert_array_equal(got, want)
 
 
+def test_batch_counters_deferred_into_one_add():
+    """nn.BatchNorm advances num_batches_tracked once per training forward; inside the Trainer's step the 29 increments
+    are collected and applied as one multi-tensor add (src/native.py).  Same counts either way; a BatchNorm with
+    momentum=None (cumulative average) needs the counter at once and is never deferred."""
+    import torch.nn as nn
+    from src import native
+    bns = [nn.BatchNorm2d(4) for _ in range(3)]
+    cum = nn.BatchNorm2d(4, momentum=None)
+    assert native.bump_batch_counter(bns[0]) == pytest.approx(0.1) and bns[0].num_batches_tracked.item() == 1
+    with native.deferred_batch_counters():
+        for b in bns:
+            assert native.bump_batch_counter(b) == pytest.approx(0.1)
+        assert [b.num_batches_tracked.item() for b in bns] == [1, 0, 0]          # nothing applied yet
+        assert native.bump_batch_counter(cum) == pytest.approx(1.0) and cum.num_batches_tracked.item() == 1
+        with native.deferred_batch_counters():                                   # nests
+            native.bump_batch_counter(bns[1])
+        assert bns[1].num_batches_tracked.item() == 1
+    assert [b.num_batches_tracked.item() for b in bns] == [2, 2, 1]
+    assert native.bump_batch_counter(cum) == pytest.approx(0.5)
+
+
 def test_shard_range_and_seeds():
     from src.training.parallel import frame_seed, shard_range
     for n, w in ((64, 8), (10, 4), (3, 8), (256, 8)):
