@@ -54,8 +54,8 @@ __device__ __forceinline__ void dw_load_taps(const float *__restrict__ w, int c0
 }
 
 // ----------------------------------------------------------------------------- forward (and stride-1 dgrad with FLIP)
-template <typename T, int STRIDE, bool FLIP>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, int STRIDE, bool FLIP, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
 dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C][9] */, T *__restrict__ out,
                      int B, int H, int W, int C, int OH, int OW, double *__restrict__ stats /* nullable [2][C] */,
                      const float *__restrict__ post_scale /* nullable [C] */, const float *__restrict__ post_shift, int post_act) {
@@ -338,7 +338,15 @@ static int dwconv_fwd_impl(const void *in, const float *weight, int dtype, int B
     const dim3 grid((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy));
     cudaStream_t st = as_stream(stream);
     if (stats) KDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-#define KDF_DW(T, S, F) dwconv3x3_fwd_kernel<T, S, F><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats, post_scale, post_shift, post_act)
+    // resident CTAs per SM the kernel is compiled for: 3 (85 registers, 128 B of spills) is 5 % faster than 2 (111 registers)
+    // at stride 1 and 15 % slower at stride 2 (measured in the step); KDF_DW_FWD_MINB forces one of them
+    static const int minb_env = getenv("KDF_DW_FWD_MINB") ? atoi(getenv("KDF_DW_FWD_MINB")) : 0;
+    const int minb = minb_env ? minb_env : (stride == 1 ? 3 : 2);
+#define KDF_DW(T, S, F)                                                                                                              \
+    do {                                                                                                                             \
+        if (minb == 3) dwconv3x3_fwd_kernel<T, S, F, 3><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats, post_scale, post_shift, post_act); \
+        else dwconv3x3_fwd_kernel<T, S, F, 2><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats, post_scale, post_shift, post_act);           \
+    } while (0)
     if (dtype == KDF_F32) { if (stride == 2) KDF_DW(float, 2, false); else if (flip) KDF_DW(float, 1, true); else KDF_DW(float, 1, false); }
     else { if (stride == 2) KDF_DW(__nv_bfloat16, 2, false); else if (flip) KDF_DW(__nv_bfloat16, 1, true); else KDF_DW(__nv_bfloat16, 1, false); }
 #undef KDF_DW

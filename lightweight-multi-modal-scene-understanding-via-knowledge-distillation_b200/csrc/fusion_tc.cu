@@ -131,7 +131,7 @@ __device__ __forceinline__ void ft_mma_hidden(uint32_t y_base, uint32_t w_base, 
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fusion_weighted_fwd_tc_kernel(FusionTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sW1 = smem + FtSmem::OFF_W1, *sY = smem + FtSmem::OFF_Y;
     uint8_t *misc = smem + FtSmem::OFF_MISC_FWD;
     uint64_t *bars = reinterpret_cast<uint64_t *>(misc);
@@ -255,9 +255,9 @@ struct FtTmaSmem {
 __global__ void __launch_bounds__(FTM_THREADS, 1)
 fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorMap tm_cam, const __grid_constant__ CUtensorMap tm_lid) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sW1 = smem + FtTmaSmem::OFF_W1;
-    uint8_t *sY[2] = {smem + FtTmaSmem::OFF_Y0, smem + FtTmaSmem::OFF_Y1};
+    auto sY = [smem](int b) -> uint8_t * { return smem + (b ? FtTmaSmem::OFF_Y1 : FtTmaSmem::OFF_Y0); };   // one shared base: LDS/STS
     uint8_t *misc = smem + FtTmaSmem::OFF_MISC;
     uint64_t *bar_raw = reinterpret_cast<uint64_t *>(misc);           // [2]
     uint64_t *bar_mma = bar_raw + 2;
@@ -269,10 +269,10 @@ fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorM
     auto issue_tile = [&](int64_t tile, int buf) {                     // one thread: 4 boxes of 64 columns x 128 rows
         tma::mbar_expect_tx(&bar_raw[buf], 4 * FT_PANEL);
         const int r0 = (int)(tile * FT_ROWS);
-        tma::load_2d(sY[buf] + 0 * FT_PANEL, &tm_cam, 0, r0, &bar_raw[buf]);
-        tma::load_2d(sY[buf] + 1 * FT_PANEL, &tm_cam, 64, r0, &bar_raw[buf]);
-        tma::load_2d(sY[buf] + 2 * FT_PANEL, &tm_lid, 0, r0, &bar_raw[buf]);
-        tma::load_2d(sY[buf] + 3 * FT_PANEL, &tm_lid, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sY(buf) + 0 * FT_PANEL, &tm_cam, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sY(buf) + 1 * FT_PANEL, &tm_cam, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sY(buf) + 2 * FT_PANEL, &tm_lid, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sY(buf) + 3 * FT_PANEL, &tm_lid, 64, r0, &bar_raw[buf]);
     };
     // barriers first, so that the first two tiles are already in flight during the rest of the setup
     if (tid == 0) {
@@ -314,7 +314,7 @@ fusion_weighted_fwd_tma_kernel(FusionTcArgs a, const __grid_constant__ CUtensorM
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const int64_t r0 = tile * FT_ROWS;
-        uint8_t *y = sY[buf];
+        uint8_t *y = sY(buf);
         tc::mbar_wait(&bar_raw[buf], (uint32_t)((it >> 1) & 1));
         // ---- BatchNorm-apply + ReLU in place (rows past M are forced to zero: TMA zero-fills them, relu(shift) would not be zero)
 #pragma unroll
@@ -401,7 +401,7 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
     constexpr int CG = NT / 128;                  // accumulator column groups (warp >> 2)
     constexpr int E1_COLS = FT_C / CG;            // hidden columns per warp in epilogue 1 (64 or 32)
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sW1 = smem + FtSmem::OFF_W1, *sY = smem + FtSmem::OFF_Y, *sG = smem + FtSmem::OFF_G, *sDH = smem + FtSmem::OFF_DH;
     uint8_t *misc = smem + FtSmem::OFF_MISC_BWD;
     uint64_t *bars = reinterpret_cast<uint64_t *>(misc);

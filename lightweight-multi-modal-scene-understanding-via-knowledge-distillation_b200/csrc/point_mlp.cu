@@ -97,8 +97,9 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
     constexpr uint32_t IDESC = tc::make_idesc(PM_ROWS, PM_N, 0, 0);
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sW = smem + L::OFF_W, *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1}, *sStage = smem + L::OFF_STAGE;
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
+    uint8_t *sW = smem + L::OFF_W, *sStage = smem + L::OFF_STAGE;
+    auto sA = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1 : L::OFF_A0); };   // offsets from ONE shared base: LDS/STS, not generic
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
     float *coef = reinterpret_cast<float *>(smem + L::OFF_MISC + 64);
@@ -188,7 +189,7 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
         tc::fence_async_smem();
     };
     auto issue_mma = [&](int buf) {                                        // one thread
-        const uint32_t a_base = tc::smem_u32(sA[buf]), w_base = tc::smem_u32(sW);
+        const uint32_t a_base = tc::smem_u32(sA(buf)), w_base = tc::smem_u32(sW);
         const uint32_t d = tmem_base + (uint32_t)buf * PM_N;
 #pragma unroll
         for (int k = 0; k < KIN / 16; ++k) {
@@ -242,7 +243,7 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
     int64_t tile = blockIdx.x;
     if (tile < n_tiles) {
         load_tile(tile);
-        stage_tile(tile, sA[0]);
+        stage_tile(tile, sA(0));
     }
     __syncthreads();
     int it = 0;
@@ -257,7 +258,7 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
         if (next < n_tiles) load_tile(next);                               // global loads in flight during the epilogue
         if (tid == 32) l2_prefetch(next + gridDim.x);                      // and the tile after it on its way into L2
         if (it > 0) epilogue(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1));
-        if (next < n_tiles) stage_tile(next, sA[buf ^ 1]);                 // A[buf^1] was consumed by the MMA just waited on
+        if (next < n_tiles) stage_tile(next, sA(buf ^ 1));                 // A[buf^1] was consumed by the MMA just waited on
         __syncthreads();
         prev_tile = tile;
     }
@@ -328,8 +329,9 @@ mlp_eval3_kernel(MlpEvalArgs a) {
     constexpr uint32_t PANEL = PM_ROWS * tc::ROW_BYTES;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sW2 = smem + L::OFF_W2, *sW3 = smem + L::OFF_W3, *sA1[2] = {smem + L::OFF_A1_0, smem + L::OFF_A1_1};
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
+    uint8_t *sW2 = smem + L::OFF_W2, *sW3 = smem + L::OFF_W3;
+    auto sA1 = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1_1 : L::OFF_A1_0); };
     uint8_t *sA2 = smem + L::OFF_A2, *sStage = smem + L::OFF_STAGE;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [0] MMA 1 done, [1] MMA 2 done
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
@@ -402,7 +404,7 @@ mlp_eval3_kernel(MlpEvalArgs a) {
         tc::fence_async_smem();
     };
     auto issue_mma1 = [&](int buf) {                                       // one thread
-        const uint32_t a_base = tc::smem_u32(sA1[buf]), w_base = tc::smem_u32(sW2);
+        const uint32_t a_base = tc::smem_u32(sA1(buf)), w_base = tc::smem_u32(sW2);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             tc::mma_bf16(tmem_base, tc::desc_kmajor(a_base + (uint32_t)k * 32u), tc::desc_kmajor(w_base + (uint32_t)k * 32u), IDESC, k > 0);
@@ -432,12 +434,17 @@ mlp_eval3_kernel(MlpEvalArgs a) {
             for (int j = 0; j < 4; ++j) {
                 const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j;
                 const int col = chunk * 8;
+                // coefficients as four 16-byte broadcast loads per chunk (not sixteen 4-byte ones)
+                const float4 sa = *reinterpret_cast<const float4 *>(tsc + col), sb = *reinterpret_cast<const float4 *>(tsc + col + 4);
+                const float4 ha = *reinterpret_cast<const float4 *>(tsh + col), hb = *reinterpret_cast<const float4 *>(tsh + col + 4);
+                const float cs[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float ch_[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
                 uint32_t o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t zz = pack_bf16(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));   // z2 as stored
-                    const float v0 = fmaxf(fmaf(bf16_lo(zz), tsc[col + 2 * e], tsh[col + 2 * e]), 0.f);
-                    const float v1 = fmaxf(fmaf(bf16_hi(zz), tsc[col + 2 * e + 1], tsh[col + 2 * e + 1]), 0.f);
+                    const float v0 = fmaxf(fmaf(bf16_lo(zz), cs[2 * e], ch_[2 * e]), 0.f);
+                    const float v1 = fmaxf(fmaf(bf16_hi(zz), cs[2 * e + 1], ch_[2 * e + 1]), 0.f);
                     o[e] = pack_bf16(v0, v1);
                 }
                 *reinterpret_cast<uint4 *>(sA2 + (uint32_t)(chunk >> 3) * PANEL + tc::sw128_offset(erow, chunk & 7)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -479,7 +486,7 @@ mlp_eval3_kernel(MlpEvalArgs a) {
     int64_t tile = blockIdx.x;
     if (tile < n_tiles) {
         load_tile(tile);
-        stage_tile(tile, sA1[0]);
+        stage_tile(tile, sA1(0));
     }
     __syncthreads();
     int it = 0;
@@ -494,7 +501,7 @@ mlp_eval3_kernel(MlpEvalArgs a) {
         if (next < n_tiles) load_tile(next);
         if (tid == 32) l2_prefetch(next + gridDim.x);
         if (it > 0) epilogue2(prev_tile, (uint32_t)((it - 1) & 1));        // also: MMA 2 of the previous tile has consumed A2
-        if (next < n_tiles) stage_tile(next, sA1[buf ^ 1]);
+        if (next < n_tiles) stage_tile(next, sA1(buf ^ 1));
         epilogue1((uint32_t)(it & 1));
         __syncthreads();
         if (tid == 0) {
@@ -577,10 +584,10 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     constexpr uint32_t TMEM_COLS = (3 * KIN > 256) ? 512 : 256;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sW = smem + L::OFF_W;
-    uint8_t *sD[2] = {smem + L::OFF_D0, smem + L::OFF_D1};
-    uint8_t *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1};
+    auto sD = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_D1 : L::OFF_D0); };   // offsets from ONE shared base: LDS/STS, not generic
+    auto sA = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1 : L::OFF_A0); };
     float4 *sPts = reinterpret_cast<float4 *>(smem + L::OFF_PTS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
@@ -673,7 +680,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                     for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
                     v = pack8(g);
                 }
-                *reinterpret_cast<uint4 *>(sD[buf] + (dch >> 3) * PANEL + tc::sw128_offset(r, dch & 7)) = v;
+                *reinterpret_cast<uint4 *>(sD(buf) + (dch >> 3) * PANEL + tc::sw128_offset(r, dch & 7)) = v;
             }
         }
         {
@@ -701,13 +708,13 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                         v = affine_relu_chunk(raw_in[p], c0, c1);
                     }
                 }
-                *reinterpret_cast<uint4 *>(sA[buf] + (ach >> 3) * PANEL + tc::sw128_offset(r, ach & 7)) = v;
+                *reinterpret_cast<uint4 *>(sA(buf) + (ach >> 3) * PANEL + tc::sw128_offset(r, ach & 7)) = v;
             }
         }
         tc::fence_async_smem();
     };
     auto issue_mma = [&](int buf, bool first) {                            // one thread
-        const uint32_t d_base = tc::smem_u32(sD[buf]), a_base = tc::smem_u32(sA[buf]), w_base = tc::smem_u32(sW);
+        const uint32_t d_base = tc::smem_u32(sD(buf)), a_base = tc::smem_u32(sA(buf)), w_base = tc::smem_u32(sW);
         const uint32_t acc_d = tmem_base + (uint32_t)buf * KIN, acc_w = tmem_base + 2u * KIN;
 #pragma unroll
         for (int k = 0; k < PM_N / 16; ++k) {                              // dgrad: K = the 128 gradient channels
@@ -733,7 +740,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 
     auto epilogue = [&](int64_t tile, int buf, uint32_t parity) {
         const int64_t r0 = tile * PM_ROWS;
-        uint8_t *sStage = sD[buf];                                         // the dz tile is dead once the MMAs have completed
+        uint8_t *sStage = sD(buf);                                         // the dz tile is dead once the MMAs have completed
         uint4 zk[MODE == 1 ? D_PASSES : 1];
         if (MODE == 1) {                                                   // z_prev chunks of the store phase (L2 hits), issued early
 #pragma unroll
@@ -757,7 +764,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j;   // 16-byte chunk of the 256-byte row
-                    const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
+                    const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
                     float act[8], v[8];
                     unpack8(av, act);
 #pragma unroll
@@ -774,7 +781,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 #pragma unroll
             for (int j = 0; j < COLS_W / 8; ++j) {
                 const int chunk = (warp >> 2) * (COLS_W / 8) + j;           // 8 channels of the 64-channel activation row
-                const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + tc::sw128_offset(row, chunk));
+                const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + tc::sw128_offset(row, chunk));
                 float act[8];
                 unpack8(av, act);
 #pragma unroll
@@ -845,7 +852,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     if (it > 0) epilogue(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1));
 
     // ---- column sums -> fp64 atomics
-    float *red = reinterpret_cast<float *>(sD[0]);
+    float *red = reinterpret_cast<float *>(sD(0));
     if (MODE == 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) red[(orow0 * 16 + och) * 16 + j] = acc[j];
@@ -941,10 +948,10 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
     constexpr uint32_t TMEM_COLS = (3 * KIN > 256) ? 512 : 256;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sW = smem + L::OFF_W;
-    uint8_t *sD[2] = {smem + L::OFF_D0, smem + L::OFF_D1};
-    uint8_t *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1};
+    auto sD = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_D1 : L::OFF_D0); };   // offsets from ONE shared base: LDS/STS, not generic
+    auto sA = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1 : L::OFF_A0); };
     uint8_t *sStage = smem + L::OFF_STAGE;
     float4 *sPts = reinterpret_cast<float4 *>(smem + L::OFF_PTS);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [2]
@@ -988,7 +995,7 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
         const int mb = mit & 1;
         tc::mbar_wait(&bar_full[mb], (uint32_t)((mit >> 1) & 1));
         tc::fence_after_sync();
-        const uint32_t d_base = tc::smem_u32(sD[mb]), a_base = tc::smem_u32(sA[mb]), w_base = tc::smem_u32(sW);
+        const uint32_t d_base = tc::smem_u32(sD(mb)), a_base = tc::smem_u32(sA(mb)), w_base = tc::smem_u32(sW);
         const uint32_t acc_d = tmem_base + (uint32_t)mb * KIN, acc_w = tmem_base + 2u * KIN;
 #pragma unroll
         for (int k = 0; k < PM_N / 16; ++k) {
@@ -1065,8 +1072,8 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
                 }
                 if (p + PF < D_PASSES) issue(tile, p + PF, slot); else issue(next, p + PF - D_PASSES, slot);
                 const uint32_t off = (dch >> 3) * PANEL + tc::sw128_offset(r, dch & 7);
-                *reinterpret_cast<uint4 *>(sD[buf] + off) = v;
-                if (MODE == 1) *reinterpret_cast<uint4 *>(sA[buf] + off) = av;
+                *reinterpret_cast<uint4 *>(sD(buf) + off) = v;
+                if (MODE == 1) *reinterpret_cast<uint4 *>(sA(buf) + off) = av;
             }
             if (MODE == 0) {
                 float c0[32], c1[8];
@@ -1084,7 +1091,7 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
                         v = first_layer_chunk(pt, c0, c1);
                         if (ach == 0) sPts[buf * PM_ROWS + r] = pt;
                     }
-                    *reinterpret_cast<uint4 *>(sA[buf] + tc::sw128_offset(r, ach)) = v;
+                    *reinterpret_cast<uint4 *>(sA(buf) + tc::sw128_offset(r, ach)) = v;
                 }
                 issue_pts(next);
             }
@@ -1128,7 +1135,7 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int chunk = (ewarp >> 2) * 8 + half * 4 + j;
-                        const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
+                        const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
                         float act[8], v[8];
                         unpack8(av, act);
 #pragma unroll
@@ -1161,7 +1168,7 @@ mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int chunk = (ewarp >> 2) * 4 + j;
-                    const uint4 av = *reinterpret_cast<const uint4 *>(sA[buf] + tc::sw128_offset(row, chunk));
+                    const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + tc::sw128_offset(row, chunk));
                     float act[8];
                     unpack8(av, act);
 #pragma unroll
@@ -1272,11 +1279,11 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
     constexpr uint32_t IDESC_D = tc::make_idesc(PM_ROWS, KIN, 0, 1);       // dgrad: A K-major, B MN-major
     constexpr uint32_t IDESC_W = tc::make_idesc(PM_N, KIN, 1, 1);          // wgrad: both MN-major
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sWs = smem + L::OFF_WS, *sWb = smem + L::OFF_WB;
-    uint8_t *sDy[2] = {smem + L::OFF_DY0, smem + L::OFF_DY1};
-    uint8_t *sZ[2] = {smem + L::OFF_Z0, smem + L::OFF_Z1};
-    uint8_t *sA[2] = {smem + L::OFF_A0, smem + L::OFF_A1};
+    auto sDy = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_DY1 : L::OFF_DY0); };
+    auto sZ = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_Z1 : L::OFF_Z0); };
+    auto sA = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1 : L::OFF_A0); };
     uint8_t *sStage = smem + L::OFF_STAGE;
     float4 *sPts = reinterpret_cast<float4 *>(smem + L::OFF_PTS);
     uint64_t *bar_raw = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);            // [2]
@@ -1292,10 +1299,10 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
     auto issue_tile = [&](int64_t tile, int buf) {                   // one thread: dy and z tiles, 2 boxes each
         tma::mbar_expect_tx(&bar_raw[buf], 4 * PANEL);
         const int r0 = (int)(tile * PM_ROWS);
-        tma::load_2d(sDy[buf], &tm_dy, 0, r0, &bar_raw[buf]);
-        tma::load_2d(sDy[buf] + PANEL, &tm_dy, 64, r0, &bar_raw[buf]);
-        tma::load_2d(sZ[buf], &tm_z, 0, r0, &bar_raw[buf]);
-        tma::load_2d(sZ[buf] + PANEL, &tm_z, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sDy(buf), &tm_dy, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sDy(buf) + PANEL, &tm_dy, 64, r0, &bar_raw[buf]);
+        tma::load_2d(sZ(buf), &tm_z, 0, r0, &bar_raw[buf]);
+        tma::load_2d(sZ(buf) + PANEL, &tm_z, 64, r0, &bar_raw[buf]);
     };
     if (tid == 0) {
         tc::mbar_init(&bar_raw[0], 1); tc::mbar_init(&bar_raw[1], 1);
@@ -1365,14 +1372,14 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
                 for (int j = 0; j < 8; ++j) a_sum[j] += f[j];
                 if (ach == 0) sPts[buf * PM_ROWS + r] = pt;
             }
-            *reinterpret_cast<uint4 *>(sA[buf] + tc::sw128_offset(r, ach)) = v;
+            *reinterpret_cast<uint4 *>(sA(buf) + tc::sw128_offset(r, ach)) = v;
         }
         tc::fence_async_smem();
     };
     auto issue_mma = [&](int buf, bool first, uint32_t raw_parity) {     // one thread
         tc::mbar_wait(&bar_raw[buf], raw_parity);                        // dy / z of this tile have landed
         tc::fence_after_sync();
-        const uint32_t dy = tc::smem_u32(sDy[buf]), z = tc::smem_u32(sZ[buf]), act = tc::smem_u32(sA[buf]);
+        const uint32_t dy = tc::smem_u32(sDy(buf)), z = tc::smem_u32(sZ(buf)), act = tc::smem_u32(sA(buf));
         const uint32_t ws = tc::smem_u32(sWs), wb = tc::smem_u32(sWb);
         const uint32_t acc_d = tmem_base + (uint32_t)buf * KIN, acc_ws = tmem_base + 2u * KIN, acc_wb = tmem_base + 3u * KIN;
 #pragma unroll
@@ -1418,7 +1425,7 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
             for (int j = 0; j < 2; ++j) {
                 const int chunk = (col0 >> 3) + j;
                 float act[8], v[8];
-                unpack8(*reinterpret_cast<const uint4 *>(sA[buf] + tc::sw128_offset(row, chunk)), act);
+                unpack8(*reinterpret_cast<const uint4 *>(sA(buf) + tc::sw128_offset(row, chunk)), act);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = act[e] > 0.f ? __uint_as_float(r[8 * j + e]) + cvec[chunk * 8 + e] : 0.f;
                 *reinterpret_cast<uint4 *>(sStage + tc::sw128_offset(row, chunk)) = pack8(v);

@@ -22,6 +22,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// First 1024-byte-aligned address of the dynamic shared memory, as pointer arithmetic ON the __shared__ array: the
+// compiler keeps the address space and emits LDS / STS with 32-bit addresses.  (Rounding the pointer up through
+// uintptr_t loses it: every shared-memory access of the kernel became a generic LD.E / ST.E with 64-bit address math.)
+__device__ __forceinline__ uint8_t *align_smem_1024(uint8_t *raw) {
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(raw));
+    return raw + ((1024u - (base & 1023u)) & 1023u);
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside one panel
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
     return (uint32_t)row * ROW_BYTES + (uint32_t)((chunk ^ (row & 7)) << 4);

@@ -688,7 +688,9 @@ def test_frozen_conv_bf16_weight_cache(ops):
         assert ops.run_fused(seq, x).data_ptr() != a.data_ptr() and conv._kdf_w16[1] is w16      # cached
         conv.weight.mul_(2.0)                                                                   # in-place update: new version
         c = ops.run_fused(seq, x)
-        assert conv._kdf_w16[1] is not w16 and torch.equal(c, conv(x))
+        assert conv._kdf_w16[1] is not w16
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():      # a fresh context: autocast's own cast cache is per context
+        assert torch.equal(c, conv(x)) and not torch.equal(c, a)
     with torch.autocast("cuda", dtype=torch.bfloat16):                                          # training: the module itself
         y = ops.run_fused(seq, x)
         assert y.requires_grad
