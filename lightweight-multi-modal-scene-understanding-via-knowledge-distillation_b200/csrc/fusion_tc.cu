@@ -67,8 +67,13 @@ __device__ __forceinline__ uint4 ft_pack8(const float (&v)[8]) {
 __device__ __forceinline__ uint4 ft_affine_relu(const uint4 &raw, const float *sc, const float *sh) {
     float v[8];
     ft_unpack8(raw, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+    // the 8 coefficients of a chunk are 32-byte aligned in the table: four 16-byte loads, not sixteen 4-byte ones
+    const float4 s0 = *reinterpret_cast<const float4 *>(sc), s1 = *reinterpret_cast<const float4 *>(sc + 4);
+    const float4 h0 = *reinterpret_cast<const float4 *>(sh), h1 = *reinterpret_cast<const float4 *>(sh + 4);
+    v[0] = fmaxf(fmaf(v[0], s0.x, h0.x), 0.f); v[1] = fmaxf(fmaf(v[1], s0.y, h0.y), 0.f);
+    v[2] = fmaxf(fmaf(v[2], s0.z, h0.z), 0.f); v[3] = fmaxf(fmaf(v[3], s0.w, h0.w), 0.f);
+    v[4] = fmaxf(fmaf(v[4], s1.x, h1.x), 0.f); v[5] = fmaxf(fmaf(v[5], s1.y, h1.y), 0.f);
+    v[6] = fmaxf(fmaf(v[6], s1.z, h1.z), 0.f); v[7] = fmaxf(fmaf(v[7], s1.w, h1.w), 0.f);
     return ft_pack8(v);
 }
 

@@ -85,6 +85,17 @@ template <> struct VecIO<__nv_bfloat16, 8> {
     }
 };
 
+// VEC per-channel coefficients of this thread's channel group from shared memory as 16-byte loads (the group starts at a
+// multiple of VEC floats, so it is 16-byte aligned; left to the compiler these are VEC 4-byte loads per table)
+template <int VEC>
+__device__ __forceinline__ void ld_coef(const float *p, float (&v)[VEC]) {
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p + q);
+        v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
+    }
+}
+
 __device__ __forceinline__ float act_fwd(float y, int act) {
     if (act == 1) return fmaxf(y, 0.f);
     if (act == 2) return fminf(fmaxf(y, 0.f), 6.f);
@@ -312,13 +323,14 @@ rowbn_apply_bwd_kernel(const T *__restrict__ g, const T *__restrict__ x, T *__re
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < M) {
-                float xv[VEC], gv[VEC], o[VEC];
+                float xv[VEC], gv[VEC], o[VEC], vsc[VEC], vsh[VEC], vA[VEC], vB[VEC];
                 IO::unpack(xr[u], xv);
                 IO::unpack(gr[u], gv);
+                ld_coef<VEC>(sc, vsc); ld_coef<VEC>(sh, vsh); ld_coef<VEC>(A, vA); ld_coef<VEC>(B, vB);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    const float dy = act_open(fmaf(xv[q], sc[q], sh[q]), act) ? gv[q] : 0.f;
-                    o[q] = fmaf(dy, sc[q], fmaf(B[q], xv[q], A[q]));
+                    const float dy = act_open(fmaf(xv[q], vsc[q], vsh[q]), act) ? gv[q] : 0.f;
+                    o[q] = fmaf(dy, vsc[q], fmaf(vB[q], xv[q], vA[q]));
                 }
                 IO::store(dx + rr * C + c, o);
             }
@@ -438,13 +450,14 @@ rowbn_bwd_coop_kernel(ReduceArgs a, T *__restrict__ dx) {
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < a.M) {
-                float xv[VEC], gv[VEC], o[VEC];
+                float xv[VEC], gv[VEC], o[VEC], vsc[VEC], vsh[VEC], vA[VEC], vB[VEC];
                 IO::unpack(xr[u], xv);
                 IO::unpack(gr[u], gv);
+                ld_coef<VEC>(csc + c, vsc); ld_coef<VEC>(csh + c, vsh); ld_coef<VEC>(cA + c, vA); ld_coef<VEC>(cB + c, vB);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    const float dy = act_open(fmaf(xv[q], csc[c + q], csh[c + q]), a.act) ? gv[q] : 0.f;
-                    o[q] = fmaf(dy, csc[c + q], fmaf(cB[c + q], xv[q], cA[c + q]));
+                    const float dy = act_open(fmaf(xv[q], vsc[q], vsh[q]), a.act) ? gv[q] : 0.f;
+                    o[q] = fmaf(dy, vsc[q], fmaf(vB[q], xv[q], vA[q]));
                 }
                 IO::store(dx + rr * a.C + c, o);
             }
@@ -557,12 +570,13 @@ rowbn_fwd_coop_kernel(ReduceArgs a, const T *__restrict__ res, T *__restrict__ y
         for (int u = 0; u < U; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < a.M) {
-                float xv[VEC], rv[VEC], o[VEC];
+                float xv[VEC], rv[VEC], o[VEC], vsc[VEC], vsh[VEC];
                 IO::unpack(xr[u], xv);
                 if (res) IO::unpack(rr_[u], rv);
+                ld_coef<VEC>(csc + c, vsc); ld_coef<VEC>(csh + c, vsh);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    o[q] = act_fwd(fmaf(xv[q], csc[c + q], csh[c + q]), a.act);
+                    o[q] = act_fwd(fmaf(xv[q], vsc[q], vsh[q]), a.act);
                     if (res) o[q] += rv[q];
                 }
                 IO::store(y + rr * a.C + c, o);
