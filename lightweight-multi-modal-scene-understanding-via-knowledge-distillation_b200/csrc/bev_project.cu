@@ -813,15 +813,17 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
             Raw16<T>::unpack(av, a3);
             Raw16<T>::unpack(ze, zf);
 #pragma unroll
+            for (int q = 0; q < 8; ++q) sh[q] = (a3[q] > 0.f && k[q] > 0) ? g[q] / (float)k[q] : 0.f;
+            const uint4 share = Raw16<T>::pack(sh);                         // rounded to bf16 as stored ...
+            Raw16<T>::unpack(share, sh);                                    // ... and the sums use exactly those values
+#pragma unroll
             for (int q = 0; q < 8; ++q) {
-                sh[q] = (a3[q] > 0.f && k[q] > 0) ? bf16_round(g[q] / (float)k[q]) : 0.f;
                 if (sub == 0) {
                     const float tot = sh[q] * (float)k[q];
                     red[warp][0][q * LPR + rl] += tot;
                     red[warp][1][q * LPR + rl] = fmaf(tot, zf[q], red[warp][1][q * LPR + rl]);
                 }
             }
-            const uint4 share = Raw16<T>::pack(sh);
             // pass B: write the gradient rows
 #pragma unroll
             for (int u = 0; u < U; ++u) ida[u] = idn[u];

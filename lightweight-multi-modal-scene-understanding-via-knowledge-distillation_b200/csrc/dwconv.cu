@@ -31,6 +31,7 @@ template <> struct DwChunk<float> {
         v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
     }
     static __device__ __forceinline__ void st(float *p, const float *v) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ void round(float *) {}                      // storage rounding: none for fp32
 };
 template <> struct DwChunk<__nv_bfloat16> {
     typedef uint2 raw_t;
@@ -41,6 +42,12 @@ template <> struct DwChunk<__nv_bfloat16> {
     }
     static __device__ __forceinline__ void st(__nv_bfloat16 *p, const float *v) {
         *reinterpret_cast<uint2 *>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    }
+    // the values as they are stored: two packed conversions + four shifts (a scalar cvt.rn.bf16.f32 per element compiles
+    // to F2F on the conversion pipe, 8x the issue cost of an FMA -- it was as expensive as the convolution itself)
+    static __device__ __forceinline__ void round(float *v) {
+        const uint32_t a = pack_bf16(v[0], v[1]), b = pack_bf16(v[2], v[3]);
+        v[0] = bf16_lo(a); v[1] = bf16_hi(a); v[2] = bf16_lo(b); v[3] = bf16_hi(b);
     }
 };
 
@@ -126,9 +133,10 @@ dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C
             const int oy = oy0 + r;
             if (oy < OH) {
                 if (post_scale) {
+                    K::round(acc[r]);
 #pragma unroll
                     for (int q = 0; q < DW_V; ++q) {
-                        const float z = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(acc[r][q])) : acc[r][q];
+                        const float z = acc[r][q];
                         float y = fmaf(z, psc[q], psh[q]);
                         if (post_act == 1) y = fmaxf(y, 0.f);
                         else if (post_act == 2) y = fminf(fmaxf(y, 0.f), 6.f);
@@ -137,9 +145,10 @@ dwconv3x3_fwd_kernel(const T *__restrict__ in, const float *__restrict__ w /* [C
                 }
                 K::st(out + (((int64_t)b * OH + oy) * OW + ox) * C + g * DW_V, acc[r]);
                 if (stats) {
+                    K::round(acc[r]);                                              // the values stored
 #pragma unroll
                     for (int q = 0; q < DW_V; ++q) {
-                        const float v = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(acc[r][q])) : acc[r][q];   // the value stored
+                        const float v = acc[r][q];
                         s_sum[q] += v;
                         s_sq[q] = fmaf(v, v, s_sq[q]);
                     }
