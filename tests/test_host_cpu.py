@@ -185,6 +185,27 @@ def test_batch_counters_deferred_into_one_add():
     assert native.bump_batch_counter(cum) == pytest.approx(0.5)
 
 
+def test_microbench_torch_scatter_baseline_is_the_reference_op():
+    """tools/projection_microbench.py times `torch_scatter_projection` as "the reference's PyTorch scatter": it must be
+    the reference's statements (lidar_encoder.py:42-55, 69-99) -- checked here on the CPU against the oracle (which is
+    pinned bit-exact against the reference) on frames with edge cases: exact +-50, NaN / inf, zero-padding rows, ties."""
+    import importlib.util
+    from oracle import bev_oracle
+    from oracle.weights import synthetic_frames
+    spec = importlib.util.spec_from_file_location("_pmb", os.path.join(ROOT, "tools", "projection_microbench.py"))
+    pmb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pmb)
+    B, N, C = 2, 6000, 16
+    _, pts, _ = synthetic_frames(17, B, N, image_hw=(8, 8), edge_cases=True)
+    g = np.random.default_rng(3)
+    feats = np.maximum(g.standard_normal((B, N, C)).astype(np.float32), 0)
+    feats[:, 8:12] = feats[:, 12:13]                                            # ties
+    got = pmb.torch_scatter_projection(pts, torch.from_numpy(feats), 64, 64)     # [B,H,W,C]
+    cell = bev_oracle.bev_cells(pts.numpy(), (64, 64))
+    ref, _ = bev_oracle.bev_scatter_max(feats, cell, (64, 64))
+    np.testing.assert_array_equal(got.reshape(B, 4096, C).numpy(), ref)
+
+
 def test_shard_range_and_seeds():
     from src.training.parallel import frame_seed, shard_range
     for n, w in ((64, 8), (10, 4), (3, 8), (256, 8)):
