@@ -136,7 +136,11 @@ int kdf_bev_project_bwd(const void *grad_grid, const void *feats, const void *gr
  * kdf_rowbn_bwd      d x, d gamma, d beta from grad_out: dy = g*act'(x*scale+shift);
  *                    batch_stats != 0 chains through the batch mean / variance (training mode),
  *                    batch_stats == 0 is eval mode (running statistics are constants).
- * Workspaces: kdf_rowbn_workspace_bytes(C) for stats, kdf_rowbn_bwd_workspace_bytes(C) for bwd.
+ *                    Inputs of up to 250 MB (grad_out + x) run as ONE cooperative kernel (column sums, grid
+ *                    barrier, coefficients, apply: the second read is an L2 hit); larger ones as two kernels.
+ * Workspaces: kdf_rowbn_workspace_bytes(C) for stats / fwd_train, kdf_rowbn_bwd_workspace_bytes(C) for bwd
+ * (a ticket + 8 fp64 accumulator sets [2][C], zeroed by each call; the column sums are spread over the sets because
+ * same-address atomics serialise in L2).
  */
 size_t kdf_rowbn_workspace_bytes(int C);
 size_t kdf_rowbn_bwd_workspace_bytes(int C);
