@@ -19,9 +19,7 @@ math and every statistic stay fp32/fp64.  The per-channel coefficient algebra be
 from __future__ import annotations
 
 import os
-
 import weakref
-from typing import Optional, Tuple
 
 import torch
 
