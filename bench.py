@@ -67,7 +67,8 @@ def workload_config(args, n_gpus):
     return {"workload": f"teacher(concat/256, eval) -> student({args.student}/{width}, train) KD training step, 2-class, "
                         f"{'fp32' if args.fp32 else 'bf16'} activations, {args.batch} frames/GPU, "
                         f"{args.points}-pt sweeps, 256x256 images, 64x64 BEV",
-            "global_batch": args.batch * n_gpus, "frames_per_gpu": args.batch, "points_per_frame": args.points,
+            "global_batch": args.batch * n_gpus, "frames_per_gpu": args.batch, "frames_per_step": args.batch * n_gpus,
+            "points_per_frame": args.points,
             "parallelism": f"dp{n_gpus}", "loss": "0.5*CE + 0.5*T^2*KL(T=4) + 1.0*MSE(lidar_feat, camera_feat)",
             "optimizer": "AdamW lr 1e-3 wd 1e-3 (flat, one kernel)",
             "launch": "eager" if args.no_graph else "whole step replayed as one CUDA graph",
@@ -124,7 +125,12 @@ def run_reference(args):
     cb = time_cpu(args.cpu_batch, args.points, max(1, args.steps), max(0, args.warmup), args.student)
     cfg = workload_config(args, args.gpus)
     cfg["sample"] = f"each step is a bounded sample of {args.cpu_batch} frames of the same workload"
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+    # what this arm really ran, machine-readable: ONE host process whatever --gpus says, a bounded sample per step,
+    # fp32 (the reference has no bf16 path: SURVEY.md section 0.3)
+    cfg.update({"frames_per_step": args.cpu_batch, "same_config": False, "activations": "fp32", "processes": 1,
+                "kind": "port (oracle restatement of the reference's eager CPU path; the reference has no packaging to install)"})
+    line = {"impl": "reference", "kind": "port", "same_config": False, "frames_per_step": args.cpu_batch,
+            "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -537,14 +543,11 @@ def run_native(args):
                 "loss_terms_last_step": dict(zip(("loss", "ce", "kl", "mse"), loss_terms))}
         emit(line)
     if world > 1:
-        # Leave without tearing the communicator down: destroying an NCCL communicator whose all-reduce sits inside
-        # a captured CUDA graph blocked for minutes on the 2-GPU box (NCCL 2.28.9).  Everything is synchronised and
-        # flushed, so a hard exit loses nothing.
+        # the captured step graph holds the communicator's all-reduce: drop the graphs first, then tear down
         dist.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        trainer.release_graphs()
+        dist.destroy_process_group()
 
 
 _JSON_FD = None

@@ -65,6 +65,19 @@ int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
                   float x0, float xspan, float y0, float yspan, int H, int W,
                   int32_t *cell, int32_t *rank, int32_t *count, void *stream);
 
+/* BEV label rasterisation (reference src/data_loading/pandaset_dataset.py:23-45, rasterize_bev):
+ *   inside = x_min <= x <= x_max && y_min <= y <= y_max     on the RAW fp32 coordinates (:33)
+ *   col = clip(trunc((x - x_min) / xspan * (W-1)), 0, W-1), row likewise (:39-40; xspan = x_max - x_min
+ *         formed on the host like the reference's Python scalars)
+ *   a cell keeps the FIRST non-zero label that lands in it, in point order (:42-44)
+ *     = the label of the lowest-index non-zero-labelled point of the cell (an integer min-reduction).
+ *   points   f32 [B,N,point_stride]     labels i64 [B,N]
+ *   first_ws i32 [B,H*W] scratch        out i64 [B,H,W] (0 where no labelled point landed)
+ */
+int kdf_bev_rasterize(const float *points, int point_stride, const int64_t *labels, int B, int64_t N,
+                      float x_min, float x_max, float y_min, float y_max, float xspan, float yspan,
+                      int H, int W, int32_t *first_ws, int64_t *out, void *stream);
+
 /* bytes of scratch kdf_bev_project_fwd needs */
 size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W);
 

@@ -6,7 +6,7 @@ The loader itself is outside the accelerated path (it needs the real dataset and
 pandas/PIL on the host); what matters here is that it feeds the same batch
 contract as ``synthetic_frames``.  The BEV label rasterisation, a Python loop over
 ~100k points per frame in the reference (:42-44), has a device version built on the
-bit-exact index kernel: ``rasterize_bev_cuda``.
+same index arithmetic: ``rasterize_bev_cuda`` (``kdf_bev_rasterize``).
 """
 from __future__ import annotations
 
@@ -49,19 +49,31 @@ def rasterize_bev(x: np.ndarray, y: np.ndarray, labels: np.ndarray, grid_size: T
 
 
 def rasterize_bev_cuda(points: torch.Tensor, labels: torch.Tensor, grid_size: Tuple[int, int] = (64, 64),
-                       point_cloud_range=(-50, -50, -5, 50, 50, 3)) -> torch.Tensor:
-    """Device rasteriser for binary labels: points f32[B,N,>=2], labels int[B,N] in {0,1}
-    -> int64[B,H,W]; cell ids come from ``kdf_bev_index`` (same arithmetic as the
-    encoder), the per-cell max is an index_reduce over them."""
-    from .. import ops
+                       pc_range: Tuple[float, float, float, float] = (-50, 50, -50, 50)) -> torch.Tensor:
+    """Device rasteriser with exactly ``rasterize_bev``'s semantics (reference :23-45) for a whole batch:
+    points f32[B,N,>=2] (x, y first), labels int[B,N] (any alphabet) -> int64[B,H,W].  One call into
+    ``kdf_bev_rasterize``: cell ids by the reference's fp32 formula, "first non-zero label in point order wins"
+    as a per-cell integer min-reduction over point indices.  ``pc_range`` = (x_min, x_max, y_min, y_max) like the
+    host function."""
+    from ..native import call, ptr, require_cuda, stream_ptr
+    dev = require_cuda(points, labels)
+    if points.dim() != 3 or points.shape[-1] < 2 or points.dtype != torch.float32:
+        raise ValueError(f"points must be float32 [B, N, >=2], got {points.dtype} {tuple(points.shape)}")
+    B, N, D = points.shape
+    if tuple(labels.shape) != (B, N):
+        raise ValueError(f"labels must be [B, N] = {(B, N)}, got {tuple(labels.shape)}")
+    points, labels = points.contiguous(), labels.long().contiguous()
     H, W = grid_size
-    cell, _ = ops.bev_index(points.float(), ops.bev_range_constants(list(point_cloud_range)), (H, W))
-    B, N = cell.shape
-    flat = (cell.long() + torch.arange(B, device=cell.device).view(B, 1) * (H * W)).reshape(-1)
-    ok = (cell >= 0).reshape(-1)
-    out = torch.zeros(B * H * W, dtype=torch.int64, device=cell.device)
-    out.scatter_reduce_(0, flat[ok], labels.reshape(-1).long()[ok], reduce="amax", include_self=True)
-    return out.view(B, H, W)
+    x_min, x_max, y_min, y_max = pc_range
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))
+    # the reference subtracts Python scalars: an integral range gives an exact integer span before it meets fp32
+    xspan = f32(x_max - x_min) if isinstance(x_min, int) and isinstance(x_max, int) else f32(f32(x_max) - f32(x_min))
+    yspan = f32(y_max - y_min) if isinstance(y_min, int) and isinstance(y_max, int) else f32(f32(y_max) - f32(y_min))
+    first = torch.empty(B, H * W, dtype=torch.int32, device=dev)
+    out = torch.empty(B, H, W, dtype=torch.int64, device=dev)
+    call("kdf_bev_rasterize", ptr(points), D, ptr(labels), B, N, f32(x_min), f32(x_max), f32(y_min), f32(y_max),
+         xspan, yspan, H, W, ptr(first), ptr(out), stream_ptr(dev))
+    return out
 
 
 class PandaSetDataset(Dataset):
@@ -117,9 +129,15 @@ class PandaSetDataset(Dataset):
 
 
 def create_pandaset_dataloaders(root: str, train_scenes: List[str], val_scenes: List[str], batch_size: int = 4,
-                                num_workers: int = 0, verbose: bool = True):
+                                num_workers: int = 0, verbose: bool = True, distributed: bool = False):
+    """Same call as the reference (:144-157); ``distributed`` shards both datasets over the ranks with a
+    DistributedSampler (the Trainer advances its epoch) instead of every rank iterating everything."""
     train_ds = PandaSetDataset(root, train_scenes, verbose=verbose)
     val_ds = PandaSetDataset(root, val_scenes, verbose=verbose)
+    ts = vs = None
+    if distributed:
+        from torch.utils.data.distributed import DistributedSampler
+        ts, vs = DistributedSampler(train_ds, shuffle=True), DistributedSampler(val_ds, shuffle=False)
     pin = torch.cuda.is_available()
-    return (DataLoader(train_ds, batch_size=batch_size, shuffle=True, num_workers=num_workers, pin_memory=pin),
-            DataLoader(val_ds, batch_size=batch_size, shuffle=False, num_workers=num_workers, pin_memory=pin))
+    return (DataLoader(train_ds, batch_size=batch_size, shuffle=ts is None, sampler=ts, num_workers=num_workers, pin_memory=pin),
+            DataLoader(val_ds, batch_size=batch_size, shuffle=False, sampler=vs, num_workers=num_workers, pin_memory=pin))

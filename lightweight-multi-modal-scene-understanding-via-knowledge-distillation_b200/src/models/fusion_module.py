@@ -127,8 +127,6 @@ class ConcatenationFusion(_PairFusion):
 
     def __init__(self, camera_channels=128, lidar_channels=128, out_channels=256):
         super().__init__()
-        if camera_channels != lidar_channels:
-            raise ValueError("the fused concat kernel needs equal camera and LiDAR widths")
         self.camera_proj = Conv1x1(camera_channels, camera_channels)
         self.lidar_proj = Conv1x1(lidar_channels, lidar_channels)
         cat = camera_channels + lidar_channels
@@ -139,6 +137,16 @@ class ConcatenationFusion(_PairFusion):
             nn.BatchNorm2d(out_channels), nn.ReLU())
 
     def forward_with_pre(self, cam_feat, lidar_feat):
+        if self.camera_proj.conv[0].out_channels != self.lidar_proj.conv[0].out_channels:
+            # unequal branch widths (the reference accepts any pair, fusion_module.py:74-76): the pair kernel wants one
+            # row width, so each projection block runs on its own and the rows are concatenated
+            if not (cam_feat.is_cuda and lidar_feat.is_cuda):
+                raise RuntimeError("fusion runs on CUDA tensors only (no CPU fallback)")
+            if cam_feat.shape[-2:] != lidar_feat.shape[-2:]:
+                lidar_feat = F.interpolate(lidar_feat, size=cam_feat.shape[-2:], mode="bilinear", align_corners=False)
+            cam_p, lid_p = self.camera_proj(cam_feat), self.lidar_proj(lidar_feat)
+            pre = torch.cat([cam_p, lid_p.to(cam_p.dtype)], dim=1).contiguous(memory_format=torch.channels_last)
+            return pre, ops.run_fused(self.fuse, pre)
         pre, _ = self.fuse_rows(cam_feat, lidar_feat)
         return pre, ops.run_fused(self.fuse, pre)
 

@@ -91,17 +91,27 @@ class SpatialLiDAREncoder(nn.Module):
         return grid
 
     def forward_iterative(self, points: torch.Tensor) -> torch.Tensor:
-        """The reference keeps a second, per-point Python implementation for
-        cross-checking (lidar_encoder.py:101-143).  Here the second opinion is the
-        same kernels driven frame by frame: batch statistics are still taken over
-        the whole batch, only the projection is launched per frame."""
+        """The reference keeps a second, independent implementation of the projection for cross-checking
+        (lidar_encoder.py:101-143: a Python loop over the valid points that writes ``max(cell, feature)``).
+        Ours is independent of the projection kernels in the same way: the cell of every point comes from the
+        reference's own tensor arithmetic (``points_to_bev_coords`` + ``.long()`` + clamp, :108-117) and the per-cell
+        maximum is taken frame by frame by ``Tensor.index_reduce_('amax')`` -- none of kdf_bev_*.  With post-ReLU
+        features (>= 0) the running maximum from a zero grid equals the reference's first-write-then-max (:137-141)."""
         if not points.is_cuda:
             raise RuntimeError("SpatialLiDAREncoder runs on CUDA tensors only (no CPU fallback)")
         points = points.float()
-        feats = self.point_features(points)
-        frames = [ops.bev_project(points[b:b + 1], feats[b:b + 1], self._geom, tuple(self.grid_size), "max")[0]
-                  for b in range(points.shape[0])]
-        return torch.cat(frames, dim=0)
+        B, N, _ = points.shape
+        H, W = self.grid_size
+        feats = self.point_features(points)                                  # [B,N,C]; batch statistics over the batch
+        coords, valid = self.points_to_bev_coords(points)                    # :108
+        cells = (coords * self.grid_tensor.to(coords.dtype)).long()          # :111
+        col, row = cells[..., 0].clamp(0, W - 1), cells[..., 1].clamp(0, H - 1)
+        grid = torch.zeros(B, H * W, feats.shape[-1], dtype=feats.dtype, device=feats.device)
+        for b in range(B):                                                   # :120 one frame at a time
+            keep = valid[b]
+            flat = (row[b] * W + col[b])[keep]
+            grid[b].index_reduce_(0, flat, feats[b][keep], "amax", include_self=True)
+        return grid.view(B, H, W, -1).permute(0, 3, 1, 2)
 
     def forward(self, points: torch.Tensor) -> torch.Tensor:
         return self.forward_vectorized(points) if self.use_vectorized else self.forward_iterative(points)

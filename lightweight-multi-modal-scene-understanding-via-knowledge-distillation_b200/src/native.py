@@ -24,6 +24,7 @@ _SIGNATURES = {
     "kdf_last_error": (C.c_char_p, []),
     "kdf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "kdf_bev_index": (C.c_int, [_vp, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "kdf_bev_rasterize": (C.c_int, [_vp, _i, _vp, _i, _i64, _f, _f, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp]),
     "kdf_bev_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "kdf_bev_project_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _i,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -91,7 +92,7 @@ def check(rc: int, what: str = "") -> None:
 
 # kernels launched per ABI call (memsets not counted) -- bench.py reports the total
 KERNELS_PER_CALL = {
-    "kdf_bev_index": 1, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
+    "kdf_bev_index": 1, "kdf_bev_rasterize": 3, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
     "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
     "kdf_fusion_affine_relu_pair_fwd": 1, "kdf_fusion_affine_relu_pair_bwd": 1,
     "kdf_kd_loss_fwd_bwd": 2, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
@@ -142,6 +143,33 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+# ----------------------------------------------------------------------------- parameter generation
+# The kernels update parameters and BatchNorm buffers through raw pointers (kdf_adamw_flat on the flat buffer, the
+# running statistics inside kdf_rowbn_stats / kdf_bn_finalize / kdf_mlp_l1_stats -- also inside a replayed CUDA graph,
+# where no Python runs at all), which never advances torch's per-tensor ``_version``.  Everything that caches a value
+# derived from parameters (eval-mode BatchNorm affine, bf16 weight copies) therefore also keys on this counter, which
+# every optimizer step, every training step and every running-statistics update advances.  Modules marked
+# ``_kdf_frozen`` (the Trainer marks the frozen teacher) are exempt: nothing writes to them.
+_generation = 0
+
+
+def bump_generation() -> int:
+    global _generation
+    _generation += 1
+    return _generation
+
+
+def cache_generation(module) -> int:
+    """The generation a cache entry of ``module`` is valid for (constant for frozen modules)."""
+    return -1 if getattr(module, "_kdf_frozen", False) else _generation
+
+
+def mark_frozen(module, frozen: bool = True) -> None:
+    """Declare that no kernel writes to ``module``'s parameters / buffers (inference-only teacher)."""
+    for m in module.modules():
+        m._kdf_frozen = frozen
+
+
 # ----------------------------------------------------------------------------- BatchNorm batch counters
 # nn.BatchNorm increments num_batches_tracked once per training forward: 29 one-element kernels per student step.  Inside
 # ``deferred_batch_counters()`` (the Trainer's step) the increments are collected and issued as ONE multi-tensor add.
@@ -151,6 +179,7 @@ _pending_counters = None
 def bump_batch_counter(bn) -> float:
     """Advance bn.num_batches_tracked like nn.BatchNorm does and return the momentum of this update."""
     global _pending_counters
+    bump_generation()                                 # the running statistics change behind torch's back
     if bn.momentum is not None and _pending_counters is not None:
         _pending_counters.append(bn.num_batches_tracked)
         return float(bn.momentum)

@@ -81,8 +81,8 @@ class _RowBNActFn(torch.autograd.Function):
 def _eval_affine(bn, pre_bias=None):
     """(scale, shift, mean, invstd) of a BatchNorm in eval mode, cached until its tensors change.
     ``pre_bias`` (the producing layer's bias, applied as BN(x + bias)) is folded into the shift."""
-    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, pre_bias)
-                if t is not None)
+    key = (_n.cache_generation(bn),) + tuple((t.data_ptr(), t._version) for t in
+                                             (bn.weight, bn.bias, bn.running_mean, bn.running_var, pre_bias) if t is not None)
     cache = getattr(bn, "_kdf_eval_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -262,7 +262,7 @@ def _conv_frozen(m, x: torch.Tensor) -> torch.Tensor:
             and torch.get_autocast_dtype("cuda") == torch.bfloat16 and m.weight.dtype == torch.float32
             and m.padding_mode == "zeros" and not isinstance(m.padding, str)):
         return m(x)
-    key = (m.weight.data_ptr(), m.weight._version, None if m.bias is None else m.bias._version)
+    key = (_n.cache_generation(m), m.weight.data_ptr(), m.weight._version, None if m.bias is None else m.bias._version)
     cache = getattr(m, "_kdf_w16", None)
     if cache is None or cache[0] != key:
         cache = (key, m.weight.detach().to(torch.bfloat16), None if m.bias is None else m.bias.detach().to(torch.bfloat16))

@@ -152,7 +152,8 @@ def _bn_bwd_coeffs(sums, mean, invstd, scale, M):
 
 def _eval_first_layer(bn1, w1, b1):
     """(q, r) of the folded first layer with running statistics, cached until the tensors involved change."""
-    key = tuple((t.data_ptr(), t._version) for t in (bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, w1, b1))
+    key = (_n.cache_generation(bn1),) + tuple((t.data_ptr(), t._version) for t in
+                                              (bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, w1, b1))
     cache = getattr(bn1, "_kdf_l1_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]

@@ -18,6 +18,7 @@ from typing import Iterable, List
 
 import torch
 
+from .. import native as _native
 from .. import ops
 
 
@@ -99,6 +100,7 @@ class FlatAdamW(torch.optim.Optimizer):
         if update_hyper:
             self._step += 1
             self.set_hyper(g["lr"], self._step)
+        _native.bump_generation()                         # parameters change through the flat buffer (no _version bump)
         ops.adamw_flat_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._hyper,
                         g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], grad_scale)
 

@@ -59,7 +59,12 @@ class SegmentationMetrics:
 
     def update(self, preds, targets):
         if not preds.is_cuda:
-            raise RuntimeError("SegmentationMetrics.update takes CUDA logits (no CPU fallback)")
+            # host tensors (reference tooling evaluates on the CPU, trainer.py:18-26) are counted by the same kernel:
+            # they are copied to the device first -- there is no host implementation of the count
+            if not torch.cuda.is_available():
+                raise RuntimeError("SegmentationMetrics.update counts on a CUDA device (no CPU fallback)")
+            dev = self._dev.device if self._dev is not None else torch.device("cuda", torch.cuda.current_device())
+            preds, targets = preds.to(dev), targets.to(dev)
         if preds.shape[1] > self.num_classes:
             # reference semantics: predictions outside [0, num_classes) are skipped (trainer.py:25)
             pred_idx = preds.argmax(dim=1)
@@ -136,6 +141,7 @@ class Trainer:
             teacher.eval()
             for p in teacher.parameters():
                 p.requires_grad_(False)
+            _native.mark_frozen(teacher)          # nothing writes to it: its eval-mode caches never go stale
         self.kd_temperature, self.kd_alpha, self.kd_beta = kd_temperature, kd_alpha, kd_beta
         self.amp_dtype = amp_dtype
 
@@ -161,10 +167,37 @@ class Trainer:
                 teacher.branch_streams = bs >= 2
         self.use_cuda_graph = use_cuda_graph
         self.graph_warmup_steps = graph_warmup_steps
-        self._graph = None
-        self._graph_key = None
-        self._static: Dict[str, torch.Tensor] = {}
+        # one captured graph per input shape (the last, partial batch of an epoch gets its own instead of evicting the
+        # full-batch one twice per epoch); beyond ``max_graphs`` shapes a step runs eagerly
+        self._graphs: Dict[tuple, dict] = {}
+        self.max_graphs = 2
         self._eager_steps = 0
+        self.sync_replicas()
+
+    # ------------------------------------------------------------------ data-parallel replicas
+    @torch.no_grad()
+    def sync_replicas(self):
+        """Every rank continues from rank 0's parameters, optimizer moments and buffers (BatchNorm running statistics,
+        batch counters).  Replicas that start from different random initialisations would apply the averaged gradient
+        to different points and never meet; called at construction and after ``load_checkpoint``."""
+        if self.world_size <= 1:
+            return
+        opt = self.optimizer
+        for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq):
+            dist.broadcast(t, src=0)
+        step = torch.tensor([opt._step], dtype=torch.int64, device=self.device)
+        dist.broadcast(step, src=0)
+        opt._step = int(step.item())
+        for b in self.model.buffers():
+            dist.broadcast(b, src=0)
+        _native.bump_generation()
+
+    def release_graphs(self):
+        """Drop the captured step graphs (and their static buffers).  Call before
+        ``torch.distributed.destroy_process_group()``: a communicator whose all-reduce still sits in a live
+        captured graph cannot be torn down."""
+        self._graphs.clear()
+        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ one optimisation step
     def _autocast(self):
@@ -223,19 +256,20 @@ class Trainer:
             from .. import point_mlp
             point_mlp.cached_build_order(pts, enc._geom, tuple(enc.grid_size))
 
-    def _capture(self, imgs, pts, seg):
-        self._static = {"image": torch.empty_like(imgs), "points": torch.empty_like(pts), "seg": torch.empty_like(seg)}
+    def _capture(self, key, imgs, pts, seg):
+        static = {"image": torch.empty_like(imgs), "points": torch.empty_like(pts), "seg": torch.empty_like(seg)}
         for k, v in (("image", imgs), ("points", pts), ("seg", seg)):
-            self._static[k].copy_(v)
+            static[k].copy_(v)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         k0 = _native.launch_stats["kernels"]
         with torch.cuda.graph(graph):
-            out = self._step_impl(self._static["image"], self._static["points"], self._static["seg"], update_hyper=False)
-        self._graph_kernels = _native.launch_stats["kernels"] - k0      # our kernels inside one replay
+            out = self._step_impl(static["image"], static["points"], static["seg"], update_hyper=False)
+        kernels = _native.launch_stats["kernels"] - k0                  # our kernels inside one replay
         _native.launch_stats["kernels"] = k0
-        self._graph, self._graph_out = graph, out
-        self._graph_key = (imgs.shape, pts.shape, seg.shape, imgs.dtype, self.model.training)
+        self._graphs[key] = {"graph": graph, "static": static, "out": out, "kernels": kernels}
+        self._graph_kernels = kernels
+        return self._graphs[key]
 
     def training_step(self, imgs: torch.Tensor, pts: torch.Tensor, seg: torch.Tensor):
         """zero_grad -> forward(s) -> fused loss+grad -> backward -> (all-reduce) -> AdamW.
@@ -243,29 +277,33 @@ class Trainer:
         ``use_cuda_graph`` the first ``graph_warmup_steps`` calls run eagerly, then the whole step is
         captured once per input shape and replayed (outputs are then static buffers, valid until the
         next call)."""
+        _native.bump_generation()            # parameters / running statistics move (also inside a replayed graph)
         if not self.use_cuda_graph:
             out = self._step_impl(imgs, pts, seg, update_hyper=True)
             self.last_loss_terms = out[0]
             return out
         key = (imgs.shape, pts.shape, seg.shape, imgs.dtype, self.model.training)
-        if self._graph is None or key != self._graph_key:
-            if self._eager_steps < self.graph_warmup_steps:
+        entry = self._graphs.get(key)
+        fresh = False
+        if entry is None:
+            if self._eager_steps < self.graph_warmup_steps or len(self._graphs) >= self.max_graphs:
                 self._eager_steps += 1
                 out = self._step_impl(imgs, pts, seg, update_hyper=True)
                 self.last_loss_terms = out[0]
                 return out
-            self._capture(imgs, pts, seg)
-        else:
-            self._static["image"].copy_(imgs, non_blocking=True)
-            self._static["points"].copy_(pts, non_blocking=True)
-            self._static["seg"].copy_(seg, non_blocking=True)
+            entry, fresh = self._capture(key, imgs, pts, seg), True
+        if not fresh:
+            st = entry["static"]
+            st["image"].copy_(imgs, non_blocking=True)
+            st["points"].copy_(pts, non_blocking=True)
+            st["seg"].copy_(seg, non_blocking=True)
         opt = self.optimizer
         opt._step += 1
         opt.set_hyper(opt.param_groups[0]["lr"], opt._step)      # device-side (lr, step) the captured AdamW reads
-        self._graph.replay()
-        _native.launch_stats["kernels"] += self._graph_kernels
-        self.last_loss_terms = self._graph_out[0]
-        return self._graph_out
+        entry["graph"].replay()
+        _native.launch_stats["kernels"] += entry["kernels"]
+        self.last_loss_terms = entry["out"][0]
+        return entry["out"]
 
     # ------------------------------------------------------------------ epochs
     def _to_device(self, batch):
@@ -324,6 +362,8 @@ class Trainer:
             self.scheduler.load_state_dict(ckpt["scheduler_state"])
         self.best_miou = ckpt.get("val_miou", 0.0)
         start_epoch = ckpt.get("epoch", 0) + 1
+        _native.bump_generation()
+        self.sync_replicas()
         if self.verbose:
             print(f"Resumed from {path}, starting at epoch {start_epoch}, best mIoU {self.best_miou:.4f}")
         return start_epoch
@@ -343,6 +383,10 @@ class Trainer:
         for epoch in range(start_epoch, self.num_epochs):
             log(f"\nEpoch {epoch + 1}/{self.num_epochs}")
             log("-" * 60)
+            for loader in (self.train_loader, self.val_loader):
+                sampler = getattr(loader, "sampler", None)
+                if hasattr(sampler, "set_epoch"):                # DistributedSampler: a new shuffle every epoch
+                    sampler.set_epoch(epoch)
             train_loss, train_metrics = self.train_epoch()
             val_loss, val_metrics = self.validate()
             self.scheduler.step()

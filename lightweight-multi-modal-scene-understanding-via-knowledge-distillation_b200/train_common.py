@@ -56,7 +56,7 @@ def make_loaders(args, verbose: bool):
         if verbose:
             print(f"Found {len(scenes)} scenes\nTrain: {n_train} scenes | Val: {len(scenes) - n_train} scenes")
         return create_pandaset_dataloaders(args.root, scenes[:n_train], scenes[n_train:], batch_size=args.batch_size,
-                                           num_workers=args.workers, verbose=verbose)
+                                           num_workers=args.workers, verbose=verbose, distributed=distributed)
     if verbose:
         print(f"Dataset root {args.root!r} not found -> seeded synthetic PandaSet-shaped frames")
     n_tr, n_va = args.synthetic_samples
@@ -81,4 +81,23 @@ def build_teacher(args, num_classes: int, device):
     if args.teacher_ckpt:
         state = torch.load(args.teacher_ckpt, map_location=device)
         teacher.load_state_dict(state.get("model_state", state))
+    elif int(os.environ.get("RANK", 0)) == 0:
+        print("\n" + "!" * 80 + "\nWARNING: --kd without --teacher-ckpt distils from a RANDOMLY INITIALISED concat teacher "
+              "(eval mode, running\nstatistics at their initial values): the KL and feature-mimic terms then pull the student "
+              "towards noise.\nUse this only for throughput runs; pass --teacher-ckpt <reference-format .pth> for real "
+              "training.\n" + "!" * 80 + "\n")
     return teacher.eval()
+
+
+def decide_resume(args, ckpt_path: str) -> bool:
+    """ONE decision for all ranks: rank 0 looks at the checkpoint (and asks when ``--resume ask``), every rank gets
+    its answer -- otherwise only rank 0 would load and the ranks would disagree on the start epoch."""
+    rank0 = int(os.environ.get("RANK", 0)) == 0
+    resume = False
+    if rank0 and os.path.exists(ckpt_path) and args.resume != "no":
+        resume = args.resume == "yes" or input(f"\nFound checkpoint at {ckpt_path}. Resume training? (y/n): ").lower() == "y"
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        box = [resume]
+        dist.broadcast_object_list(box, src=0)
+        resume = bool(box[0])
+    return resume

@@ -11,7 +11,7 @@ import os
 import torch
 
 from src.training.trainer import Trainer
-from train_common import base_parser, build_model, build_teacher, init_distributed, make_loaders
+from train_common import base_parser, build_model, build_teacher, decide_resume, init_distributed, make_loaders
 
 CLASS_WEIGHTS = {3: [0.39, 2.61, 33.09], 2: [0.4, 3.5]}       # train_pandaset.py:136, train_with_fusion_ablation.py:47
 
@@ -48,11 +48,8 @@ def main(argv=None):
 
     start_epoch = 0
     ckpt = os.path.join(args.save_dir, "latest.pth")
-    if os.path.exists(ckpt) and args.resume != "no":
-        resume = args.resume == "yes" or (
-            rank0 and input(f"\nFound checkpoint at {ckpt}. Resume training? (y/n): ").lower() == "y")
-        if resume:
-            start_epoch = trainer.load_checkpoint(ckpt)
+    if decide_resume(args, ckpt):                      # train_pandaset.py:155-160, decided once for all ranks
+        start_epoch = trainer.load_checkpoint(ckpt)
     return trainer.train(start_epoch=start_epoch)
 
 

@@ -17,7 +17,7 @@ import numpy as np
 
 __all__ = [
     "range_constants", "bev_coords", "bev_cells", "bev_occupancy",
-    "bev_scatter_max", "bev_scatter_mean", "bev_scatter_max_backward",
+    "bev_scatter_max", "bev_scatter_mean", "bev_scatter_max_backward", "rasterize_bev",
 ]
 
 
@@ -155,3 +155,33 @@ def bev_scatter_max_backward(grad_grid: np.ndarray, feats: np.ndarray, grid: np.
         div = (ties[b, cc] + (grid[b, cc] == 0)).astype(feats.dtype)
         out[b, sel] = np.where(hit, grad_grid[b, cc] / np.maximum(div, 1), 0).astype(feats.dtype)
     return out
+
+
+def rasterize_bev(x: np.ndarray, y: np.ndarray, labels: np.ndarray, grid_size=(64, 64),
+                  pc_range=(-50, 50, -50, 50)) -> np.ndarray:
+    """``rasterize_bev`` (``src/data_loading/pandaset_dataset.py:23-45``), restated with the integer
+    reduction the device kernel uses instead of the reference's per-point Python loop: a cell keeps the
+    first non-zero label in point order = the label of its lowest-index non-zero-labelled point.
+
+    x, y f32[N], labels int[N] -> int64[H, W].  Pinned against the reference's loop in
+    ``tests/test_oracle_vs_reference.py`` and by ``tests/golden/raster_labels.npz``.
+    """
+    H, W = grid_size
+    x_min, x_max, y_min, y_max = pc_range
+    x, y = np.asarray(x, dtype=np.float32), np.asarray(y, dtype=np.float32)
+    labels = np.asarray(labels).astype(np.int64)
+    mask = np.zeros(H * W, dtype=np.int64)
+    with np.errstate(invalid="ignore"):
+        m = (x >= x_min) & (x <= x_max) & (y >= y_min) & (y <= y_max)              # :33 raw closed range
+    idx = np.nonzero(m & (labels != 0))[0]                                          # :43 only non-zero labels claim
+    if idx.size == 0:
+        return mask.reshape(H, W)
+    xs, ys = x[idx], y[idx]
+    col = np.clip(((xs - x_min) / (x_max - x_min) * (W - 1)).astype(int), 0, W - 1)  # :39
+    row = np.clip(((ys - y_min) / (y_max - y_min) * (H - 1)).astype(int), 0, H - 1)  # :40
+    cell = row * W + col
+    first = np.full(H * W, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first, cell, idx)
+    hit = first != np.iinfo(np.int64).max
+    mask[hit] = labels[first[hit]]
+    return mask.reshape(H, W)

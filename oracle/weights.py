@@ -92,3 +92,23 @@ def synthetic_frames(seed: int, B: int, N: int, image_hw=(256, 256), grid_size=(
         pts[:, 8:12, :] = pts[:, 12:13, :]           # exact duplicates -> positive ties
         lab[:, 0, :3] = -1
     return torch.from_numpy(img), torch.from_numpy(pts), torch.from_numpy(lab)
+
+
+def raster_inputs(seed, N, alphabet):
+    """Labelled points for the rasteriser fixtures: sweep-like x,y plus the edge cases (exact range ends, the
+    floats just outside them, NaN / inf, zero padding), labels from ``alphabet`` (0 = background)."""
+    g = np.random.default_rng(seed)
+    x, y = (g.normal(0, 40, N).astype(np.float32) for _ in range(2))
+    edge = np.array([50.0, -50.0, np.nextafter(np.float32(50), np.float32(60)), np.nextafter(np.float32(-50), np.float32(-60)),
+                     np.nan, np.inf, -np.inf, 0.0, 49.999996, -49.999996], dtype=np.float32)
+    k = edge.size
+    x[:k], y[:k] = edge, edge[::-1]
+    x[k:2 * k], y[k:2 * k] = edge, 0.0
+    x[-64:], y[-64:] = 0.0, 0.0                                        # zero padding rows (all in one cell)
+    labels = g.choice(np.asarray(alphabet), size=N).astype(np.int64)
+    return x, y, labels
+
+
+RASTER_CASES = [("bin64", 11, 30000, (0, 1), (64, 64), (-50, 50, -50, 50)),
+                ("multi64", 12, 20000, (0, 0, 3, 7, 12), (64, 64), (-50, 50, -50, 50)),
+                ("bin48x80f", 13, 15000, (0, 0, 0, 1), (48, 80), (-40.5, 40.5, -30.25, 61.0))]

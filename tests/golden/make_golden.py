@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))          # tests/
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))  # repo root
 from conftest import build_reference_model, load_reference_module  # noqa: E402
-from oracle.weights import make_state_dict, synthetic_frames  # noqa: E402
+from oracle.weights import RASTER_CASES, make_state_dict, raster_inputs, synthetic_frames  # noqa: E402
 
 SAMPLE_STRIDE = 97
 GRAD_KEYS = ["head.cls.weight", "head.cls.bias", "lidar_encoder.encoder.point_mlp.0.weight",
@@ -56,6 +56,15 @@ def golden_bev():
     np.savez_compressed(os.path.join(HERE, "bev_cells.npz"), **out)
 
 
+def golden_raster():
+    ds = load_reference_module("data_loading/pandaset_dataset")
+    out = {}
+    for name, seed, N, alphabet, grid, rng in RASTER_CASES:
+        x, y, labels = raster_inputs(seed, N, alphabet)
+        out[name] = ds.rasterize_bev(x, y, labels, grid_size=grid, pc_range=rng).astype(np.int8)   # pandaset_dataset.py:23-45
+    np.savez_compressed(os.path.join(HERE, "raster_labels.npz"), **out)
+
+
 def golden_model(fusion_type, train):
     torch.manual_seed(0)
     model = build_reference_model(fusion_type, 2)
@@ -83,6 +92,7 @@ def golden_model(fusion_type, train):
 
 if __name__ == "__main__":
     golden_bev()
+    golden_raster()
     for ft in ("weighted", "concat", "minimal"):
         for train in (True, False):
             golden_model(ft, train)

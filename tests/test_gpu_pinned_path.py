@@ -1,0 +1,282 @@
+"""Parity evidence for the path the benchmark measures: CUDA-graph replay, bf16 activations, the side-stream
+teacher, multi-epoch training with eval-mode validation in between, and (with >= 2 GPUs) the NCCL data-parallel
+step.  Everything here goes through ``Trainer.training_step`` -- the call ``bench.py`` times."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle
+from oracle.weights import make_state_dict, synthetic_frames
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def build(fusion_type):
+    from src.models.camera_encoder import TwinLiteEncoder
+    from src.models.fusion_module import CompleteSegmentationModel
+    from src.models.lidar_encoder import LiDAREncoder
+    return CompleteSegmentationModel(
+        TwinLiteEncoder(return_multiscale=True), LiDAREncoder("spatial", grid_size=(64, 64), use_vectorized=True),
+        num_classes=2, fusion_type=fusion_type, fusion_out_channels=256 if fusion_type == "concat" else 128,
+        camera_fpn_stages=["stage3", "stage4", "stage5"], camera_fpn_channels=128, output_mode="same")
+
+
+def make_trainer(tmp, amp, graph, overlap, student="weighted", lr=1e-3):
+    from src.training.trainer import Trainer
+    s, t = build(student), build("concat")
+    s.load_state_dict(make_state_dict(5, fusion_type=student))
+    t.load_state_dict(make_state_dict(6, fusion_type="concat", random_running_stats=True))
+    s.cuda().train()
+    t.cuda()
+    return Trainer(s, [], [], "cuda", lr=lr, class_weights=[0.4, 3.5], save_dir=str(tmp), teacher=t, verbose=False,
+                   amp_dtype=amp, use_cuda_graph=graph, graph_warmup_steps=1, overlap_teacher=overlap)
+
+
+def frames(k, B=2, N=4000):
+    out = []
+    for i in range(k):
+        img, pts, lab = synthetic_frames(100 + i, B, N, edge_cases=True, nonfinite=False)
+        out.append((img.cuda(), pts.cuda(), lab.cuda()))
+    return out
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+@pytest.mark.parametrize("amp", [None, torch.bfloat16], ids=["fp32", "bf16"])
+def test_graph_replay_equals_eager_steps(tmp_path, amp):
+    """Five optimisation steps issued eagerly (teacher on the main stream) against the same five steps with the
+    whole step captured once and replayed as a CUDA graph with the teacher on a side stream -- the configuration
+    bench.py times.  Same kernels in the same order, so only the order of floating-point atomics differs:
+    loss terms to 1e-5 (fp32) / 2e-3 (bf16: an atomics-order flip of one fp32 sum can move a bf16 rounding), the
+    parameter UPDATE (theta_k - theta_0) to 1e-3 / 3e-2 relative L2, BatchNorm running statistics likewise."""
+    data = frames(5)
+    eager = make_trainer(tmp_path / "e", amp, graph=False, overlap=False)
+    graph = make_trainer(tmp_path / "g", amp, graph=True, overlap=True)
+    theta0 = eager.optimizer.flat_param.clone()
+    assert torch.equal(theta0, graph.optimizer.flat_param)
+    tol_terms, tol_upd = (1e-5, 1e-3) if amp is None else (2e-3, 3e-2)
+    for i, (img, pts, lab) in enumerate(data):
+        te, le = eager.training_step(img, pts, lab)
+        tg, lg = graph.training_step(img, pts, lab)
+        te, tg = te.clone(), tg.clone()
+        for j, name in enumerate(("loss", "ce", "kl", "mse")):
+            assert tg[j].item() == pytest.approx(te[j].item(), rel=tol_terms * (1 + i)), (i, name)
+        assert rel_l2(lg.float(), le.float()) < 50 * tol_terms * (1 + i), i
+    assert len(graph._graphs) == 1 and graph.optimizer._step == eager.optimizer._step == 5
+    upd_e, upd_g = eager.optimizer.flat_param - theta0, graph.optimizer.flat_param - theta0
+    assert upd_e.abs().max().item() > 1e-4                      # the steps did move the parameters
+    assert rel_l2(upd_g, upd_e) < tol_upd, rel_l2(upd_g, upd_e)
+    for (n, be), (_, bg) in zip(eager.model.named_buffers(), graph.model.named_buffers()):
+        if "running" in n:
+            assert rel_l2(bg, be) < tol_upd, n
+        elif "num_batches" in n:
+            assert torch.equal(bg, be) and int(bg) == 5, n
+
+
+def test_graph_per_shape_and_release(tmp_path):
+    """A second batch shape (the partial last batch of an epoch) gets its own captured graph instead of evicting the
+    first; ``release_graphs`` drops them and the next call captures again."""
+    tr = make_trainer(tmp_path, torch.bfloat16, graph=True, overlap=True)
+    full, part = frames(1)[0], frames(1, B=1)[0]
+    for _ in range(3):
+        tr.training_step(*full)
+    tr.training_step(*part)
+    tr.training_step(*full)
+    tr.training_step(*part)
+    assert len(tr._graphs) == 2
+    torch.cuda.synchronize()
+    tr.release_graphs()
+    assert len(tr._graphs) == 0
+    terms, _ = tr.training_step(*full)
+    assert torch.isfinite(terms[:4]).all()
+
+
+def test_bf16_error_is_what_bf16_autocast_costs(monkeypatch):
+    """The whole-network bf16 bar, justified: the SAME weights and frames through (a) this implementation under bf16
+    autocast and (b) the oracle's eager-PyTorch network under ``torch.autocast(bf16)`` on the same GPU, both against
+    the fp32 oracle.  (b) is what bf16 activations cost in stock PyTorch; ours must not be worse than 1.5x that."""
+    sd = make_state_dict(5, fusion_type="weighted")
+    img, pts, lab = synthetic_frames(21, 2, 4000, edge_cases=True, nonfinite=False)
+    with torch.no_grad():
+        ref, ref_mid = model_oracle.model_forward(img, pts, model_oracle.clone_state(sd), fusion_type="weighted", train=True)
+    model = build("weighted")
+    model.load_state_dict(sd)
+    model.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        ours, ours_mid = model(img.cuda(), pts.cuda(), return_intermediates=True)
+    # the reference cannot run its scatter under autocast (fp32 grid, bf16 features: SURVEY.md section 0.3); the oracle's
+    # point MLP output is cast back to fp32 for the scatter, everything else is stock autocast
+    orig = model_oracle.point_mlp
+    monkeypatch.setattr(model_oracle, "point_mlp", lambda *a, **k: orig(*a, **k).float())
+    sd_gpu = {k: v.cuda() for k, v in model_oracle.clone_state(sd).items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        auto, auto_mid = model_oracle.model_forward(img.cuda(), pts.cuda(), sd_gpu, fusion_type="weighted", train=True)
+
+    def rms(a, b):
+        a, b = a.float().cpu(), b.float().cpu()
+        return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    e_ours, e_auto = rms(ours, ref), rms(auto, ref)
+    assert e_ours < 1.5 * e_auto + 5e-3, (e_ours, e_auto)
+    for k in ("camera_feat", "lidar_feat", "pre_fusion"):
+        assert rms(ours_mid[k], ref_mid[k]) < 1.5 * rms(auto_mid[k], ref_mid[k]) + 5e-3, k
+
+
+def test_bf16_training_tracks_fp32_loss_curve(tmp_path):
+    """30 optimisation steps on the same frames in fp32 and in bf16 (graph replay): the loss curves stay together
+    (mean relative deviation < 5 %, worst step < 15 %) and both go down."""
+    data = frames(3)
+    runs = {}
+    for name, amp in (("fp32", None), ("bf16", torch.bfloat16)):
+        tr = make_trainer(tmp_path / name, amp, graph=amp is not None, overlap=True)
+        curve = []
+        for i in range(30):
+            terms, _ = tr.training_step(*data[i % 3])
+            curve.append(terms[:4].clone())
+        runs[name] = torch.stack(curve).cpu().double()
+    a, b = runs["fp32"][:, 0], runs["bf16"][:, 0]
+    dev = ((a - b).abs() / a.abs())
+    assert torch.isfinite(b).all() and dev.mean().item() < 5e-2 and dev.max().item() < 1.5e-1, (dev.mean().item(), dev.max().item())
+    assert a[-3:].mean() < a[:3].mean() and b[-3:].mean() < b[:3].mean()
+
+
+def test_validation_after_training_sees_current_weights(tmp_path):
+    """Two epochs with a validation pass after each (the Trainer's own loop): the kernels move parameters and running
+    statistics through raw pointers, so anything cached for eval mode must notice.  The eval logits of the trained
+    model must equal those of a FRESH model loaded from its state_dict (nothing cached there)."""
+    from src.data_loading.synthetic_frames import create_synthetic_dataloaders
+    from src.training.trainer import Trainer
+    torch.manual_seed(0)
+    tl, vl = create_synthetic_dataloaders(4, 2, batch_size=2, num_points=2000)
+    for amp in (None, torch.bfloat16):
+        model = build("weighted").cuda()
+        tr = Trainer(model, tl, vl, "cuda", class_weights=[0.4, 3.5], save_dir=str(tmp_path), num_epochs=2, verbose=False,
+                     amp_dtype=amp)
+        tr.train()
+        img, pts, _ = synthetic_frames(9, 2, 2000)
+        model.eval()
+        fresh = build("weighted").cuda()
+        fresh.load_state_dict({k: v.clone() for k, v in model.state_dict().items()})
+        fresh.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp is not None):
+            got = model(img.cuda(), pts.cuda())
+            want = fresh(img.cuda(), pts.cuda())
+        assert rel_l2(got.float(), want.float()) < 1e-5, (amp, rel_l2(got.float(), want.float()))
+        assert tr.history["val_loss"][0] != tr.history["val_loss"][1]
+
+
+def test_rasterize_bev_cuda_golden_and_edges():
+    """kdf_bev_rasterize against the REFERENCE's rasterize_bev outputs (tests/golden/raster_labels.npz, made by
+    tests/golden/make_golden.py) and the oracle, bit for bit: binary and multi-valued labels, a non-square grid with a
+    fractional range, range ends, the floats just outside them, NaN / inf, zero padding, empty frames."""
+    from oracle import bev_oracle
+    from oracle.weights import RASTER_CASES, raster_inputs
+    from src.data_loading.pandaset_dataset import rasterize_bev, rasterize_bev_cuda
+    z = np.load(os.path.join(ROOT, "tests", "golden", "raster_labels.npz"))
+    for name, seed, N, alphabet, grid, rng in RASTER_CASES:
+        x, y, labels = raster_inputs(seed, N, alphabet)
+        pts = torch.from_numpy(np.stack([x, y, np.zeros_like(x), np.zeros_like(x)], 1))[None].cuda()
+        got = rasterize_bev_cuda(pts, torch.from_numpy(labels)[None].cuda(), grid, rng)
+        assert got.dtype == torch.int64 and tuple(got.shape) == (1, *grid)
+        np.testing.assert_array_equal(got[0].cpu().numpy(), z[name].astype(np.int64), err_msg=name)
+        np.testing.assert_array_equal(got[0].cpu().numpy(), bev_oracle.rasterize_bev(x, y, labels, grid, rng))
+        np.testing.assert_array_equal(got[0].cpu().numpy(), rasterize_bev(x, y, labels, grid, rng))
+    # a batch: frames are independent; strided (x, y) points; a frame with nothing inside; N = 0
+    xs, ys, ls = zip(*(raster_inputs(40 + b, 5000, (0, 1, 2)) for b in range(3)))
+    xs, ys = list(xs), list(ys)
+    xs[2] = xs[2] + 500.0                                                  # all outside
+    pts2 = torch.from_numpy(np.stack([np.stack([a, b], 1) for a, b in zip(xs, ys)])).cuda()     # [3, N, 2]
+    got = rasterize_bev_cuda(pts2, torch.from_numpy(np.stack(ls)).cuda())
+    for b in range(3):
+        np.testing.assert_array_equal(got[b].cpu().numpy(), bev_oracle.rasterize_bev(xs[b], ys[b], ls[b]))
+    assert got[2].abs().sum().item() == 0
+    empty = rasterize_bev_cuda(torch.zeros(2, 0, 4, device="cuda"), torch.zeros(2, 0, dtype=torch.int64, device="cuda"))
+    assert tuple(empty.shape) == (2, 64, 64) and empty.abs().sum().item() == 0
+
+
+def test_iterative_is_an_independent_second_implementation():
+    """forward_iterative shares no projection kernel with forward_vectorized (cell ids by torch tensor arithmetic,
+    per-frame index_reduce) and must still agree bit for bit, train and eval, fp32 and bf16; all-outside sweeps give
+    an all-zero map (the reference's commented assertion, test_lidar_encoder.py:227-233)."""
+    from src.models.lidar_encoder import SpatialLiDAREncoder, create_test_point_cloud
+    torch.manual_seed(1)
+    enc = SpatialLiDAREncoder(grid_size=(64, 64)).cuda()
+    pts = create_test_point_cloud(3, 6000, device="cuda")
+    pts[0, :50, :2] = torch.tensor([50.0, -50.0], device="cuda")
+    pts[1, :200] = 0.0
+    for train in (False, True):
+        enc.train(train)
+        for amp in (False, True):
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                enc.fuse_point_mlp = False                        # the same per-point features on both sides
+                a = enc.forward_vectorized(pts)
+                b = enc.forward_iterative(pts)
+            assert a.shape == b.shape == (3, 128, 64, 64)
+            # eval: bit for bit; train: the batch statistics are reduced with fp64 atomics, whose order may differ
+            assert torch.equal(a, b) if not train else rel_l2(a.float(), b.float()) < 1e-6, (train, amp)
+    far = pts.clone()
+    far[..., :2] += 1000.0
+    with torch.no_grad():
+        assert enc.eval().forward_vectorized(far).abs().max().item() == 0.0
+        assert enc.forward_iterative(far).abs().max().item() == 0.0
+
+
+def test_concat_fusion_accepts_unequal_widths():
+    """fusion_module.py:74-76: the reference builds ConcatenationFusion for any (camera, lidar) width pair."""
+    from src.models.fusion_module import ConcatenationFusion
+    torch.manual_seed(0)
+    fus = ConcatenationFusion(camera_channels=64, lidar_channels=128, out_channels=96).cuda().train()
+    cam = torch.randn(2, 64, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    lid = torch.randn(2, 128, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    out = fus(cam, lid)
+    assert out.shape == (2, 96, 16, 16)
+    want_pre = torch.cat([torch.relu(torch.nn.functional.batch_norm(torch.nn.functional.conv2d(cam, fus.camera_proj.conv[0].weight),
+                                                                     None, None, fus.camera_proj.conv[1].weight, fus.camera_proj.conv[1].bias, True)),
+                          torch.relu(torch.nn.functional.batch_norm(torch.nn.functional.conv2d(lid, fus.lidar_proj.conv[0].weight),
+                                                                     None, None, fus.lidar_proj.conv[1].weight, fus.lidar_proj.conv[1].bias, True))], 1)
+    pre, _ = fus.forward_with_pre(cam, lid)
+    assert rel_l2(pre, want_pre.detach()) < 1e-5
+    out.sum().backward()
+    assert cam.grad is not None and lid.grad is not None and torch.isfinite(cam.grad).all()
+
+
+def test_segmentation_metrics_accepts_host_tensors():
+    """Reference tooling calls SegmentationMetrics.update with CPU tensors (trainer.py:18-26)."""
+    from src.training.trainer import SegmentationMetrics
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(2, 2, 64, 64, generator=g)
+    labels = (torch.rand(2, 64, 64, generator=g) < 0.3).long()
+    labels[0, :3] = -1
+    a, b = SegmentationMetrics(2), SegmentationMetrics(2)
+    a.update(logits, labels)
+    b.update(logits.cuda(), labels.cuda())
+    np.testing.assert_array_equal(a.confusion, b.confusion)
+    assert a.compute() == b.compute()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_nccl_data_parallel_step_two_ranks(tmp_path):
+    """torchrun, 2 ranks over NCCL (tests/dist_nccl_worker.py): replicas that start from DIFFERENT seeds are
+    synchronised by the Trainer, the all-reduced flat bucket equals the sum of the per-rank gradients, parameters stay
+    bit-identical across ranks through graph-replayed steps, and the process group is torn down cleanly (no
+    os._exit) after ``release_graphs``."""
+    env = dict(os.environ, NCCL_DEBUG="WARN")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "tests", "dist_nccl_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "NCCL_WORKER_OK rank 0" in r.stdout and "NCCL_WORKER_OK rank 1" in r.stdout, r.stdout[-2000:]

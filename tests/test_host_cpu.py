@@ -253,3 +253,28 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"rank {r} ok" in o, o
+
+
+def test_eval_caches_follow_the_parameter_generation():
+    """Kernels move parameters and running statistics through raw pointers (no ``_version`` bump), so the eval-mode
+    BatchNorm affine cache also keys on src.native's generation counter: every optimizer / training step and every
+    running-statistics update invalidates it -- except for modules marked frozen (the teacher)."""
+    import torch.nn as nn
+    from src import native, ops
+    bn = nn.BatchNorm2d(4).eval()
+    a = ops._eval_affine(bn)
+    assert ops._eval_affine(bn) is a                                   # cached
+    with torch.no_grad():
+        bn.running_var.data_ptr()                                      # a raw-pointer write looks like this to torch:
+        bn.running_var.view(-1).numpy()[:] = 4.0                       # memory changes, _version does not
+    assert ops._eval_affine(bn) is a                                   # ... and nothing else noticed either
+    native.bump_generation()                                           # what training_step / FlatAdamW.step / stats updates do
+    b = ops._eval_affine(bn)
+    assert b is not a and torch.allclose(b[3], torch.full((4,), (4.0 + bn.eps) ** -0.5))
+    native.mark_frozen(bn)
+    c = ops._eval_affine(bn)
+    native.bump_generation()
+    assert ops._eval_affine(bn) is c                                   # frozen modules keep their cache
+    g0 = native._generation
+    native.bump_batch_counter(nn.BatchNorm2d(4))
+    assert native._generation == g0 + 1

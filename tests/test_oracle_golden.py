@@ -92,3 +92,18 @@ def test_scatter_mean_matches_torch_scatter_reduce():
     out.scatter_reduce_(0, flat[valid].unsqueeze(1).expand(-1, 16), torch.from_numpy(feats)[valid],
                         reduce="mean", include_self=False)
     np.testing.assert_allclose(got.reshape(-1, 16), out.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_rasterize_oracle_golden():
+    """oracle.bev_oracle.rasterize_bev against outputs of the reference's rasterize_bev
+    (src/data_loading/pandaset_dataset.py:23-45; tests/golden/raster_labels.npz), and the product's host rasteriser."""
+    from oracle.weights import RASTER_CASES, raster_inputs
+    from src.data_loading.pandaset_dataset import rasterize_bev
+    z = np.load(os.path.join(GOLDEN, "raster_labels.npz"))
+    for name, seed, N, alphabet, grid, rng in RASTER_CASES:
+        x, y, labels = raster_inputs(seed, N, alphabet)
+        want = z[name].astype(np.int64)
+        np.testing.assert_array_equal(bev_oracle.rasterize_bev(x, y, labels, grid, rng), want, err_msg=name)
+        np.testing.assert_array_equal(rasterize_bev(x, y, labels, grid, rng), want, err_msg=name)
+    empty = bev_oracle.rasterize_bev(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.int64))
+    assert empty.shape == (64, 64) and empty.sum() == 0

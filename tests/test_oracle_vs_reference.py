@@ -148,3 +148,15 @@ def test_ce_and_metrics_vs_reference_trainer():
     conf = kd_oracle.confusion_matrix(logits, labels, 2)
     np.testing.assert_array_equal(conf.numpy(), m.confusion)
     assert kd_oracle.miou(conf)["miou"] == pytest.approx(m.compute()["miou"], abs=1e-12)
+
+
+def test_rasterize_oracle_vs_reference_loop():
+    """The integer-min restatement equals the reference's per-point loop (pandaset_dataset.py:23-45) on sweep-like
+    inputs with edge cases, for binary and multi-valued labels and a fractional, non-square geometry."""
+    from oracle import bev_oracle
+    from oracle.weights import RASTER_CASES, raster_inputs
+    ds = load_reference_module("data_loading/pandaset_dataset")
+    for name, seed, N, alphabet, grid, rng in RASTER_CASES:
+        x, y, labels = raster_inputs(seed + 100, N // 3, alphabet)
+        want = ds.rasterize_bev(x, y, labels, grid_size=grid, pc_range=rng)
+        np.testing.assert_array_equal(bev_oracle.rasterize_bev(x, y, labels, grid, rng), want, err_msg=name)
