@@ -248,6 +248,27 @@ int kdf_bn_bwd_coeffs(const double *sums, int C, int64_t M, const float *mean, c
 int kdf_mlp_l1_bwd(const double *sums5x64, const double *moments14, int64_t M, const float *W1, const float *mean,
                    const float *invstd, const float *scale, float *dW1, float *dgamma, float *dbeta, void *stream);
 
+/* ---------------------------------------------------------------- pointwise (1x1) convolution layers (tcgen05)
+ * Replaces the 1x1 nn.Conv2d + nn.BatchNorm2d + nn.ReLU/ReLU6 groups of the camera branch, the FPN, the fusion
+ * projections and the head (reference src/models/camera_encoder.py:19-51, src/models/fusion_module.py:8-34, 51-64,
+ * 111-120, 162-173) over channels-last maps, i.e. pixel-major rows:
+ *
+ *   a   = pro_act(x * pro_scale + pro_shift)          the PREVIOUS BatchNorm + activation, when pro_scale != NULL
+ *   z   = a . W^T                                     bf16 operands, fp32 accumulation on the tensor cores
+ *   out = z                                           and, when stats != NULL, stats[0][n] += sum_rows bf16(z),
+ *                                                     stats[1][n] += sum_rows bf16(z)^2  (this layer's batch statistics)
+ *   out = epi_act(z * epi_scale + epi_shift) [+ residual]     when epi_scale != NULL (running-statistics BatchNorm folded)
+ *
+ *   x        bf16 [M, K]   K a multiple of 64          W   bf16 [N, K]   N a multiple of 32
+ *   pro_*    f32 [K]       epi_* f32 [N]               residual bf16 [M, N], nullable (only with epi_scale)
+ *   out      bf16 [M, N]   stats f64 [2, N], nullable (zeroed by the call; not together with epi_scale)
+ *   act codes: 0 none, 1 ReLU, 2 ReLU6
+ */
+int kdf_pw_conv_fwd(const void *x, int64_t M, int K, int N, const void *W,
+                    const float *pro_scale, const float *pro_shift, int pro_act,
+                    const float *epi_scale, const float *epi_shift, int epi_act, const void *residual,
+                    void *out, double *stats, void *stream);
+
 /* ---------------------------------------------------------------- (2) camera-LiDAR fusion
  * Inputs are the PRE-BatchNorm outputs of the two 1x1 projection convolutions
  * in pixel-major (NHWC) layout; BatchNorm is applied as y = x*scale + shift with

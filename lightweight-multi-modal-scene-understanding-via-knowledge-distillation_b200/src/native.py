@@ -54,6 +54,7 @@ _SIGNATURES = {
     "kdf_bn_bwd_coeffs": (C.c_int, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kdf_mlp_l1_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kdf_bn_finalize": (C.c_int, [_vp, _i64, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdf_pw_conv_fwd": (C.c_int, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "kdf_fusion_weighted_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp, _vp, _vp]),
     "kdf_fusion_weighted_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i64, _i] + [_vp] * 8 + [_vp] + [_vp] * 7 + [_vp]),
     "kdf_fusion_affine_relu_pair_fwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -93,7 +94,7 @@ def check(rc: int, what: str = "") -> None:
 # kernels launched per ABI call (memsets not counted) -- bench.py reports the total
 KERNELS_PER_CALL = {
     "kdf_bev_index": 1, "kdf_bev_rasterize": 3, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
-    "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
+    "kdf_pw_conv_fwd": 1, "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
     "kdf_fusion_affine_relu_pair_fwd": 1, "kdf_fusion_affine_relu_pair_bwd": 1,
     "kdf_kd_loss_fwd_bwd": 2, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
     "kdf_rowbn_stats": 1, "kdf_rowbn_apply_fwd": 1, "kdf_rowbn_fwd_train": 1, "kdf_rowbn_bwd": 2,

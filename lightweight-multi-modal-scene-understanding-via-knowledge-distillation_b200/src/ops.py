@@ -18,7 +18,7 @@ from .native import call, dtype_code, lib, ptr, require_cuda, stream_ptr
 __all__ = [
     "bn_act", "run_fused", "fpn_merge",
     "bev_range_constants", "bev_index", "bev_project", "BevProjectFn",
-    "fused_fusion", "kd_loss_fwd_bwd", "KDLossFn", "confusion_matrix_", "adamw_flat_",
+    "pw_conv_fwd", "fused_fusion", "kd_loss_fwd_bwd", "KDLossFn", "confusion_matrix_", "adamw_flat_",
 ]
 
 
@@ -271,14 +271,65 @@ def _conv_frozen(m, x: torch.Tensor) -> torch.Tensor:
                     m.dilation, m.groups)
 
 
+def _is_pw_conv(m) -> bool:
+    import torch.nn as nn
+    return (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1) and m.groups == 1
+            and m.dilation == (1, 1) and m.padding in ((0, 0), 0) and m.padding_mode == "zeros")
+
+
+def _pw_weight_cached(conv, pack: int) -> torch.Tensor:
+    """bf16 (block-diagonal when packed) operand of a 1x1 convolution, cached until its weight changes."""
+    key = (_n.cache_generation(conv), conv.weight.data_ptr(), conv.weight._version, pack)
+    cache = getattr(conv, "_kdf_pw_w", None)
+    if cache is None or cache[0] != key:
+        cache = (key, pw_conv_weight(conv.weight, pack))
+        conv._kdf_pw_w = cache
+    return cache[1]
+
+
+class _PwConvFn(torch.autograd.Function):
+    """z = x . W^T over pixel rows on the fused layer kernel, with the batch statistics of z from its epilogue.
+    Backward: data and weight gradients as plain library GEMMs over the same rows."""
+
+    @staticmethod
+    def forward(ctx, x_rows, weight, wb, pack):
+        z, stats = pw_conv_fwd(x_rows, wb, pack, want_stats=True)
+        ctx.save_for_backward(x_rows, weight)
+        ctx.mark_non_differentiable(stats)
+        return z, stats
+
+    @staticmethod
+    def backward(ctx, g, _gs):
+        x_rows, weight = ctx.saved_tensors
+        g = g.contiguous()
+        w16 = weight.detach().reshape(weight.shape[0], -1).to(g.dtype)
+        gx = torch.mm(g, w16) if ctx.needs_input_grad[0] else None
+        gw = torch.mm(g.t(), x_rows).float().view(weight.shape) if ctx.needs_input_grad[1] else None
+        return gx, gw, None, None
+
+
+def _pw_usable(conv, x: torch.Tensor) -> bool:
+    """The fused 1x1 layer serves dense channels-last bf16 CUDA maps (the autocast path)."""
+    if not (_is_pw_conv(conv) and x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and _nhwc_rows(x) is not None):
+        return False
+    B, C, H, W = x.shape
+    return pw_conv_supported(conv.in_channels, conv.out_channels, B * H * W) and os.environ.get("KDF_NO_PW_CONV") is None
+
+
 def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run an ``nn.Sequential`` of conv / BatchNorm / ReLU(6) layers with every BatchNorm(+activation)
     group executed by the fused row kernels; ``residual`` is added after the LAST BatchNorm group.
-    The Sequential keeps its layers (and state_dict keys); only the execution is fused."""
+    The Sequential keeps its layers (and state_dict keys); only the execution is fused.
+
+    bf16 maps: a 1x1 convolution runs on ``kdf_pw_conv_fwd`` -- with the BatchNorm behind it folded into the kernel's
+    epilogue in inference (running statistics, no autograd), or with that BatchNorm's batch statistics coming out of
+    the epilogue in training (no separate statistics pass)."""
     import torch.nn as nn
     mods = list(seq)
     last_bn = max((i for i, m in enumerate(mods) if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d))), default=-1)
     i, col_sums = 0, None
+    if torch.is_autocast_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and _is_pw_conv(mods[0]):
+        x = x.to(torch.get_autocast_dtype("cuda"))
     while i < len(mods):
         m = mods[i]
         if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
@@ -290,21 +341,44 @@ def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> 
             i += step
         else:
             # depthwise 3x3 on the stencil kernels (which also reduce the statistics of a train-mode BatchNorm that
-            # follows), everything else on the library
+            # follows), 1x1 on the fused tensor-core layer kernel, everything else on the library
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             fuse_stats = isinstance(nxt, nn.BatchNorm2d) and (nxt.training or nxt.running_mean is None)
-            if (isinstance(nxt, nn.BatchNorm2d) and not fuse_stats and not torch.is_grad_enabled()
-                    and not (residual is not None and i + 1 == last_bn)):
+            inference = isinstance(nxt, nn.BatchNorm2d) and not fuse_stats and not torch.is_grad_enabled()
+            act, step = None, 2
+            if inference and i + 2 < len(mods) and isinstance(mods[i + 2], (nn.ReLU, nn.ReLU6)):
+                act, step = ("relu6" if isinstance(mods[i + 2], nn.ReLU6) else "relu"), 3
+            if inference and _pw_usable(m, x):
+                # inference: conv + running-statistics BatchNorm (+ activation, + shortcut) = one kernel
+                B, _, H, W = x.shape
+                pack = _pw_pack_factor(m.in_channels, m.out_channels)
+                scale, shift, _, _ = _eval_affine(nxt, m.bias)
+                res = None
+                if residual is not None and i + 1 == last_bn:
+                    res = _nhwc_rows(residual)
+                    res = None if res is None else res.reshape(B * H * W, -1)
+                if residual is None or i + 1 != last_bn or (res is not None and res.dtype == torch.bfloat16):
+                    rows = pw_conv_fwd(_nhwc_rows(x).reshape(B * H * W, -1), _pw_weight_cached(m, pack), pack,
+                                       epi=(scale, shift, _ACT[act]), residual=res)
+                    x = rows.view(B, H, W, -1).permute(0, 3, 1, 2)
+                    i += step
+                    continue
+            if inference and not (residual is not None and i + 1 == last_bn):
                 # inference: the running-statistics BatchNorm (+ activation) rides in the stencil kernel's epilogue
-                act, step = None, 2
-                if i + 2 < len(mods) and isinstance(mods[i + 2], (nn.ReLU, nn.ReLU6)):
-                    act, step = ("relu6" if isinstance(mods[i + 2], nn.ReLU6) else "relu"), 3
                 scale, shift, _, _ = _eval_affine(nxt)
                 y = dwconv3x3(m, x, post=(scale, shift, _ACT[act]))
                 if y is not None:
                     x = y
                     i += step
                     continue
+            if fuse_stats and m.bias is None and _pw_usable(m, x) and torch.is_grad_enabled():
+                # training: rows + the batch statistics of the BatchNorm that follows, from one kernel
+                B, _, H, W = x.shape
+                pack = _pw_pack_factor(m.in_channels, m.out_channels)
+                rows, col_sums = _PwConvFn.apply(_nhwc_rows(x).reshape(B * H * W, -1), m.weight, _pw_weight_cached(m, pack), pack)
+                x = rows.view(B, H, W, -1).permute(0, 3, 1, 2)
+                i += 1
+                continue
             y = dwconv3x3(m, x, want_stats=fuse_stats)
             if y is None:
                 x = _conv_frozen(m, x)
@@ -726,3 +800,73 @@ def mlp_layer_bwd(mode: int, dy: torch.Tensor, z: torch.Tensor, gs: torch.Tensor
     call("kdf_mlp_layer_bwd", mode, ptr(dy), ptr(z), ptr(f(gs)), ptr(f(ga)), ptr(f(gb)), ptr(x), M, ptr(f(pro_a)), ptr(f(pro_b)),
          ptr(weight_bf16.contiguous()), Kin, ptr(dy_prev), ptr(sums), ptr(dW), ptr(row_cell), stream_ptr(dev))
     return dy_prev, sums, dW
+
+
+# ----------------------------------------------------------------------------- pointwise (1x1) convolution layers (tcgen05)
+def _pw_pack_factor(K: int, N: int) -> int:
+    """Rows are handed to the tensor cores in 64-channel panels and the accumulator wants N % 32 == 0.  Narrow
+    layers (K = 32: the first two blocks of the camera encoder) are run on PAIRS of pixel rows: x [M,32] is the same
+    memory as [M/2, 64], and a block-diagonal weight [[W,0],[0,W]] makes the GEMM produce the pair's two output rows
+    side by side -- [M/2, 2N] is the same memory as [M, N].  (The zero blocks cost flops the tensor cores do not
+    notice; bytes moved are unchanged.)"""
+    f = 1
+    while (K * f) % 64 or (N * f) % 32:
+        f *= 2
+        if f > 8:
+            raise ValueError(f"pw_conv: cannot pack K={K}, N={N} into 64-channel panels")
+    return f
+
+
+def pw_conv_supported(K: int, N: int, M: int) -> bool:
+    try:
+        f = _pw_pack_factor(K, N)
+    except ValueError:
+        return False
+    return M % f == 0 and K * f <= 1024
+
+
+def pw_conv_weight(weight: torch.Tensor, pack: int = 1) -> torch.Tensor:
+    """bf16 [N*pack, K*pack] operand of ``pw_conv_fwd`` from a conv weight [N, K(,1,1)] (block-diagonal when packed)."""
+    w = weight.detach().reshape(weight.shape[0], -1).to(torch.bfloat16)
+    if pack > 1:
+        w = torch.block_diag(*([w] * pack))
+    return w.contiguous()
+
+
+def pw_conv_fwd(x: torch.Tensor, weight_bf16: torch.Tensor, pack: int = 1, pro=None, epi=None,
+                residual: Optional[torch.Tensor] = None, want_stats: bool = False):
+    """One fused 1x1-convolution layer over pixel rows (``kdf_pw_conv_fwd``).
+    x bf16 [M, K]; ``weight_bf16`` from ``pw_conv_weight`` (same ``pack``); ``pro`` = (scale f32[K], shift f32[K], act code)
+    of the BatchNorm + activation in FRONT of the convolution, applied on the fly; ``epi`` = (scale f32[N], shift f32[N],
+    act code) of a folded (running-statistics) BatchNorm + activation BEHIND it, with optional ``residual`` [M, N];
+    ``want_stats``: also return the fp64 column sums [2, N] of the stored rows (the batch statistics of the
+    BatchNorm behind the convolution).  -> out bf16 [M, N] (or (out, stats))."""
+    dev = require_cuda(x, weight_bf16, residual)
+    if x.dtype != torch.bfloat16 or weight_bf16.dtype != torch.bfloat16:
+        raise TypeError("pw_conv_fwd runs on bf16 rows and weights")
+    M, K = x.shape
+    Np, Kp = weight_bf16.shape
+    if Kp != K * pack or Np % pack or M % pack:
+        raise ValueError(f"pw_conv_fwd: weight {tuple(weight_bf16.shape)} does not match rows {tuple(x.shape)} at pack {pack}")
+    N = Np // pack
+    x = x.contiguous()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    stats = torch.empty(2, Np, dtype=torch.float64, device=dev) if want_stats else None
+    tile = (lambda v: v.float().repeat(pack).contiguous()) if pack > 1 else (lambda v: v.float().contiguous())
+    ps = psh = es = esh = None
+    pact = eact = 0
+    if pro is not None:
+        ps, psh, pact = tile(pro[0]), tile(pro[1]), int(pro[2])
+    if epi is not None:
+        es, esh, eact = tile(epi[0]), tile(epi[1]), int(epi[2])
+    if residual is not None:
+        residual = residual.contiguous()
+        if residual.dtype != torch.bfloat16 or tuple(residual.shape) != (M, N):
+            raise ValueError("pw_conv_fwd: residual must be bf16 [M, N]")
+    call("kdf_pw_conv_fwd", ptr(x), M // pack, Kp, Np, ptr(weight_bf16), ptr(ps), ptr(psh), pact, ptr(es), ptr(esh), eact,
+         ptr(residual), ptr(out), ptr(stats), stream_ptr(dev))
+    if want_stats:
+        if pack > 1:
+            stats = stats.view(2, pack, N).sum(1)
+        return out, stats
+    return out

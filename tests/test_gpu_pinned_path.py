@@ -61,31 +61,43 @@ def rel_l2(a, b):
 def test_graph_replay_equals_eager_steps(tmp_path, amp):
     """Five optimisation steps issued eagerly (teacher on the main stream) against the same five steps with the
     whole step captured once and replayed as a CUDA graph with the teacher on a side stream -- the configuration
-    bench.py times.  Same kernels in the same order, so only the order of floating-point atomics differs:
-    loss terms to 1e-5 (fp32) / 2e-3 (bf16: an atomics-order flip of one fp32 sum can move a bf16 rounding), the
-    parameter UPDATE (theta_k - theta_0) to 1e-3 / 3e-2 relative L2, BatchNorm running statistics likewise."""
+    bench.py times.  Same kernels in the same order, so only the order of floating-point atomics differs -- but AdamW
+    amplifies that noise (its normalised update turns a sign flip of a near-zero gradient into a 2*lr move), so the
+    bar is SELF-CALIBRATED: a second eager run of the same steps measures how far two executions of the identical
+    program drift apart, and the graph run must stay within 4x that drift (plus a floor for the case where the eager
+    runs happen to agree bit for bit).  Loss terms, logits, the parameter update theta_k - theta_0, running
+    statistics and batch counters are all compared."""
     data = frames(5)
     eager = make_trainer(tmp_path / "e", amp, graph=False, overlap=False)
+    again = make_trainer(tmp_path / "e2", amp, graph=False, overlap=False)
     graph = make_trainer(tmp_path / "g", amp, graph=True, overlap=True)
     theta0 = eager.optimizer.flat_param.clone()
-    assert torch.equal(theta0, graph.optimizer.flat_param)
-    tol_terms, tol_upd = (1e-5, 1e-3) if amp is None else (2e-3, 3e-2)
+    assert torch.equal(theta0, graph.optimizer.flat_param) and torch.equal(theta0, again.optimizer.flat_param)
+    floor_terms, floor_logits, floor_upd = (1e-5, 5e-4, 1e-3) if amp is None else (2e-3, 2e-2, 3e-2)
+    report = []
     for i, (img, pts, lab) in enumerate(data):
         te, le = eager.training_step(img, pts, lab)
+        ta, la = again.training_step(img, pts, lab)
         tg, lg = graph.training_step(img, pts, lab)
-        te, tg = te.clone(), tg.clone()
-        for j, name in enumerate(("loss", "ce", "kl", "mse")):
-            assert tg[j].item() == pytest.approx(te[j].item(), rel=tol_terms * (1 + i)), (i, name)
-        assert rel_l2(lg.float(), le.float()) < 50 * tol_terms * (1 + i), i
+        te, ta, tg = te.clone().double(), ta.clone().double(), tg.clone().double()
+        drift_t = ((ta[:4] - te[:4]).abs() / te[:4].abs()).max().item()
+        diff_t = ((tg[:4] - te[:4]).abs() / te[:4].abs()).max().item()
+        drift_l, diff_l = rel_l2(la.float(), le.float()), rel_l2(lg.float(), le.float())
+        report.append((i, drift_t, diff_t, drift_l, diff_l))
+        assert diff_t <= 4 * drift_t + floor_terms * (1 + i), report
+        assert diff_l <= 4 * drift_l + floor_logits * (1 + i), report
     assert len(graph._graphs) == 1 and graph.optimizer._step == eager.optimizer._step == 5
-    upd_e, upd_g = eager.optimizer.flat_param - theta0, graph.optimizer.flat_param - theta0
+    upd_e, upd_a, upd_g = (t.optimizer.flat_param - theta0 for t in (eager, again, graph))
     assert upd_e.abs().max().item() > 1e-4                      # the steps did move the parameters
-    assert rel_l2(upd_g, upd_e) < tol_upd, rel_l2(upd_g, upd_e)
-    for (n, be), (_, bg) in zip(eager.model.named_buffers(), graph.model.named_buffers()):
+    drift_u, diff_u = rel_l2(upd_a, upd_e), rel_l2(upd_g, upd_e)
+    assert diff_u <= 4 * drift_u + floor_upd, (drift_u, diff_u, report)
+    for (n, be), (_, ba), (_, bg) in zip(eager.model.named_buffers(), again.model.named_buffers(), graph.model.named_buffers()):
         if "running" in n:
-            assert rel_l2(bg, be) < tol_upd, n
+            assert rel_l2(bg, be) <= 4 * rel_l2(ba, be) + floor_upd, n
         elif "num_batches" in n:
             assert torch.equal(bg, be) and int(bg) == 5, n
+    print("graph-vs-eager report (step, eager drift terms, graph diff terms, eager drift logits, graph diff logits):", report,
+          "update drift/diff:", drift_u, diff_u)
 
 
 def test_graph_per_shape_and_release(tmp_path):
