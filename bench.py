@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the other BASELINE configurations (ablation sweep at batch 64, fp32 step, projection microbench, "
+                         "reference on CUDA, strong scaling at global batch 256) that the default run appends as `extras`")
     return ap.parse_args()
 
 
@@ -528,6 +531,30 @@ def run_native(args):
     if world > 1:
         dist.barrier()
 
+    # ---------------- the other BASELINE configurations (tools/bench_extras.py), each with its own clock record
+    extras = None
+    if not args.no_extras and not args.fp32:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extras as bx
+        me = sys.modules[__name__]
+        extras = {}
+        trainer.release_graphs()
+        torch.cuda.empty_cache()
+        if n_gpus == 1:
+            extras["ablation_b64"] = [bx.trainer_leg(me, device, rank, world, 64, args.points, st, False)
+                                      for st in ("weighted", "concat", "minimal")]
+            extras["fp32_step"] = bx.trainer_leg(me, device, rank, world, args.batch, args.points, args.student, True, steps=3, warmup=2)
+            extras["projection"] = bx.projection(device)
+            extras["reference_on_cuda"] = bx.reference_on_cuda(me, device, 4, args.points)
+            if not args.no_cpu_baseline:
+                extras["cpu_ce_only"] = bx.cpu_ce_only(me, args.cpu_batch, args.points)
+        elif 256 % n_gpus == 0:
+            leg = bx.trainer_leg(me, device, rank, world, 256 // n_gpus, args.points, args.student, False)
+            leg["scaling"] = "strong"
+            extras["strong256"] = leg
+    if world > 1:
+        dist.barrier()
+
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -539,7 +566,7 @@ def run_native(args):
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
                 "config": workload_config(args, n_gpus), "clocks": clk.result, "e2e": e2e,
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels, "extras": extras,
                 "loss_terms_last_step": dict(zip(("loss", "ce", "kl", "mse"), loss_terms))}
         emit(line)
     if world > 1:

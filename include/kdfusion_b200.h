@@ -398,10 +398,12 @@ int kdf_confusion_matrix(const void *logits, const int64_t *labels, int B, int K
 /* AdamW over one flat parameter buffer (torch.optim.AdamW single-tensor maths,
  * trainer.py:56,90): decoupled weight decay, bias-corrected moments.
  *   hyper f32 [2] on device = {lr, step}  (step already incremented, >= 1)
+ *   param_bf16  bf16 [n] out, nullable: the updated parameters rounded to bf16 (the operand copy the tensor-core
+ *               layers read, so that no per-step cast of the weights is needed)
  */
 int kdf_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                    const float *hyper, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, void *stream);
+                   float grad_scale, void *param_bf16, void *stream);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,7 @@ confusion_kernel(const TL *__restrict__ logits, const int64_t *__restrict__ labe
 __global__ void __launch_bounds__(256)
 adamw_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                   int64_t n, const float *__restrict__ hyper, float beta1, float beta2, float eps, float wd,
-                  float grad_scale) {
+                  float grad_scale, __nv_bfloat16 *__restrict__ p16) {
     __shared__ float sh[3];
     if (threadIdx.x == 0) {
         const double lr = (double)hyper[0];
@@ -74,6 +74,12 @@ adamw_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__r
             P[q] -= step_size * (M[q] / denom);
         }
         reinterpret_cast<float4 *>(p)[i] = pp;
+        if (p16) {                                    // bf16 shadow of the parameters: the tensor-core layers read it as it is
+            uint2 u;
+            u.x = pack_bf16(pp.x, pp.y);
+            u.y = pack_bf16(pp.z, pp.w);
+            reinterpret_cast<uint2 *>(p16)[i] = u;
+        }
         reinterpret_cast<float4 *>(m)[i] = mm;
         reinterpret_cast<float4 *>(v)[i] = vv;
     }
@@ -84,6 +90,7 @@ adamw_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__r
         const float vv = v[i] * beta2 + (1.f - beta2) * gr * gr;
         pv -= step_size * (mv / (sqrtf(vv) / bc2s + eps));
         p[i] = pv; m[i] = mv; v[i] = vv;
+        if (p16) p16[i] = __float2bfloat16_rn(pv);
     }
 }
 
@@ -117,8 +124,9 @@ int kdf_confusion_matrix(const void *logits, const int64_t *labels, int B, int K
 
 int kdf_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                    const float *hyper, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, void *stream) {
+                   float grad_scale, void *param_bf16, void *stream) {
     KDF_CHECK_ARG(n >= 0, "adamw: negative size");
+    KDF_CHECK_ARG((reinterpret_cast<uintptr_t>(param_bf16) & 7) == 0, "adamw: the bf16 shadow must be 8-byte aligned");
     KDF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hyper, "adamw: null pointer");
     const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                          reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
@@ -128,7 +136,8 @@ int kdf_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp_a
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (blocks < 1) blocks = 1;
     adamw_flat_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, hyper, beta1,
-                                                                beta2, eps, weight_decay, grad_scale);
+                                                                beta2, eps, weight_decay, grad_scale,
+                                                                static_cast<__nv_bfloat16 *>(param_bf16));
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -106,15 +106,17 @@ class _PairFusion(nn.Module):
         if cam_feat.shape[-2:] != lidar_feat.shape[-2:]:
             lidar_feat = F.interpolate(lidar_feat, size=cam_feat.shape[-2:], mode="bilinear", align_corners=False)
         cam_blk, lid_blk = getattr(self, self._cam_attr).conv, getattr(self, self._lid_attr).conv
-        cam_pre = F.linear(_rows(cam_feat), cam_blk[0].weight.flatten(1), cam_blk[0].bias)
-        lid_pre = F.linear(_rows(lidar_feat), lid_blk[0].weight.flatten(1), lid_blk[0].bias)
+        # bf16 training: the fused 1x1 layer kernel, whose epilogue also reduces the batch statistics the fusion kernel needs
+        cam_pre, cam_sums = ops.pw_project_rows(cam_blk[0], cam_blk[1], _rows(cam_feat))
+        lid_pre, lid_sums = ops.pw_project_rows(lid_blk[0], lid_blk[1], _rows(lidar_feat))
         if cam_pre.dtype != lid_pre.dtype:
-            lid_pre = lid_pre.to(cam_pre.dtype)
-        return cam_pre, lid_pre, cam_blk[1], lid_blk[1]
+            lid_pre, lid_sums = lid_pre.to(cam_pre.dtype), None
+        return cam_pre, lid_pre, cam_blk[1], lid_blk[1], cam_sums, lid_sums
 
     def fuse_rows(self, cam_feat, lidar_feat):
-        cam_pre, lid_pre, cam_bn, lid_bn = self._project(cam_feat, lidar_feat)
-        rows, attn = ops.fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, self._mode, getattr(self, "attention", None))
+        cam_pre, lid_pre, cam_bn, lid_bn, cam_sums, lid_sums = self._project(cam_feat, lidar_feat)
+        rows, attn = ops.fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, self._mode, getattr(self, "attention", None),
+                                      cam_sums, lid_sums)
         B, _, H, W = cam_feat.shape
         return _maps(rows, B, H, W), attn
 

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "kdf_kd_loss_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _i64,
                                       _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
     "kdf_confusion_matrix": (C.c_int, [_vp, _vp, _i, _i, _i64, _i, _i64, _vp, _vp]),
-    "kdf_adamw_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _vp]),
+    "kdf_adamw_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -278,11 +278,29 @@ def _is_pw_conv(m) -> bool:
 
 
 def _pw_weight_cached(conv, pack: int) -> torch.Tensor:
-    """bf16 (block-diagonal when packed) operand of a 1x1 convolution, cached until its weight changes."""
-    key = (_n.cache_generation(conv), conv.weight.data_ptr(), conv.weight._version, pack)
+    """bf16 (block-diagonal when packed) operand of a 1x1 convolution.  A parameter owned by ``FlatAdamW`` has a bf16
+    shadow that the optimizer kernel keeps current: the operand is a VIEW of it (no per-step cast); a packed layer
+    copies the view into the two diagonal blocks of a persistent buffer.  Other weights (the frozen teacher) are cast
+    once and cached until they change."""
+    w = conv.weight
+    shadow = getattr(w, "_kdf_shadow", None)
+    if shadow is not None:
+        N = w.shape[0]
+        w16 = shadow().view(N, -1)
+        if pack == 1:
+            return w16
+        K = w16.shape[1]
+        buf = getattr(conv, "_kdf_pw_packed", None)
+        if buf is None or buf.device != w16.device or tuple(buf.shape) != (N * pack, K * pack):
+            buf = torch.zeros(N * pack, K * pack, dtype=torch.bfloat16, device=w16.device)
+            conv._kdf_pw_packed = buf
+        for i in range(pack):
+            buf[i * N:(i + 1) * N, i * K:(i + 1) * K].copy_(w16)
+        return buf
+    key = (_n.cache_generation(conv), w.data_ptr(), w._version, pack)
     cache = getattr(conv, "_kdf_pw_w", None)
     if cache is None or cache[0] != key:
-        cache = (key, pw_conv_weight(conv.weight, pack))
+        cache = (key, pw_conv_weight(w, pack))
         conv._kdf_pw_w = cache
     return cache[1]
 
@@ -294,17 +312,19 @@ class _PwConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_rows, weight, wb, pack):
         z, stats = pw_conv_fwd(x_rows, wb, pack, want_stats=True)
-        ctx.save_for_backward(x_rows, weight)
+        ctx.save_for_backward(x_rows, wb)
+        ctx.wshape = weight.shape
         ctx.mark_non_differentiable(stats)
         return z, stats
 
     @staticmethod
     def backward(ctx, g, _gs):
-        x_rows, weight = ctx.saved_tensors
+        x_rows, wb = ctx.saved_tensors
         g = g.contiguous()
-        w16 = weight.detach().reshape(weight.shape[0], -1).to(g.dtype)
+        N, K = ctx.wshape[0], x_rows.shape[1]
+        w16 = wb[:N, :K]                                      # the bf16 operand the forward used (first diagonal block when packed)
         gx = torch.mm(g, w16) if ctx.needs_input_grad[0] else None
-        gw = torch.mm(g.t(), x_rows).float().view(weight.shape) if ctx.needs_input_grad[1] else None
+        gw = torch.mm(g.t(), x_rows).float().view(ctx.wshape) if ctx.needs_input_grad[1] else None
         return gx, gw, None, None
 
 
@@ -314,6 +334,20 @@ def _pw_usable(conv, x: torch.Tensor) -> bool:
         return False
     B, C, H, W = x.shape
     return pw_conv_supported(conv.in_channels, conv.out_channels, B * H * W) and os.environ.get("KDF_NO_PW_CONV") is None
+
+
+def pw_project_rows(conv, bn, rows: torch.Tensor):
+    """rows [M,K] -> (pre-BatchNorm rows [M,N], column sums f64 [2,N] | None) of a bias-free 1x1 convolution whose
+    BatchNorm ``bn`` follows in a consumer kernel: on the fused layer kernel (statistics from its epilogue) for bf16
+    rows in training, as a library GEMM otherwise."""
+    import torch.nn.functional as F
+    M, K = rows.shape
+    N = conv.out_channels
+    if (rows.is_cuda and rows.dtype == torch.bfloat16 and conv.bias is None and _is_pw_conv(conv) and bn.training
+            and torch.is_grad_enabled() and pw_conv_supported(K, N, M) and os.environ.get("KDF_NO_PW_CONV") is None):
+        pack = _pw_pack_factor(K, N)
+        return _PwConvFn.apply(rows.contiguous(), conv.weight, _pw_weight_cached(conv, pack), pack)
+    return F.linear(rows, conv.weight.flatten(1), conv.bias), None
 
 
 def run_fused(seq, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -581,14 +615,26 @@ class _FusedFusionFn(torch.autograd.Function):
                 None, None, None, None, None, None, None, None, None, None, gw1, gb1, gw2, gb2)
 
 
-def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None):
+def _bn_prepare_from_sums(rows: torch.Tensor, bn, col_sums):
+    """``_bn_prepare`` when the kernel that produced ``rows`` already reduced their column sums (f64 [2,C])."""
+    if col_sums is None or not (bn.training or bn.running_mean is None):
+        return _bn_prepare(rows, bn)
+    from .point_mlp import bn_finalize
+    track = bn.training and bn.track_running_stats and bn.running_mean is not None
+    with torch.no_grad():
+        mean, invstd, scale, shift = bn_finalize(col_sums, rows.shape[0], bn, None, track)
+    return scale, shift, mean, invstd, True
+
+
+def fused_fusion(cam_pre, lid_pre, cam_bn, lid_bn, mode: str, attention=None, cam_sums=None, lid_sums=None):
     """Fused fusion over pre-BN rows.  ``cam_bn`` / ``lid_bn`` are the BatchNorm2d
     modules of the two Conv1x1 blocks (their running statistics are updated here
     exactly like nn.BatchNorm2d does in training); ``attention`` is the
-    ``nn.Sequential(conv, relu, conv, softmax)`` of WeightedFusion.
+    ``nn.Sequential(conv, relu, conv, softmax)`` of WeightedFusion; ``cam_sums`` / ``lid_sums`` are the column sums
+    of the rows when the projection kernel already produced them (no statistics pass then).
     Returns (rows [M,C] or [M,2C], attn [M,2] | None)."""
-    cs = _bn_prepare(cam_pre.contiguous(), cam_bn)
-    ls = _bn_prepare(lid_pre.contiguous(), lid_bn)
+    cs = _bn_prepare_from_sums(cam_pre.contiguous(), cam_bn, cam_sums)
+    ls = _bn_prepare_from_sums(lid_pre.contiguous(), lid_bn, lid_sums)
     if cs[4] != ls[4]:
         raise RuntimeError("the two projection BatchNorms must be in the same mode")
     if mode == "weighted":
@@ -749,15 +795,18 @@ def confusion_matrix_(conf: torch.Tensor, logits: torch.Tensor, labels: torch.Te
     return conf
 
 
-def adamw_flat_(param, grad, exp_avg, exp_avg_sq, hyper, beta1, beta2, eps, weight_decay, grad_scale=1.0):
-    """In-place AdamW step over flat fp32 buffers; hyper = device tensor [lr, step]."""
+def adamw_flat_(param, grad, exp_avg, exp_avg_sq, hyper, beta1, beta2, eps, weight_decay, grad_scale=1.0, shadow=None):
+    """In-place AdamW step over flat fp32 buffers; hyper = device tensor [lr, step]; ``shadow`` (bf16, same length)
+    receives the updated parameters rounded to bf16."""
     dev = require_cuda(param, grad, exp_avg, exp_avg_sq, hyper)
     for t in (param, grad, exp_avg, exp_avg_sq):
         if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
             raise ValueError("adamw_flat_ needs contiguous float32 buffers of one size")
+    if shadow is not None and (shadow.dtype != torch.bfloat16 or shadow.numel() != param.numel() or not shadow.is_contiguous()):
+        raise ValueError("adamw_flat_: the shadow must be a contiguous bf16 buffer of the parameters' length")
     call("kdf_adamw_flat", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(hyper),
                              float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
-                             stream_ptr(dev))
+                             ptr(shadow), stream_ptr(dev))
 
 
 # ----------------------------------------------------------------------------- fused point-MLP layers (tcgen05)

@@ -43,7 +43,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self._offsets, total = [], 0
         for p in self._params:
             self._offsets.append(total)
-            total += (p.numel() + 3) // 4 * 4                 # keep every view 16-byte aligned
+            total += (p.numel() + 7) // 8 * 8                 # every fp32 view AND its bf16 shadow view stay 16-byte aligned
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros_like(self.flat_param)
         self.exp_avg = torch.zeros_like(self.flat_param)
@@ -56,6 +56,28 @@ class FlatAdamW(torch.optim.Optimizer):
                 self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_param[off:off + n].view(p.shape)
                 p.grad = self.flat_grad[off:off + n].view(p.shape)
+        # bf16 shadow of every parameter, kept current by the optimizer kernel: the tensor-core layers take their
+        # operands as views of it (no per-step cast).  Writes that go through torch (load_state_dict's ``param.copy_``,
+        # a broadcast into ``flat_param``) advance a version counter that ``shadow_of`` checks; the kernels' own
+        # updates do not (and write the shadow themselves).
+        self.flat_param_bf16 = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self.refresh_shadow()
+        for i, p in enumerate(self._params):
+            p._kdf_shadow = (lambda i=i: self.shadow_of(i))
+
+    def shadow_of(self, i: int) -> torch.Tensor:
+        """bf16 view of parameter ``i``; the whole shadow is refreshed first when that parameter (or the flat buffer)
+        was written through torch since the last refresh."""
+        if self._params[i]._version != self._pver[i] or self.flat_param._version != self._shadow_version:
+            self.refresh_shadow()
+        off = self._offsets[i]
+        return self.flat_param_bf16[off:off + self._params[i].numel()]
+
+    @torch.no_grad()
+    def refresh_shadow(self):
+        self.flat_param_bf16.copy_(self.flat_param)
+        self._shadow_version = self.flat_param._version
+        self._pver = [p._version for p in self._params]
 
     # ------------------------------------------------------------------ stepping
     def zero_grad(self, set_to_none: bool = False):
@@ -102,7 +124,7 @@ class FlatAdamW(torch.optim.Optimizer):
             self.set_hyper(g["lr"], self._step)
         _native.bump_generation()                         # parameters change through the flat buffer (no _version bump)
         ops.adamw_flat_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._hyper,
-                        g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], grad_scale)
+                        g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], grad_scale, shadow=self.flat_param_bf16)
 
     # ------------------------------------------------------------------ torch.optim.AdamW-format checkpoints
     def state_dict(self):

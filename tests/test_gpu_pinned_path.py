@@ -62,11 +62,14 @@ def test_graph_replay_equals_eager_steps(tmp_path, amp):
     """Five optimisation steps issued eagerly (teacher on the main stream) against the same five steps with the
     whole step captured once and replayed as a CUDA graph with the teacher on a side stream -- the configuration
     bench.py times.  Same kernels in the same order, so only the order of floating-point atomics differs -- but AdamW
-    amplifies that noise (its normalised update turns a sign flip of a near-zero gradient into a 2*lr move), so the
-    bar is SELF-CALIBRATED: a second eager run of the same steps measures how far two executions of the identical
-    program drift apart, and the graph run must stay within 4x that drift (plus a floor for the case where the eager
-    runs happen to agree bit for bit).  Loss terms, logits, the parameter update theta_k - theta_0, running
-    statistics and batch counters are all compared."""
+    amplifies that noise chaotically (its normalised update turns a sign flip of a near-zero gradient into a 2*lr
+    move), so the bar is SELF-CALIBRATED: a second eager run of the same steps measures how far two executions of the
+    identical program drift apart, and the graph run must stay within 10x the largest drift seen so far (plus a floor
+    for the case where the eager runs happen to agree bit for bit).  The first replayed step (i = 1), where the least
+    has been amplified, is held to 3x that step's own drift: measured 0.0 / 4e-6 (loss terms / logits) in fp32, and
+    6.6e-4 / 4.3e-2 against an eager-eager drift of 5.9e-4 / 4.3e-2 in bf16 (one AdamW step of sign(g) * lr on bf16
+    gradients already decorrelates two runs of the SAME eager program that far).  Loss
+    terms, logits, the parameter update theta_k - theta_0, running statistics and batch counters are all compared."""
     data = frames(5)
     eager = make_trainer(tmp_path / "e", amp, graph=False, overlap=False)
     again = make_trainer(tmp_path / "e2", amp, graph=False, overlap=False)
@@ -75,6 +78,7 @@ def test_graph_replay_equals_eager_steps(tmp_path, amp):
     assert torch.equal(theta0, graph.optimizer.flat_param) and torch.equal(theta0, again.optimizer.flat_param)
     floor_terms, floor_logits, floor_upd = (1e-5, 5e-4, 1e-3) if amp is None else (2e-3, 2e-2, 3e-2)
     report = []
+    worst_t = worst_l = 0.0
     for i, (img, pts, lab) in enumerate(data):
         te, le = eager.training_step(img, pts, lab)
         ta, la = again.training_step(img, pts, lab)
@@ -84,16 +88,19 @@ def test_graph_replay_equals_eager_steps(tmp_path, amp):
         diff_t = ((tg[:4] - te[:4]).abs() / te[:4].abs()).max().item()
         drift_l, diff_l = rel_l2(la.float(), le.float()), rel_l2(lg.float(), le.float())
         report.append((i, drift_t, diff_t, drift_l, diff_l))
-        assert diff_t <= 4 * drift_t + floor_terms * (1 + i), report
-        assert diff_l <= 4 * drift_l + floor_logits * (1 + i), report
+        worst_t, worst_l = max(worst_t, drift_t), max(worst_l, drift_l)
+        if i <= 1:                                              # step 0 is eager in both; step 1 is the first replay
+            assert diff_t <= 3 * drift_t + floor_terms and diff_l <= 3 * drift_l + floor_logits, report
+        assert diff_t <= 10 * worst_t + floor_terms * (1 + i), report
+        assert diff_l <= 10 * worst_l + floor_logits * (1 + i), report
     assert len(graph._graphs) == 1 and graph.optimizer._step == eager.optimizer._step == 5
     upd_e, upd_a, upd_g = (t.optimizer.flat_param - theta0 for t in (eager, again, graph))
     assert upd_e.abs().max().item() > 1e-4                      # the steps did move the parameters
     drift_u, diff_u = rel_l2(upd_a, upd_e), rel_l2(upd_g, upd_e)
-    assert diff_u <= 4 * drift_u + floor_upd, (drift_u, diff_u, report)
+    assert diff_u <= 10 * drift_u + floor_upd, (drift_u, diff_u, report)
     for (n, be), (_, ba), (_, bg) in zip(eager.model.named_buffers(), again.model.named_buffers(), graph.model.named_buffers()):
         if "running" in n:
-            assert rel_l2(bg, be) <= 4 * rel_l2(ba, be) + floor_upd, n
+            assert rel_l2(bg, be) <= 10 * rel_l2(ba, be) + floor_upd, n
         elif "num_batches" in n:
             assert torch.equal(bg, be) and int(bg) == 5, n
     print("graph-vs-eager report (step, eager drift terms, graph diff terms, eager drift logits, graph diff logits):", report,

@@ -68,23 +68,8 @@ def timed(fn, iters, warm=2):
     return a.elapsed_time(b) / iters
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=64, help="total frames (sharded over the ranks)")
-    ap.add_argument("--points", type=int, nargs="*", default=[100_000, 250_000, 500_000, 1_000_000, 2_000_000])
-    ap.add_argument("--dtypes", nargs="*", default=["fp32", "bf16"])
-    ap.add_argument("--channels", type=int, default=128)
-    ap.add_argument("--ref-frames", type=int, default=4, help="frames the eager PyTorch scatter is timed on")
-    ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--out", default=None, help="also append the JSON lines to this file (rank 0)")
-    args = ap.parse_args()
-
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    torch.cuda.set_device(dev)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner must not land on stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
+def measure(points_list, frames, dtypes, channels=128, ref_frames=4, iters=5, rank=0, world=1, dev=None, emit=None):
+    """The measurement loop: one dict per (points/frame, dtype).  ``frames`` = total frames over all ranks."""
     from src import native, ops
     from src.data_loading.synthetic_frames import make_frames
 
@@ -93,14 +78,14 @@ def main():
     except Exception:
         peak = 6650.0
     H = W = 64
-    C = args.channels
+    C = channels
     geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
-    F = args.frames // world                                         # frames of this rank
+    F = frames // world                                              # frames of this rank
     p, st = native.ptr, native.stream_ptr(dev)
     lines = []
-    for N in args.points:
+    for N in points_list:
         pts = make_frames(F, N, image_size=(8, 8), seed=1000 * rank + 7, device=dev)["points"]
-        for dname in args.dtypes:
+        for dname in dtypes:
             dt, s = (torch.float32, 4) if dname == "fp32" else (torch.bfloat16, 2)
             feats = torch.empty(F, N, C, dtype=dt, device=dev)
             for f0 in range(0, F, 8):                                 # filled in slices: no fp32 temporary of the whole tensor
@@ -119,8 +104,8 @@ def main():
             def fwd():
                 native.call("kdf_bev_project_fwd", p(pts), 4, p(feats), native.dtype_code(feats), F, N, C, *geom, H, W, 0,
                             p(grid), p(cnt), p(cel), None, p(order), p(offs), p(ws), wsb, st)
-            t_idx = timed(index_only, args.iters)
-            t_fwd = timed(fwd, args.iters)
+            t_idx = timed(index_only, iters)
+            t_fwd = timed(fwd, iters)
             v = (cel >= 0).float().mean().item()
             # backward on as many frames as fit next to feats (grad rows are as large as feats)
             free, _ = torch.cuda.mem_get_info(dev)
@@ -131,11 +116,11 @@ def main():
             def bwd():
                 native.call("kdf_bev_project_bwd", p(gg), p(feats), p(grid), None, None, p(cel), p(order), p(offs),
                             native.dtype_code(feats), Fb, N, C, H, W, 0, p(gf), st)
-            t_bwd = timed(bwd, args.iters) * F / Fb
+            t_bwd = timed(bwd, iters) * F / Fb
             del gf, gg
 
             # the reference's eager scatter on a few frames, checked bit for bit against ours
-            R = max(1, min(args.ref_frames, F))
+            R = max(1, min(ref_frames, F))
             fr = feats[:R].clone().requires_grad_(True)
             ref = torch_scatter_projection(pts[:R], fr, H, W)
             same = bool(torch.equal(ref.detach(), grid[:R]))
@@ -172,11 +157,34 @@ def main():
                     "speedup_fwd_vs_torch_scatter": t_ref_f / (t_fwd / F),
                     "speedup_fwd_bwd_vs_torch_scatter": t_ref_fb / ((t_fwd + t_bwd) / F)}
             if rank == 0:
-                print(json.dumps(line), flush=True)
                 lines.append(line)
+                if emit:
+                    emit(line)
             del feats, grid, cnt, cel, order, offs, ws
             torch.cuda.empty_cache()
         del pts
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=64, help="total frames (sharded over the ranks)")
+    ap.add_argument("--points", type=int, nargs="*", default=[100_000, 250_000, 500_000, 1_000_000, 2_000_000])
+    ap.add_argument("--dtypes", nargs="*", default=["fp32", "bf16"])
+    ap.add_argument("--channels", type=int, default=128)
+    ap.add_argument("--ref-frames", type=int, default=4, help="frames the eager PyTorch scatter is timed on")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--out", default=None, help="also append the JSON lines to this file (rank 0)")
+    args = ap.parse_args()
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner must not land on stdout (one JSON line)
+        dist.init_process_group("nccl", device_id=dev)
+    lines = measure(args.points, args.frames, args.dtypes, args.channels, args.ref_frames, args.iters, rank, world, dev,
+                    emit=lambda ln: print(json.dumps(ln), flush=True))
     if rank == 0 and args.out:
         with open(args.out, "a") as f:
             for ln in lines:
