@@ -66,6 +66,9 @@ def main():
     assert err < 1e-6, f"all-reduced bucket != sum of per-rank gradients ({err})"
     assert not torch.equal(parts[0], parts[1]), "per-rank gradients should differ (different frames)"
     opt.zero_grad()
+    # nothing of that hand-made step may outlive it: a live autograd graph keeps the parameters' AccumulateGrad nodes --
+    # and the (legacy default) stream they were created on -- alive, and a later CUDA-graph capture would reuse them
+    del logits, loss
     # the running statistics moved differently on each rank in that forward: put the replicas back together
     tr.sync_replicas()
 
