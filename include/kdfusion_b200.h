@@ -162,12 +162,6 @@ int kdf_rowbn_stats(const void *x, int dtype, int64_t M, int C, const float *gam
                     float *mean, float *invstd, float *scale, float *shift, void *workspace, void *stream);
 int kdf_rowbn_apply_fwd(const void *x, const void *residual, int dtype, int64_t M, int C,
                         const float *scale, const float *shift, int act, void *y, void *stream);
-/* Training-mode forward in one call: batch statistics (as kdf_rowbn_stats, running statistics advanced) followed by
- * y = act(x*scale + shift) [+ residual] (as kdf_rowbn_apply_fwd).  Tensors that stay in L2 between the two passes run as
- * ONE cooperative kernel (column sums, grid barrier, apply); larger ones as the two kernels above.  Same results. */
-int kdf_rowbn_fwd_train(const void *x, const void *residual, int dtype, int64_t M, int C, const float *gamma, const float *beta,
-                        const float *pre_bias, float eps, float momentum, float *running_mean, float *running_var,
-                        float *mean, float *invstd, float *scale, float *shift, int act, void *y, void *workspace, void *stream);
 int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int C,
                   const float *scale, const float *shift, const float *mean, const float *invstd,
                   int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,

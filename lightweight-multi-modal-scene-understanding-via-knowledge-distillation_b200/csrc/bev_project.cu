@@ -1097,11 +1097,10 @@ static int launch_index(const float *points, int B, int64_t N, int stride, const
     KDF_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)B * g.H * g.W, st));
     if (total == 0) return KDF_OK;
     const bool vec4 = (stride == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
-    static const bool warp_atomics = getenv("KDF_BEV_INDEX_WARP_ATOMICS") != nullptr;             // experiment knob
     const size_t hist_bytes = sizeof(int) * (size_t)g.H * g.W;
-    if (vec4 && rank == nullptr && !warp_atomics && hist_bytes <= 96 * 1024 && B <= 65535) {
+    if (vec4 && rank == nullptr && hist_bytes <= 96 * 1024 && B <= 65535) {
         // slices of >= 8192 points, about four 512-thread CTAs per SM over the whole batch
-        static const int per_sm = getenv("KDF_BEV_INDEX_CTAS_PER_SM") ? atoi(getenv("KDF_BEV_INDEX_CTAS_PER_SM")) : 4;
+        constexpr int per_sm = 4;
         int64_t slice = (total + (int64_t)sm_count() * per_sm - 1) / ((int64_t)sm_count() * per_sm);
         if (slice < 8192) slice = 8192;
         slice = (slice + 2047) / 2048 * 2048;
@@ -1200,9 +1199,8 @@ static int build_order(const float *points, int point_stride, int B, int64_t N, 
                        int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets, int32_t *rank, cudaStream_t st) {
     const int HW = g.H * g.W;
     const int64_t total = (int64_t)B * N;
-    static const bool atomic_path = getenv("KDF_BEV_ATOMIC_SORT") != nullptr;         // experiment knob
     const int64_t nchunk = (N + BEV_CHUNK - 1) / BEV_CHUNK;
-    if (!atomic_path && point_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0 && HW * sizeof(int) <= 96 * 1024 &&
+    if (point_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0 && HW * sizeof(int) <= 96 * 1024 &&
         N > 0 && nchunk <= 65535 && B <= 65535) {
         // the histograms live behind rank / (unused second [B,N] block) / offsets in the workspace
         const size_t bn = align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256);
@@ -1389,13 +1387,12 @@ int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const voi
                   "bev_bwd_affine: null pointer");
     const int64_t n_cells = (int64_t)B * H * W;
     int64_t blocks = (n_cells + 7) / 8;
-    static const int minb = getenv("KDF_BEV_BWD_MINB") ? atoi(getenv("KDF_BEV_BWD_MINB")) : 3;   // tuning knob
-    if (blocks > (int64_t)sm_count() * minb) blocks = (int64_t)sm_count() * minb;    // persistent: per-CTA sums -> few atomics
+    if (blocks > (int64_t)sm_count() * 3) blocks = (int64_t)sm_count() * 3;          // persistent: per-CTA sums -> few atomics
     typedef const __nv_bfloat16 *cb;
 #define KDF_BA(L, MB)                                                                                           \
     bev_bwd_affine_kernel<L, MB><<<(int)blocks, 256, 0, st>>>((cb)grad_grid_bf16, (cb)z_bf16, (cb)grid_bf16, (cb)grid_z_bf16, \
         order, offsets, cell, reinterpret_cast<__nv_bfloat16 *>(dy_bf16), sums, n_cells, N, H * W, total)
-    if (C == 64) KDF_BA(8, 3); else if (C == 128) { if (minb == 2) KDF_BA(16, 2); else KDF_BA(16, 3); } else KDF_BA(32, 3);
+    if (C == 64) KDF_BA(8, 3); else if (C == 128) KDF_BA(16, 3); else KDF_BA(32, 3);
 #undef KDF_BA
     KDF_LAUNCH_CHECK();
     return KDF_OK;

@@ -340,17 +340,14 @@ static int dwconv_fwd_impl(const void *in, const float *weight, int dtype, int B
                   "dwconv3x3_fwd: map too large for 32-bit indexing");
     const int row_blocks = B * ((OH + DW_R - 1) / DW_R);
     const int gx = (OW * cg + nt - 1) / nt;
-    static const int per_sm_stats = getenv("KDF_DW_STATS_CTAS_PER_SM") ? atoi(getenv("KDF_DW_STATS_CTAS_PER_SM")) : 8;   // tuning knob
-    const int per_sm = stats ? per_sm_stats : 8;             // with statistics every CTA ends with 2C fp64 atomics
-    int gy = (sm_count() * per_sm + gx - 1) / gx;            // ~8 CTAs per SM in total; a thread then walks several row blocks
+    int gy = (sm_count() * 8 + gx - 1) / gx;                 // ~8 CTAs per SM in total; a thread then walks several row blocks
     if (gy > row_blocks) gy = row_blocks;
     const dim3 grid((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy));
     cudaStream_t st = as_stream(stream);
     if (stats) KDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
     // resident CTAs per SM the kernel is compiled for: 3 (85 registers, 128 B of spills) is 5 % faster than 2 (111 registers)
-    // at stride 1 and 15 % slower at stride 2 (measured in the step); KDF_DW_FWD_MINB forces one of them
-    static const int minb_env = getenv("KDF_DW_FWD_MINB") ? atoi(getenv("KDF_DW_FWD_MINB")) : 0;
-    const int minb = minb_env ? minb_env : (stride == 1 ? 3 : 2);
+    // at stride 1 and 15 % slower at stride 2 (measured in the step)
+    const int minb = stride == 1 ? 3 : 2;
 #define KDF_DW(T, S, F)                                                                                                              \
     do {                                                                                                                             \
         if (minb == 3) dwconv3x3_fwd_kernel<T, S, F, 3><<<grid, nt, 0, st>>>((const T *)in, weight, (T *)out, B, H, W, C, OH, OW, stats, post_scale, post_shift, post_act); \
@@ -414,8 +411,7 @@ int kdf_dwconv3x3_bwd_weight(const void *in, const void *grad_out, int dtype, in
     const int64_t nitems = (int64_t)B * OH * ((OW + DW_L - 1) / DW_L);
     KDF_CHECK_ARG(nitems < (1ll << 30), "dwconv3x3_bwd_weight: map too large for 32-bit indexing");
     int64_t blocks = (nitems + rows - 1) / rows;
-    static const int wg_per_sm = getenv("KDF_DW_WGRAD_CTAS_PER_SM") ? atoi(getenv("KDF_DW_WGRAD_CTAS_PER_SM")) : 4;      // tuning knob
-    if (blocks > (int64_t)sm_count() * wg_per_sm) blocks = (int64_t)sm_count() * wg_per_sm;
+    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
     const size_t smem = sizeof(float) * (size_t)nt * 36;
 #define KDF_DWW(T, S)                                                                                          \
     do {                                                                                                       \

@@ -132,115 +132,8 @@ __device__ __forceinline__ void ft_mma_hidden(uint32_t y_base, uint32_t w_base, 
     tc::mma_commit(bar);
 }
 
-// ============================================================================= forward
-__global__ void __launch_bounds__(FT_THREADS, 1)
-fusion_weighted_fwd_tc_kernel(FusionTcArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = tc::align_smem_1024(smem_raw);
-    uint8_t *sW1 = smem + FtSmem::OFF_W1, *sY = smem + FtSmem::OFF_Y;
-    uint8_t *misc = smem + FtSmem::OFF_MISC_FWD;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(misc);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(misc + 16);
-    float *tb1 = reinterpret_cast<float *>(misc + 64), *tw2 = tb1 + 128, *taff = tw2 + 256, *rowS = taff + 512, *part = rowS + 512;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int och = tid & 15, orow0 = tid >> 4;
-    const int64_t n_tiles = (a.M + FT_ROWS - 1) / FT_ROWS;
-    ft_setup(a, sW1, tb1, tw2, taff, bars, tmem_slot, 128);
-    const uint32_t tmem_base = *tmem_slot;
-    const float bb0 = __ldg(a.b2), bb1 = __ldg(a.b2 + 1);
-
-    uint4 raw_c[8], raw_l[8];
-    auto load_tile = [&](int64_t tile) {
-        const int64_t r0 = tile * FT_ROWS;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int64_t row = r0 + orow0 + p * 16;
-            if (row < a.M) {
-                raw_c[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.cam + row * FT_C + och * 8));
-                raw_l[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.lid + row * FT_C + och * 8));
-            }
-        }
-    };
-    int64_t tile = blockIdx.x;
-    if (tile < n_tiles) load_tile(tile);
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int64_t r0 = tile * FT_ROWS;
-        // ---- stage the activation tile
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = orow0 + p * 16;
-            uint4 yc = make_uint4(0u, 0u, 0u, 0u), yl = yc;
-            if (r0 + r < a.M) {
-                yc = ft_affine_relu(raw_c[p], taff + och * 8, taff + 128 + och * 8);
-                yl = ft_affine_relu(raw_l[p], taff + 256 + och * 8, taff + 384 + och * 8);
-            }
-            const uint32_t off = (och >> 3) * FT_PANEL + tc::sw128_offset(r, och & 7);
-            *reinterpret_cast<uint4 *>(sY + off) = yc;
-            *reinterpret_cast<uint4 *>(sY + 2 * FT_PANEL + off) = yl;
-        }
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            ft_mma_hidden(tc::smem_u32(sY), tc::smem_u32(sW1), tmem_base, &bars[0]);
-        }
-        if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);       // in flight during the MMA and both epilogues
-        // ---- epilogue A: attention logits per pixel (two threads share a pixel: 64 hidden units each)
-        tc::mbar_wait(&bars[0], (uint32_t)(it & 1));
-        tc::fence_after_sync();
-        const int row = (warp & 3) * 32 + lane;
-        float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            const int col0 = (warp >> 2) * 64 + half * 32;
-            tc::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0, r);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float h = fmaxf(__uint_as_float(r[j]) + tb1[col0 + j], 0.f);
-                p0 = fmaf(h, tw2[col0 + j], p0);
-                p1 = fmaf(h, tw2[128 + col0 + j], p1);
-            }
-        }
-        if (warp >= 4) { part[2 * row] = p0; part[2 * row + 1] = p1; }
-        tc::fence_before_sync();
-        __syncthreads();
-        if (warp < 4) {
-            const float s0 = p0 + part[2 * row] + bb0, s1 = p1 + part[2 * row + 1] + bb1;
-            const float mx = fmaxf(s0, s1);
-            const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
-            const float inv = 1.f / (e0 + e1);
-            rowS[2 * row] = e0 * inv;
-            rowS[2 * row + 1] = e1 * inv;
-            if (r0 + row < a.M) *reinterpret_cast<float2 *>(a.attn + 2 * (r0 + row)) = make_float2(e0 * inv, e1 * inv);
-        }
-        __syncthreads();
-        // ---- epilogue B: blend, coalesced 16-byte stores
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = orow0 + p * 16;
-            if (r0 + r < a.M) {
-                const uint32_t off = (och >> 3) * FT_PANEL + tc::sw128_offset(r, och & 7);
-                float yc[8], yl[8], o[8];
-                ft_unpack8(*reinterpret_cast<const uint4 *>(sY + off), yc);
-                ft_unpack8(*reinterpret_cast<const uint4 *>(sY + 2 * FT_PANEL + off), yl);
-                const float w0 = rowS[2 * r], w1 = rowS[2 * r + 1];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = yc[j] * w0 + yl[j] * w1;
-                *reinterpret_cast<uint4 *>(a.out + (r0 + r) * FT_C + och * 8) = ft_pack8(o);
-            }
-        }
-        __syncthreads();                                                   // the Y tile is rewritten next iteration
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
-}
-
 // ============================================================================= forward, TMA-staged tiles
-// Same arithmetic as fusion_weighted_fwd_tc_kernel; the pre-BatchNorm rows of a tile arrive by TMA
+// The pre-BatchNorm rows of a tile arrive by TMA
 // (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps over the [M,128] row tensors, 4 boxes of 64 columns x 128
 // rows) DIRECTLY in the panel layout the tensor cores read, are BatchNorm-applied + ReLU'd in place, and two
 // operand tiles are kept in flight: the loads of tile i+1 land while tile i is transformed, multiplied and
@@ -656,8 +549,7 @@ fusion_weighted_bwd_tc_kernel(FusionTcArgs a) {
 
 // ----------------------------------------------------------------------------- launchers (called from fusion.cu's ABI entry points)
 bool fusion_tc_enabled() {
-    static const bool off = getenv("KDF_FUSION_FMA") != nullptr;          // debugging knob: force the fp32-FMA kernels
-    return !off;
+    return true;
 }
 
 int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
@@ -673,16 +565,11 @@ int fusion_weighted_fwd_tc(const void *cam_pre, const void *lid_pre, int64_t M,
     a.out = reinterpret_cast<__nv_bfloat16 *>(out); a.attn = attn;
     const int64_t n_tiles = (M + FT_ROWS - 1) / FT_ROWS;
     const int blocks = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    static const bool no_tma = getenv("KDF_FUSION_NO_TMA") != nullptr;      // experiment knob: register-staged tiles
     CUtensorMap tm_cam, tm_lid;
-    if (!no_tma && M < (1ll << 31) && tma::make_row_map(&tm_cam, cam_pre, M, FT_C) && tma::make_row_map(&tm_lid, lid_pre, M, FT_C)) {
-        KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtTmaSmem::TOTAL));
-        fusion_weighted_fwd_tma_kernel<<<blocks, FTM_THREADS, FtTmaSmem::TOTAL, st>>>(a, tm_cam, tm_lid);
-        KDF_LAUNCH_CHECK();
-        return KDF_OK;
-    }
-    KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_FWD));
-    fusion_weighted_fwd_tc_kernel<<<blocks, FT_THREADS, FtSmem::TOTAL_FWD, st>>>(a);
+    KDF_CHECK_ARG(M < (1ll << 31) && tma::make_row_map(&tm_cam, cam_pre, M, FT_C) && tma::make_row_map(&tm_lid, lid_pre, M, FT_C),
+                  "fusion_weighted_fwd: cuTensorMapEncodeTiled failed");
+    KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FtTmaSmem::TOTAL));
+    fusion_weighted_fwd_tma_kernel<<<blocks, FTM_THREADS, FtTmaSmem::TOTAL, st>>>(a, tm_cam, tm_lid);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }
@@ -705,14 +592,8 @@ int fusion_weighted_bwd_tc(const void *grad_out, const void *cam_pre, const void
     a.gaff = gaff; a.gw1 = gw1; a.gb1 = gb1; a.gw2 = gw2; a.gb2 = gb2;
     const int64_t n_tiles = (M + FT_ROWS - 1) / FT_ROWS;
     const int blocks = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    static const int nt = getenv("KDF_FUSION_BWD_THREADS") ? atoi(getenv("KDF_FUSION_BWD_THREADS")) : 512;     // tuning knob
-    if (nt == 256) {
-        KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_bwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_BWD));
-        fusion_weighted_bwd_tc_kernel<256><<<blocks, 256, FtSmem::TOTAL_BWD, st>>>(a);
-    } else {
-        KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_bwd_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_BWD));
-        fusion_weighted_bwd_tc_kernel<512><<<blocks, 512, FtSmem::TOTAL_BWD, st>>>(a);
-    }
+    KDF_CUDA(cudaFuncSetAttribute(fusion_weighted_bwd_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, FtSmem::TOTAL_BWD));
+    fusion_weighted_bwd_tc_kernel<512><<<blocks, 512, FtSmem::TOTAL_BWD, st>>>(a);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -10,7 +10,6 @@
 // and reduces the loss terms with warp shuffles -> per-CTA partials -> a fixed
 // order final sum by the last CTA (bitwise deterministic).
 // HBM-bound: K*s*3 + 8 bytes per pixel plus 3*s bytes per tap element.
-#include <cooperative_groups.h>
 #include <stddef.h>
 #include <stdlib.h>
 
@@ -138,11 +137,7 @@ __device__ __forceinline__ float kd_tap(const TF *__restrict__ s, const TF *__re
     return acc;
 }
 
-// COOP: launched cooperatively (the grid is one resident wave anyway), the label histogram is the kernel's first phase
-// instead of a pre-kernel: every CTA counts its share of the labels, then streams the mimic taps -- 98 % of the bytes,
-// and independent of the CE normaliser -- and only then meets the others at a grid barrier, which by that time costs
-// nothing; the per-pixel CE / KL phase follows with the exact normaliser.  One launch instead of two (~10 us of ~48).
-template <typename TL, typename TF, bool COOP>
+template <typename TL, typename TF>
 __global__ void __launch_bounds__(KD_THREADS, 3)
 kd_loss_kernel(KdParams p) {
     __shared__ float red[KD_THREADS / 32];
@@ -155,25 +150,6 @@ kd_loss_kernel(KdParams p) {
     const int K = p.K;
     const int64_t HW = p.HW, npix = (int64_t)p.B * HW;
     float m0 = 0.f, m1 = 0.f;
-    if (COOP) {
-        __shared__ unsigned int hist[KD_MAX_K];
-        if (threadIdx.x < KD_MAX_K) hist[threadIdx.x] = 0u;
-        __syncthreads();
-        for (int64_t i = tid; i < npix; i += nthreads) {
-            const int64_t y = p.labels[i];
-            if (y != p.ignore_index && y >= 0 && y < K) atomicAdd(&hist[y], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x < K && hist[threadIdx.x]) atomicAdd(&p.ws->class_count[threadIdx.x], hist[threadIdx.x]);
-        __threadfence();
-        if (p.n0 > 0)
-            m0 = kd_tap<TF>(reinterpret_cast<const TF *>(p.s0), reinterpret_cast<const TF *>(p.t0),
-                            reinterpret_cast<TF *>(p.d0), p.n0, p.grad_scale * p.beta * 2.f / (float)p.n0, tid, nthreads);
-        if (p.n1 > 0)
-            m1 = kd_tap<TF>(reinterpret_cast<const TF *>(p.s1), reinterpret_cast<const TF *>(p.t1),
-                            reinterpret_cast<TF *>(p.d1), p.n1, p.grad_scale * p.beta * 2.f / (float)p.n1, tid, nthreads);
-        cooperative_groups::this_grid().sync();
-    }
     float wsum, n_valid;
     kd_normaliser(p.ws, p.cw, K, wsum, n_valid);
     const float inv_wsum = 1.f / wsum;                       // 0/0 -> NaN like torch when nothing is valid
@@ -233,10 +209,10 @@ kd_loss_kernel(KdParams p) {
     }
 
     // --- feature-mimic taps
-    if (!COOP && p.n0 > 0)
+    if (p.n0 > 0)
         m0 = kd_tap<TF>(reinterpret_cast<const TF *>(p.s0), reinterpret_cast<const TF *>(p.t0),
                         reinterpret_cast<TF *>(p.d0), p.n0, p.grad_scale * p.beta * 2.f / (float)p.n0, tid, nthreads);
-    if (!COOP && p.n1 > 0)
+    if (p.n1 > 0)
         m1 = kd_tap<TF>(reinterpret_cast<const TF *>(p.s1), reinterpret_cast<const TF *>(p.t1),
                         reinterpret_cast<TF *>(p.d1), p.n1, p.grad_scale * p.beta * 2.f / (float)p.n1, tid, nthreads);
 
@@ -313,11 +289,7 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
     KdWorkspace *ws = reinterpret_cast<KdWorkspace *>(workspace);
     const int64_t npix = (int64_t)B * HW;
     KDF_CUDA(cudaMemsetAsync(ws, 0, offsetof(KdWorkspace, partial), st));
-    // KDF_KD_COOP=1: one cooperative launch (histogram phase, taps, grid barrier, pixels) instead of histogram pre-kernel +
-    // main kernel.  Measured at the bench shape: 0.051 ms either way (a cooperative launch costs what the tiny pre-kernel
-    // costs), so the plain two-launch form stays the default.
-    static const bool two_kernels = getenv("KDF_KD_COOP") == nullptr;
-    if (two_kernels) {
+    {
         int64_t nb = (npix + KD_THREADS * 4 - 1) / (KD_THREADS * 4);
         if (nb > sm_count() * 4) nb = sm_count() * 4;
         kd_label_count_kernel<<<(int)nb, KD_THREADS, 0, st>>>(labels, K, npix, ignore_index, ws);
@@ -338,22 +310,11 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
     const int64_t need = (work + KD_THREADS - 1) / KD_THREADS;
     if (need < blocks) blocks = (int)(need < 1 ? 1 : need);
     if (blocks > KD_MAX_BLOCKS) blocks = KD_MAX_BLOCKS;
-    if (two_kernels) {
-        if (dtype_logits == KDF_F32 && dtype_feat == KDF_F32)        kd_loss_kernel<float, float, false><<<blocks, KD_THREADS, 0, st>>>(p);
-        else if (dtype_logits == KDF_F32 && dtype_feat == KDF_BF16)  kd_loss_kernel<float, __nv_bfloat16, false><<<blocks, KD_THREADS, 0, st>>>(p);
-        else if (dtype_logits == KDF_BF16 && dtype_feat == KDF_F32)  kd_loss_kernel<__nv_bfloat16, float, false><<<blocks, KD_THREADS, 0, st>>>(p);
-        else                                                         kd_loss_kernel<__nv_bfloat16, __nv_bfloat16, false><<<blocks, KD_THREADS, 0, st>>>(p);
-        KDF_LAUNCH_CHECK();
-        return KDF_OK;
-    }
-    // one cooperative launch: the grid is at most the resident wave (3 CTAs of 256 threads per SM)
-    const void *fn;
-    if (dtype_logits == KDF_F32 && dtype_feat == KDF_F32)        fn = reinterpret_cast<const void *>(&kd_loss_kernel<float, float, true>);
-    else if (dtype_logits == KDF_F32 && dtype_feat == KDF_BF16)  fn = reinterpret_cast<const void *>(&kd_loss_kernel<float, __nv_bfloat16, true>);
-    else if (dtype_logits == KDF_BF16 && dtype_feat == KDF_F32)  fn = reinterpret_cast<const void *>(&kd_loss_kernel<__nv_bfloat16, float, true>);
-    else                                                         fn = reinterpret_cast<const void *>(&kd_loss_kernel<__nv_bfloat16, __nv_bfloat16, true>);
-    void *args[] = {&p};
-    KDF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(KD_THREADS), args, 0, st));
+    if (dtype_logits == KDF_F32 && dtype_feat == KDF_F32)        kd_loss_kernel<float, float><<<blocks, KD_THREADS, 0, st>>>(p);
+    else if (dtype_logits == KDF_F32 && dtype_feat == KDF_BF16)  kd_loss_kernel<float, __nv_bfloat16><<<blocks, KD_THREADS, 0, st>>>(p);
+    else if (dtype_logits == KDF_BF16 && dtype_feat == KDF_F32)  kd_loss_kernel<__nv_bfloat16, float><<<blocks, KD_THREADS, 0, st>>>(p);
+    else                                                         kd_loss_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, KD_THREADS, 0, st>>>(p);
+    KDF_LAUNCH_CHECK();
     return KDF_OK;
 }
 

@@ -896,353 +896,6 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 }
 
 
-// ============================================================================= warp-specialised backward layer
-// Same arithmetic as mlp_layer_bwd_kernel, different schedule: the lock-step version runs prologue, MMA issue and
-// epilogue as phases of ONE instruction stream separated by CTA barriers (issue slots 30 % busy, latency-bound).
-// Here three roles run concurrently and meet only at mbarriers:
-//   warps 0-7   producers : global -> registers (rolling 4-pass prefetch ring) -> BatchNorm backward / activation
-//                           recompute -> swizzled operand tiles; arrive on full[buf]
-//   warps 8-15  epilogue  : waits mma_done[buf], TMEM -> mask -> staging -> coalesced stores + column sums;
-//                           arrives on smem_free[buf] once the operand tile / accumulator have been read
-//   MMA issue             : producer thread 0, right after its own arrive: waits full[buf] (the other 255
-//                           producers), issues dgrad + wgrad, tcgen05.commit -> mma_done[buf]
-// so global loads, tensor pipe and the CUDA-core work of two different tiles overlap.
-constexpr int WS_GROUP = 256;
-constexpr int WS_THREADS = 2 * WS_GROUP;
-
-template <int KIN>
-struct MlpBwdWsSmem {
-    static constexpr int W_BYTES = PM_N * KIN * 2;
-    static constexpr int D_BYTES = PM_ROWS * PM_N * 2;
-    static constexpr int A_BYTES = PM_ROWS * KIN * 2;
-    static constexpr int OFF_W = 0;
-    static constexpr int OFF_D0 = OFF_W + W_BYTES;
-    static constexpr int OFF_D1 = OFF_D0 + D_BYTES;
-    static constexpr int OFF_A0 = OFF_D1 + D_BYTES;
-    static constexpr int OFF_A1 = OFF_A0 + A_BYTES;
-    static constexpr int OFF_STAGE = OFF_A1 + A_BYTES;            // epilogue staging tile (32 KB)
-    static constexpr int OFF_PTS = OFF_STAGE + PM_ROWS * 256;     // MODE 0: the tile's raw points, 2 x 128 float4
-    static constexpr int OFF_MISC = OFF_PTS + 2 * PM_ROWS * 16;
-    static constexpr int MISC_BYTES = 64 + 4 * (3 * 128 + 8 * 36 + 64 + 2 * 128);
-    static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void group_sync(int id) {               // the 256 threads of one role
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(WS_GROUP) : "memory");
-}
-
-template <int MODE, int KIN>
-__global__ void __launch_bounds__(WS_THREADS, 1)
-mlp_layer_bwd_ws_kernel(MlpBwdArgs a) {
-    using L = MlpBwdWsSmem<KIN>;
-    constexpr int ACH = KIN / 8;
-    constexpr int A_ROWS_PER_PASS = WS_GROUP / ACH;               // 16 (MODE 1) or 32 (MODE 0)
-    constexpr int A_PASSES = PM_ROWS / A_ROWS_PER_PASS;           // 8 or 4
-    constexpr int D_PASSES = 8, PF = 4;                           // dz tile: 16 rows per pass; prefetch ring depth
-    constexpr uint32_t PANEL = PM_ROWS * tc::ROW_BYTES;
-    constexpr uint32_t IDESC_D = tc::make_idesc(PM_ROWS, KIN, 0, 1);
-    constexpr uint32_t IDESC_W = tc::make_idesc(PM_N, KIN, 1, 1);
-    constexpr uint32_t TMEM_COLS = (3 * KIN > 256) ? 512 : 256;
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = tc::align_smem_1024(smem_raw);
-    uint8_t *sW = smem + L::OFF_W;
-    auto sD = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_D1 : L::OFF_D0); };   // offsets from ONE shared base: LDS/STS, not generic
-    auto sA = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1 : L::OFF_A0); };
-    uint8_t *sStage = smem + L::OFF_STAGE;
-    float4 *sPts = reinterpret_cast<float4 *>(smem + L::OFF_PTS);
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [2]
-    uint64_t *bar_mma = bar_full + 2, *bar_free = bar_full + 4;                       // [2], [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 48);
-    float *cgs = reinterpret_cast<float *>(smem + L::OFF_MISC + 64), *cga = cgs + 128, *cgb = cga + 128;
-    float *coef = cgb + 128;                                      // MODE 0: q (8 chunks x 36), r at 288;  MODE 1: scale[128], shift[128]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
-
-    for (int i = tid; i < 128; i += WS_THREADS) { cgs[i] = a.gs[i]; cga[i] = a.ga[i]; cgb[i] = a.gb[i]; }
-    if (MODE == 0) {
-        for (int i = tid; i < 64 * 4; i += WS_THREADS) coef[(i >> 5) * 36 + (i & 31)] = a.pro_a[i];
-        for (int i = tid; i < 64; i += WS_THREADS) coef[288 + i] = a.pro_b[i];
-    } else {
-        for (int i = tid; i < KIN; i += WS_THREADS) { coef[i] = a.pro_a[i]; coef[KIN + i] = a.pro_b[i]; }
-    }
-    for (int idx = tid; idx < PM_N * ACH; idx += WS_THREADS) {
-        const int n = idx / ACH, ch = idx % ACH;
-        const uint4 w = *reinterpret_cast<const uint4 *>(a.W + (int64_t)n * KIN + ch * 8);
-        *reinterpret_cast<uint4 *>(sW + (ch >> 3) * PANEL + tc::sw128_offset(n, ch & 7)) = w;
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            tc::mbar_init(&bar_full[b], WS_GROUP);
-            tc::mbar_init(&bar_mma[b], 1);
-            tc::mbar_init(&bar_free[b], WS_GROUP);
-        }
-        tc::mbar_fence_init();
-    }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-    tc::fence_async_smem();
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    auto issue_mma = [&](int mit) {                                        // one thread: tile number mit of this CTA
-        const int mb = mit & 1;
-        tc::mbar_wait(&bar_full[mb], (uint32_t)((mit >> 1) & 1));
-        tc::fence_after_sync();
-        const uint32_t d_base = tc::smem_u32(sD(mb)), a_base = tc::smem_u32(sA(mb)), w_base = tc::smem_u32(sW);
-        const uint32_t acc_d = tmem_base + (uint32_t)mb * KIN, acc_w = tmem_base + 2u * KIN;
-#pragma unroll
-        for (int k = 0; k < PM_N / 16; ++k) {
-            const uint32_t koff = (uint32_t)(k >> 2) * PANEL + (uint32_t)(k & 3) * 32u;
-            tc::mma_bf16(acc_d, tc::desc_kmajor(d_base + koff), tc::desc_mnmajor(w_base + (uint32_t)k * 2048u, PANEL), IDESC_D, k > 0);
-        }
-#pragma unroll
-        for (int k = 0; k < PM_ROWS / 16; ++k) {
-            tc::mma_bf16(acc_w, tc::desc_mnmajor(d_base + (uint32_t)k * 2048u, PANEL), tc::desc_mnmajor(a_base + (uint32_t)k * 2048u, PANEL),
-                         IDESC_W, !(mit == 0 && k == 0));
-        }
-        tc::mma_commit(&bar_mma[mb]);
-    };
-    if (tid < WS_GROUP) {
-        // ------------------------------------------------------------------ producers
-        const int dch = tid & 15, drow0 = tid >> 4;
-        const int ach = tid % ACH, arow0 = tid / ACH;
-        uint4 rdy[PF], rz[PF], rin[MODE == 1 ? PF : 1], rpt[MODE == 0 ? A_PASSES : 1];
-        int rcell[PF];
-        float gs[8], ga[8], gb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { gs[j] = cgs[dch * 8 + j]; ga[j] = cga[dch * 8 + j]; gb[j] = cgb[dch * 8 + j]; }
-        auto issue = [&](int64_t tile, int p, int slot) {
-            const int64_t row = tile * PM_ROWS + drow0 + p * 16;
-            rcell[slot] = 0;
-            if (tile < n_tiles && row < a.M) {
-                if (a.row_cell) rcell[slot] = __ldg(a.row_cell + row);
-                rdy[slot] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
-                rz[slot] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
-                if (MODE == 1) rin[slot] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + row * KIN + dch * 8);
-            }
-        };
-        auto issue_pts = [&](int64_t tile) {
-            if (MODE == 0) {
-#pragma unroll
-                for (int p = 0; p < A_PASSES; ++p) {
-                    const int64_t row = tile * PM_ROWS + arow0 + p * A_ROWS_PER_PASS;
-                    if (tile < n_tiles && row < a.M) rpt[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.input) + row);
-                }
-            }
-        };
-        int64_t tile = blockIdx.x;
-#pragma unroll
-        for (int p = 0; p < PF; ++p) issue(tile, p, p);
-        issue_pts(tile);
-        for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int64_t r0 = tile * PM_ROWS, next = tile + gridDim.x;
-            if (tid == 32) {                                                   // two tiles ahead: DRAM -> L2, no registers involved
-                const int64_t pt = next + gridDim.x;
-                if (pt < n_tiles) {
-                    const int64_t q0 = pt * PM_ROWS;
-                    const int64_t rows = (a.M - q0 < PM_ROWS) ? (a.M - q0) : PM_ROWS;
-                    tc::prefetch_l2(a.dy + q0 * PM_N, (uint32_t)(rows * PM_N * 2));
-                    tc::prefetch_l2(a.z + q0 * PM_N, (uint32_t)(rows * PM_N * 2));
-                    if (MODE == 0) tc::prefetch_l2(reinterpret_cast<const uint4 *>(a.input) + q0, (uint32_t)(rows * 16));
-                    else tc::prefetch_l2(reinterpret_cast<const __nv_bfloat16 *>(a.input) + q0 * KIN, (uint32_t)(rows * KIN * 2));
-                }
-            }
-            if (it >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)(((it - 2) >> 1) & 1));
-#pragma unroll
-            for (int p = 0; p < D_PASSES; ++p) {
-                const int slot = p & (PF - 1);
-                const int r = drow0 + p * 16;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u), av = v;
-                if (r0 + r < a.M) {
-                    float g[8], zz[8];
-                    unpack8(rcell[slot] >= 0 ? rdy[slot] : make_uint4(0u, 0u, 0u, 0u), g);
-                    unpack8(rz[slot], zz);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
-                    v = pack8(g);
-                    if (MODE == 1) av = affine_relu_chunk(rin[slot], coef + dch * 8, coef + KIN + dch * 8);
-                }
-                if (p + PF < D_PASSES) issue(tile, p + PF, slot); else issue(next, p + PF - D_PASSES, slot);
-                const uint32_t off = (dch >> 3) * PANEL + tc::sw128_offset(r, dch & 7);
-                *reinterpret_cast<uint4 *>(sD(buf) + off) = v;
-                if (MODE == 1) *reinterpret_cast<uint4 *>(sA(buf) + off) = av;
-            }
-            if (MODE == 0) {
-                float c0[32], c1[8];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) c0[j] = coef[ach * 36 + j];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) c1[j] = coef[288 + ach * 8 + j];
-#pragma unroll
-                for (int p = 0; p < A_PASSES; ++p) {
-                    const int r = arow0 + p * A_ROWS_PER_PASS;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (r0 + r < a.M) {
-                        const float4 pt = make_float4(__uint_as_float(rpt[p].x), __uint_as_float(rpt[p].y),
-                                                      __uint_as_float(rpt[p].z), __uint_as_float(rpt[p].w));
-                        v = first_layer_chunk(pt, c0, c1);
-                        if (ach == 0) sPts[buf * PM_ROWS + r] = pt;
-                    }
-                    *reinterpret_cast<uint4 *>(sA(buf) + tc::sw128_offset(r, ach)) = v;
-                }
-                issue_pts(next);
-            }
-            tc::fence_async_smem();
-            mbar_arrive(&bar_full[buf]);
-            if (tid == 0) issue_mma(it);                                       // waits for the other 255 producers, then fires the tile
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue
-        const int et = tid - WS_GROUP, ewarp = et >> 5;                        // hardware warp 8+ewarp: TMEM lanes 32*(ewarp%4)..
-        const int och = et & 15, orow0 = et >> 4;                              // MODE 1 store phase
-        const int ccol = et & 63, crq = et >> 6;                               // MODE 0 column-owner phase (4 groups x 32 rows)
-        const int row = (ewarp & 3) * 32 + lane;
-        const uint32_t lane_bits = (uint32_t)((ewarp & 3) * 32) << 16;
-        constexpr int NACC = MODE == 1 ? 16 : 5;
-        float acc[NACC];
-#pragma unroll
-        for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int64_t r0 = tile * PM_ROWS;
-            uint4 zk[MODE == 1 ? D_PASSES : 1];
-            if (MODE == 1) {
-#pragma unroll
-                for (int p = 0; p < D_PASSES; ++p) {
-                    const int64_t rr = r0 + orow0 + p * 16;
-                    zk[p] = make_uint4(0u, 0u, 0u, 0u);
-                    if (rr < a.M) zk[p] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.input) + rr * KIN + och * 8);
-                }
-            }
-            tc::mbar_wait(&bar_mma[buf], (uint32_t)((it >> 1) & 1));
-            tc::fence_after_sync();
-            if (MODE == 1) {
-                const uint32_t taddr = tmem_base + lane_bits + (uint32_t)buf * KIN + (uint32_t)(ewarp >> 2) * 64;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    tc::tmem_ld32(taddr + half * 32, r);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int chunk = (ewarp >> 2) * 8 + half * 4 + j;
-                        const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
-                        float act[8], v[8];
-                        unpack8(av, act);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = act[e] > 0.f ? __uint_as_float(r[8 * j + e]) : 0.f;
-                        *reinterpret_cast<uint4 *>(sStage + row * 256 + ((chunk ^ (row & 7)) << 4)) = pack8(v);
-                    }
-                }
-                tc::fence_before_sync();
-                mbar_arrive(&bar_free[buf]);                                   // accumulator and activation tile have been read
-                group_sync(1);
-#pragma unroll
-                for (int p = 0; p < D_PASSES; ++p) {
-                    const int r = orow0 + p * 16;
-                    if (r0 + r < a.M) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
-                        *reinterpret_cast<uint4 *>(a.dy_prev + (r0 + r) * PM_N + och * 8) = v;
-                        float f[8], zz[8];
-                        unpack8(v, f);
-                        unpack8(zk[p], zz);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] = fmaf(f[j], zz[j], acc[8 + j]); }
-                    }
-                }
-                group_sync(1);                                                 // the staging tile is rewritten by the next tile
-            } else {
-                const uint32_t taddr = tmem_base + lane_bits + (uint32_t)buf * KIN + (uint32_t)(ewarp >> 2) * 32;
-                uint32_t r[32];
-                tc::tmem_ld32(taddr, r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int chunk = (ewarp >> 2) * 4 + j;
-                    const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + tc::sw128_offset(row, chunk));
-                    float act[8];
-                    unpack8(av, act);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c4 = chunk * 2 + h;
-                        float4 o;
-                        o.x = act[4 * h + 0] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 0]) : 0.f;
-                        o.y = act[4 * h + 1] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 1]) : 0.f;
-                        o.z = act[4 * h + 2] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 2]) : 0.f;
-                        o.w = act[4 * h + 3] > 0.f ? __uint_as_float(r[8 * j + 4 * h + 3]) : 0.f;
-                        *reinterpret_cast<float4 *>(sStage + row * 256 + ((c4 ^ (row & 15)) << 4)) = o;
-                    }
-                }
-                tc::fence_before_sync();
-                group_sync(1);
-                const int rows = (int)((a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS);
-                const int rbeg = crq * 32, rend = (rbeg + 32 < rows) ? rbeg + 32 : rows;
-                for (int r = rbeg; r < rend; ++r) {
-                    const float v = *reinterpret_cast<const float *>(sStage + r * 256 + (((ccol >> 2) ^ (r & 15)) << 4) + (ccol & 3) * 4);
-                    const float4 pt = sPts[buf * PM_ROWS + r];
-                    acc[0] += v;
-                    acc[1] = fmaf(v, pt.x, acc[1]); acc[2] = fmaf(v, pt.y, acc[2]);
-                    acc[3] = fmaf(v, pt.z, acc[3]); acc[4] = fmaf(v, pt.w, acc[4]);
-                }
-                mbar_arrive(&bar_free[buf]);                                   // the point tile of this buffer has been read too
-                group_sync(1);
-            }
-        }
-        // ---- column sums -> fp64 atomics (epilogue threads only)
-        float *red = reinterpret_cast<float *>(sStage);
-        if (MODE == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) red[(orow0 * 16 + och) * 16 + j] = acc[j];
-            group_sync(1);
-            {
-                const int ch = et >> 4, j = et & 15;
-                float v = 0.f;
-                for (int r = 0; r < 16; ++r) v += red[(r * 16 + ch) * 16 + j];
-                atomicAdd(a.sums + (j >> 3) * PM_N + ch * 8 + (j & 7), (double)v);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) red[(crq * 64 + ccol) * 5 + j] = acc[j];
-            group_sync(1);
-            for (int i = et; i < 64 * 5; i += WS_GROUP) {
-                const int c = i / 5, j = i % 5;
-                float v = 0.f;
-                for (int q = 0; q < 4; ++q) v += red[(q * 64 + c) * 5 + j];
-                atomicAdd(a.sums + j * 64 + c, (double)v);
-            }
-        }
-        // ---- weight gradient: every MMA has completed (the last tile's barrier was waited on)
-        if (it > 0) {
-            tc::fence_after_sync();
-            const int n = (ewarp & 3) * 32 + lane;
-            constexpr int COLS_PER_WARP = KIN / 2;
-#pragma unroll
-            for (int h = 0; h < COLS_PER_WARP / 32; ++h) {
-                const int col = (ewarp >> 2) * COLS_PER_WARP + h * 32;
-                uint32_t r[32];
-                tc::tmem_ld32(tmem_base + lane_bits + 2u * KIN + (uint32_t)col, r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    tc::red_add_v4(a.dW + n * KIN + col + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-
 // ============================================================================= layers 2+1 backward, TMA-staged
 // mlp_layer_bwd_kernel<0> spends a third of its instructions forming dz = gs*dy + ga + gb*z element by element before
 // the GEMMs.  The GEMMs are linear and gs/ga/gb are per-channel, so the BatchNorm backward folds into the WEIGHTS:
@@ -1649,16 +1302,11 @@ int kdf_mlp_layer_fwd(int mode, const void *input, int64_t M, const float *pro_a
     if (n_tiles < blocks) blocks = (int)n_tiles;
     if (mode == 0) {
         const int smem = MlpSmem<64>::TOTAL;
-        static const int per_sm = getenv("KDF_MLP_FWD0_CTAS_PER_SM") ? atoi(getenv("KDF_MLP_FWD0_CTAS_PER_SM")) : 2;    // tuning knob
-        if (per_sm == 2) {
-            blocks = 2 * sm_count();
-            if (n_tiles < blocks) blocks = (int)n_tiles;
-            KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            mlp_layer_fwd_kernel<0, 64, 256, 2><<<blocks, 256, smem, st>>>(a);
-        } else {
-            KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            mlp_layer_fwd_kernel<0, 64, 256><<<blocks, 256, smem, st>>>(a);
-        }
+        // two co-resident CTAs per SM (measured 0.447 -> 0.416 ms against one)
+        blocks = 2 * sm_count();
+        if (n_tiles < blocks) blocks = (int)n_tiles;
+        KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<0, 64, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mlp_layer_fwd_kernel<0, 64, 256, 2><<<blocks, 256, smem, st>>>(a);
     } else {
         const int smem = MlpSmem<128>::TOTAL;
         KDF_CUDA(cudaFuncSetAttribute(mlp_layer_fwd_kernel<1, 128, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1682,15 +1330,9 @@ int kdf_mlp_eval3_fwd(const float *points, int64_t M, const float *q, const floa
     const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
     int blocks = sm_count();
     if (n_tiles < blocks) blocks = (int)n_tiles;
-    static const int nt = getenv("KDF_MLP_EVAL_THREADS") ? atoi(getenv("KDF_MLP_EVAL_THREADS")) : 256;    // tuning knob
     const int smem = MlpEvalSmem::TOTAL;
-    if (nt == 256) {
-        KDF_CUDA(cudaFuncSetAttribute(mlp_eval3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_eval3_kernel<256><<<blocks, 256, smem, st>>>(a);
-    } else {
-        KDF_CUDA(cudaFuncSetAttribute(mlp_eval3_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mlp_eval3_kernel<512><<<blocks, 512, smem, st>>>(a);
-    }
+    KDF_CUDA(cudaFuncSetAttribute(mlp_eval3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_eval3_kernel<256><<<blocks, 256, smem, st>>>(a);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }
@@ -1716,25 +1358,11 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
     const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
     int blocks = sm_count();
     if (n_tiles < blocks) blocks = (int)n_tiles;
-    static const bool no_tma = getenv("KDF_MLP_NO_TMA") != nullptr;                  // experiment knob: register-staged mode-0 backward
+    // mode 0: TMA-staged kernel; the register-staged one serves callers that mask rows by cell id (row_cell)
     CUtensorMap tm_dy, tm_z;
-    if (mode == 0 && !no_tma && row_cell == nullptr && tma::make_row_map(&tm_dy, dy, M, PM_N) && tma::make_row_map(&tm_z, z, M, PM_N)) {
+    if (mode == 0 && row_cell == nullptr && tma::make_row_map(&tm_dy, dy, M, PM_N) && tma::make_row_map(&tm_z, z, M, PM_N)) {
         KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd0_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpBwd0TmaSmem::TOTAL));
         mlp_layer_bwd0_tma_kernel<<<blocks, B0T_THREADS, MlpBwd0TmaSmem::TOTAL, st>>>(a, tm_dy, tm_z);
-        KDF_LAUNCH_CHECK();
-        return KDF_OK;
-    }
-    static const bool warp_spec = getenv("KDF_MLP_WARP_SPECIALISED") != nullptr;   // experiment knob (measured slower: 1.64 / 1.90 ms
-    if (warp_spec) {                                                                 // against 1.48 / 1.38 ms)
-        if (mode == 0) {
-            const int smem = MlpBwdWsSmem<64>::TOTAL;
-            KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_ws_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            mlp_layer_bwd_ws_kernel<0, 64><<<blocks, WS_THREADS, smem, st>>>(a);
-        } else {
-            const int smem = MlpBwdWsSmem<128>::TOTAL;
-            KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_ws_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            mlp_layer_bwd_ws_kernel<1, 128><<<blocks, WS_THREADS, smem, st>>>(a);
-        }
         KDF_LAUNCH_CHECK();
         return KDF_OK;
     }

@@ -465,136 +465,6 @@ rowbn_bwd_coop_kernel(ReduceArgs a, T *__restrict__ dx) {
     }
 }
 
-// Training-mode forward as ONE cooperative kernel: column sums of x and x^2, grid barrier, statistics -> scale / shift
-// (every CTA; CTA 0 publishes them and advances the running statistics), apply (+activation, +residual).
-// Same arithmetic as rowbn_reduce_kernel<MODE 0> + rowbn_apply_fwd_kernel.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
-rowbn_fwd_coop_kernel(ReduceArgs a, const T *__restrict__ res, T *__restrict__ y) {
-    extern __shared__ float sm[];                     // phase 1: [rows][G][2*VEC]; phase 2: scale, shift [2][C]
-    const RowMap m = row_map<VEC>(a.C);
-    const T *x = reinterpret_cast<const T *>(a.x);
-    const int c = m.g * VEC;
-    const int64_t stride = (int64_t)gridDim.x * m.rows;
-    constexpr int U = 4;
-    using IO = VecIO<T, VEC>;
-    {
-        float s0[VEC], s1[VEC];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) { s0[q] = 0.f; s1[q] = 0.f; }
-        if (m.active) {
-            for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < a.M; row += stride * U) {
-                typename IO::Raw xr[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int64_t rr = row + u * stride;
-                    if (rr < a.M) xr[u] = *reinterpret_cast<const typename IO::Raw *>(x + rr * a.C + c);   // L2-allocating
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (row + u * stride < a.M) {
-                        float xv[VEC];
-                        IO::unpack(xr[u], xv);
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) { s0[q] += xv[q]; s1[q] = fmaf(xv[q], xv[q], s1[q]); }
-                    }
-                }
-            }
-            float *dst = sm + (m.r * m.G + m.g) * 2 * VEC;
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) { dst[q] = s0[q]; dst[VEC + q] = s1[q]; }
-        }
-        __syncthreads();
-        double *acc0 = reinterpret_cast<double *>(a.ws + 1);
-        double *acc = acc0 + (size_t)(blockIdx.x % RB_COPIES) * 2 * a.C;
-        if (m.active && m.r == 0) {
-            for (int rr = 1; rr < m.rows; ++rr) {
-                const float *src = sm + (rr * m.G + m.g) * 2 * VEC;
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) { s0[q] += src[q]; s1[q] += src[VEC + q]; }
-            }
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) {
-                atomicAdd(acc + m.g * VEC + q, (double)s0[q]);
-                atomicAdd(acc + a.C + m.g * VEC + q, (double)s1[q]);
-            }
-        }
-    }
-    __threadfence();
-    cooperative_groups::this_grid().sync();
-    float *csc = sm, *csh = sm + a.C;
-    {
-        const double *acc0 = reinterpret_cast<const double *>(a.ws + 1);
-        const double invM = 1.0 / (double)a.M;
-        for (int ch = threadIdx.x; ch < a.C; ch += RB_THREADS) {
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < RB_COPIES; ++k) {
-                t0 += __ldcg(acc0 + (size_t)k * 2 * a.C + ch);
-                t1 += __ldcg(acc0 + (size_t)k * 2 * a.C + a.C + ch);
-            }
-            const double mean = t0 * invM;
-            double var = t1 * invM - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
-            const float scl = (a.gamma ? a.gamma[ch] : 1.f) * invstd;
-            const float shf = (a.beta ? a.beta[ch] : 0.f) - (float)mean * scl;
-            csc[ch] = scl; csh[ch] = shf;
-            if (blockIdx.x == 0) {
-                a.mean[ch] = (float)mean;
-                a.invstd[ch] = invstd;
-                a.out_scale[ch] = scl;
-                a.out_shift[ch] = shf;
-                if (a.running_mean) {
-                    const double unb = a.M > 1 ? var * ((double)a.M / (double)(a.M - 1)) : var;
-                    const float bias = a.pre_bias ? a.pre_bias[ch] : 0.f;
-                    a.running_mean[ch] = (1.f - a.momentum) * a.running_mean[ch] + a.momentum * ((float)mean + bias);
-                    a.running_var[ch] = (1.f - a.momentum) * a.running_var[ch] + a.momentum * (float)unb;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (!m.active) return;
-    for (int64_t row = (int64_t)blockIdx.x * m.rows + m.r; row < a.M; row += stride * U) {
-        typename IO::Raw xr[U], rr_[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t rr = row + u * stride;
-            if (rr < a.M) {
-                xr[u] = IO::load(x + rr * a.C + c);
-                if (res) rr_[u] = IO::load(res + rr * a.C + c);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t rr = row + u * stride;
-            if (rr < a.M) {
-                float xv[VEC], rv[VEC], o[VEC], vsc[VEC], vsh[VEC];
-                IO::unpack(xr[u], xv);
-                if (res) IO::unpack(rr_[u], rv);
-                ld_coef<VEC>(csc + c, vsc); ld_coef<VEC>(csh + c, vsh);
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) {
-                    o[q] = act_fwd(fmaf(xv[q], vsc[q], vsh[q]), a.act);
-                    if (res) o[q] += rv[q];
-                }
-                IO::store(y + rr * a.C + c, o);
-            }
-        }
-    }
-}
-
-template <typename T, int VEC>
-static int launch_fwd_coop(ReduceArgs a, const void *res, void *y, int blocks, size_t smem, cudaStream_t st) {
-    const T *rp = reinterpret_cast<const T *>(res);
-    T *yp = reinterpret_cast<T *>(y);
-    void *args[] = {&a, &rp, &yp};
-    KDF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&rowbn_fwd_coop_kernel<T, VEC>), dim3(blocks), dim3(RB_THREADS),
-                                         args, smem, st));
-    return KDF_OK;
-}
-
 template <typename T, int VEC>
 static int launch_bwd_coop(ReduceArgs a, void *dx, int blocks, size_t smem, cudaStream_t st) {
     T *dxp = reinterpret_cast<T *>(dx);
@@ -630,9 +500,7 @@ static int launch_reduce(const ReduceArgs &a, int dtype, cudaStream_t st) {
     const int vec = rb_vec(dtype, a.C);
     // every CTA ends with 2C fp64 atomics on the same 2C addresses: the grid is capped (measured: more, smaller CTAs
     // lose more to the serialised atomics than they gain in latency hiding)
-    static const int cap = getenv("KDF_ROWBN_REDUCE_CAP") ? atoi(getenv("KDF_ROWBN_REDUCE_CAP")) : 2 * sm_count();      // tuning knob
-    static const int ptr_ = getenv("KDF_ROWBN_REDUCE_ROWS") ? atoi(getenv("KDF_ROWBN_REDUCE_ROWS")) : 16;
-    const int blocks = rb_blocks(a.M, a.C, vec, ptr_, cap);
+    const int blocks = rb_blocks(a.M, a.C, vec, 16, 2 * sm_count());
     const int rows = RB_THREADS / (a.C / vec);
     const size_t smem = sizeof(float) * (size_t)rows * (a.C / vec) * 2 * vec;
     KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * RB_COPIES * (size_t)a.C, st));
@@ -717,38 +585,6 @@ int kdf_rowbn_apply_fwd(const void *x, const void *residual, int dtype, int64_t 
     return KDF_OK;
 }
 
-int kdf_rowbn_fwd_train(const void *x, const void *residual, int dtype, int64_t M, int C, const float *gamma, const float *beta,
-                        const float *pre_bias, float eps, float momentum, float *running_mean, float *running_var,
-                        float *mean, float *invstd, float *scale, float *shift, int act, void *y, void *workspace, void *stream) {
-    if (int e = rb_check(dtype, M, C, "rowbn_fwd_train")) return e;
-    KDF_CHECK_ARG(act >= 0 && act <= 2, "rowbn_fwd_train: bad activation %d", act);
-    KDF_CHECK_ARG(M > 0, "rowbn_fwd_train: batch statistics need at least one row");
-    KDF_CHECK_ARG(x && y && mean && invstd && scale && shift && workspace, "rowbn_fwd_train: null pointer");
-    KDF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "rowbn_fwd_train: running stats come in pairs");
-    static const long coop_mb = getenv("KDF_ROWBN_COOP_MB") ? atol(getenv("KDF_ROWBN_COOP_MB")) : 250;
-    const size_t in_bytes = (size_t)M * C * (dtype == KDF_F32 ? 4 : 2) * (residual ? 2 : 1);
-    if (coop_mb > 0 && in_bytes <= (size_t)coop_mb << 19) {                // half the backward's budget: one input tensor (+ residual)
-        cudaStream_t st = as_stream(stream);
-        ReduceArgs a{};
-        a.x = x; a.M = M; a.C = C; a.act = act; a.gamma = gamma; a.beta = beta; a.pre_bias = pre_bias; a.eps = eps; a.momentum = momentum;
-        a.mean = mean; a.invstd = invstd; a.out_scale = scale; a.out_shift = shift;
-        a.running_mean = running_mean; a.running_var = running_var;
-        a.ws = reinterpret_cast<RowBnWs *>(workspace);
-        const int vec = rb_vec(dtype, C);
-        const int rows = RB_THREADS / (C / vec);
-        size_t smem = sizeof(float) * (size_t)rows * (C / vec) * 2 * vec;
-        if (smem < sizeof(float) * 2 * (size_t)C) smem = sizeof(float) * 2 * (size_t)C;
-        const int cblocks = rb_blocks(M, C, vec, 4, 2 * sm_count());
-        KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * RB_COPIES * (size_t)C, st));
-        if (dtype == KDF_F32) return launch_fwd_coop<float, 4>(a, residual, y, cblocks, smem, st);
-        if (vec == 8) return launch_fwd_coop<__nv_bfloat16, 8>(a, residual, y, cblocks, smem, st);
-        return launch_fwd_coop<__nv_bfloat16, 4>(a, residual, y, cblocks, smem, st);
-    }
-    if (int e = kdf_rowbn_stats(x, dtype, M, C, gamma, beta, pre_bias, eps, momentum, running_mean, running_var, mean, invstd, scale,
-                                shift, workspace, stream)) return e;
-    return kdf_rowbn_apply_fwd(x, residual, dtype, M, C, scale, shift, act, y, stream);
-}
-
 int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int C,
                   const float *scale, const float *shift, const float *mean, const float *invstd,
                   int act, int batch_stats, void *grad_x, float *dgamma, float *dbeta,
@@ -768,9 +604,9 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
     a.dgamma = dgamma; a.dbeta = dbeta; a.coefA = coefA; a.coefB = coefB;
     a.ws = reinterpret_cast<RowBnWs *>(workspace);
     const int vec = rb_vec(dtype, C);
-    // one cooperative kernel (reduce, grid barrier, apply) up to KDF_ROWBN_COOP_MB of input; measured in the step
-    // (B=32): 0 MB 12.02 ms, 72 MB 12.00 ms, 250 MB 11.88 ms (all but the 2 x 201 MB expand BatchNorm of stage 2)
-    static const long coop_mb = getenv("KDF_ROWBN_COOP_MB") ? atol(getenv("KDF_ROWBN_COOP_MB")) : 250;       // 0 disables
+    // one cooperative kernel (reduce, grid barrier, apply) up to 250 MB of input; measured in the step (B=32): never
+    // 12.02 ms, up to 72 MB 12.00 ms, up to 250 MB 11.88 ms (all but the 2 x 201 MB expand BatchNorm of stage 2)
+    constexpr long coop_mb = 250;
     const size_t in_bytes = 2 * (size_t)M * C * (dtype == KDF_F32 ? 4 : 2);
     if (coop_mb > 0 && in_bytes <= (size_t)coop_mb << 20) {
         const int rows = RB_THREADS / (C / vec);

@@ -263,33 +263,10 @@ class CompleteSegmentationModel(nn.Module):
             raise ValueError(f"Unknown output_mode: {output_mode}")
         self.head = _HEADS[output_mode](in_channels=head_in, num_classes=num_classes)
 
-    # The two encoders do not depend on each other until the fusion: with ``branch_streams`` set (the Trainer does it) the
-    # LiDAR encoder runs on a side stream, forward AND backward (autograd replays an op on the stream of its forward), so
-    # the camera branch's chains of small kernels fill the SMs next to the LiDAR branch's few long ones.
-    branch_streams = False
-
-    def _lidar_side_stream(self, device):
-        st = getattr(self, "_lidar_stream", None)
-        if st is None or st.device != device:
-            st = torch.cuda.Stream(device)
-            object.__setattr__(self, "_lidar_stream", st)
-        return st
-
     def forward(self, images: torch.Tensor, points: torch.Tensor, return_intermediates: bool = False):
-        if self.branch_streams and points.is_cuda and images.is_cuda:
-            main = torch.cuda.current_stream(points.device)
-            side = self._lidar_side_stream(points.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                lidar_feat = self.lidar_encoder(points)
-            cam = self.camera_encoder(images)
-            cam_feat = self.camera_fpn(cam) if isinstance(cam, dict) else cam
-            main.wait_stream(side)
-            lidar_feat.record_stream(main)
-        else:
-            cam = self.camera_encoder(images)
-            cam_feat = self.camera_fpn(cam) if isinstance(cam, dict) else cam
-            lidar_feat = self.lidar_encoder(points)
+        cam = self.camera_encoder(images)
+        cam_feat = self.camera_fpn(cam) if isinstance(cam, dict) else cam
+        lidar_feat = self.lidar_encoder(points)
         if cam_feat.shape[-2:] != lidar_feat.shape[-2:]:
             lidar_feat = F.interpolate(lidar_feat, size=cam_feat.shape[-2:], mode="bilinear", align_corners=False)
         if lidar_feat.dtype != cam_feat.dtype:

@@ -6,8 +6,6 @@ only -- there is no CPU path.
 """
 from __future__ import annotations
 
-import os
-
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -24,31 +22,17 @@ __all__ = [
 
 # ----------------------------------------------------------------------------- BatchNorm (+act) over rows
 _ACT = {None: 0, "none": 0, "relu": 1, "relu6": 2}
-# Training-mode forward as one cooperative kernel (kdf_rowbn_fwd_train) instead of statistics + apply: measured in the
-# step (B=32) 12.03 ms against 11.88 ms -- the student's forward shares the GPU with the teacher's side stream, and a
-# cooperative grid waits for every SM; the backward (nothing else running) does gain from the same fusion.  Off by default.
-_FWD_FUSED = os.environ.get("KDF_ROWBN_FWD_FUSED") == "1"
-
-
 class _RowBNActFn(torch.autograd.Function):
     """y = act(x*scale + shift) [+ residual] over rows [M,C]; scale/shift/mean/invstd are the fp32
     per-channel vectors prepared by ``bn_act`` (batch statistics in training, running statistics in
     eval).  Backward = kdf_rowbn_bwd (reduce + apply, chaining through the batch statistics)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, mean, invstd, act, batch_stats, residual, pre_bias, train=None):
+    def forward(ctx, x, gamma, beta, scale, shift, mean, invstd, act, batch_stats, residual, pre_bias):
         M, C = x.shape
         y = torch.empty_like(x)
-        if train is not None:
-            # batch statistics and apply in one call (one cooperative kernel while the tensor stays in L2): fills
-            # scale / shift / mean / invstd and advances the running statistics
-            eps, mom, rmean, rvar, pb = train
-            ws = torch.empty(lib.kdf_rowbn_workspace_bytes(C), dtype=torch.uint8, device=x.device)
-            call("kdf_rowbn_fwd_train", ptr(x), ptr(residual), dtype_code(x), M, C, ptr(gamma), ptr(beta), ptr(pb), eps, mom,
-                 ptr(rmean), ptr(rvar), ptr(mean), ptr(invstd), ptr(scale), ptr(shift), act, ptr(y), ptr(ws), stream_ptr(x.device))
-        else:
-            call("kdf_rowbn_apply_fwd", ptr(x), ptr(residual), dtype_code(x), M, C, ptr(scale), ptr(shift), act, ptr(y),
-                 stream_ptr(x.device))
+        call("kdf_rowbn_apply_fwd", ptr(x), ptr(residual), dtype_code(x), M, C, ptr(scale), ptr(shift), act, ptr(y),
+             stream_ptr(x.device))
         ctx.save_for_backward(x, scale, shift, mean, invstd)
         ctx.act, ctx.batch_stats = act, batch_stats
         ctx.has_res = residual is not None
@@ -75,7 +59,7 @@ class _RowBNActFn(torch.autograd.Function):
             # b acts like a shift in front of the scale
             dbias = torch.zeros_like(dbeta) if ctx.batch_stats else dbeta * scale
         return (dx, dgamma if ctx.affine[0] else None, dbeta if ctx.affine[1] else None,
-                None, None, None, None, None, None, g if ctx.has_res else None, dbias, None)
+                None, None, None, None, None, None, g if ctx.has_res else None, dbias)
 
 
 def _eval_affine(bn, pre_bias=None):
@@ -151,20 +135,6 @@ def bn_act(x: torch.Tensor, bn, act: Optional[str] = None, residual: Optional[to
             mean, invstd, scale, shift = bn_finalize(col_sums, rows.shape[0], bn,
                                                      pre_bias.detach().float().contiguous() if pre_bias is not None else None, track)
         use_batch = True
-    elif (bn.training or bn.running_mean is None) and _FWD_FUSED:
-        # batch statistics + apply fused (kdf_rowbn_fwd_train); the autograd function fills the per-channel vectors
-        f32 = dict(dtype=torch.float32, device=dev)
-        C_ = rows.shape[1]
-        mean, invstd, scale, shift = (torch.empty(C_, **f32) for _ in range(4))
-        track = bn.training and bn.track_running_stats and bn.running_mean is not None
-        mom = 0.0
-        if track:
-            mom = _n.bump_batch_counter(bn)
-        train = (float(bn.eps), float(mom), bn.running_mean if track else None, bn.running_var if track else None,
-                 pre_bias.detach().float().contiguous() if pre_bias is not None else None)
-        use_batch = True
-        y = _RowBNActFn.apply(rows, bn.weight, bn.bias, scale, shift, mean, invstd, _ACT[act], use_batch, res, pre_bias, train)
-        return y.view(B, H, W, C).permute(0, 3, 1, 2) if four_d else y
     else:
         scale, shift, mean, invstd, use_batch = _bn_prepare(rows, bn, pre_bias)
     y = _RowBNActFn.apply(rows, bn.weight, bn.bias, scale, shift, mean, invstd, _ACT[act], use_batch, res, pre_bias)
@@ -333,7 +303,7 @@ def _pw_usable(conv, x: torch.Tensor) -> bool:
     if not (_is_pw_conv(conv) and x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and _nhwc_rows(x) is not None):
         return False
     B, C, H, W = x.shape
-    return pw_conv_supported(conv.in_channels, conv.out_channels, B * H * W) and os.environ.get("KDF_NO_PW_CONV") is None
+    return pw_conv_supported(conv.in_channels, conv.out_channels, B * H * W)
 
 
 def pw_project_rows(conv, bn, rows: torch.Tensor):
@@ -344,7 +314,7 @@ def pw_project_rows(conv, bn, rows: torch.Tensor):
     M, K = rows.shape
     N = conv.out_channels
     if (rows.is_cuda and rows.dtype == torch.bfloat16 and conv.bias is None and _is_pw_conv(conv) and bn.training
-            and torch.is_grad_enabled() and pw_conv_supported(K, N, M) and os.environ.get("KDF_NO_PW_CONV") is None):
+            and torch.is_grad_enabled() and pw_conv_supported(K, N, M)):
         pack = _pw_pack_factor(K, N)
         return _PwConvFn.apply(rows.contiguous(), conv.weight, _pw_weight_cached(conv, pack), pack)
     return F.linear(rows, conv.weight.flatten(1), conv.bias), None

@@ -18,7 +18,6 @@ math and every statistic stay fp32/fp64.  The per-channel coefficient algebra be
 """
 from __future__ import annotations
 
-import os
 import weakref
 
 import torch
@@ -209,7 +208,7 @@ class _FusedLidarFn(torch.autograd.Function):
             q, r = _eval_first_layer(bn1, w1, b1)
 
         # ---- layers 2 and 3 on the tensor cores
-        if not batch and not need_grad and os.environ.get("KDF_MLP_NO_EVAL3") is None:
+        if not batch and not need_grad:
             # running statistics: nothing separates the layers -> one kernel, z2 never leaves the SM
             from .ops import _eval_affine
             scale2, shift2, _, _ = _eval_affine(bn2, b2.detach())

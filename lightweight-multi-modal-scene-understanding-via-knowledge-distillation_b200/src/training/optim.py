@@ -95,20 +95,33 @@ class FlatAdamW(torch.optim.Optimizer):
             p.grad = None
 
     @torch.no_grad()
-    def gather_grads_(self):
+    def gather_grads_(self, indices=None):
         """flat_grad <- the gradients autograd produced since ``detach_grads`` (zeros where a parameter got none);
-        ``p.grad`` are views of ``flat_grad`` again afterwards."""
+        ``p.grad`` are views of ``flat_grad`` again afterwards.  ``indices`` restricts the move to those parameters
+        (the Trainer gathers and all-reduces the early-arriving bucket while the rest of the backward still runs)."""
         srcs, dsts = [], []
-        for p, off in zip(self._params, self._offsets):
+        it = range(len(self._params)) if indices is None else indices
+        for i in it:
+            p, off = self._params[i], self._offsets[i]
             view = self.flat_grad[off:off + p.numel()].view(p.shape)
             if p.grad is None:
                 view.zero_()
-            else:
+            elif p.grad.data_ptr() != view.data_ptr():
                 srcs.append(p.grad if p.grad.dtype == torch.float32 else p.grad.float())
                 dsts.append(view)
             p.grad = view
         if srcs:
             torch._foreach_copy_(dsts, srcs)
+
+    def span(self, indices):
+        """(lo, hi) element range of ``flat_grad`` that exactly covers the parameters ``indices`` when they are
+        consecutive in the flat layout (padding included), else None."""
+        idx = sorted(indices)
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            return None
+        lo = self._offsets[idx[0]]
+        hi = self._offsets[idx[-1] + 1] if idx[-1] + 1 < len(self._offsets) else self.flat_grad.numel()
+        return lo, hi
 
     def set_hyper(self, lr: float, step: int):
         """Device-side (lr, step); called by step(), or by the caller before replaying a captured graph."""

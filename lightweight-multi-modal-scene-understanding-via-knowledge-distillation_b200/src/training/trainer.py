@@ -116,7 +116,8 @@ class Trainer:
                  teacher: Optional[nn.Module] = None, kd_temperature: float = 4.0,
                  kd_alpha: float = 0.5, kd_beta: float = 1.0,
                  amp_dtype: Optional[torch.dtype] = None, verbose: bool = True,
-                 use_cuda_graph: bool = False, graph_warmup_steps: int = 3, overlap_teacher: bool = True):
+                 use_cuda_graph: bool = False, graph_warmup_steps: int = 3, overlap_teacher: bool = True,
+                 overlap_allreduce: bool = True):
         self.model = model
         self.train_loader = train_loader
         self.val_loader = val_loader
@@ -156,15 +157,10 @@ class Trainer:
         # ~800 launches of mostly small kernels, so at B200 speeds the host cannot issue them fast enough
         self.overlap_teacher = overlap_teacher and teacher is not None
         self._side = None
-        # LiDAR and camera encoders of a model on two streams (KDF_BRANCH_STREAMS: 0 off, 1 student, 2 student + teacher).
-        # Measured on B200 (B=32, N=170k): 12.04 / 12.02 / 12.05 ms per step -- the LiDAR branch's persistent kernels hold
-        # every SM's registers, so the camera kernels cannot co-reside; off by default.
-        import os as _os
-        bs = int(_os.environ.get("KDF_BRANCH_STREAMS", "0"))
-        if hasattr(model, "branch_streams") and torch.device(device).type == "cuda":
-            model.branch_streams = bs >= 1
-            if teacher is not None and hasattr(teacher, "branch_streams"):
-                teacher.branch_streams = bs >= 2
+        self.overlap_allreduce = overlap_allreduce and self.world_size > 1
+        self._plan, self._arrival, self._order_hooks = None, None, []
+        self._overlap_armed = self._overlap_fired = False
+        self._comm_stream = None
         self.use_cuda_graph = use_cuda_graph
         self.graph_warmup_steps = graph_warmup_steps
         # one captured graph per input shape (the last, partial batch of an epoch gets its own instead of evicting the
@@ -235,11 +231,80 @@ class Trainer:
         terms, d_logits, d_feats = ops.kd_loss_fwd_bwd(
             logits, t_logits, seg, self.class_weights, s_feats, t_feats,
             T=self.kd_temperature, alpha=alpha, beta=beta, ignore_index=-1)
+        plan = self._overlap_plan() if self.world_size > 1 else None
+        if plan is not None:
+            self._overlap_armed = True
         torch.autograd.backward([logits] + list(s_feats), [d_logits] + list(d_feats))
-        self.optimizer.gather_grads_()                                  # one multi-tensor copy into the flat bucket
-        allreduce_gradients_(self.optimizer.flat_grad)                  # one flat NCCL bucket (no-op at world 1)
+        if plan is not None and self._overlap_fired:
+            # the early bucket is already being reduced on the communication stream (launched from the sentinel
+            # parameter's hook while the rest of the backward ran): only the late, small bucket is left
+            self._overlap_armed = self._overlap_fired = False
+            self.optimizer.gather_grads_(plan["late"])
+            lo, hi = plan["late_span"]
+            allreduce_gradients_(self.optimizer.flat_grad[lo:hi])
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        else:
+            self._overlap_armed = False
+            self.optimizer.gather_grads_()                              # one multi-tensor copy into the flat bucket
+            allreduce_gradients_(self.optimizer.flat_grad)              # one flat NCCL bucket (no-op at world 1)
         self.optimizer.step(grad_scale=1.0 / self.world_size, update_hyper=update_hyper)
         return terms, logits.detach()
+
+    # ------------------------------------------------------------------ gradient all-reduce overlapped with the backward
+    # The flat bucket is latency-bound (2.1 MB), so what matters is WHEN it is launched, not how it is split: the first
+    # data-parallel step records the order in which the parameters' gradients arrive; the parameters whose gradients
+    # arrive last (the first layers of the camera encoder, at most ``overlap_tail_bytes``) form the late bucket, all
+    # others the early one.  From then on a hook on the early bucket's last-arriving parameter gathers that bucket and
+    # launches its all-reduce on a communication stream -- a parallel branch of the captured step graph -- while the
+    # backward of the remaining layers runs; after the backward only the small late bucket is reduced in line.
+    overlap_tail_bytes = 96 * 1024
+
+    def _overlap_plan(self):
+        if not self.overlap_allreduce:
+            return None
+        if self._plan is not None:
+            return self._plan or None
+        opt = self.optimizer
+        if self._arrival is None:                                      # first step: record the arrival order
+            self._arrival = []
+            self._order_hooks = [p.register_post_accumulate_grad_hook(lambda _p, i=i: self._arrival.append(i))
+                                 for i, p in enumerate(opt._params)]
+            return None
+        for h in self._order_hooks:
+            h.remove()
+        self._order_hooks = []
+        order, late, acc = self._arrival, [], 0
+        for i in reversed(order):
+            nbytes = opt._params[i].numel() * 4
+            if acc + nbytes > self.overlap_tail_bytes:
+                break
+            late.append(i)
+            acc += nbytes
+        never = [i for i in range(len(opt._params)) if i not in set(order)]      # parameters that get no gradient
+        early = [i for i in order if i not in set(late)]
+        late_all = late + never
+        e_span, l_span = opt.span(early), opt.span(late_all) if late_all else None
+        if not early or not late_all or e_span is None or l_span is None:
+            self._plan = {}                                            # buckets not contiguous in the flat layout: one bucket
+            return None
+        sentinel = early[-1]                                           # the early bucket is complete when this gradient lands
+        self._plan = {"early": early, "late": late_all, "early_span": e_span, "late_span": l_span, "sentinel": sentinel}
+        self._comm_stream = torch.cuda.Stream(self.device)
+        opt._params[sentinel].register_post_accumulate_grad_hook(self._launch_early_bucket)
+        return self._plan
+
+    def _launch_early_bucket(self, _param):
+        if not self._overlap_armed or self._overlap_fired:
+            return
+        plan = self._plan
+        with torch.no_grad():
+            self.optimizer.gather_grads_(plan["early"])
+            here = torch.cuda.current_stream(self.device)
+            self._comm_stream.wait_stream(here)
+            lo, hi = plan["early_span"]
+            with torch.cuda.stream(self._comm_stream):
+                allreduce_gradients_(self.optimizer.flat_grad[lo:hi])
+        self._overlap_fired = True
 
     def _side_stream(self):
         if not self.overlap_teacher:

@@ -83,7 +83,28 @@ def main():
     moved = (parts[0] - gathered(opt.exp_avg)[0]).abs().max().item()
     assert moved > 0
 
-    # 4. clean teardown with a captured all-reduce alive until now
+    # 4. the overlapped two-bucket all-reduce (early bucket launched from the sentinel parameter's hook on a communication
+    #    stream, late bucket in line) gives the same parameters as the single in-line bucket
+    assert tr._plan and tr._plan["late_span"][0] == 0 and tr._plan["early_span"][1] == opt.flat_grad.numel(), tr._plan
+    assert tr._plan["late_span"][1] == tr._plan["early_span"][0] and 0 < tr._plan["late_span"][1] * 4 <= tr.overlap_tail_bytes + 64
+    import copy
+    pair = []
+    for overlap in (True, False):
+        torch.manual_seed(7)
+        s2 = make("weighted", 128)
+        t2 = Trainer(s2, [], [], dev, class_weights=[0.4, 3.5], save_dir=os.path.join(sys.argv[1], f"o{rank}{overlap}"), teacher=teacher,
+                     verbose=False, amp_dtype=None, use_cuda_graph=False, overlap_allreduce=overlap)
+        s2.train()
+        theta0 = t2.optimizer.flat_param.clone()
+        for i in range(3):
+            b = make_frames(2, 3000, seed=1000 * rank + 30 + i, device=dev)
+            t2.training_step(b["image"], b["points"], b["segmentation"])
+        assert bool(t2._plan) == overlap
+        pair.append(t2.optimizer.flat_param - theta0)
+    err = ((pair[0] - pair[1]).double().norm() / pair[1].double().norm()).item()
+    assert err < 2e-2, f"overlapped all-reduce changes the update: {err}"
+
+    # 5. clean teardown with a captured all-reduce alive until now
     torch.cuda.synchronize()
     dist.barrier()
     tr.release_graphs()

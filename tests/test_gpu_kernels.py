@@ -482,34 +482,6 @@ def test_rowbn_fp32_vs_torch_batchnorm(ops, C, act, train, residual):
     assert bn_cuda.num_batches_tracked.item() == bn_ref.num_batches_tracked.item()
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("residual", [False, True])
-def test_rowbn_train_forward_one_call_matches_two_kernels(ops, dtype, residual, monkeypatch):
-    """kdf_rowbn_fwd_train (statistics + apply in one cooperative kernel; KDF_ROWBN_FWD_FUSED=1) against the
-    statistics kernel followed by the apply kernel: outputs, statistics, running statistics and the backward."""
-    import copy
-    import torch.nn as nn
-    C, M = 192, 3 * 20 * 28
-    g = torch.Generator().manual_seed(3)
-    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(dtype).cuda()
-    res = torch.randn(M, C, generator=g).to(dtype).cuda() if residual else None
-    gout = torch.randn(M, C, generator=g).to(dtype).cuda()
-    bn = nn.BatchNorm2d(C).cuda().train()
-    with torch.no_grad():
-        bn.weight.copy_(torch.rand(C) + 0.5); bn.bias.copy_(torch.randn(C) * 0.2)
-    outs = []
-    for fused in (False, True):
-        monkeypatch.setattr(ops, "_FWD_FUSED", fused)
-        b = copy.deepcopy(bn)
-        xi = x.clone().requires_grad_(True)
-        y = ops.bn_act(xi, b, "relu6", res)
-        y.backward(gout)
-        outs.append((y.detach().float(), xi.grad.float(), b.weight.grad, b.bias.grad, b.running_mean, b.running_var))
-    tol = 1e-6 if dtype == torch.float32 else 1e-2
-    for a, b_ in zip(*outs):
-        assert rel_err(a.cpu(), b_.cpu()) < tol
-
-
 def test_rowbn_rows_bf16_and_large_m(ops):
     """2-D rows (the point MLP case), bf16 storage with fp32 statistics: stated tolerance 1e-2 relative
     against fp32 BatchNorm1d+ReLU on the bf16-rounded input; M large enough for several CTAs per column."""

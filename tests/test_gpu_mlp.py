@@ -57,12 +57,11 @@ def test_mlp_layer_fwd_mode0_first_layer_recomputed(M):
 
 
 @pytest.mark.parametrize("M", [1, 129, 5000, 128 * 148 * 3 + 17, 32 * 170_000])
-@pytest.mark.parametrize("threads", ["256", "512"])
-def test_mlp_eval3_bit_identical_to_layer_kernels(M, threads, monkeypatch):
+def test_mlp_eval3_bit_identical_to_layer_kernels(M):
     """The one-kernel eval-mode MLP (running statistics; z2 stays on the SM) against kdf_mlp_layer_fwd mode 0
     followed by mode 1: the same operations in the same order, so the pre-BatchNorm-3 rows must be bit-identical."""
     import subprocess, sys, os, textwrap
-    # the thread count is read once per process: run each variant in its own interpreter
+    # runs in its own interpreter: the largest case allocates 8 GB that the test process would otherwise keep cached
     code = textwrap.dedent(f"""
         import sys, torch
         sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
@@ -86,8 +85,7 @@ def test_mlp_eval3_bit_identical_to_layer_kernels(M, threads, monkeypatch):
         assert z3.float().abs().max() > 0
         print("ok")
     """)
-    env = dict(os.environ, KDF_MLP_EVAL_THREADS=threads)
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
