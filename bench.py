@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap-allreduce", action="store_true",
+                    help="one in-line gradient bucket after the backward instead of the overlapped early + late buckets (N > 1)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the other BASELINE configurations (ablation sweep at batch 64, fp32 step, projection microbench, "
                          "reference on CUDA, strong scaling at global batch 256) that the default run appends as `extras`")
@@ -74,6 +76,9 @@ def workload_config(args, n_gpus):
             "points_per_frame": args.points,
             "parallelism": f"dp{n_gpus}", "loss": "0.5*CE + 0.5*T^2*KL(T=4) + 1.0*MSE(lidar_feat, camera_feat)",
             "optimizer": "AdamW lr 1e-3 wd 1e-3 (flat, one kernel)",
+            "allreduce": ("none (1 GPU)" if n_gpus == 1 else "one in-line flat bucket" if getattr(args, "no_overlap_allreduce", False) else
+                          "flat bucket in two parts: early part launched from a gradient hook on a communication stream while the "
+                          "backward of the first camera stages runs, late part (<= 96 KB) in line"),
             "launch": "eager" if args.no_graph else "whole step replayed as one CUDA graph",
             "l2": "per-step working set (>= 10 GB of activations, 113 MB of inputs) far exceeds the 126 MB L2; no flush"}
 
@@ -216,6 +221,9 @@ class ClockSampler:
 
 
 # ============================================================================= native arm
+OVERLAP_ALLREDUCE = True
+
+
 def build_models(device, fp32, use_graph=False, student_fusion="weighted"):
     from src.models.camera_encoder import TwinLiteEncoder
     from src.models.fusion_module import CompleteSegmentationModel
@@ -232,7 +240,8 @@ def build_models(device, fp32, use_graph=False, student_fusion="weighted"):
     student, teacher = make(student_fusion, 256 if student_fusion == "concat" else 128), make("concat", 256)
     trainer = Trainer(student, [], [], device, lr=1e-3, weight_decay=1e-3, class_weights=CLASS_WEIGHTS,
                       save_dir=os.path.join(ROOT, "gpurun_out", "bench_ckpt"), teacher=teacher,
-                      amp_dtype=None if fp32 else torch.bfloat16, verbose=False, use_cuda_graph=use_graph)
+                      amp_dtype=None if fp32 else torch.bfloat16, verbose=False, use_cuda_graph=use_graph,
+                      overlap_allreduce=OVERLAP_ALLREDUCE)
     student.train()
     return trainer
 
@@ -437,6 +446,8 @@ def run_native(args):
     from src.data_loading.synthetic_frames import make_frames
     from src.training.parallel import frame_seed, reduce_max
 
+    global OVERLAP_ALLREDUCE
+    OVERLAP_ALLREDUCE = not args.no_overlap_allreduce
     trainer = build_models(device, args.fp32, use_graph=not args.no_graph, student_fusion=args.student)
     B, N = args.batch, args.points
     n_data = 3
