@@ -271,11 +271,14 @@ def time_kernel(fn, iters=20, warm=3):
 def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each hand-written kernel at the bench
     shapes, from the committed `ncu --set full` captures (profiles/r01_ncu_traffic.json names the capture files)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-            return json.load(f)["bytes_per_launch"]
-    except Exception:
-        return {}
+    out = {}
+    for name in ("r01_ncu_traffic.json", "r02_ncu_traffic.json"):          # the later capture wins for kernels it covers
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                out.update(json.load(f)["bytes_per_launch"])
+        except Exception:
+            pass
+    return out
 
 
 def kernel_rooflines(args, device, fp32):
@@ -426,7 +429,55 @@ def kernel_rooflines(args, device, fp32):
                     p(taps_s[0]), p(taps_t[0]), p(d_l[0]), taps_s[0].numel(), p(taps_s[1]), p(taps_t[1]), p(d_l[1]),
                     taps_s[1].numel(), native.dtype_code(taps_s[0]), 1.0, p(dz), p(scal), p(kws), st)
     add("kd_loss_kernel (label histogram + loss fwd+bwd)", time_kernel(with_flush(kd)) - t_flush, M * (2 * K * s + 8 + K * s + 2 * 3 * C * s),
-        "per pixel 2K*s + 8 + K*s logits/labels + 3*C*s per mimic tap (2 taps)")
+        "per pixel 2K*s + 8 + K*s logits/labels + 3*C*s per mimic tap (2 taps); the stand-alone call (histogram inside)", in_step=False)
+
+    def kd_count():
+        native.call("kdf_kd_label_count", p(lab), B, K, H * W, -1, p(kws), st)
+
+    def kd_counted():
+        native.call("kdf_kd_loss_fwd_bwd_counted", p(zs), p(zt), p(lab), p(cw), B, K, H * W, native.dtype_code(zs), 4.0, 0.5, 1.0, -1,
+                    p(taps_s[0]), p(taps_t[0]), p(d_l[0]), taps_s[0].numel(), p(taps_s[1]), p(taps_t[1]), p(d_l[1]),
+                    taps_s[1].numel(), native.dtype_code(taps_s[0]), 1.0, p(dz), p(scal), p(kws), st)
+    kd_count()
+
+    t_cnt = time_kernel(with_flush(kd_count)) - t_flush
+
+    def kd_pair():
+        kd_count()
+        kd_counted()
+    t_pair = time_kernel(with_flush(kd_pair)) - t_flush
+    add("kd_loss_kernel (loss fwd+bwd; label histogram taken on the side stream when the batch arrives)", t_pair - t_cnt,
+        M * (2 * K * s + K * s + 2 * 3 * C * s),
+        "per pixel 2K*s + K*s logits + 3*C*s per mimic tap (2 taps); the step's form: kdf_kd_label_count runs next to the "
+        "teacher's forward, kdf_kd_loss_fwd_bwd_counted is what sits between the logits and the backward "
+        "(timed as [count + loss] - [count])")
+    add("kd_label_count (memset + histogram, side stream)", t_cnt, M * 8, "8 B label per pixel", in_step=True)
+    # ---- fused 1x1-convolution layers of the camera branch (tcgen05 + TMA): three representative layers and the sum over all
+    #      seventeen layers of the student's forward (tools/pw_conv_bench.py lists each)
+    if not fp32:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import pw_conv_bench as pwb
+        scale_m = B / 32.0
+        tot_ms, tot_bytes = 0.0, 0
+        named = {"stage2 expand": "pw_conv_fwd stage2 expand 32->192 @128x128 (rows + statistics)",
+                 "stage3 project": "pw_conv_fwd stage3 project 384->64 @64x64 (BN+ReLU6 prologue, rows + statistics)",
+                 "fpn post / fusion proj": "pw_conv_fwd fpn post 128->128 @64x64 (BN+ReLU prologue, rows + statistics)"}
+        for lname, Mp, Kp, Np, pro in pwb.LAYERS[:14]:
+            Mp = int(Mp * scale_m)
+            x = torch.randn(Mp, Kp, device=device).to(torch.bfloat16)
+            wq = torch.randn(Np, Kp, device=device) * (2.0 / Kp) ** 0.5
+            pack = ops._pw_pack_factor(Kp, Np)
+            wb = ops.pw_conv_weight(wq, pack)
+            psc, psh = torch.rand(Kp, **f32) + 0.5, torch.randn(Kp, **f32) * 0.1
+            ms_l = time_kernel(with_flush(lambda: ops.pw_conv_fwd(x, wb, pack, pro=(psc, psh, 2) if pro else None, want_stats=True))) - t_flush
+            reps = {"fpn lateral4": 2, "fpn post / fusion proj": 3}.get(lname, 1)      # shapes that occur more than once in the network
+            tot_ms += ms_l * reps
+            tot_bytes += Mp * (Kp + Np) * 2 * reps
+            if lname in named:
+                add(named[lname], ms_l, Mp * (Kp + Np) * 2, "rows in + rows out, once (K*s + N*s per pixel row); L2 flushed between launches")
+            del x
+        add("pw_conv_fwd, the 17 1x1 convolutions of the student's forward (sum)", tot_ms, tot_bytes,
+            "sum over the layers of rows in + rows out; batch statistics come out of the same kernels")
     return out, v
 
 

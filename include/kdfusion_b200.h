@@ -341,6 +341,17 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
                         const void *s_feat1, const void *t_feat1, void *d_feat1, int64_t numel1,
                         int dtype_feat, float grad_scale,
                         void *d_logits, float *scalars, void *workspace, void *stream);
+/* The label histogram (the CE normaliser sum_i w[y_i] needs it) depends on the labels only: it can be taken when the
+ * batch arrives -- on a side stream, off the loss's critical path -- with kdf_kd_label_count into the SAME workspace,
+ * followed later by kdf_kd_loss_fwd_bwd_counted (identical arguments and results, no histogram phase). */
+int kdf_kd_label_count(const int64_t *labels, int B, int K, int64_t HW, int64_t ignore_index, void *workspace, void *stream);
+int kdf_kd_loss_fwd_bwd_counted(const void *s_logits, const void *t_logits, const int64_t *labels,
+                        const float *class_w, int B, int K, int64_t HW, int dtype_logits,
+                        float T, float alpha, float beta, int64_t ignore_index,
+                        const void *s_feat0, const void *t_feat0, void *d_feat0, int64_t numel0,
+                        const void *s_feat1, const void *t_feat1, void *d_feat1, int64_t numel1,
+                        int dtype_feat, float grad_scale,
+                        void *d_logits, float *scalars, void *workspace, void *stream);
 
 /* g[m,c] += bc[c]*x[m,c] + ac[c] over rows [M,C] (in place): the batch-statistics part of a BatchNorm backward
  * (nn.BatchNorm2d inside Conv1x1, fusion_module.py:11-15) whose per-row part and column sums came out of the fused

@@ -266,13 +266,28 @@ extern "C" {
 
 size_t kdf_kd_loss_workspace_bytes(void) { return sizeof(KdWorkspace); }
 
-int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_t *labels,
+int kdf_kd_label_count(const int64_t *labels, int B, int K, int64_t HW, int64_t ignore_index, void *workspace, void *stream) {
+    KDF_CHECK_ARG(B > 0 && HW > 0, "kd_label_count: empty batch");
+    KDF_CHECK_ARG(K >= 1 && K <= KD_MAX_K, "kd_label_count: K=%d outside [1,%d]", K, KD_MAX_K);
+    KDF_CHECK_ARG(labels && workspace, "kd_label_count: null pointer");
+    cudaStream_t st = as_stream(stream);
+    KdWorkspace *ws = reinterpret_cast<KdWorkspace *>(workspace);
+    const int64_t npix = (int64_t)B * HW;
+    KDF_CUDA(cudaMemsetAsync(ws, 0, offsetof(KdWorkspace, partial), st));
+    int64_t nb = (npix + KD_THREADS * 4 - 1) / (KD_THREADS * 4);
+    if (nb > sm_count() * 4) nb = sm_count() * 4;
+    kd_label_count_kernel<<<(int)nb, KD_THREADS, 0, st>>>(labels, K, npix, ignore_index, ws);
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+static int kd_loss_impl(const void *s_logits, const void *t_logits, const int64_t *labels,
                         const float *class_w, int B, int K, int64_t HW, int dtype_logits,
                         float T, float alpha, float beta, int64_t ignore_index,
                         const void *s_feat0, const void *t_feat0, void *d_feat0, int64_t numel0,
                         const void *s_feat1, const void *t_feat1, void *d_feat1, int64_t numel1,
                         int dtype_feat, float grad_scale,
-                        void *d_logits, float *scalars, void *workspace, void *stream) {
+                        void *d_logits, float *scalars, void *workspace, void *stream, bool counts_ready) {
     KDF_CHECK_ARG(B > 0 && HW > 0, "kd_loss: empty batch");
     KDF_CHECK_ARG(K >= 1 && K <= KD_MAX_K, "kd_loss: K=%d outside [1,%d]", K, KD_MAX_K);
     KDF_CHECK_ARG(s_logits && labels && d_logits && scalars && workspace, "kd_loss: null pointer");
@@ -288,12 +303,8 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
     cudaStream_t st = as_stream(stream);
     KdWorkspace *ws = reinterpret_cast<KdWorkspace *>(workspace);
     const int64_t npix = (int64_t)B * HW;
-    KDF_CUDA(cudaMemsetAsync(ws, 0, offsetof(KdWorkspace, partial), st));
-    {
-        int64_t nb = (npix + KD_THREADS * 4 - 1) / (KD_THREADS * 4);
-        if (nb > sm_count() * 4) nb = sm_count() * 4;
-        kd_label_count_kernel<<<(int)nb, KD_THREADS, 0, st>>>(labels, K, npix, ignore_index, ws);
-        KDF_LAUNCH_CHECK();
+    if (!counts_ready) {
+        if (int e = kdf_kd_label_count(labels, B, K, HW, ignore_index, workspace, stream)) return e;
     }
 
     KdParams p;
@@ -316,6 +327,30 @@ int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_
     else                                                         kd_loss_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, KD_THREADS, 0, st>>>(p);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
+}
+
+int kdf_kd_loss_fwd_bwd(const void *s_logits, const void *t_logits, const int64_t *labels,
+                        const float *class_w, int B, int K, int64_t HW, int dtype_logits,
+                        float T, float alpha, float beta, int64_t ignore_index,
+                        const void *s_feat0, const void *t_feat0, void *d_feat0, int64_t numel0,
+                        const void *s_feat1, const void *t_feat1, void *d_feat1, int64_t numel1,
+                        int dtype_feat, float grad_scale,
+                        void *d_logits, float *scalars, void *workspace, void *stream) {
+    return kd_loss_impl(s_logits, t_logits, labels, class_w, B, K, HW, dtype_logits, T, alpha, beta, ignore_index, s_feat0, t_feat0,
+                        d_feat0, numel0, s_feat1, t_feat1, d_feat1, numel1, dtype_feat, grad_scale, d_logits, scalars, workspace,
+                        stream, false);
+}
+
+int kdf_kd_loss_fwd_bwd_counted(const void *s_logits, const void *t_logits, const int64_t *labels,
+                                const float *class_w, int B, int K, int64_t HW, int dtype_logits,
+                                float T, float alpha, float beta, int64_t ignore_index,
+                                const void *s_feat0, const void *t_feat0, void *d_feat0, int64_t numel0,
+                                const void *s_feat1, const void *t_feat1, void *d_feat1, int64_t numel1,
+                                int dtype_feat, float grad_scale,
+                                void *d_logits, float *scalars, void *workspace, void *stream) {
+    return kd_loss_impl(s_logits, t_logits, labels, class_w, B, K, HW, dtype_logits, T, alpha, beta, ignore_index, s_feat0, t_feat0,
+                        d_feat0, numel0, s_feat1, t_feat1, d_feat1, numel1, dtype_feat, grad_scale, d_logits, scalars, workspace,
+                        stream, true);
 }
 
 }  // extern "C"

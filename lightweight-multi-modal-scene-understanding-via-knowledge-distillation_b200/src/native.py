@@ -61,6 +61,9 @@ _SIGNATURES = {
     "kdf_kd_loss_workspace_bytes": (_sz, []),
     "kdf_kd_loss_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _i64,
                                       _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
+    "kdf_kd_label_count": (C.c_int, [_vp, _i, _i, _i64, _i64, _vp, _vp]),
+    "kdf_kd_loss_fwd_bwd_counted": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _i64,
+                                              _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
     "kdf_confusion_matrix": (C.c_int, [_vp, _vp, _i, _i, _i64, _i, _i64, _vp, _vp]),
     "kdf_adamw_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _vp, _vp]),
 }
@@ -95,7 +98,7 @@ KERNELS_PER_CALL = {
     "kdf_bev_index": 1, "kdf_bev_rasterize": 3, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
     "kdf_pw_conv_fwd": 1, "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
     "kdf_fusion_affine_relu_pair_fwd": 1, "kdf_fusion_affine_relu_pair_bwd": 1,
-    "kdf_kd_loss_fwd_bwd": 2, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
+    "kdf_kd_loss_fwd_bwd": 2, "kdf_kd_label_count": 1, "kdf_kd_loss_fwd_bwd_counted": 1, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
     "kdf_rowbn_stats": 1, "kdf_rowbn_apply_fwd": 1, "kdf_rowbn_bwd": 2,
     "kdf_mlp_layer_fwd": 1, "kdf_mlp_eval3_fwd": 1, "kdf_mlp_layer_bwd": 1, "kdf_bn_finalize": 1, "kdf_bev_reduce_affine": 1, "kdf_bev_bwd_affine": 1,
     "kdf_point_moments": 1, "kdf_bev_build_order": 3, "kdf_fpn_merge_fwd": 1, "kdf_fpn_up2_bwd": 1, "kdf_rows_axpb": 1, "kdf_mlp_l1_stats": 1, "kdf_bn_bwd_coeffs": 1, "kdf_mlp_l1_bwd": 1, "kdf_dwconv3x3_fwd": 1, "kdf_dwconv3x3_affine_fwd": 1, "kdf_dwconv3x3_bwd_data": 1, "kdf_dwconv3x3_bwd_weight": 1,

@@ -684,12 +684,28 @@ def _dense(s: torch.Tensor) -> torch.Tensor:
     return s.contiguous()
 
 
+def kd_label_count(labels: torch.Tensor, num_classes: int, ignore_index: int = -1) -> torch.Tensor:
+    """Histogram of the valid labels into a fresh loss workspace (``kdf_kd_label_count``), on the current stream.  It
+    depends on the labels only, so a training step takes it when the batch arrives (next to the teacher's forward on
+    its side stream) and hands the workspace to ``kd_loss_fwd_bwd(..., counted_ws=...)``."""
+    dev = require_cuda(labels)
+    if labels.dtype != torch.int64 or labels.dim() != 3:
+        raise ValueError(f"labels must be int64 [B,H,W], got {labels.dtype} {tuple(labels.shape)}")
+    labels = labels.contiguous()
+    B = labels.shape[0]
+    ws = torch.empty(lib.kdf_kd_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
+    call("kdf_kd_label_count", ptr(labels), B, int(num_classes), labels.numel() // max(B, 1), int(ignore_index), ptr(ws),
+         stream_ptr(dev))
+    return ws
+
+
 def kd_loss_fwd_bwd(student_logits, teacher_logits, labels, class_weights=None,
                     student_feats: Sequence[torch.Tensor] = (), teacher_feats: Sequence[torch.Tensor] = (),
                     T: float = 4.0, alpha: float = 0.5, beta: float = 1.0, ignore_index: int = -1,
-                    grad_scale: float = 1.0):
+                    grad_scale: float = 1.0, counted_ws: Optional[torch.Tensor] = None):
     """One pass: loss terms + gradients.  -> (scalars f32[8] = loss, ce, kl, mse, wsum, mse0, mse1, n_valid;
-    d_logits like student_logits; [d_feat like each student feat]).  No host sync."""
+    d_logits like student_logits; [d_feat like each student feat]).  No host sync.  ``counted_ws``: a workspace that
+    ``kd_label_count`` already filled for THESE labels (same class count and ignore index)."""
     dev = require_cuda(student_logits, teacher_logits, labels, class_weights, *student_feats, *teacher_feats)
     if student_logits.dim() != 4:
         raise ValueError("logits must be [B,K,H,W]")
@@ -720,8 +736,9 @@ def kd_loss_fwd_bwd(student_logits, teacher_logits, labels, class_weights=None,
             taps += [None, None, None, 0]
     d_logits = torch.empty_like(zs)
     scalars = torch.empty(8, dtype=torch.float32, device=dev)
-    ws = torch.empty(lib.kdf_kd_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
-    call("kdf_kd_loss_fwd_bwd", ptr(zs), ptr(zt), ptr(labels), ptr(cw), B, K, H * W, dtype_code(zs),
+    ws = counted_ws if counted_ws is not None else torch.empty(lib.kdf_kd_loss_workspace_bytes(), dtype=torch.uint8, device=dev)
+    call("kdf_kd_loss_fwd_bwd_counted" if counted_ws is not None else "kdf_kd_loss_fwd_bwd",
+         ptr(zs), ptr(zt), ptr(labels), ptr(cw), B, K, H * W, dtype_code(zs),
                                   float(T), float(alpha), float(beta), int(ignore_index), *taps, fd, float(grad_scale),
                                   ptr(d_logits), ptr(scalars), ptr(ws), stream_ptr(dev))
     return scalars, d_logits, d_list

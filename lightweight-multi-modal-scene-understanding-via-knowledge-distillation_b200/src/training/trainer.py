@@ -144,6 +144,8 @@ class Trainer:
                 p.requires_grad_(False)
             _native.mark_frozen(teacher)          # nothing writes to it: its eval-mode caches never go stale
         self.kd_temperature, self.kd_alpha, self.kd_beta = kd_temperature, kd_alpha, kd_beta
+        cls = getattr(getattr(model, "head", None), "cls", None)
+        self._num_classes = int(getattr(cls, "out_channels", 0) or 0)       # 0: unknown head, the loss call counts itself
         self.amp_dtype = amp_dtype
 
         self.save_dir = save_dir
@@ -201,6 +203,7 @@ class Trainer:
 
     def _step_impl(self, imgs, pts, seg, update_hyper: bool):
         self.optimizer.detach_grads()                    # gradients arrive as fresh tensors, gathered below in one copy
+        counted = None
         with self._autocast(), _native.deferred_batch_counters():
             if self.teacher is not None:
                 # The frozen teacher's forward does not depend on the student's: it runs on a side stream (a parallel
@@ -213,6 +216,10 @@ class Trainer:
                     self._prepare_shared(pts)
                     side.wait_stream(main)
                     with torch.cuda.stream(side), torch.no_grad():
+                        # the label histogram the loss normaliser needs depends on the labels only: taken here, on the
+                        # side stream, it is off the critical path between the student's logits and the loss kernel
+                        if self._num_classes:
+                            counted = ops.kd_label_count(seg, self._num_classes, ignore_index=-1)
                         t_logits, t_mid = self.teacher(imgs, pts, return_intermediates=True)
                 else:
                     with torch.no_grad():
@@ -220,8 +227,10 @@ class Trainer:
                 logits, mid = self.model(imgs, pts, return_intermediates=True)
                 if side is not None:
                     main.wait_stream(side)
-                    for t in [t_logits] + [t_mid[k] for k in MIMIC_TAPS]:
+                    for t in [t_logits] + [t_mid[k] for k in MIMIC_TAPS] + ([counted] if counted is not None else []):
                         t.record_stream(main)
+                if counted is not None and logits.shape[1] != self._num_classes:
+                    counted = None                               # a head with another class count: count inside the call
                 s_feats = [mid[k] for k in MIMIC_TAPS]
                 t_feats = [t_mid[k] for k in MIMIC_TAPS]
                 alpha, beta = self.kd_alpha, self.kd_beta
@@ -230,7 +239,7 @@ class Trainer:
                 t_logits, s_feats, t_feats, alpha, beta = None, [], [], 0.0, 0.0
         terms, d_logits, d_feats = ops.kd_loss_fwd_bwd(
             logits, t_logits, seg, self.class_weights, s_feats, t_feats,
-            T=self.kd_temperature, alpha=alpha, beta=beta, ignore_index=-1)
+            T=self.kd_temperature, alpha=alpha, beta=beta, ignore_index=-1, counted_ws=counted)
         plan = self._overlap_plan() if self.world_size > 1 else None
         if plan is not None:
             self._overlap_armed = True

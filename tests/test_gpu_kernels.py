@@ -284,6 +284,25 @@ def test_kd_loss_fp32_vs_oracle(ops, K, weights):
         assert rel_err(d.cpu(), s.grad) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kd_loss_with_hoisted_label_count_is_bit_identical(ops, dtype):
+    """kdf_kd_label_count (taken early, on another stream) + kdf_kd_loss_fwd_bwd_counted == kdf_kd_loss_fwd_bwd, bit for
+    bit: terms, logit gradients, tap gradients."""
+    zs, zt, lab, sf, tf = _kd_inputs(3, 2, seed=11)
+    w = torch.tensor([0.4, 3.5]).cuda()
+    args = (zs.cuda().to(dtype), zt.cuda().to(dtype), lab.cuda(), w, [s.cuda().to(dtype) for s in sf], [t.cuda().to(dtype) for t in tf])
+    ref = ops.kd_loss_fwd_bwd(*args)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ws = ops.kd_label_count(lab.cuda(), 2)
+    torch.cuda.current_stream().wait_stream(side)
+    got = ops.kd_loss_fwd_bwd(*args, counted_ws=ws)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    for a, b in zip(got[2], ref[2]):
+        assert torch.equal(a, b)
+    assert got[0][7].item() == (lab != -1).sum().item()
+
+
 def test_kd_loss_ce_only_matches_reference_criterion(ops):
     """teacher=None, alpha=beta=0 -> exactly nn.CrossEntropyLoss(ignore_index=-1, weight) (trainer.py:55)."""
     zs, _, lab, _, _ = _kd_inputs(2, 2, seed=7)

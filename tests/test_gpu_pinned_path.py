@@ -61,50 +61,46 @@ def rel_l2(a, b):
 def test_graph_replay_equals_eager_steps(tmp_path, amp):
     """Five optimisation steps issued eagerly (teacher on the main stream) against the same five steps with the
     whole step captured once and replayed as a CUDA graph with the teacher on a side stream -- the configuration
-    bench.py times.  Same kernels in the same order, so only the order of floating-point atomics differs -- but AdamW
-    amplifies that noise chaotically (its normalised update turns a sign flip of a near-zero gradient into a 2*lr
-    move), so the bar is SELF-CALIBRATED: a second eager run of the same steps measures how far two executions of the
-    identical program drift apart, and the graph run must stay within 10x the largest drift seen so far (plus a floor
-    for the case where the eager runs happen to agree bit for bit).  The first replayed step (i = 1), where the least
-    has been amplified, is held to 3x that step's own drift: measured 0.0 / 4e-6 (loss terms / logits) in fp32, and
-    6.6e-4 / 4.3e-2 against an eager-eager drift of 5.9e-4 / 4.3e-2 in bf16 (one AdamW step of sign(g) * lr on bf16
-    gradients already decorrelates two runs of the SAME eager program that far).  Loss
-    terms, logits, the parameter update theta_k - theta_0, running statistics and batch counters are all compared."""
+    bench.py times.  Same kernels in the same order, so only the order of floating-point atomics differs.
+
+    Part 1, learning rate 0: the parameters stay put, so every step must agree to atomics noise -- loss terms, logits,
+    the gathered gradient bucket, AdamW's moments (which do move at lr = 0: they integrate the gradients of all five
+    steps), BatchNorm running statistics and batch counters.  This is the tight pin on graph replay.
+    Part 2, the real learning rate: AdamW amplifies atomics noise chaotically (its normalised update turns a sign
+    flip of a near-zero gradient into a 2*lr move; two runs of the SAME eager program drift 4 % apart in bf16 logits
+    after one step), so here only the sane things are asserted: finite, parameters moved, losses within 10 %."""
     data = frames(5)
-    eager = make_trainer(tmp_path / "e", amp, graph=False, overlap=False)
-    again = make_trainer(tmp_path / "e2", amp, graph=False, overlap=False)
-    graph = make_trainer(tmp_path / "g", amp, graph=True, overlap=True)
+    tol_terms, tol_logits, tol_grad, tol_stats = (1e-5, 1e-4, 2e-3, 1e-5) if amp is None else (2e-3, 2e-2, 3e-2, 2e-3)
+    eager = make_trainer(tmp_path / "e", amp, graph=False, overlap=False, lr=0.0)
+    graph = make_trainer(tmp_path / "g", amp, graph=True, overlap=True, lr=0.0)
     theta0 = eager.optimizer.flat_param.clone()
-    assert torch.equal(theta0, graph.optimizer.flat_param) and torch.equal(theta0, again.optimizer.flat_param)
-    floor_terms, floor_logits, floor_upd = (1e-5, 5e-4, 1e-3) if amp is None else (2e-3, 2e-2, 3e-2)
-    report = []
-    worst_t = worst_l = 0.0
+    assert torch.equal(theta0, graph.optimizer.flat_param)
     for i, (img, pts, lab) in enumerate(data):
         te, le = eager.training_step(img, pts, lab)
-        ta, la = again.training_step(img, pts, lab)
         tg, lg = graph.training_step(img, pts, lab)
-        te, ta, tg = te.clone().double(), ta.clone().double(), tg.clone().double()
-        drift_t = ((ta[:4] - te[:4]).abs() / te[:4].abs()).max().item()
-        diff_t = ((tg[:4] - te[:4]).abs() / te[:4].abs()).max().item()
-        drift_l, diff_l = rel_l2(la.float(), le.float()), rel_l2(lg.float(), le.float())
-        report.append((i, drift_t, diff_t, drift_l, diff_l))
-        worst_t, worst_l = max(worst_t, drift_t), max(worst_l, drift_l)
-        if i <= 1:                                              # step 0 is eager in both; step 1 is the first replay
-            assert diff_t <= 3 * drift_t + floor_terms and diff_l <= 3 * drift_l + floor_logits, report
-        assert diff_t <= 10 * worst_t + floor_terms * (1 + i), report
-        assert diff_l <= 10 * worst_l + floor_logits * (1 + i), report
+        te, tg = te.clone().double(), tg.clone().double()
+        assert ((tg[:4] - te[:4]).abs() / te[:4].abs()).max().item() <= tol_terms, (i, te[:4], tg[:4])
+        assert rel_l2(lg.float(), le.float()) <= tol_logits, i
+        assert rel_l2(graph.optimizer.flat_grad, eager.optimizer.flat_grad) <= tol_grad, i
     assert len(graph._graphs) == 1 and graph.optimizer._step == eager.optimizer._step == 5
-    upd_e, upd_a, upd_g = (t.optimizer.flat_param - theta0 for t in (eager, again, graph))
-    assert upd_e.abs().max().item() > 1e-4                      # the steps did move the parameters
-    drift_u, diff_u = rel_l2(upd_a, upd_e), rel_l2(upd_g, upd_e)
-    assert diff_u <= 10 * drift_u + floor_upd, (drift_u, diff_u, report)
-    for (n, be), (_, ba), (_, bg) in zip(eager.model.named_buffers(), again.model.named_buffers(), graph.model.named_buffers()):
+    assert torch.equal(eager.optimizer.flat_param, theta0) and torch.equal(graph.optimizer.flat_param, theta0)
+    assert eager.optimizer.exp_avg.abs().max().item() > 0
+    assert rel_l2(graph.optimizer.exp_avg, eager.optimizer.exp_avg) <= tol_grad
+    assert rel_l2(graph.optimizer.exp_avg_sq, eager.optimizer.exp_avg_sq) <= 2 * tol_grad
+    for (n, be), (_, bg) in zip(eager.model.named_buffers(), graph.model.named_buffers()):
         if "running" in n:
-            assert rel_l2(bg, be) <= 10 * rel_l2(ba, be) + floor_upd, n
+            assert rel_l2(bg, be) <= tol_stats, n
         elif "num_batches" in n:
             assert torch.equal(bg, be) and int(bg) == 5, n
-    print("graph-vs-eager report (step, eager drift terms, graph diff terms, eager drift logits, graph diff logits):", report,
-          "update drift/diff:", drift_u, diff_u)
+    # part 2: the real learning rate
+    eager = make_trainer(tmp_path / "e2", amp, graph=False, overlap=False)
+    graph = make_trainer(tmp_path / "g2", amp, graph=True, overlap=True)
+    for i, (img, pts, lab) in enumerate(data):
+        te, _ = eager.training_step(img, pts, lab)
+        tg, _ = graph.training_step(img, pts, lab)
+        assert torch.isfinite(tg[:4]).all() and abs(tg[0].item() - te[0].item()) <= 0.1 * abs(te[0].item()), (i, te[:4], tg[:4])
+    upd = graph.optimizer.flat_param - theta0
+    assert torch.isfinite(upd).all() and upd.abs().max().item() > 1e-4
 
 
 def test_graph_per_shape_and_release(tmp_path):

@@ -59,6 +59,7 @@ if "kd" in only:
     ts = [torch.randn(B, H, W, C, device=dev, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
     tt = [torch.randn(B, H, W, C, device=dev, dtype=dt).permute(0, 3, 1, 2) for _ in range(2)]
     timeit("kd_loss", lambda: ops.kd_loss_fwd_bwd(zs, zt, lab, cw, ts, tt), B * H * W * (2 * 3 * C * 2))
+    timeit("kd_loss (hoisted label count)", lambda: ops.kd_loss_fwd_bwd(zs, zt, lab, cw, ts, tt, counted_ws=ops.kd_label_count(lab, 2)), B * H * W * (2 * 3 * C * 2))
 if "fusion" in only:
     Mp = B * H * W
     f32 = dict(device=dev, dtype=torch.float32)
@@ -72,6 +73,17 @@ if "fusion" in only:
     gaff, gw1, gb1 = torch.empty(4, C, **f32), torch.empty(C, 2 * C, **f32), torch.empty(C, **f32)
     gw2, gb2 = torch.empty(2, C, **f32), torch.empty(2, **f32)
     timeit("fusion_weighted_bwd", lambda: native.call("kdf_fusion_weighted_bwd", p(go), p(cam), p(lid), 1, Mp, C, p(sc[0]), p(sh[0]), p(sc[1]), p(sh[1]), p(w1), p(b1), p(w2), p(b2), p(attn), p(g1), p(g2), p(gaff), p(gw1), p(gb1), p(gw2), p(gb2), st), Mp * 5 * C * 2)
+if "pw" in only:
+    # three representative 1x1-convolution layers of the student's forward (tools/pw_conv_bench.py has all sixteen)
+    for name, Mp, K, Nn, pro in (("pw stage2 expand 32->192", 524288, 32, 192, False), ("pw stage3 project 384->64 +BN/ReLU6", 131072, 384, 64, True),
+                                 ("pw fpn post 128->128 +BN/ReLU", 131072, 128, 128, True)):
+        x = torch.randn(Mp, K, device=dev).to(dt)
+        w = torch.randn(Nn, K, device=dev) * (2.0 / K) ** 0.5
+        pack = ops._pw_pack_factor(K, Nn)
+        wb = ops.pw_conv_weight(w, pack)
+        sc, sh = torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1
+        timeit(name, lambda: ops.pw_conv_fwd(x, wb, pack, pro=(sc, sh, 2) if pro else None, want_stats=True), Mp * (K + Nn) * 2)
+        del x
 if "mlp" in only:
     zprev = torch.randn(M, 128, device=dev, dtype=dt)
     sc, sh = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
