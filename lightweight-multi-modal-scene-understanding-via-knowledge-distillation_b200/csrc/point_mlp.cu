@@ -569,6 +569,16 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
+// Per-channel coefficient tables of 128 floats are read as "the 8 channels of 16-byte chunk d" by threads whose d is their
+// lane id modulo 16: stored linearly that is two LDS.128 at a 32-byte lane stride, a 4-way bank conflict each (ncu: 2.7e6
+// excess wavefronts per such load, 3e7 in the layer-3 backward).  Stored as two halves -- channels 8d..8d+3 of every chunk
+// first, 8d+4..8d+7 behind them -- the same loads walk 16 bytes per lane: conflict-free.
+__device__ __forceinline__ int coef_slot(int c) { return ((c & 4) << 4) + ((c >> 3) << 2) + (c & 3); }
+__device__ __forceinline__ void coef_load8(const float *tab, int d, float (&v)[8]) {
+    const float4 lo = *reinterpret_cast<const float4 *>(tab + d * 4), hi = *reinterpret_cast<const float4 *>(tab + 64 + d * 4);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
 template <int MODE, int KIN, int NT>
 __global__ void __launch_bounds__(NT, 1)
 mlp_layer_bwd_kernel(MlpBwdArgs a) {
@@ -597,12 +607,12 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (a.M + PM_ROWS - 1) / PM_ROWS;
 
-    for (int i = tid; i < 128; i += PM_THREADS) { cgs[i] = a.gs[i]; cga[i] = a.ga[i]; cgb[i] = a.gb[i]; }
+    for (int i = tid; i < 128; i += PM_THREADS) { cgs[coef_slot(i)] = a.gs[i]; cga[coef_slot(i)] = a.ga[i]; cgb[coef_slot(i)] = a.gb[i]; }
     if (MODE == 0) {                                              // q rows padded to 36 floats per 8-channel chunk: conflict-free LDS.128
         for (int i = tid; i < 64 * 4; i += PM_THREADS) coef[(i >> 5) * 36 + (i & 31)] = a.pro_a[i];
         for (int i = tid; i < 64; i += PM_THREADS) coef[288 + i] = a.pro_b[i];
     } else {
-        for (int i = tid; i < KIN; i += PM_THREADS) { coef[i] = a.pro_a[i]; coef[KIN + i] = a.pro_b[i]; }
+        for (int i = tid; i < KIN; i += PM_THREADS) { coef[coef_slot(i)] = a.pro_a[i]; coef[KIN + coef_slot(i)] = a.pro_b[i]; }
     }
     for (int idx = tid; idx < PM_N * ACH; idx += PM_THREADS) {
         const int n = idx / ACH, ch = idx % ACH;
@@ -666,8 +676,7 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         const int64_t r0 = tile * PM_ROWS;
         {
             float gs[8], ga[8], gb[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { gs[j] = cgs[dch * 8 + j]; ga[j] = cga[dch * 8 + j]; gb[j] = cgb[dch * 8 + j]; }
+            coef_load8(cgs, dch, gs); coef_load8(cga, dch, ga); coef_load8(cgb, dch, gb);
 #pragma unroll
             for (int p = 0; p < D_PASSES; ++p) {
                 const int r = drow0 + p * PM_OROWS;
@@ -691,8 +700,10 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) c1[j] = coef[288 + ach * 8 + j];
             } else {
+                float t0[8], t1[8];
+                coef_load8(coef, ach, t0); coef_load8(coef + KIN, ach, t1);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { c0[j] = coef[ach * 8 + j]; c1[j] = coef[KIN + ach * 8 + j]; }
+                for (int j = 0; j < 8; ++j) { c0[j] = t0[j]; c1[j] = t1[j]; }
             }
 #pragma unroll
             for (int p = 0; p < A_PASSES; ++p) {
