@@ -65,6 +65,22 @@ int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
                   float x0, float xspan, float y0, float yspan, int H, int W,
                   int32_t *cell, int32_t *rank, int32_t *count, void *stream);
 
+/* Range-view (spherical) projection: the same index / sort / per-cell reduce machinery over the cells of a range image
+ * instead of the bird's-eye-view grid (BASELINE north star: "projection into the range/BEV grid").  The reference has no
+ * range-view code, so this half is parity-unpinned; the convention is the one of range-image LiDAR networks:
+ *   depth = |(x,y,z)| ; yaw = -atan2(y, x) ; pitch = asin(z / depth)
+ *   col = floor(0.5 * (yaw/pi + 1) * W) ; row = floor((1 - (pitch - fov_down) / (fov_up - fov_down)) * H), clamped
+ *   invalid (-1): depth == 0, non-finite coordinates, pitch outside [fov_down, fov_up]   (angles in radians)
+ * kdf_range_index = kdf_bev_index, kdf_range_project_fwd = kdf_bev_project_fwd with that cell function (fp32 device
+ * atan2f / asinf: cell ids agree with a float64 evaluation except for points within rounding of a cell boundary);
+ * gradients go through kdf_bev_project_bwd unchanged (it only sees cells). */
+int kdf_range_index(const float *points, int B, int64_t N, int point_stride, float fov_up, float fov_down, int H, int W,
+                    int32_t *cell, int32_t *count, void *stream);
+int kdf_range_project_fwd(const float *points, int point_stride, const void *feats, int dtype, int B, int64_t N, int C,
+                          float fov_up, float fov_down, int H, int W, int reduce,
+                          void *grid, int32_t *count, int32_t *cell, int32_t *ties, int32_t *order, int32_t *offsets,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* BEV label rasterisation (reference src/data_loading/pandaset_dataset.py:23-45, rasterize_bev):
  *   inside = x_min <= x <= x_max && y_min <= y <= y_max     on the RAW fp32 coordinates (:33)
  *   col = clip(trunc((x - x_min) / xspan * (W-1)), 0, W-1), row likewise (:39-40; xspan = x_max - x_min

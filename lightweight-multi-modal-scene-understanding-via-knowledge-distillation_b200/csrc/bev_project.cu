@@ -28,6 +28,8 @@ namespace kdf {
 struct BevGeom {
     float x0, xspan, y0, yspan, sx, sy;   // sx = W-1, sy = H-1 as fp32 (grid_tensor)
     int H, W;
+    int range_view;                       // 0: bird's-eye-view cells (the reference's grid); 1: spherical range image
+    float fov_down, fov_span;             // range view: lowest elevation and vertical field of view, radians
 };
 
 // lidar_encoder.py:47-53,69-71 -- every operation rounded to fp32 separately
@@ -42,6 +44,28 @@ __device__ __forceinline__ int bev_cell_of(float x, float y, const BevGeom &g) {
     col = min(max(col, 0), g.W - 1);
     row = min(max(row, 0), g.H - 1);
     return row * g.W + col;
+}
+
+// Range-view (spherical) cell of a point: the other projection the distillation pipeline names next to the BEV grid.  The
+// reference has no range-view code (parity unpinned); the convention is the usual one of
+// range-image LiDAR networks: yaw = -atan2(y, x), pitch = asin(z / depth),
+//   col = floor(0.5 * (yaw / pi + 1) * W),  row = floor((1 - (pitch - fov_down) / fov) * H),  both clamped to the image;
+// points at the origin, with non-finite coordinates or outside the vertical field of view are invalid (-1).
+__device__ __forceinline__ int range_cell_of(float x, float y, float z, const BevGeom &g) {
+    const float depth = sqrtf(fmaf(x, x, fmaf(y, y, z * z)));
+    if (!(depth > 0.f) || !(depth < 3.0e38f)) return -1;                 // origin, NaN, inf
+    const float pitch = asinf(z / depth);
+    const float t = (pitch - g.fov_down) / g.fov_span;
+    if (!(t >= 0.f) || !(t <= 1.f)) return -1;
+    const float yaw = -atan2f(y, x);
+    int col = (int)floorf(0.5f * (yaw * 0.318309886183790672f + 1.0f) * (float)g.W);
+    int row = (int)floorf((1.0f - t) * (float)g.H);
+    col = min(max(col, 0), g.W - 1);
+    row = min(max(row, 0), g.H - 1);
+    return row * g.W + col;
+}
+__device__ __forceinline__ int cell_of(float x, float y, float z, const BevGeom &g) {
+    return g.range_view ? range_cell_of(x, y, z, g) : bev_cell_of(x, y, g);
 }
 
 // ----------------------------------------------------------------------------- index
@@ -59,15 +83,16 @@ bev_index_kernel(const float *__restrict__ points, int64_t total, int64_t N, int
         int cell = -1;
         int64_t key = -1;
         if (i < total) {
-            float x, y;
+            float x, y, z = 0.f;
             if (VEC4) {
                 const float4 p = ldg_stream_f4(reinterpret_cast<const float4 *>(points) + i);
-                x = p.x; y = p.y;
+                x = p.x; y = p.y; z = p.z;
             } else {
                 x = __ldg(points + i * stride);
                 y = __ldg(points + i * stride + 1);
+                if (g.range_view) z = __ldg(points + i * stride + 2);
             }
-            cell = bev_cell_of(x, y, g);
+            cell = cell_of(x, y, z, g);
             cell_out[i] = cell;
             if (cell >= 0) key = (i / N) * HW + cell;
         }
@@ -107,7 +132,7 @@ bev_index_hist_kernel(const float4 *__restrict__ points, int64_t N, int64_t slic
         for (int u = 0; u < 4; ++u) {
             const int64_t i = i0 + u * 512;
             if (i < end) {
-                const int cell = bev_cell_of(p[u].x, p[u].y, g);
+                const int cell = cell_of(p[u].x, p[u].y, p[u].z, g);
                 cb[i] = cell;
                 if (cell >= 0) atomicAdd(&hist[cell], 1);
             }
@@ -196,7 +221,7 @@ bev_chunk_count_kernel(const float4 *__restrict__ points, int64_t N, BevGeom g, 
         for (int u = 0; u < 4; ++u) {
             const int64_t i = i0 + u * 256;
             if (i < end) {
-                const int cell = bev_cell_of(p[u].x, p[u].y, g);
+                const int cell = cell_of(p[u].x, p[u].y, p[u].z, g);
                 cb[i] = cell;
                 if (cell >= 0) rb[i] = atomicAdd(&hist[cell], 1);
             }
@@ -1186,6 +1211,23 @@ int kdf_bev_index(const float *points, int B, int64_t N, int point_stride,
     return launch_index(points, B, N, point_stride, g, cell, rank, count, as_stream(stream));
 }
 
+static int range_geom(BevGeom &g, int B, int64_t N, int H, int W, float fov_up, float fov_down, int point_stride) {
+    if (int e = check_geom(B, N, H, W, 1.f, 1.f)) return e;
+    KDF_CHECK_ARG(point_stride >= 3, "range view: points need (x, y, z): point_stride must be >= 3");
+    KDF_CHECK_ARG(fov_up > fov_down && fov_up <= 1.5708f && fov_down >= -1.5708f, "range view: bad vertical field of view [%g, %g] rad",
+                  (double)fov_down, (double)fov_up);
+    g = BevGeom{0.f, 1.f, 0.f, 1.f, 0.f, 0.f, H, W, 1, fov_down, fov_up - fov_down};
+    return KDF_OK;
+}
+
+int kdf_range_index(const float *points, int B, int64_t N, int point_stride, float fov_up, float fov_down, int H, int W,
+                    int32_t *cell, int32_t *count, void *stream) {
+    BevGeom g;
+    if (int e = range_geom(g, B, N, H, W, fov_up, fov_down, point_stride)) return e;
+    KDF_CHECK_ARG(((points && cell) || (int64_t)B * N == 0) && (count || B == 0), "range_index: null pointer");
+    return launch_index(points, B, N, point_stride, g, cell, nullptr, count, as_stream(stream));
+}
+
 size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W) {
     const size_t bn = align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256);
     const size_t off = align_up(sizeof(int32_t) * (size_t)B * ((size_t)H * W + 1), 256);
@@ -1244,14 +1286,10 @@ int kdf_bev_build_order(const float *points, int point_stride, int B, int64_t N,
                        as_stream(stream));
 }
 
-int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats, int dtype,
-                        int B, int64_t N, int C,
-                        float x0, float xspan, float y0, float yspan, int H, int W, int reduce,
-                        void *grid, int32_t *count, int32_t *cell, int32_t *ties,
-                        int32_t *order, int32_t *offsets,
-                        void *workspace, size_t workspace_bytes, void *stream) {
-    if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
-    KDF_CHECK_ARG(point_stride >= 2, "bev: point_stride must be >= 2");
+static int project_fwd_impl(const float *points, int point_stride, const void *feats, int dtype, int B, int64_t N, int C,
+                            const BevGeom &g, int reduce, void *grid, int32_t *count, int32_t *cell, int32_t *ties,
+                            int32_t *order, int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream) {
+    const int H = g.H, W = g.W;
     KDF_CHECK_ARG(C > 0 && C % 4 == 0, "bev: C=%d must be a positive multiple of 4", C);
     KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "bev: bad dtype %d", dtype);
     KDF_CHECK_ARG(reduce == KDF_REDUCE_MAX || reduce == KDF_REDUCE_MEAN, "bev: bad reduce %d", reduce);
@@ -1268,10 +1306,32 @@ int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats
     int32_t *rank = reinterpret_cast<int32_t *>(ws);
     if (!order) order = reinterpret_cast<int32_t *>(ws + bn);
     if (!offsets) offsets = reinterpret_cast<int32_t *>(ws + 2 * bn);
-    BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
     if (B == 0) return KDF_OK;
     if (int e = build_order(points, point_stride, B, N, g, count, cell, order, offsets, rank, st)) return e;
     return launch_reduce(feats, dtype, order, offsets, B, N, C, HW, reduce, grid, ties, st);
+}
+
+int kdf_bev_project_fwd(const float *points, int point_stride, const void *feats, int dtype,
+                        int B, int64_t N, int C,
+                        float x0, float xspan, float y0, float yspan, int H, int W, int reduce,
+                        void *grid, int32_t *count, int32_t *cell, int32_t *ties,
+                        int32_t *order, int32_t *offsets,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
+    KDF_CHECK_ARG(point_stride >= 2, "bev: point_stride must be >= 2");
+    BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
+    return project_fwd_impl(points, point_stride, feats, dtype, B, N, C, g, reduce, grid, count, cell, ties, order, offsets, workspace,
+                            workspace_bytes, stream);
+}
+
+int kdf_range_project_fwd(const float *points, int point_stride, const void *feats, int dtype, int B, int64_t N, int C,
+                          float fov_up, float fov_down, int H, int W, int reduce,
+                          void *grid, int32_t *count, int32_t *cell, int32_t *ties, int32_t *order, int32_t *offsets,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    BevGeom g;
+    if (int e = range_geom(g, B, N, H, W, fov_up, fov_down, point_stride)) return e;
+    return project_fwd_impl(points, point_stride, feats, dtype, B, N, C, g, reduce, grid, count, cell, ties, order, offsets, workspace,
+                            workspace_bytes, stream);
 }
 
 int kdf_bev_reduce(const void *feats, int dtype, const int32_t *order, const int32_t *offsets,

@@ -24,6 +24,9 @@ _SIGNATURES = {
     "kdf_last_error": (C.c_char_p, []),
     "kdf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "kdf_bev_index": (C.c_int, [_vp, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "kdf_range_index": (C.c_int, [_vp, _i, _i64, _i, _f, _f, _i, _i, _vp, _vp, _vp]),
+    "kdf_range_project_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i64, _i, _f, _f, _i, _i, _i,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "kdf_bev_rasterize": (C.c_int, [_vp, _i, _vp, _i, _i64, _f, _f, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp]),
     "kdf_bev_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "kdf_bev_project_fwd": (C.c_int, [_vp, _i, _vp, _i, _i, _i64, _i, _f, _f, _f, _f, _i, _i, _i,
@@ -95,7 +98,7 @@ def check(rc: int, what: str = "") -> None:
 
 # kernels launched per ABI call (memsets not counted) -- bench.py reports the total
 KERNELS_PER_CALL = {
-    "kdf_bev_index": 1, "kdf_bev_rasterize": 3, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
+    "kdf_bev_index": 1, "kdf_range_index": 1, "kdf_range_project_fwd": 4, "kdf_bev_rasterize": 3, "kdf_bev_project_fwd": 4, "kdf_bev_reduce": 1, "kdf_bev_project_bwd": 1,
     "kdf_pw_conv_fwd": 1, "kdf_fusion_weighted_fwd": 1, "kdf_fusion_weighted_bwd": 1,
     "kdf_fusion_affine_relu_pair_fwd": 1, "kdf_fusion_affine_relu_pair_bwd": 1,
     "kdf_kd_loss_fwd_bwd": 2, "kdf_kd_label_count": 1, "kdf_kd_loss_fwd_bwd_counted": 1, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,

@@ -15,7 +15,7 @@ from .native import call, dtype_code, lib, ptr, require_cuda, stream_ptr
 
 __all__ = [
     "bn_act", "run_fused", "fpn_merge",
-    "bev_range_constants", "bev_index", "bev_project", "BevProjectFn",
+    "bev_range_constants", "bev_index", "bev_project", "BevProjectFn", "range_index", "range_project",
     "pw_conv_fwd", "fused_fusion", "kd_loss_fwd_bwd", "KDLossFn", "confusion_matrix_", "adamw_flat_",
 ]
 
@@ -491,6 +491,66 @@ class BevProjectFn(torch.autograd.Function):
         call("kdf_bev_project_bwd", ptr(gg), ptr(feats), ptr(grid), ptr(ties), ptr(count), ptr(cell), ptr(order), ptr(offsets),
              dtype_code(gg), B, N, C, H, W, ctx.reduce, ptr(out), stream_ptr(gg.device))
         return None, out, None, None, None
+
+
+def range_index(points: torch.Tensor, grid_size: Tuple[int, int], fov_deg: Tuple[float, float] = (3.0, -25.0)):
+    """Range-image cell id per point (int32, -1 invalid) and per-cell occupancy (int32 [B,H*W]): the spherical
+    counterpart of ``bev_index`` (``kdf_range_index``; convention in include/kdfusion_b200.h).  ``fov_deg`` = (up, down)
+    vertical field of view in degrees; points f32 [B,N,>=3]."""
+    import math
+    B, N, D = _check_points(points)
+    if D < 3:
+        raise ValueError("the range view needs (x, y, z) points")
+    points = points.contiguous()
+    H, W = grid_size
+    cell = torch.empty(B, N, dtype=torch.int32, device=points.device)
+    count = torch.empty(B, H * W, dtype=torch.int32, device=points.device)
+    call("kdf_range_index", ptr(points), B, N, D, math.radians(fov_deg[0]), math.radians(fov_deg[1]), H, W, ptr(cell), ptr(count),
+         stream_ptr(points.device))
+    return cell, count
+
+
+class RangeProjectFn(torch.autograd.Function):
+    """range image [B,C,H,W] (NHWC memory) = per-cell max/mean of point-major feats [B,N,C]; the backward is the BEV one
+    (``kdf_bev_project_bwd`` only sees cells)."""
+
+    @staticmethod
+    def forward(ctx, points, feats, fov, grid_size, reduce):
+        import math
+        B, N, D = _check_points(points)
+        require_cuda(points, feats)
+        if D < 3 or feats.dim() != 3 or feats.shape[0] != B or feats.shape[1] != N:
+            raise ValueError(f"range_project: points [B,N,>=3] and feats [B,N,C] expected, got {tuple(points.shape)}, {tuple(feats.shape)}")
+        points, feats = points.contiguous(), feats.contiguous()
+        C = feats.shape[2]
+        H, W = grid_size
+        dev = points.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        grid = torch.empty(B, H, W, C, dtype=feats.dtype, device=dev)
+        count, cell = torch.empty(B, H * W, **i32), torch.empty(B, N, **i32)
+        lanes, rem = divmod(C * feats.element_size(), 16)
+        need_ties = reduce == _n.REDUCE_MAX and feats.requires_grad and not (rem == 0 and lanes in (8, 16, 32))
+        ties = torch.empty(B, H * W, C, **i32) if need_ties else None
+        order, offsets = torch.empty(B, N, **i32), torch.empty(B, H * W + 1, **i32)
+        nb = lib.kdf_bev_workspace_bytes(B, N, H, W)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        call("kdf_range_project_fwd", ptr(points), D, ptr(feats), dtype_code(feats), B, N, C, math.radians(fov[0]), math.radians(fov[1]),
+             H, W, reduce, ptr(grid), ptr(count), ptr(cell), ptr(ties), ptr(order), ptr(offsets), ptr(ws), nb, stream_ptr(dev))
+        ctx.reduce, ctx.dims = reduce, (B, N, C, H, W)
+        if reduce == _n.REDUCE_MAX:
+            ctx.save_for_backward(feats, grid, ties, cell, order, offsets)
+        else:
+            ctx.save_for_backward(count, cell, order, offsets)
+        ctx.mark_non_differentiable(count, cell)
+        return grid.permute(0, 3, 1, 2), count, cell
+
+    backward = staticmethod(BevProjectFn.backward)
+
+
+def range_project(points: torch.Tensor, feats: torch.Tensor, grid_size, fov_deg=(3.0, -25.0), reduce: str = "max"):
+    """-> (range image [B,C,H,W] over NHWC memory, count int32 [B,H*W], cell int32 [B,N])."""
+    code = {"max": _n.REDUCE_MAX, "amax": _n.REDUCE_MAX, "mean": _n.REDUCE_MEAN}[reduce]
+    return RangeProjectFn.apply(points, feats, tuple(fov_deg), tuple(grid_size), code)
 
 
 def bev_project(points: torch.Tensor, feats: torch.Tensor, geom, grid_size, reduce: str = "max"):

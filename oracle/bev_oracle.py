@@ -17,7 +17,7 @@ import numpy as np
 
 __all__ = [
     "range_constants", "bev_coords", "bev_cells", "bev_occupancy",
-    "bev_scatter_max", "bev_scatter_mean", "bev_scatter_max_backward", "rasterize_bev",
+    "bev_scatter_max", "bev_scatter_mean", "bev_scatter_max_backward", "rasterize_bev", "range_cells",
 ]
 
 
@@ -185,3 +185,31 @@ def rasterize_bev(x: np.ndarray, y: np.ndarray, labels: np.ndarray, grid_size=(6
     hit = first != np.iinfo(np.int64).max
     mask[hit] = labels[first[hit]]
     return mask.reshape(H, W)
+
+
+def range_cells(points: np.ndarray, grid_size=(64, 512), fov_deg=(3.0, -25.0)):
+    """Range-image cell per point in FLOAT64 (the spherical projection is not in the reference: parity unpinned; this is
+    the written convention of include/kdfusion_b200.h evaluated exactly enough to judge the fp32 device version).
+
+    points [..., >=3] -> (cell int32 [...] with -1 invalid, margin float64 [...]): ``margin`` is the distance of the
+    point's fractional image coordinates (and of its pitch from the field-of-view limits, in rows) to the nearest cell
+    boundary -- the fp32 kernel may legitimately differ only where it is tiny."""
+    H, W = grid_size
+    p = np.asarray(points, dtype=np.float32).astype(np.float64)
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    up, down = np.radians(np.float32(fov_deg[0]).astype(np.float64)), np.radians(np.float32(fov_deg[1]).astype(np.float64))
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        depth = np.sqrt(x * x + y * y + z * z)
+        ok = np.isfinite(depth) & (depth > 0)
+        pitch = np.arcsin(np.clip(z / np.where(ok, depth, 1.0), -1.0, 1.0))
+        t = (pitch - down) / (up - down)
+        ok &= (t >= 0) & (t <= 1)
+        u = 0.5 * (-np.arctan2(y, x) / np.pi + 1.0) * W
+        v = (1.0 - t) * H
+    col = np.clip(np.floor(np.where(ok, u, 0.0)), 0, W - 1).astype(np.int64)
+    row = np.clip(np.floor(np.where(ok, v, 0.0)), 0, H - 1).astype(np.int64)
+    cell = np.where(ok, row * W + col, -1).astype(np.int32)
+    frac = lambda a: np.minimum(a - np.floor(a), np.ceil(a) - a)
+    with np.errstate(invalid="ignore"):
+        margin = np.minimum(np.minimum(frac(u), frac(v)), np.minimum(np.abs(t), np.abs(1.0 - t)) * H)
+    return cell, np.where(np.isfinite(margin), margin, 0.0)

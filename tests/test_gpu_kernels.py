@@ -697,3 +697,61 @@ def test_camera_side_kernels_accept_empty_batches(ops):
     lo = torch.empty(0, 64, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)
     out = ops.fpn_merge(base, [lo])
     assert out is not None and tuple(out.shape) == (0, 64, 8, 8)
+
+
+# ----------------------------------------------------------------------------- range-view projection (parity unpinned: not in the reference)
+def _sweep(B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.randn(B, N, 4, generator=g)
+    pts[..., :2] *= 30.0
+    pts[..., 2] = pts[..., 2] * 1.5 - 1.0
+    pts[0, :6] = torch.tensor([[0.0, 0.0, 0.0, 1.0], [float("nan"), 1.0, 0.0, 0.0], [float("inf"), 0.0, 0.0, 0.0],
+                               [10.0, 0.0, 30.0, 0.0], [10.0, 0.0, -30.0, 0.0], [-5.0, 0.0, 0.0, 0.0]])   # origin, NaN, inf, above, below, behind
+    return pts
+
+
+@pytest.mark.parametrize("grid,fov", [((64, 512), (3.0, -25.0)), ((32, 1024), (15.0, -15.0))])
+def test_range_index_vs_float64_oracle(ops, grid, fov):
+    """kdf_range_index (fp32 atan2f / asinf) against the float64 evaluation of the written convention: identical cells
+    except for points whose image coordinates are within 1e-3 of a cell boundary (or of the field-of-view limit); the
+    occupancy is the histogram of the kernel's own cells; invalid points (origin, NaN / inf, outside the vertical field
+    of view) are -1."""
+    from oracle import bev_oracle
+    pts = _sweep(3, 40000, 5)
+    cell, count = ops.range_index(pts.cuda(), grid, fov)
+    ref, margin = bev_oracle.range_cells(pts.numpy(), grid, fov)
+    got = cell.cpu().numpy()
+    differ = got != ref
+    assert differ.mean() < 2e-3 and (margin[differ] < 1e-3).all(), (differ.sum(), margin[differ].max() if differ.any() else 0)
+    assert (got[0, :5] == -1).all() and got[0, 5] >= 0
+    assert ((got >= 0).mean() > 0.3) and got.max() < grid[0] * grid[1]
+    H, W = grid
+    occ = np.stack([np.bincount(c[c >= 0], minlength=H * W) for c in got]).astype(np.int32)
+    np.testing.assert_array_equal(count.cpu().numpy(), occ)
+
+
+@pytest.mark.parametrize("dtype,reduce", [(torch.float32, "max"), (torch.bfloat16, "max"), (torch.float32, "mean")])
+def test_range_project_matches_torch_scatter_on_its_cells(ops, dtype, reduce):
+    """The range image is the per-cell max / mean over the kernel's own cell ids (exact for max), and the gradient is
+    ATen's for the same scatter (even tie split)."""
+    B, N, C, H, W = 2, 20000, 128, 32, 256
+    pts = _sweep(B, N, 9).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feats = torch.rand(B, N, C, generator=g, device="cuda").to(dtype).requires_grad_(True)
+    img, count, cell = ops.range_project(pts, feats, (H, W), (3.0, -25.0), reduce)
+    assert img.shape == (B, C, H, W) and img.dtype == dtype
+    flat = (cell.long() + torch.arange(B, device="cuda").view(B, 1) * (H * W)).reshape(-1)
+    ok = (cell >= 0).reshape(-1)
+    fr = feats.detach().float().reshape(-1, C).requires_grad_(True)
+    ref = torch.zeros(B * H * W, C, device="cuda").scatter_reduce(0, flat[ok][:, None].expand(-1, C), fr[ok],
+                                                                     "amax" if reduce == "max" else "mean", include_self=False)
+    got = img.permute(0, 2, 3, 1).reshape(B * H * W, C).float()
+    if reduce == "max":
+        assert torch.equal(got, ref.detach())
+    else:
+        assert rel_err(got.cpu(), ref.detach().cpu()) < 1e-5
+    gout = torch.randn(B, C, H, W, device="cuda").to(dtype)
+    img.backward(gout)
+    ref.backward(gout.permute(0, 2, 3, 1).reshape(B * H * W, C).float())
+    assert rel_err(feats.grad.float().cpu(), fr.grad.view(B, N, C).cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert (feats.grad[~(cell >= 0)] == 0).all()
