@@ -164,12 +164,15 @@ class _DwConv3x3Fn(torch.autograd.Function):
              stream_ptr(x.device))
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.wshape, ctx.wdtype = stride, weight.shape, weight.dtype
+        ctx.set_materialize_grads(False)        # no zero tensor for the statistics output's (absent) gradient: a launch per layer
         if want_stats:
             ctx.mark_non_differentiable(stats)
         return out.permute(0, 3, 1, 2), stats
 
     @staticmethod
     def backward(ctx, g, _gs=None):
+        if g is None:
+            return None, None, None, None
         x, w = ctx.saved_tensors
         B, C, H, W = x.shape
         if g.dtype != x.dtype:
@@ -284,11 +287,14 @@ class _PwConvFn(torch.autograd.Function):
         z, stats = pw_conv_fwd(x_rows, wb, pack, want_stats=True)
         ctx.save_for_backward(x_rows, wb)
         ctx.wshape = weight.shape
+        ctx.set_materialize_grads(False)        # no zero tensor for the statistics output's (absent) gradient
         ctx.mark_non_differentiable(stats)
         return z, stats
 
     @staticmethod
     def backward(ctx, g, _gs):
+        if g is None:
+            return None, None, None, None
         x_rows, wb = ctx.saved_tensors
         g = g.contiguous()
         N, K = ctx.wshape[0], x_rows.shape[1]
@@ -597,6 +603,7 @@ class _FusedFusionFn(torch.autograd.Function):
                                                       ptr(lsh), mode, ptr(out), st)
             ctx.save_for_backward(cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd)
         ctx.mode, ctx.batch_stats = mode, batch_stats
+        ctx.set_materialize_grads(False)        # the attention map output carries no gradient: do not materialise zeros for it
         ctx.param_dtypes = (cam_g.dtype, w1.dtype if w1 is not None else None)
         ctx.w_shapes = (w1.shape, w2.shape) if mode == 2 else None
         if attn is not None:
@@ -606,6 +613,8 @@ class _FusedFusionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out, _ga):
+        if grad_out is None:
+            return (None,) * 20
         saved = ctx.saved_tensors
         cam_pre, lid_pre, csc, csh, lsc, lsh, cam_mean, cam_invstd, lid_mean, lid_invstd = saved[:10]
         M, C = cam_pre.shape
