@@ -25,6 +25,14 @@ __device__ __forceinline__ void load_2d(void *smem_dst, const CUtensorMap *tmap,
         ::"r"(tc::smem_u32(smem_dst)), "l"(tmap), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// one box of a 4-D tensor (channels, x, y, frame); coordinates may be negative or run past the extents: the hardware
+// zero-fills what lies outside, which is exactly a convolution's zero padding
+__device__ __forceinline__ void load_4d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(tmap), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // the same box DRAM -> L2 only (no shared memory, no barrier): issued well ahead of the load that will want it
 __device__ __forceinline__ void prefetch_2d(const CUtensorMap *tmap, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
@@ -54,6 +62,19 @@ static inline bool make_row_map(CUtensorMap *tm, const void *base, int64_t M, in
     const cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// [B, H, W, C] bf16 map (pixel-major), boxes of box_c channels x box_w columns x box_h rows of one frame, no swizzle:
+// a box lands densely as [row][column][channel]
+static inline bool make_nhwc_map(CUtensorMap *tm, const void *base, int B, int H, int W, int C, int box_c, int box_w, int box_h) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || B <= 0 || box_c > 256 || box_w > 256 || box_h > 256 || (C * 2) % 16 != 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tma

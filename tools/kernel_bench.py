@@ -7,6 +7,7 @@ import torch
 from src import native, ops
 from src.data_loading.synthetic_frames import make_frames
 ap = argparse.ArgumentParser(); ap.add_argument("--iters", type=int, default=3); ap.add_argument("--only", default="rowbn,bev,kd,fusion")
+ap.add_argument("--dw-shapes", default="32:128:1,192:128:2,384:64:1,384:64:2,768:32:1,128:64:1,64:64:1,256:64:1")
 ap.add_argument("--batch", type=int, default=32); ap.add_argument("--points", type=int, default=170000)
 a = ap.parse_args()
 dev = torch.device("cuda", 0); p = native.ptr; st = native.stream_ptr(dev)
@@ -121,7 +122,7 @@ if "affine" in only:
     timeit("point_moments", lambda: point_mlp.point_moments(pts), B * N * 16)
 if "dw" in only:
     import torch.nn as nn
-    for (Cc, Hh, st_) in ((384, 64, 1), (192, 128, 2), (32, 128, 1), (768, 32, 1)):
+    for (Cc, Hh, st_) in (tuple(int(v) for v in t.split(":")) for t in a.dw_shapes.split(",")):
         conv = nn.Conv2d(Cc, Cc, 3, stride=st_, padding=1, groups=Cc, bias=False).to(dev)
         x = torch.randn(B, Cc, Hh, Hh, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last).requires_grad_(True)
         y = ops.dwconv3x3(conv, x)
@@ -130,6 +131,8 @@ if "dw" in only:
         with torch.no_grad():
             timeit(f"dwconv fwd C={Cc} {Hh}x{Hh} s{st_}", lambda: ops.dwconv3x3(conv, x), nb_in + nb_out)
         w9 = conv.weight.detach().reshape(Cc, 9).float().contiguous()
+        xr_ = x.detach().permute(0, 2, 3, 1); yo = torch.empty_like(y.permute(0, 2, 3, 1)); sts = torch.empty(2, Cc, dtype=torch.float64, device=dev)
+        timeit(f"dwconv fwd+stats C={Cc} s{st_} (C ABI)", lambda: native.call("kdf_dwconv3x3_fwd", p(xr_), p(w9), 1, B, Hh, Hh, Cc, st_, 0, p(yo), p(sts), st), nb_in + nb_out)
         gx = torch.empty(B, Hh, Hh, Cc, device=dev, dtype=dt); gw = torch.empty(Cc, 9, device=dev)
         xr, gr = x.detach().permute(0, 2, 3, 1), g.permute(0, 2, 3, 1)
         timeit(f"dwconv dgrad C={Cc} s{st_}", lambda: native.call("kdf_dwconv3x3_bwd_data", p(gr), p(w9), 1, B, Hh, Hh, Cc, st_, p(gx), st), nb_in + nb_out)
