@@ -588,6 +588,209 @@ dwconv3x3_wgrad_kernel(const T *__restrict__ in, const T *__restrict__ gout, flo
     }
 }
 
+// ----------------------------------------------------------------------------- stride 2, bf16: the input tile arrives by TMA
+// DW_RT2 output rows x XT output columns per CTA read 2*DW_RT2+1 input rows x 2*XT+1 input columns (the box is one column
+// wider to stay even); boxes of DW_RB2 rows.  Same thread layout as the stride-1 kernel.
+constexpr int DW_RT2 = 4;        // output rows per tile
+constexpr int DW_RB2 = 3;        // input rows per TMA box
+
+template <int MODE, int CT>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float *__restrict__ w, __nv_bfloat16 *__restrict__ out,
+                        int OH, int OW, int C, int nxt, double *__restrict__ stats,
+                        const float *__restrict__ post_scale, const float *__restrict__ post_shift, int post_act) {
+    typedef __nv_bfloat16 T;
+    typedef DwChunk<T> K;
+    constexpr int G = CT / DW_V, XPT = 256 / G, XT = 2 * XPT, COLS = 2 * XT + 2;
+    constexpr int R = DW_RT2, NJ = 2 * R + 1, NB = NJ / DW_RB2;
+    constexpr uint32_t ROW_BYTES = COLS * CT * 2, BOX_BYTES = DW_RB2 * ROW_BYTES;
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    __shared__ uint64_t bars[NB];
+    __shared__ float sred[MODE == DW_STATS ? 256 * 2 * DW_V : 1];
+    const int tid = threadIdx.x;
+    const int xt = blockIdx.x % nxt, slab = blockIdx.x / nxt;
+    const int nrb = (OH + R - 1) / R;
+    const int b = blockIdx.y / nrb, oy0 = (blockIdx.y - b * nrb) * R;
+    uint8_t *tile = dw_smem + ((128u - (tc::smem_u32(dw_smem) & 127u)) & 127u);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) tc::mbar_init(&bars[k], 1);
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            tma::mbar_expect_tx(&bars[k], BOX_BYTES);
+            tma::load_4d(tile + k * BOX_BYTES, &tm_in, slab * CT, 2 * xt * XT - 1, 2 * oy0 - 1 + k * DW_RB2, b, &bars[k]);
+        }
+    }
+    const int xp = tid / G, g = tid - xp * G;
+    const int c0 = slab * CT + g * DW_V;
+    const int ox0 = xt * XT + 2 * xp;
+    const bool live = ox0 < OW, okx1 = ox0 + 1 < OW;
+    u64 s_sum[2] = {0ull, 0ull}, s_sq[2] = {0ull, 0ull};
+    if (live) {
+        u64 wr[9][2];
+        dw_load_taps<false>(w, c0, wr);
+        float psc[DW_V], psh[DW_V];
+#pragma unroll
+        for (int q = 0; q < DW_V; ++q) {
+            psc[q] = MODE == DW_POST ? __ldg(post_scale + c0 + q) : 1.f;
+            psh[q] = MODE == DW_POST ? __ldg(post_shift + c0 + q) : 0.f;
+        }
+        const int ors = OW * C;
+        T *q0 = out + ((int64_t)b * OH + oy0) * ors + (int64_t)ox0 * C + c0;
+        const uint8_t *trow = tile + (4 * xp * CT + g * DW_V) * 2;
+        u64 acc[2][2][2];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (j % DW_RB2 == 0) tc::mbar_wait(&bars[j / DW_RB2], 0);
+            u64 v[5][2];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) K::unpack(*reinterpret_cast<const uint2 *>(trow + j * ROW_BYTES + c * CT * 2), v[c]);
+#pragma unroll
+            for (int ky = 2; ky >= 0; --ky) {
+                if (((j - ky) & 1) != 0) continue;
+                const int r = (j - ky) / 2;
+                if (r >= 0 && r < R && j - ky >= 0) {
+                    const int s = r & 1;
+                    if (ky == 0) { acc[s][0][0] = 0ull; acc[s][0][1] = 0ull; acc[s][1][0] = 0ull; acc[s][1][1] = 0ull; }
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                            for (int p = 0; p < 2; ++p) acc[s][xo][p] = fma2(wr[ky * 3 + kx][p], v[2 * xo + kx][p], acc[s][xo][p]);
+                }
+            }
+            if (j >= 2 && (j & 1) == 0) {
+                const int r = j / 2 - 1, s = r & 1;
+                if (oy0 + r < OH) {
+                    dw_finish<T, MODE>(acc[s][0], q0 + r * ors, psc, psh, post_act, s_sum, s_sq);
+                    if (okx1) dw_finish<T, MODE>(acc[s][1], q0 + r * ors + C, psc, psh, post_act, s_sum, s_sq);
+                }
+            }
+        }
+    }
+    if (MODE == DW_STATS) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            upk2(s_sum[p], sred[tid * 2 * DW_V + 2 * p], sred[tid * 2 * DW_V + 2 * p + 1]);
+            upk2(s_sq[p], sred[tid * 2 * DW_V + DW_V + 2 * p], sred[tid * 2 * DW_V + DW_V + 2 * p + 1]);
+        }
+        __syncthreads();
+        for (int i = tid; i < G * 2 * DW_V; i += 256) {
+            const int gg = i / (2 * DW_V), e = i - gg * 2 * DW_V;
+            float v = 0.f;
+#pragma unroll 4
+            for (int t = gg; t < 256; t += G) v += sred[t * 2 * DW_V + e];
+            const int which = e / DW_V, q = e - which * DW_V;
+            if (v != 0.f) atomicAdd(stats + which * C + slab * CT + gg * DW_V + q, (double)v);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- weight gradient, bf16: both tiles arrive by TMA
+// The input tile (with its halo) in boxes of rows, the gradient tile as one box; rows / columns past the maps are zero
+// (hardware fill), so the loop has no predicates at all.  36 partial sums per thread, reduced over the CTA's column pairs
+// through the (by then free) tile memory, one 16-byte vector reduction per 4 gradients.
+template <int STRIDE, int CT>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_g,
+                           float *__restrict__ dw /* [C][9] */, int OH, int nxt) {
+    typedef __nv_bfloat16 T;
+    typedef DwChunk<T> K;
+    constexpr int G = CT / DW_V, XPT = 256 / G, XT = 2 * XPT;
+    constexpr int R = STRIDE == 1 ? 8 : DW_RT2, NJ = STRIDE == 1 ? R + 2 : 2 * R + 1;
+    constexpr int RB = STRIDE == 1 ? DW_RB : DW_RB2, NB = NJ / RB;
+    constexpr int COLS = STRIDE == 1 ? XT + 2 : 2 * XT + 2, NC = STRIDE == 1 ? 4 : 5, NS = STRIDE == 1 ? 3 : 2;
+    constexpr uint32_t ROW_BYTES = COLS * CT * 2, BOX_BYTES = RB * ROW_BYTES, G_ROW_BYTES = XT * CT * 2, G_BYTES = R * G_ROW_BYTES;
+    static_assert(NJ % RB == 0, "whole boxes");
+    static_assert(NJ * ROW_BYTES + G_BYTES >= 256 * 36 * 4, "the reduction scratch aliases the tiles");
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    __shared__ uint64_t bars[NB];
+    const int tid = threadIdx.x;
+    const int xt = blockIdx.x % nxt, slab = blockIdx.x / nxt;
+    const int nrb = (OH + R - 1) / R;
+    const int b = blockIdx.y / nrb, oy0 = (blockIdx.y - b * nrb) * R;
+    uint8_t *tile = dw_smem + ((128u - (tc::smem_u32(dw_smem) & 127u)) & 127u);
+    uint8_t *gtile = tile + NJ * ROW_BYTES;
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) tc::mbar_init(&bars[k], 1);
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(&bars[0], BOX_BYTES + G_BYTES);
+        tma::load_4d(gtile, &tm_g, slab * CT, xt * XT, oy0, b, &bars[0]);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            if (k > 0) tma::mbar_expect_tx(&bars[k], BOX_BYTES);
+            tma::load_4d(tile + k * BOX_BYTES, &tm_in, slab * CT, STRIDE * xt * XT - 1, STRIDE * oy0 - 1 + k * RB, b, &bars[k]);
+        }
+    }
+    const int xp = tid / G, g = tid - xp * G;
+    u64 acc[9][2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { acc[k][0] = 0ull; acc[k][1] = 0ull; }
+    const uint8_t *trow = tile + (2 * STRIDE * xp * CT + g * DW_V) * 2;
+    const uint8_t *grow = gtile + (2 * xp * CT + g * DW_V) * 2;
+    u64 gv[NS][2][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (j % RB == 0) tc::mbar_wait(&bars[j / RB], 0);
+        u64 v[NC][2];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) K::unpack(*reinterpret_cast<const uint2 *>(trow + j * ROW_BYTES + c * CT * 2), v[c]);
+        if (j % STRIDE == 0 && j / STRIDE < R) {                          // gradient row r first meets input row j = r * STRIDE
+            const int r = j / STRIDE;
+            K::unpack(*reinterpret_cast<const uint2 *>(grow + r * G_ROW_BYTES), gv[r % NS][0]);
+            K::unpack(*reinterpret_cast<const uint2 *>(grow + r * G_ROW_BYTES + CT * 2), gv[r % NS][1]);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            if ((j - ky) % STRIDE != 0 || j - ky < 0) continue;
+            const int r = (j - ky) / STRIDE;
+            if (r < R) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int xo = 0; xo < 2; ++xo)
+#pragma unroll
+                        for (int p = 0; p < 2; ++p)
+                            acc[ky * 3 + kx][p] = fma2(gv[r % NS][xo][p], v[STRIDE * xo + kx][p], acc[ky * 3 + kx][p]);
+            }
+        }
+    }
+    __syncthreads();                                                       // every thread is done with the tiles
+    float *red = reinterpret_cast<float *>(tile);                          // [xp][g][36]
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        float a0, a1, a2, a3;
+        upk2(acc[k][0], a0, a1);
+        upk2(acc[k][1], a2, a3);
+        *reinterpret_cast<float4 *>(red + tid * 36 + k * DW_V) = make_float4(a0, a1, a2, a3);
+    }
+    __syncthreads();
+    // a channel group's 4 x 9 gradients are 36 consecutive floats of dw: 9 16-byte vector reductions per group
+    for (int i = tid; i < G * 9; i += 256) {
+        const int gg = i / 9, j = i - gg * 9;
+        float v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int o = j * 4 + t, q = o / 9, k = o - q * 9;              // dw[(c0 + q)*9 + k]
+            float a = 0.f;
+#pragma unroll 4
+            for (int x = 0; x < XPT; ++x) a += red[(x * G + gg) * 36 + k * DW_V + q];
+            v[t] = a;
+        }
+        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(dw + (slab * CT + gg * DW_V) * 9 + j * 4), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    }
+}
+
 static int dw_check(const char *who, int dtype, int B, int H, int W, int C, int stride) {
     KDF_CHECK_ARG(B >= 0 && H > 0 && W > 0, "%s: bad sizes", who);
     KDF_CHECK_ARG(dtype == KDF_F32 || dtype == KDF_BF16, "%s: bad dtype %d", who, dtype);
@@ -654,6 +857,29 @@ static int dwconv_fwd_impl(const void *in, const float *weight, int dtype, int B
         else if (mode == DW_STATS) KDF_DWT_CT(false, DW_STATS);
         else if (mode == DW_POST) KDF_DWT_CT(false, DW_POST);
         else KDF_DWT_CT(false, DW_PLAIN);
+#undef KDF_DWT_CT
+#undef KDF_DWT
+        KDF_LAUNCH_CHECK();
+        return KDF_OK;
+    }
+    if (dtype == KDF_BF16 && stride == 2 && C % 32 == 0 && (int64_t)B * ((OH + DW_RT2 - 1) / DW_RT2) <= 65535) {
+        const int CT = C % 64 == 0 ? 64 : 32;
+        const int XT = 2 * (256 / (CT / DW_V)), COLS = 2 * XT + 2;
+        CUtensorMap tm;
+        KDF_CHECK_ARG(tma::make_nhwc_map(&tm, in, B, H, W, C, CT, COLS, DW_RB2), "dwconv3x3_fwd: cuTensorMapEncodeTiled failed");
+        const int nxt = (OW + XT - 1) / XT;
+        const dim3 tgrid((unsigned)(nxt * (C / CT)), (unsigned)(B * ((OH + DW_RT2 - 1) / DW_RT2)));
+        const size_t smem = (size_t)(2 * DW_RT2 + 1) * COLS * CT * 2 + 128;
+#define KDF_DWT(M, CTV)                                                                                                           \
+    do {                                                                                                                          \
+        KDF_CUDA(cudaFuncSetAttribute(dwconv3x3_s2_tma_kernel<M, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dwconv3x3_s2_tma_kernel<M, CTV><<<tgrid, 256, smem, st>>>(tm, weight, (__nv_bfloat16 *)out, OH, OW, C, nxt, stats, post_scale, \
+                                                                  post_shift, post_act);                                          \
+    } while (0)
+#define KDF_DWT_CT(M) do { if (CT == 64) KDF_DWT(M, 64); else KDF_DWT(M, 32); } while (0)
+        if (stats) KDF_DWT_CT(DW_STATS);
+        else if (post_scale) KDF_DWT_CT(DW_POST);
+        else KDF_DWT_CT(DW_PLAIN);
 #undef KDF_DWT_CT
 #undef KDF_DWT
         KDF_LAUNCH_CHECK();
@@ -731,6 +957,30 @@ int kdf_dwconv3x3_bwd_weight(const void *in, const void *grad_out, int dtype, in
     KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(grad_out)) & 15) == 0,
                   "dwconv3x3_bwd_weight: maps must be 16-byte aligned");
     const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    {
+        const int RT = stride == 1 ? 8 : DW_RT2;
+        if (dtype == KDF_BF16 && C % 32 == 0 && (int64_t)B * ((OH + RT - 1) / RT) <= 65535) {
+            const int CT = C % 64 == 0 ? 64 : 32;
+            const int XT = 2 * (256 / (CT / DW_V)), COLS = stride == 1 ? XT + 2 : 2 * XT + 2;
+            const int NJ = stride == 1 ? RT + 2 : 2 * RT + 1, RB = stride == 1 ? DW_RB : DW_RB2;
+            CUtensorMap tm_in, tm_g;
+            KDF_CHECK_ARG(tma::make_nhwc_map(&tm_in, in, B, H, W, C, CT, COLS, RB) && tma::make_nhwc_map(&tm_g, grad_out, B, OH, OW, C, CT, XT, RT),
+                          "dwconv3x3_bwd_weight: cuTensorMapEncodeTiled failed");
+            const int nxt = (OW + XT - 1) / XT;
+            const dim3 tgrid((unsigned)(nxt * (C / CT)), (unsigned)(B * ((OH + RT - 1) / RT)));
+            const size_t smem = (size_t)NJ * COLS * CT * 2 + (size_t)RT * XT * CT * 2 + 128;
+#define KDF_DWWT(S, CTV)                                                                                                          \
+    do {                                                                                                                          \
+        KDF_CUDA(cudaFuncSetAttribute(dwconv3x3_wgrad_tma_kernel<S, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dwconv3x3_wgrad_tma_kernel<S, CTV><<<tgrid, 256, smem, st>>>(tm_in, tm_g, grad_weight, OH, nxt);                         \
+    } while (0)
+            if (stride == 1) { if (CT == 64) KDF_DWWT(1, 64); else KDF_DWWT(1, 32); }
+            else { if (CT == 64) KDF_DWWT(2, 64); else KDF_DWWT(2, 32); }
+#undef KDF_DWWT
+            KDF_LAUNCH_CHECK();
+            return KDF_OK;
+        }
+    }
     const int cg = C / DW_V;
     const int nt = dw_block(cg), rows = nt / cg;
     const int R = stride == 1 ? DW_R1 : DW_R2;
