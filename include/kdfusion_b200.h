@@ -126,6 +126,16 @@ int kdf_bev_build_order(const float *points, int point_stride, int B, int64_t N,
                         int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* The sort stage with the POINTS THEMSELVES written in cell order (the point MLP then runs over cell-sorted
+ * rows and the projection works on contiguous row segments): sorted_points f32 [B,N,4] -- frame b's rows
+ * [offsets[b,c], offsets[b,c+1]) are the points of cell c, the points outside the grid follow from offsets[b,HW] on --,
+ * cell_sorted i32 [B,N] = the GLOBAL cell id b*H*W + c of every sorted row (-1 outside), order (nullable) i32 [B,N] = the
+ * permutation (sorted row -> point id).  count / cell / offsets as kdf_bev_build_order (cell stays in the caller's point
+ * order: it is the reference's flat index, lidar_encoder.py:74-82).  Points must be dense (x, y, z, i), 16-byte aligned. */
+int kdf_bev_build_sorted(const float *points, int B, int64_t N, float x0, float xspan, float y0, float yspan, int H, int W,
+                         int32_t *count, int32_t *cell, int32_t *offsets, float *sorted_points, int32_t *cell_sorted,
+                         int32_t *order, void *workspace, size_t workspace_bytes, void *stream);
+
 /* The reduce stage alone, over a cell ordering produced earlier (by
  * kdf_bev_project_fwd with order/offsets supplied, e.g. to share one sort between
  * the teacher's and the student's projection of the same sweep, or to time the
@@ -202,6 +212,20 @@ int kdf_bev_bwd_affine(const void *grad_grid_bf16, const void *z_bf16, const voi
                        const int32_t *order, const int32_t *offsets, const int32_t *cell,
                        int B, int64_t N, int C, int H, int W, void *dy_bf16, double *sums, void *stream);
 int kdf_point_moments(const float *points, int64_t M, double *out14, void *stream);
+
+/* Cell-sorted rows (kdf_bev_build_sorted; kdf_bev_reduce_affine then takes order = NULL): the projection backward
+ * without gradient rows.  share bf16 [B*H*W, C] = what every row at its cell's extreme receives (g/k, bf16; rows of empty
+ * cells are not written), bits u8 [B*N, C/8] = per row and 8 channels one byte, bit q set when channel 8g+q of the row sits
+ * at the extreme (rows of points outside are not written), sums as kdf_bev_bwd_affine.  kdf_mlp_layer_bwd_share is
+ * kdf_mlp_layer_bwd (mode 1) with dy[row][c] = bit ? share[cell_sorted[row]][c] : 0 formed in its prologue: the
+ * [B*N, C] gradient tensor of lidar_encoder.py:85-96's backward is never written or read. */
+int kdf_bev_bwd_share(const void *grad_grid_bf16, const void *z_bf16, const void *grid_bf16, const void *grid_z_bf16,
+                      const int32_t *offsets, int B, int64_t N, int C, int H, int W, void *share_bf16, void *bits_u8,
+                      double *sums, void *stream);
+int kdf_mlp_layer_bwd_share(const int32_t *row_cell, const void *share, const void *bits, const void *z,
+                            const float *gs, const float *ga, const float *gb, const void *z_prev, int64_t M,
+                            const float *pro_a, const float *pro_b, const void *W_bf16, void *dy_prev, double *sums, float *dW,
+                            void *stream);
 
 /* ---------------------------------------------------------------- fused point-MLP layers (tcgen05)
  * One tensor-core layer of the point MLP (src/models/lidar_encoder.py:25-35) as ONE kernel that keeps

@@ -206,11 +206,14 @@ constexpr int BEV_CHUNK = 8192;
 template <bool RV>
 __global__ void __launch_bounds__(256)
 bev_chunk_count_kernel(const float4 *__restrict__ points, int64_t N, BevGeom g, int32_t *__restrict__ cell_out,
-                       int32_t *__restrict__ rank_out, int32_t *__restrict__ chist, int nchunk) {
+                       int32_t *__restrict__ rank_out, int32_t *__restrict__ chist, int nchunk,
+                       int32_t *__restrict__ cout /* nullable [B][nchunk]: points outside the grid, ranked too */) {
     extern __shared__ int hist[];
+    __shared__ int n_out;
     const int HW = g.H * g.W;
     const int chunk = blockIdx.x, b = blockIdx.y;
     for (int i = threadIdx.x; i < HW; i += 256) hist[i] = 0;
+    if (threadIdx.x == 0) n_out = 0;
     __syncthreads();
     const int64_t beg = (int64_t)chunk * BEV_CHUNK, end = (beg + BEV_CHUNK < N) ? beg + BEV_CHUNK : N;
     const float4 *pb = points + (int64_t)b * N;
@@ -229,17 +232,19 @@ bev_chunk_count_kernel(const float4 *__restrict__ points, int64_t N, BevGeom g, 
                 const int cell = cell_of<RV>(p[u].x, p[u].y, p[u].z, g);
                 cb[i] = cell;
                 if (cell >= 0) rb[i] = atomicAdd(&hist[cell], 1);
+                else if (cout) rb[i] = atomicAdd(&n_out, 1);
             }
         }
     }
     __syncthreads();
     int32_t *out = chist + ((int64_t)b * nchunk + chunk) * HW;
     for (int i = threadIdx.x; i < HW; i += 256) out[i] = hist[i];
+    if (cout && threadIdx.x == 0) cout[(int64_t)b * nchunk + chunk] = n_out;
 }
 
 __global__ void __launch_bounds__(1024)
 bev_chunk_scan_kernel(int32_t *__restrict__ chist /* in: histograms, out: chunk bases */, int32_t *__restrict__ count,
-                      int32_t *__restrict__ offsets, int HW, int nchunk) {
+                      int32_t *__restrict__ offsets, int HW, int nchunk, int32_t *__restrict__ cout /* nullable, in place */) {
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -290,6 +295,14 @@ bev_chunk_scan_kernel(int32_t *__restrict__ chist /* in: histograms, out: chunk 
         __syncthreads();
     }
     if (t == 0) off[HW] = carry_s;
+    if (cout && t == 0) {                                                    // outside points of chunk k start behind those of chunks < k
+        int run = 0;
+        for (int k = 0; k < nchunk; ++k) {
+            const int v = cout[(int64_t)b * nchunk + k];
+            cout[(int64_t)b * nchunk + k] = run;
+            run += v;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -315,6 +328,46 @@ bev_chunk_fill_kernel(const int32_t *__restrict__ cell, const int32_t *__restric
 #pragma unroll
         for (int u = 0; u < 4; ++u)
             if (c[u] >= 0) ob[base[c[u]] + r[u]] = (int32_t)(i0 + u * 256);
+    }
+}
+
+// The same pass writing the POINTS in cell order: frame b's rows [offsets[c], offsets[c+1]) are the points of
+// cell c, the points outside the grid follow from offsets[HW] on.  cell_sorted holds the global cell id b*HW + c of every
+// sorted row (-1 outside).  Everything downstream of the point MLP then works on contiguous row segments.
+__global__ void __launch_bounds__(256)
+bev_chunk_permute_kernel(const float4 *__restrict__ points, const int32_t *__restrict__ cell, const int32_t *__restrict__ rank,
+                         const int32_t *__restrict__ cbase, const int32_t *__restrict__ cout, const int32_t *__restrict__ offsets,
+                         float4 *__restrict__ sorted, int32_t *__restrict__ cell_sorted, int32_t *__restrict__ order /* nullable */,
+                         int64_t N, int HW, int nchunk) {
+    extern __shared__ int base[];
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int32_t *cbp = cbase + ((int64_t)b * nchunk + chunk) * HW, *off = offsets + (int64_t)b * (HW + 1);
+    for (int i = threadIdx.x; i < HW; i += 256) base[i] = cbp[i] + off[i];
+    __syncthreads();
+    const int out_base = off[HW] + cout[(int64_t)b * nchunk + chunk];
+    const int64_t beg = (int64_t)chunk * BEV_CHUNK, end = (beg + BEV_CHUNK < N) ? beg + BEV_CHUNK : N;
+    const int32_t *cb = cell + (int64_t)b * N, *rb = rank + (int64_t)b * N;
+    const float4 *pb = points + (int64_t)b * N;
+    float4 *sb = sorted + (int64_t)b * N;
+    int32_t *csb = cell_sorted + (int64_t)b * N, *ob = order ? order + (int64_t)b * N : nullptr;
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += 4 * 256) {
+        int c[4], r[4];
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 256;
+            if (i < end) { c[u] = __ldg(cb + i); r[u] = __ldg(rb + i); p[u] = ldg_stream_f4(pb + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 256;
+            if (i < end) {
+                const int pos = (c[u] >= 0 ? base[c[u]] : out_base) + r[u];
+                sb[pos] = p[u];
+                csb[pos] = c[u] >= 0 ? b * HW + c[u] : -1;
+                if (ob) ob[pos] = (int32_t)i;
+            }
+        }
     }
 }
 
@@ -687,7 +740,7 @@ __device__ __forceinline__ CellMeta cell_meta(const int32_t *__restrict__ offset
     return m;
 }
 
-template <int LPR>
+template <int LPR, bool ORD>
 __global__ void __launch_bounds__(256, 4)
 bev_reduce_affine_kernel(const __nv_bfloat16 *__restrict__ z, const float *__restrict__ scale, const float *__restrict__ shift,
                          const int32_t *__restrict__ order, const int32_t *__restrict__ offsets,
@@ -705,16 +758,16 @@ bev_reduce_affine_kernel(const __nv_bfloat16 *__restrict__ z, const float *__res
     CellMeta cur = cell_meta(offsets, cid, n_cells, N, HW);
     int idn[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < cur.n ? __ldg(order + cur.rowbase + cur.beg + j) : -1; }
+    for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn[u] = j < cur.n ? (ORD ? __ldg(order + cur.rowbase + cur.beg + j) : cur.beg + j) : -1; }
     CellMeta nxt = cell_meta(offsets, cid + nwarps, n_cells, N, HW);
     while (cid < n_cells) {
         // one cell ahead: first ids of the next cell (its offsets arrived during the previous cell), offsets of the one after
         int idn2[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn2[u] = j < nxt.n ? __ldg(order + nxt.rowbase + nxt.beg + j) : -1; }
+        for (int u = 0; u < U; ++u) { const int j = u * RPL + sub; idn2[u] = j < nxt.n ? (ORD ? __ldg(order + nxt.rowbase + nxt.beg + j) : nxt.beg + j) : -1; }
         const CellMeta nxt2 = cell_meta(offsets, cid + 2 * nwarps, n_cells, N, HW);
 
-        const int32_t *ord = order + cur.rowbase + cur.beg;
+        const int32_t *ord = ORD ? order + cur.rowbase + cur.beg : nullptr;   // !ORD: the rows are already in cell order
         const __nv_bfloat16 *zb = z + cur.rowbase * C + ch;
         uint32_t m[4] = {0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u};           // -inf, -inf
         for (int j0 = 0; j0 < cur.n; j0 += STEP) {
@@ -726,7 +779,7 @@ bev_reduce_affine_kernel(const __nv_bfloat16 *__restrict__ z, const float *__res
                 if (id[u] >= 0) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(zb + (int64_t)id[u] * C));
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < cur.n ? __ldg(ord + j) : -1; }
+            for (int u = 0; u < U; ++u) { const int j = j0 + STEP + u * RPL + sub; idn[u] = j < cur.n ? (ORD ? __ldg(ord + j) : cur.beg + j) : -1; }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (id[u] >= 0) {
@@ -894,6 +947,99 @@ bev_bwd_affine_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bf
             if (__ldg(cell + i) < 0) *reinterpret_cast<uint4 *>(dy + i * C + ch) = zero;
     }
     // S0 / S1: the 8 warps through shared memory, then fp64 atomics (only sub 0 accumulated)
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        const int c = i % C, idx = (c & 7) * LPR + (c >> 3);
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][i / C][idx];
+        atomicAdd(sums + i, (double)v);
+    }
+}
+
+// ----------------------------------------------------------------------------- cell-sorted rows (f2): shares + tie bits, no dy rows
+// With the rows of a cell contiguous (kdf_bev_build_sorted) the gradient rows need not exist: per cell this writes the
+// share every row at the extreme receives (bf16 [cells, C]) and per row ONE BYTE per 8 channels saying which of them sit at
+// the extreme (u8 [rows, C/8]); the layer-3 backward forms dy = bit ? share[cell] : 0 in its prologue (a 128-row tile meets
+// ~5 cells, so the share rows are L1 hits).  C*s/8 + ... bytes per point instead of a C*s row written and read back.
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bev_bwd_share_kernel(const __nv_bfloat16 *__restrict__ grad_grid, const __nv_bfloat16 *__restrict__ z,
+                     const __nv_bfloat16 *__restrict__ grid, const __nv_bfloat16 *__restrict__ grid_z,
+                     const int32_t *__restrict__ offsets, __nv_bfloat16 *__restrict__ share_out, uint8_t *__restrict__ bits,
+                     double *__restrict__ sums /* [2][C] */, int64_t n_cells, int64_t N, int HW) {
+    using T = __nv_bfloat16;
+    constexpr int C = LPR * 8, RPL = 32 / LPR, U = 8, STEP = RPL * U;   // 16 rows of a C = 128 cell in flight per warp
+    __shared__ float red[8][2][LPR * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, ch = (lane % LPR) * 8;
+    const int rl = lane % LPR;
+    if (sub == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { red[warp][0][q * LPR + rl] = 0.f; red[warp][1][q * LPR + rl] = 0.f; }
+    }
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t cid = warp0;
+    CellMeta cur = cell_meta(offsets, cid, n_cells, N, HW);
+    CellMeta nxt = cell_meta(offsets, cid + nwarps, n_cells, N, HW);
+    while (cid < n_cells) {
+        const CellMeta nxt2 = cell_meta(offsets, cid + 2 * nwarps, n_cells, N, HW);
+        if (cur.n > 0) {
+            const T *zb = z + (cur.rowbase + cur.beg) * C + ch;
+            uint8_t *bb = bits + (cur.rowbase + cur.beg) * LPR + rl;
+            const uint4 ze = __ldg(reinterpret_cast<const uint4 *>(grid_z + cid * C + ch));
+            const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(grad_grid + cid * C + ch));
+            const uint4 av = __ldg(reinterpret_cast<const uint4 *>(grid + cid * C + ch));
+            int k[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) k[q] = 0;
+            for (int j0 = 0; j0 < cur.n; j0 += STEP) {
+                uint4 raw[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * RPL + sub;
+                    if (j < cur.n) raw[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(zb + (int64_t)j * C));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * RPL + sub;
+                    if (j < cur.n) {
+                        const uint32_t e0 = bf16x2_eq_mask(raw[u].x, ze.x), e1 = bf16x2_eq_mask(raw[u].y, ze.y);
+                        const uint32_t e2 = bf16x2_eq_mask(raw[u].z, ze.z), e3 = bf16x2_eq_mask(raw[u].w, ze.w);
+                        k[0] += e0 & 1; k[1] += e0 >> 31; k[2] += e1 & 1; k[3] += e1 >> 31;
+                        k[4] += e2 & 1; k[5] += e2 >> 31; k[6] += e3 & 1; k[7] += e3 >> 31;
+                        // the row's tie bits for these 8 channels (bit q = channel ch + q)
+                        bb[(int64_t)j * LPR] = (uint8_t)((e0 & 1) | ((e0 >> 31) << 1) | ((e1 & 1) << 2) | ((e1 >> 31) << 3) |
+                                                         ((e2 & 1) << 4) | ((e2 >> 31) << 5) | ((e3 & 1) << 6) | ((e3 >> 31) << 7));
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) k[q] += __shfl_xor_sync(0xffffffffu, k[q], o);
+            }
+            if (sub == 0) {
+                float g[8], a3[8], zf[8], sh[8];
+                Raw16<T>::unpack(gv, g);
+                Raw16<T>::unpack(av, a3);
+                Raw16<T>::unpack(ze, zf);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sh[q] = (a3[q] > 0.f && k[q] > 0) ? g[q] / (float)k[q] : 0.f;
+                const uint4 share = Raw16<T>::pack(sh);                     // rounded to bf16 as the rows would have stored it ...
+                *reinterpret_cast<uint4 *>(share_out + cid * C + ch) = share;
+                Raw16<T>::unpack(share, sh);                                // ... and the sums use exactly those values
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float tot = sh[q] * (float)k[q];
+                    red[warp][0][q * LPR + rl] += tot;
+                    red[warp][1][q * LPR + rl] = fmaf(tot, zf[q], red[warp][1][q * LPR + rl]);
+                }
+            }
+        }
+        cid += nwarps;
+        cur = nxt;
+        nxt = nxt2;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
         const int c = i % C, idx = (c & 7) * LPR + (c >> 3);
@@ -1254,7 +1400,8 @@ size_t kdf_bev_workspace_bytes(int B, int64_t N, int H, int W) {
 
 // index -> scan -> fill: cell ids, occupancy and the cell ordering (counting sort) of every frame
 static int build_order(const float *points, int point_stride, int B, int64_t N, const BevGeom &g,
-                       int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets, int32_t *rank, cudaStream_t st) {
+                       int32_t *count, int32_t *cell, int32_t *order, int32_t *offsets, int32_t *rank, cudaStream_t st,
+                       float *sorted_points = nullptr, int32_t *cell_sorted = nullptr) {
     const int HW = g.H * g.W;
     const int64_t total = (int64_t)B * N;
     const int64_t nchunk = (N + BEV_CHUNK - 1) / BEV_CHUNK;
@@ -1264,24 +1411,33 @@ static int build_order(const float *points, int point_stride, int B, int64_t N, 
         const size_t bn = align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256);
         const size_t off = align_up(sizeof(int32_t) * (size_t)B * ((size_t)HW + 1), 256);
         int32_t *chist = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(rank) + 2 * bn + off);
+        // cell-sorted points: the per-chunk counts of points outside the grid sit in the (otherwise unused) second [B,N] block
+        int32_t *cout = sorted_points ? reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(rank) + bn) : nullptr;
+        KDF_CHECK_ARG(!sorted_points || (size_t)B * nchunk * sizeof(int32_t) <= bn, "bev_build_sorted: frames too short for the workspace layout");
         const size_t smem = sizeof(int) * (size_t)HW;
         if (smem > 48 * 1024) {
+            KDF_CUDA(cudaFuncSetAttribute(bev_chunk_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             KDF_CUDA(cudaFuncSetAttribute(bev_chunk_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             KDF_CUDA(cudaFuncSetAttribute(bev_chunk_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             KDF_CUDA(cudaFuncSetAttribute(bev_chunk_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         const dim3 grid((unsigned)nchunk, (unsigned)B);
         if (g.range_view)
-            bev_chunk_count_kernel<true><<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(points), N, g, cell, rank, chist, (int)nchunk);
+            bev_chunk_count_kernel<true><<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(points), N, g, cell, rank, chist, (int)nchunk, cout);
         else
-            bev_chunk_count_kernel<false><<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(points), N, g, cell, rank, chist, (int)nchunk);
+            bev_chunk_count_kernel<false><<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(points), N, g, cell, rank, chist, (int)nchunk, cout);
         KDF_LAUNCH_CHECK();
-        bev_chunk_scan_kernel<<<B, 1024, 0, st>>>(chist, count, offsets, HW, (int)nchunk);
+        bev_chunk_scan_kernel<<<B, 1024, 0, st>>>(chist, count, offsets, HW, (int)nchunk, cout);
         KDF_LAUNCH_CHECK();
-        bev_chunk_fill_kernel<<<grid, 256, smem, st>>>(cell, rank, chist, offsets, order, N, HW, (int)nchunk);
+        if (sorted_points)
+            bev_chunk_permute_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(points), cell, rank, chist, cout, offsets,
+                                                              reinterpret_cast<float4 *>(sorted_points), cell_sorted, order, N, HW, (int)nchunk);
+        else
+            bev_chunk_fill_kernel<<<grid, 256, smem, st>>>(cell, rank, chist, offsets, order, N, HW, (int)nchunk);
         KDF_LAUNCH_CHECK();
         return KDF_OK;
     }
+    KDF_CHECK_ARG(!sorted_points, "bev_build_sorted: needs 16-byte aligned (x, y, z, i) points, H*W <= 24576 cells and N > 0");
     if (int e = launch_index(points, B, N, point_stride, g, cell, rank, count, st)) return e;
     bev_scan_kernel<<<B, 1024, 0, st>>>(count, offsets, HW);
     KDF_LAUNCH_CHECK();
@@ -1304,6 +1460,23 @@ int kdf_bev_build_order(const float *points, int point_stride, int B, int64_t N,
     BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
     return build_order(points, point_stride, B, N, g, count, cell, order, offsets, reinterpret_cast<int32_t *>(workspace),
                        as_stream(stream));
+}
+
+// The same, with the points themselves written in cell order (f2): sorted_points f32 [B,N,4], cell_sorted i32 [B,N]
+// (global cell id b*H*W + cell of every sorted row, -1 for the rows of points outside, which close each frame);
+// order (nullable) = the permutation, sorted row -> point id.
+int kdf_bev_build_sorted(const float *points, int B, int64_t N, float x0, float xspan, float y0, float yspan, int H, int W,
+                         int32_t *count, int32_t *cell, int32_t *offsets, float *sorted_points, int32_t *cell_sorted,
+                         int32_t *order, void *workspace, size_t workspace_bytes, void *stream) {
+    if (int e = check_geom(B, N, H, W, xspan, yspan)) return e;
+    if (B == 0) return KDF_OK;
+    KDF_CHECK_ARG(((points && cell && sorted_points && cell_sorted) || N == 0) && count && offsets && workspace, "bev_build_sorted: null pointer");
+    KDF_CHECK_ARG(workspace_bytes >= kdf_bev_workspace_bytes(B, N, H, W), "bev_build_sorted: workspace too small");
+    KDF_CHECK_ARG((int64_t)B * H * W < (1ll << 31), "bev_build_sorted: too many cells for 32-bit global cell ids");
+    KDF_CHECK_ARG((reinterpret_cast<uintptr_t>(sorted_points) & 15) == 0, "bev_build_sorted: sorted_points must be 16-byte aligned");
+    BevGeom g{x0, xspan, y0, yspan, (float)(W - 1), (float)(H - 1), H, W};
+    return build_order(points, 4, B, N, g, count, cell, order, offsets, reinterpret_cast<int32_t *>(workspace), as_stream(stream),
+                       sorted_points, cell_sorted);
 }
 
 static int project_fwd_impl(const float *points, int point_stride, const void *feats, int dtype, int B, int64_t N, int C,
@@ -1439,16 +1612,48 @@ int kdf_bev_reduce_affine(const void *z_bf16, const float *scale, const float *s
     KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_reduce_affine: bad sizes");
     KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_reduce_affine: C=%d not supported (64, 128, 256)", C);
     if (B == 0) return KDF_OK;
-    KDF_CHECK_ARG(((z_bf16 && order) || N == 0) && scale && shift && offsets && grid_bf16, "bev_reduce_affine: null pointer");
+    KDF_CHECK_ARG((z_bf16 || N == 0) && scale && shift && offsets && grid_bf16, "bev_reduce_affine: null pointer");
     const int64_t n_cells = (int64_t)B * H * W;
     int64_t blocks = (n_cells + 7) / 8;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;      // persistent warps, several cells each
     cudaStream_t st = as_stream(stream);
     const __nv_bfloat16 *zz = reinterpret_cast<const __nv_bfloat16 *>(z_bf16);
     __nv_bfloat16 *gg = reinterpret_cast<__nv_bfloat16 *>(grid_bf16), *gz = reinterpret_cast<__nv_bfloat16 *>(grid_z_bf16);
-    if (C == 64)       bev_reduce_affine_kernel<8><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);
-    else if (C == 128) bev_reduce_affine_kernel<16><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);
-    else               bev_reduce_affine_kernel<32><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);
+    // order == nullptr: the rows are in cell order already (kdf_bev_build_sorted), a cell is a contiguous row segment
+#define KDF_RA(L)                                                                                                             \
+    do {                                                                                                                      \
+        if (order) bev_reduce_affine_kernel<L, true><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W); \
+        else bev_reduce_affine_kernel<L, false><<<(int)blocks, 256, 0, st>>>(zz, scale, shift, order, offsets, gg, gz, n_cells, N, H * W);      \
+    } while (0)
+    if (C == 64) KDF_RA(8); else if (C == 128) KDF_RA(16); else KDF_RA(32);
+#undef KDF_RA
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+// Projection backward over cell-sorted rows: share bf16 [B*H*W, C] (the gradient every row at its cell's extreme receives;
+// rows of empty cells are not written), bits u8 [B*N, C/8] (bit q of byte g: channel 8g+q of the row sits at the extreme;
+// rows outside the grid are not written), sums f64 [2, C] as kdf_bev_bwd_affine.  No gradient rows are materialised:
+// kdf_mlp_layer_bwd (mode 1) forms them from (cell_sorted, share, bits).
+int kdf_bev_bwd_share(const void *grad_grid_bf16, const void *z_bf16, const void *grid_bf16, const void *grid_z_bf16,
+                      const int32_t *offsets, int B, int64_t N, int C, int H, int W, void *share_bf16, void *bits_u8,
+                      double *sums, void *stream) {
+    KDF_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "bev_bwd_share: bad sizes");
+    KDF_CHECK_ARG(C == 64 || C == 128 || C == 256, "bev_bwd_share: C=%d not supported (64, 128, 256)", C);
+    KDF_CHECK_ARG(sums, "bev_bwd_share: null pointer");
+    cudaStream_t st = as_stream(stream);
+    KDF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    if ((int64_t)B * N == 0) return KDF_OK;
+    KDF_CHECK_ARG(grad_grid_bf16 && z_bf16 && grid_bf16 && grid_z_bf16 && offsets && share_bf16 && bits_u8, "bev_bwd_share: null pointer");
+    const int64_t n_cells = (int64_t)B * H * W;
+    int64_t blocks = (n_cells + 7) / 8;
+    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+    typedef const __nv_bfloat16 *cb;
+#define KDF_BS(L)                                                                                                             \
+    bev_bwd_share_kernel<L, 3><<<(int)blocks, 256, 0, st>>>((cb)grad_grid_bf16, (cb)z_bf16, (cb)grid_bf16, (cb)grid_z_bf16, offsets, \
+        reinterpret_cast<__nv_bfloat16 *>(share_bf16), reinterpret_cast<uint8_t *>(bits_u8), sums, n_cells, N, H * W)
+    if (C == 64) KDF_BS(8); else if (C == 128) KDF_BS(16); else KDF_BS(32);
+#undef KDF_BS
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

@@ -543,6 +543,10 @@ struct MlpBwdArgs {
     float *dW;                        // [128, KIN] fp32, accumulated with atomics (zeroed by the host wrapper)
     const int32_t *row_cell;          // nullable [M]: rows with row_cell < 0 have dy == 0 by contract and their dy rows are
                                       // not read as data (the producer kdf_bev_bwd_affine may then skip writing them)
+    // cell-sorted rows (SHARE kernels): dy is not materialised; row_cell holds GLOBAL cell ids and
+    // dy[row][c] = bit c of bits[row] ? share[row_cell[row]][c] : 0   (kdf_bev_bwd_share)
+    const __nv_bfloat16 *share;       // [cells,128]
+    const uint8_t *bits;              // [M,16]
 };
 
 template <int KIN>
@@ -579,9 +583,10 @@ __device__ __forceinline__ void coef_load8(const float *tab, int d, float (&v)[8
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
 }
 
-template <int MODE, int KIN, int NT>
+template <int MODE, int KIN, int NT, bool SHARE = false>
 __global__ void __launch_bounds__(NT, 1)
 mlp_layer_bwd_kernel(MlpBwdArgs a) {
+    static_assert(!SHARE || MODE == 1, "the share form is the layer-3 backward");
     KDF_PM_DERIVED(NT);
     using L = MlpBwdSmem<KIN>;
     constexpr int ACH = KIN / 8;                                  // 16-byte chunks per activation row
@@ -637,16 +642,47 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 
     uint4 raw_dy[D_PASSES], raw_z[D_PASSES], raw_in[A_PASSES];
     int raw_cell[D_PASSES];
-    auto load_tile = [&](int64_t tile) {
+    // SHARE: the share loads of a tile need its cell ids one tile earlier than everything else.  They travel through shared
+    // memory by cp.async (no register waits on them: a loop-carried register copy of a fresh load stalled every thread for a
+    // full memory latency per tile); sCell[k & 1] holds the ids of this CTA's k-th tile (the point tile is unused in mode 1).
+    int32_t *sCell = reinterpret_cast<int32_t *>(smem + L::OFF_PTS);
+    auto request_cells = [&](int64_t tile, int k) {
+        if (tid < PM_ROWS) {
+            const int64_t row = tile * PM_ROWS + tid;
+            int32_t *dst = sCell + (k & 1) * PM_ROWS + tid;
+            if (tile < n_tiles && row < a.M)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(a.row_cell + row) : "memory");
+            else
+                *dst = -1;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_tile = [&](int64_t tile, int k = 0) {
         const int64_t r0 = tile * PM_ROWS;
+        if (SHARE) {
 #pragma unroll
-        for (int p = 0; p < D_PASSES; ++p) {
-            const int64_t row = r0 + drow0 + p * PM_OROWS;
-            raw_cell[p] = 0;
-            if (row < a.M) {
-                if (a.row_cell) raw_cell[p] = __ldg(a.row_cell + row);
-                raw_dy[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
-                raw_z[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
+            for (int p = 0; p < D_PASSES; ++p) {
+                const int64_t row = r0 + drow0 + p * PM_OROWS;
+                raw_cell[p] = sCell[(k & 1) * PM_ROWS + drow0 + p * PM_OROWS];
+                if (raw_cell[p] >= 0) {                                    // (implies row < M)
+                    // the share chunk and the tie byte are read at staging time (a 128-row tile meets ~5 cells: L1 hits);
+                    // here they are only pulled towards L1 -- holding them in registers for a tile spilled the kernel
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.share + (int64_t)raw_cell[p] * PM_N + dch * 8));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.bits + row * (PM_N / 8) + dch));
+                }
+                if (row < a.M) raw_z[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
+            }
+            request_cells(tile + gridDim.x, k + 1);
+        } else {
+#pragma unroll
+            for (int p = 0; p < D_PASSES; ++p) {
+                const int64_t row = r0 + drow0 + p * PM_OROWS;
+                raw_cell[p] = 0;
+                if (row < a.M) {
+                    if (a.row_cell) raw_cell[p] = __ldg(a.row_cell + row);
+                    raw_dy[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.dy + row * PM_N + dch * 8));
+                    raw_z[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.z + row * PM_N + dch * 8));
+                }
             }
         }
 #pragma unroll
@@ -662,7 +698,8 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
         if (tile >= n_tiles) return;
         const int64_t r0 = tile * PM_ROWS;
         const int64_t rows = (a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS;
-        tc::prefetch_l2(a.dy + r0 * PM_N, (uint32_t)(rows * PM_N * 2));
+        if (SHARE) { if (((rows * (PM_N / 8)) & ~15) > 0) tc::prefetch_l2(a.bits + r0 * (PM_N / 8), (uint32_t)((rows * (PM_N / 8)) & ~15)); }
+        else tc::prefetch_l2(a.dy + r0 * PM_N, (uint32_t)(rows * PM_N * 2));
         tc::prefetch_l2(a.z + r0 * PM_N, (uint32_t)(rows * PM_N * 2));
         // the cell ids too: without it they are the one load of the tile that still sees DRAM latency (measured: the kernel
         // ran 1.45 ms with row_cell against 1.32 ms without; 1.36 ms with this prefetch).  Skipping the dy rows of points
@@ -683,7 +720,19 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (r0 + r < a.M) {
                     float g[8], zz[8];
-                    unpack8(raw_cell[p] >= 0 ? raw_dy[p] : make_uint4(0u, 0u, 0u, 0u), g);
+                    if (SHARE) {                                          // the row's share of its cell's gradient: only where it sits at the extreme
+                        uint4 sh = make_uint4(0u, 0u, 0u, 0u);
+                        uint32_t tb = 0u;
+                        if (raw_cell[p] >= 0) {
+                            sh = __ldg(reinterpret_cast<const uint4 *>(a.share + (int64_t)raw_cell[p] * PM_N + dch * 8));
+                            tb = __ldg(a.bits + (r0 + r) * (PM_N / 8) + dch);
+                        }
+                        unpack8(sh, g);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) g[j] = (tb >> j) & 1u ? g[j] : 0.f;
+                    } else {
+                        unpack8(raw_cell[p] >= 0 ? raw_dy[p] : make_uint4(0u, 0u, 0u, 0u), g);
+                    }
                     unpack8(raw_z[p], zz);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
@@ -839,10 +888,16 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
 
     // ---- software pipeline over this CTA's tiles (same schedule as the forward kernel)
     int64_t tile = blockIdx.x;
+    if (SHARE) {
+        request_cells(tile, 0);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+    }
     if (tile < n_tiles) {
-        load_tile(tile);
+        load_tile(tile, 0);
         stage_tile(tile, 0);
     }
+    if (SHARE) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     int it = 0;
     int64_t prev_tile = -1;
@@ -853,10 +908,11 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
             issue_mma(buf, it == 0);
         }
         const int64_t next = tile + gridDim.x;
-        if (next < n_tiles) load_tile(next);
+        if (next < n_tiles) load_tile(next, it + 1);
         if (tid == 32) l2_prefetch(next + gridDim.x);
         if (it > 0) epilogue(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1));
         if (next < n_tiles) stage_tile(next, buf ^ 1);
+        if (SHARE) asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
         prev_tile = tile;
     }
@@ -1365,7 +1421,7 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
                   "mlp_layer_bwd: buffers must be 16-byte aligned");
     MlpBwdArgs a{reinterpret_cast<const __nv_bfloat16 *>(dy), reinterpret_cast<const __nv_bfloat16 *>(z), gs, ga, gb, input,
                  pro_a, pro_b, reinterpret_cast<const __nv_bfloat16 *>(W_bf16), M,
-                 reinterpret_cast<__nv_bfloat16 *>(dy_prev), sums, dW, row_cell};
+                 reinterpret_cast<__nv_bfloat16 *>(dy_prev), sums, dW, row_cell, nullptr, nullptr};
     const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
     int blocks = sm_count();
     if (n_tiles < blocks) blocks = (int)n_tiles;
@@ -1386,6 +1442,35 @@ int kdf_mlp_layer_bwd(int mode, const void *dy, const void *z, const float *gs, 
         KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<1, 128, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         mlp_layer_bwd_kernel<1, 128, 512><<<blocks, 512, smem, st>>>(a);
     }
+    KDF_LAUNCH_CHECK();
+    return KDF_OK;
+}
+
+// Layer-3 backward over cell-sorted rows: the gradient rows are formed from (row_cell = global cell id per row,
+// share bf16 [cells,128], bits u8 [M,16]) as kdf_bev_bwd_share leaves them; everything else as kdf_mlp_layer_bwd mode 1.
+int kdf_mlp_layer_bwd_share(const int32_t *row_cell, const void *share, const void *bits, const void *z,
+                            const float *gs, const float *ga, const float *gb, const void *z_prev, int64_t M,
+                            const float *pro_a, const float *pro_b, const void *W_bf16, void *dy_prev, double *sums, float *dW,
+                            void *stream) {
+    KDF_CHECK_ARG(M >= 0, "mlp_layer_bwd_share: negative M");
+    KDF_CHECK_ARG(gs && ga && gb && pro_a && pro_b && W_bf16 && sums && dW, "mlp_layer_bwd_share: null pointer");
+    cudaStream_t st = as_stream(stream);
+    KDF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * PM_N, st));
+    KDF_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * PM_N * 128, st));
+    if (M == 0) return KDF_OK;
+    KDF_CHECK_ARG(row_cell && share && bits && z && z_prev && dy_prev, "mlp_layer_bwd_share: null pointer");
+    KDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(share) | reinterpret_cast<uintptr_t>(bits) | reinterpret_cast<uintptr_t>(z) |
+                    reinterpret_cast<uintptr_t>(z_prev) | reinterpret_cast<uintptr_t>(dy_prev) | reinterpret_cast<uintptr_t>(W_bf16)) & 15) == 0,
+                  "mlp_layer_bwd_share: buffers must be 16-byte aligned");
+    MlpBwdArgs a{nullptr, reinterpret_cast<const __nv_bfloat16 *>(z), gs, ga, gb, z_prev, pro_a, pro_b,
+                 reinterpret_cast<const __nv_bfloat16 *>(W_bf16), M, reinterpret_cast<__nv_bfloat16 *>(dy_prev), sums, dW, row_cell,
+                 reinterpret_cast<const __nv_bfloat16 *>(share), reinterpret_cast<const uint8_t *>(bits)};
+    const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
+    int blocks = sm_count();
+    if (n_tiles < blocks) blocks = (int)n_tiles;
+    const int smem = MlpBwdSmem<128>::TOTAL;
+    KDF_CUDA(cudaFuncSetAttribute(mlp_layer_bwd_kernel<1, 128, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_layer_bwd_kernel<1, 128, 512, true><<<blocks, 512, smem, st>>>(a);
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }

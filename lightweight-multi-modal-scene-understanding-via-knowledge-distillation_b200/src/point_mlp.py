@@ -12,6 +12,13 @@ layer that is ~9 passes over a ``[B*N, 128]`` activation per layer (forward + ba
             --(kdf_mlp_layer_bwd mode 1: BN3 backward in the prologue, dgrad+wgrad)--> dy2 + sums, dW3
             --(kdf_mlp_layer_bwd mode 0)--> 64x5 sums, dW2   --(closed form)--> dW1, BatchNorm-1 gradients
 
+The cell-sorted form of the branch is built and tested beside it -- ``bev_build_sorted`` (the points
+themselves in cell order), ``bev_reduce_affine(order=None)`` (contiguous segments), ``bev_bwd_share`` +
+``mlp_layer_bwd_share`` (no dy3 rows: per-cell shares + per-row tie bits, the gradient formed in the layer kernel's
+prologue) -- but the step does not use it: measured at the bench shapes it moves 1.3 GB less through HBM and is
+still 0.09 ms slower in total, and the arrival-order sort makes the row order, hence the bf16
+roundings, differ from run to run.
+
 Features are bf16 (this is the autocast path; the fp32 parity path stays layer by layer), points, index
 math and every statistic stay fp32/fp64.  The per-channel coefficient algebra between kernels is a few
 128-element torch ops on the device (no host sync; CUDA-graph capturable).
@@ -25,7 +32,7 @@ import torch
 from . import native as _n
 from .native import call, lib, ptr, require_cuda, stream_ptr
 
-__all__ = ["bev_build_order", "bev_reduce_affine", "bev_bwd_affine", "point_moments", "fused_lidar_branch",
+__all__ = ["bev_build_order", "bev_build_sorted", "bev_reduce_affine", "bev_bwd_affine", "bev_bwd_share", "point_moments", "fused_lidar_branch",
            "mlp_layer_fwd_raw", "bn_finalize"]
 
 
@@ -47,6 +54,28 @@ def bev_build_order(points: torch.Tensor, geom, grid_size):
     call("kdf_bev_build_order", ptr(points), D, B, N, *geom, H, W, ptr(count), ptr(cell), ptr(order), ptr(offsets),
          ptr(ws), nb, stream_ptr(dev))
     return cell, count, order, offsets
+
+
+def bev_build_sorted(points: torch.Tensor, geom, grid_size, want_order: bool = False):
+    """The cell ordering with the points themselves written in cell order:
+    (cell i32 [B,N] in the caller's point order, count i32 [B,HW], offsets i32 [B,HW+1], sorted_points f32 [B,N,4],
+    cell_sorted i32 [B,N] = global cell id b*HW+c per sorted row or -1, order i32 [B,N] | None)."""
+    dev = require_cuda(points)
+    B, N, D = points.shape
+    if points.dtype != torch.float32 or D != 4:
+        raise TypeError("points must be float32 (x, y, z, intensity)")
+    points = points.contiguous()
+    H, W = grid_size
+    i32 = dict(dtype=torch.int32, device=dev)
+    cell, cell_sorted = torch.empty(B, N, **i32), torch.empty(B, N, **i32)
+    order = torch.empty(B, N, **i32) if want_order else None
+    count, offsets = torch.empty(B, H * W, **i32), torch.empty(B, H * W + 1, **i32)
+    spts = torch.empty_like(points)
+    nb = lib.kdf_bev_workspace_bytes(B, N, H, W)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    call("kdf_bev_build_sorted", ptr(points), B, N, *geom, H, W, ptr(count), ptr(cell), ptr(offsets), ptr(spts), ptr(cell_sorted),
+         ptr(order), ptr(ws), nb, stream_ptr(dev))
+    return cell, count, offsets, spts, cell_sorted, order
 
 
 _order_cache = {"ref": None, "key": None, "val": None}
@@ -77,6 +106,36 @@ def bev_reduce_affine(z, scale, shift, order, offsets, B, N, grid_size, want_ext
     call("kdf_bev_reduce_affine", ptr(z), ptr(scale), ptr(shift), ptr(order), ptr(offsets), B, N, C, H, W,
          ptr(grid), ptr(grid_z), stream_ptr(dev))
     return grid, grid_z
+
+
+def bev_bwd_share(grad_grid, z, grid, grid_z, offsets, B, N, grid_size):
+    """Cell-sorted rows: -> (share bf16 [B*HW, C], bits u8 [B*N, C/8], sums f64 [2,C]) -- what every row at its cell's
+    extreme receives and which rows / channels those are; no gradient rows (see kdf_bev_bwd_share)."""
+    dev = require_cuda(grad_grid, z, grid, grid_z, offsets)
+    H, W = grid_size
+    C = z.shape[-1]
+    share = torch.empty(B * H * W, C, dtype=torch.bfloat16, device=dev)
+    bits = torch.empty(B * N, C // 8, dtype=torch.uint8, device=dev)
+    sums = torch.empty(2, C, dtype=torch.float64, device=dev)
+    call("kdf_bev_bwd_share", ptr(grad_grid), ptr(z), ptr(grid), ptr(grid_z), ptr(offsets), B, N, C, H, W, ptr(share), ptr(bits),
+         ptr(sums), stream_ptr(dev))
+    return share, bits, sums
+
+
+def mlp_layer_bwd_share(cell_sorted, share, bits, z, gs, ga, gb, z_prev, pro_a, pro_b, weight_bf16):
+    """Layer-3 backward over cell-sorted rows (dy formed from share / bits): (dy_prev bf16 [M,128], sums f64 [2,128],
+    dW f32 [128,128])."""
+    dev = require_cuda(cell_sorted, share, bits, z, z_prev, weight_bf16)
+    M = z.shape[0]
+    if tuple(weight_bf16.shape) != (128, 128) or z.shape[1] != 128 or z_prev.shape != z.shape or bits.shape != (M, 16):
+        raise ValueError("mlp_layer_bwd_share: the layer is 128 -> 128")
+    dy_prev = torch.empty(M, 128, dtype=torch.bfloat16, device=dev)
+    sums = torch.empty(2, 128, dtype=torch.float64, device=dev)
+    dW = torch.empty(128, 128, dtype=torch.float32, device=dev)
+    f = lambda t: t.float().contiguous()
+    call("kdf_mlp_layer_bwd_share", ptr(cell_sorted), ptr(share), ptr(bits), ptr(z), ptr(f(gs)), ptr(f(ga)), ptr(f(gb)), ptr(z_prev), M,
+         ptr(f(pro_a)), ptr(f(pro_b)), ptr(weight_bf16.contiguous()), ptr(dy_prev), ptr(sums), ptr(dW), stream_ptr(dev))
+    return dy_prev, sums, dW
 
 
 def bev_bwd_affine(grad_grid, z, grid, grid_z, order, offsets, cell, B, N, grid_size, zero_outside: bool = True):

@@ -211,3 +211,90 @@ def test_trainer_side_stream_teacher_matches_single_stream():
     # fp64 atomics in the statistics make runs differ in the last bits at most
     assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-4, atol=1e-5)
     assert _l2(outs[0][1], outs[1][1]) < 1e-2
+
+
+@pytest.mark.parametrize("B,N", [(2, 4000), (3, 20001), (1, 9000)])
+def test_bev_build_sorted_is_the_counting_sort_applied_to_the_points(B, N):
+    """the points themselves in cell order.  sorted_points = points[order] with every cell's rows
+    contiguous ([offsets[c], offsets[c+1])), the points outside the grid behind them, cell_sorted = the global cell id
+    of every sorted row; count / cell / offsets identical to kdf_bev_build_order."""
+    from src import ops, point_mlp
+    dev = "cuda"
+    pts = _frames(21, B, N, dev)
+    H = W = 64
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    cell0, count0, _order0, offsets0 = point_mlp.bev_build_order(pts, geom, (H, W))
+    cell, count, offsets, spts, cell_sorted, order = point_mlp.bev_build_sorted(pts, geom, (H, W), want_order=True)
+    assert torch.equal(cell, cell0) and torch.equal(count, count0) and torch.equal(offsets, offsets0)
+    for b in range(B):
+        o = order[b].long()
+        assert torch.equal(torch.sort(o).values, torch.arange(N, device=dev))              # a permutation
+        assert torch.equal(spts[b].view(torch.int32), pts[b][o].view(torch.int32))          # bit-exact copy of the points
+        c = cell[b][o]
+        nv = int(offsets[b, H * W])
+        assert (c[:nv] >= 0).all() and (c[nv:] < 0).all()
+        assert (c[:nv][1:] >= c[:nv][:-1]).all()                                            # grouped by cell, ascending
+        want = torch.where(c >= 0, c + b * H * W, torch.full_like(c, -1))
+        assert torch.equal(cell_sorted[b], want)
+        seg = torch.repeat_interleave(torch.arange(H * W, device=dev), count[b].long())
+        assert torch.equal(c[:nv].long(), seg)
+
+
+@pytest.mark.parametrize("B,N", [(2, 4000), (3, 20000)])
+def test_cell_sorted_projection_equals_the_indexed_one(B, N):
+    """Cell-sorted rows: the contiguous reduce gives the same grids as the indexed one on the unsorted rows, and
+    (share, bits) encode exactly the gradient rows kdf_bev_bwd_affine writes."""
+    from src import ops, point_mlp
+    dev = "cuda"
+    pts = _frames(12, B, N, dev)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    C, H, W = 128, 64, 64
+    z = (torch.randn(B * N, C, generator=g) * 1.5).to(torch.bfloat16).to(dev)
+    z[: (B * N) // 2] = z[(B * N) // 2: 2 * ((B * N) // 2)]                                 # duplicate rows: ties inside cells
+    scale = (torch.randn(C, generator=g)).to(dev)
+    shift = (torch.randn(C, generator=g) * 0.5).to(dev)
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    cell0, count0, order0, offsets0 = point_mlp.bev_build_order(pts, geom, (H, W))
+    grid0, gz0 = point_mlp.bev_reduce_affine(z, scale, shift, order0, offsets0, B, N, (H, W), True)
+    cell, count, offsets, spts, cell_sorted, order = point_mlp.bev_build_sorted(pts, geom, (H, W), want_order=True)
+    rows = (order.long() + torch.arange(B, device=dev)[:, None] * N).reshape(-1)            # sorted row -> original row
+    zs = z[rows].contiguous()
+    grid, gz = point_mlp.bev_reduce_affine(zs, scale, shift, None, offsets, B, N, (H, W), True)
+    assert torch.equal(grid, grid0) and torch.equal(gz, gz0)
+    gg = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(dev)
+    dy0, sums0 = point_mlp.bev_bwd_affine(gg, z, grid0, gz0, order0, offsets0, cell0, B, N, (H, W))
+    share, bits, sums = point_mlp.bev_bwd_share(gg, zs, grid, gz, offsets, B, N, (H, W))
+    cs = cell_sorted.reshape(-1).long()
+    inside = cs >= 0
+    bit = ((bits[inside].long()[:, :, None] >> torch.arange(8, device=dev)) & 1).reshape(-1, C).bool()
+    dy = torch.zeros(B * N, C, dtype=torch.bfloat16, device=dev)
+    dy[inside] = torch.where(bit, share[cs[inside]], torch.zeros((), dtype=torch.bfloat16, device=dev))
+    assert torch.equal(dy, dy0[rows])
+    np.testing.assert_allclose(sums.cpu().numpy(), sums0.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_mlp_layer_bwd_share_equals_the_materialised_gradient_rows():
+    """Layer-3 backward with dy formed from (cell_sorted, share, bits) in the prologue == the same kernel fed the
+    materialised rows: dy_prev bit-identical, sums / dW to summation-order noise.  Rows outside hold garbage bits."""
+    from src import point_mlp, ops
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(9)
+    M, ncell = 128 * 37 + 50, 301
+    n_in = M - 777
+    cs = torch.sort(torch.randint(0, ncell, (n_in,), generator=g)).values.to(torch.int32)
+    cs = torch.cat([cs, torch.full((M - n_in,), -1, dtype=torch.int32)]).to(dev)
+    share = (torch.randn(ncell, 128, generator=g)).to(torch.bfloat16).to(dev)
+    bits = torch.randint(0, 256, (M, 16), generator=g).to(torch.uint8).to(dev)
+    z = (torch.randn(M, 128, generator=g) * 1.5).to(torch.bfloat16).to(dev)
+    zprev = (torch.randn(M, 128, generator=g) * 2).to(torch.bfloat16).to(dev)
+    gs, ga, gb = (torch.rand(128, generator=g) + 0.5).to(dev), (torch.randn(128, generator=g) * 0.01).to(dev), (torch.randn(128, generator=g) * 0.01).to(dev)
+    scale, shift = (torch.rand(128, generator=g) + 0.5).to(dev), (torch.randn(128, generator=g) * 0.3).to(dev)
+    Wt = (torch.randn(128, 128, generator=g) / 11.3).to(torch.bfloat16).to(dev)
+    inside = cs >= 0
+    bit = ((bits.long()[:, :, None] >> torch.arange(8, device=dev)) & 1).reshape(M, 128).bool()
+    dy = torch.where(bit & inside[:, None], share[cs.clamp_min(0).long()], torch.zeros((), dtype=torch.bfloat16, device=dev))
+    ref = ops.mlp_layer_bwd(1, dy, z, gs, ga, gb, zprev, scale, shift, Wt)
+    got = point_mlp.mlp_layer_bwd_share(cs, share, bits, z, gs, ga, gb, zprev, scale, shift, Wt)
+    assert torch.equal(got[0], ref[0])
+    np.testing.assert_allclose(got[1].cpu().numpy(), ref[1].cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert _l2(got[2], ref[2]) < 1e-5

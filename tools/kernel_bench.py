@@ -120,6 +120,32 @@ if "affine" in only:
     gg = torch.randn(B, H, W, C, device=dev, dtype=dt)
     timeit("bev_bwd_affine", lambda: point_mlp.bev_bwd_affine(gg, z3, grid, grid_z, order, offsets, cell, B, N, (H, W), zero_outside=False), B * (2 * C * 2 * v * N + 3 * C * 2 * H * W))
     timeit("point_moments", lambda: point_mlp.point_moments(pts), B * N * 16)
+if "sorted" in only:
+    from src import point_mlp
+    pts = make_frames(B, N, seed=1, device=dev)["points"]
+    geom = ops.bev_range_constants([-50, -50, -5, 50, 50, 3])
+    v = 0.622
+    timeit("bev_build_order", lambda: point_mlp.bev_build_order(pts, geom, (H, W)), B * N * (16 + 4 + 4 + 4 + 4))
+    timeit("bev_build_sorted", lambda: point_mlp.bev_build_sorted(pts, geom, (H, W)), B * N * (16 + 4 + 4 + 4 + 16 + 16 + 4))
+    cell0, count0, order0, offsets0 = point_mlp.bev_build_order(pts, geom, (H, W))
+    cell, count, offsets, spts, cs, _ = point_mlp.bev_build_sorted(pts, geom, (H, W))
+    z3 = torch.randn(M, 128, device=dev, dtype=dt)
+    sc, sh = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
+    timeit("bev_reduce_affine indexed", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, order0, offsets0, B, N, (H, W), True), B * (C * 2 * v * N + C * 2 * H * W))
+    timeit("bev_reduce_affine contiguous", lambda: point_mlp.bev_reduce_affine(z3, sc, sh, None, offsets, B, N, (H, W), True), B * (C * 2 * v * N + C * 2 * H * W))
+    grid, grid_z = point_mlp.bev_reduce_affine(z3, sc, sh, None, offsets, B, N, (H, W), True)
+    gg = torch.randn(B, H, W, C, device=dev, dtype=dt)
+    grid0, grid_z0 = point_mlp.bev_reduce_affine(z3, sc, sh, order0, offsets0, B, N, (H, W), True)
+    timeit("bev_bwd_affine (dy rows)", lambda: point_mlp.bev_bwd_affine(gg, z3, grid0, grid_z0, order0, offsets0, cell0, B, N, (H, W), zero_outside=False), B * (2 * C * 2 * v * N + 3 * C * 2 * H * W))
+    timeit("bev_bwd_share (share + bits)", lambda: point_mlp.bev_bwd_share(gg, z3, grid, grid_z, offsets, B, N, (H, W)), B * (C * 2 * v * N + 16 * v * N + 4 * C * 2 * H * W))
+    share, bits, _s = point_mlp.bev_bwd_share(gg, z3, grid, grid_z, offsets, B, N, (H, W))
+    dy0, _s0 = point_mlp.bev_bwd_affine(gg, z3, grid0, grid_z0, order0, offsets0, cell0, B, N, (H, W), zero_outside=False)
+    zprev = torch.randn(M, 128, device=dev, dtype=dt)
+    W3 = (torch.randn(128, 128, device=dev) / 11.3).to(dt)
+    gs, ga, gb = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.01, torch.randn(128, device=dev) * 0.01
+    timeit("mlp_layer_bwd mode1 (dy rows)", lambda: ops.mlp_layer_bwd(1, dy0, z3, gs, ga, gb, zprev, sc, sh, W3, row_cell=cell0.view(-1)), M * 1024)
+    timeit("mlp_layer_bwd_share", lambda: point_mlp.mlp_layer_bwd_share(cs.view(-1), share, bits, z3, gs, ga, gb, zprev, sc, sh, W3), M * (768 + 16 + 4))
+    del z3, zprev, dy0
 if "dw" in only:
     import torch.nn as nn
     for (Cc, Hh, st_) in (tuple(int(v) for v in t.split(":")) for t in a.dw_shapes.split(",")):
