@@ -398,6 +398,16 @@ int kdf_kd_loss_fwd_bwd_counted(const void *s_logits, const void *t_logits, cons
  * fusion backward; bc / ac f32 [C] are formed by the caller from those sums. */
 int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const float *bc, const float *ac, void *stream);
 
+/* The camera stem (camera_encoder.py:63-67): Conv2d(3, 32, 3, stride 2, padding 1, bias=False) read straight from the fp32
+ * NCHW image [B,3,H,W] (inputs and taps rounded to bf16 as the autocast convolution does, fp32 accumulation) into bf16
+ * pixel-major rows out [B,OH,OW,32].  stats (nullable, f64 [2,32], zeroed by the call): column sums of the stored values
+ * for the train-mode BatchNorm that follows; post_scale / post_shift (nullable, f32 [32]) + post_act (0 none, 1 ReLU,
+ * 2 ReLU6): the folded running-statistics BatchNorm + activation of inference instead.  kdf_stem_conv_bwd_weight: the weight
+ * gradient f32 [32,3,3,3] (zeroed by the call) from the gradient rows bf16 [B,OH,OW,32]; the image needs no gradient. */
+int kdf_stem_conv_fwd(const float *image, const float *weight, int B, int H, int W,
+                      const float *post_scale, const float *post_shift, int post_act, void *out_bf16, double *stats, void *stream);
+int kdf_stem_conv_bwd_weight(const float *image, const void *grad_out_bf16, int B, int H, int W, float *grad_weight, void *stream);
+
 /* ---------------------------------------------------------------- depthwise 3x3 convolution
  * nn.Conv2d(C, C, 3, stride, padding=1, groups=C, bias=False) of the inverted-residual blocks
  * (camera_encoder.py:27-33), DWSeparableConv (fusion_module.py:24-27) and the concat fusion (:80-82), over

@@ -16,7 +16,7 @@ from typing import Dict, List, Union
 import torch
 import torch.nn as nn
 
-from ..ops import run_fused
+from ..ops import run_fused, stem_conv
 
 
 def _conv_bn(cin: int, cout: int, kernel: int, stride: int = 1, groups: int = 1, act: bool = True) -> List[nn.Module]:
@@ -72,8 +72,11 @@ class TwinLiteEncoder(nn.Module):
     def forward(self, x) -> Union[torch.Tensor, Dict[str, torch.Tensor]]:
         if not x.is_cuda:
             raise RuntimeError("TwinLiteEncoder runs on CUDA tensors only (no CPU fallback)")
-        x = x.contiguous(memory_format=torch.channels_last)         # NHWC end to end
-        x = run_fused(self.stem, x)
+        y = stem_conv(self.stem, x)                                  # fp32 NCHW image -> bf16 NHWC rows in one kernel
+        if y is None:
+            x = x.contiguous(memory_format=torch.channels_last)     # NHWC end to end
+            y = run_fused(self.stem, x)
+        x = y
         feats = {}
         for name, *_ in self._STAGES:
             x = getattr(self, name)(x)

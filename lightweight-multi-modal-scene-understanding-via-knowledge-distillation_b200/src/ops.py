@@ -226,6 +226,78 @@ def dwconv3x3(conv, x: torch.Tensor, want_stats: bool = False, post=None):
     return (out, stats) if want_stats else out
 
 
+# ----------------------------------------------------------------------------- the camera stem
+class _StemConvFn(torch.autograd.Function):
+    """nn.Conv2d(3, 32, 3, stride 2, padding 1, bias=False) from the fp32 NCHW image to bf16 channels-last rows, with the
+    column sums of the BatchNorm that follows (camera_encoder.py:63-67); backward = the weight gradient only."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        B, _, H, W = x.shape
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        w = weight.detach().float().contiguous()
+        out = torch.empty(B, OH, OW, 32, dtype=torch.bfloat16, device=x.device)
+        stats = torch.empty(2, 32, dtype=torch.float64, device=x.device)
+        call("kdf_stem_conv_fwd", ptr(x), ptr(w), B, H, W, None, None, 0, ptr(out), ptr(stats), stream_ptr(x.device))
+        ctx.save_for_backward(x)
+        ctx.wshape, ctx.wdtype = weight.shape, weight.dtype
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(stats)
+        return out.permute(0, 3, 1, 2), stats
+
+    @staticmethod
+    def backward(ctx, g, _gs=None):
+        if g is None or not ctx.needs_input_grad[1]:
+            return None, None
+        (x,) = ctx.saved_tensors
+        B, _, H, W = x.shape
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        gr = _nhwc_rows(g)
+        if gr is None:
+            gr = g.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+        gw = torch.empty(32, 27, dtype=torch.float32, device=x.device)
+        call("kdf_stem_conv_bwd_weight", ptr(x), ptr(gr), B, H, W, ptr(gw), stream_ptr(x.device))
+        return None, gw.view(ctx.wshape).to(ctx.wdtype)
+
+
+def stem_conv(seq, x: torch.Tensor) -> Optional[torch.Tensor]:
+    """The camera stem ``Sequential(Conv2d(3, 32, 3, s2, p1, bias=False), BatchNorm2d, ReLU6)`` on the stem kernel when the
+    image is a dense fp32 NCHW CUDA tensor under bf16 autocast (what the loader delivers); None otherwise (the caller then
+    takes the library path).  Training: rows + batch statistics from the kernel, BatchNorm + ReLU6 by the row kernel;
+    inference: convolution + folded BatchNorm + ReLU6 in one kernel."""
+    import torch.nn as nn
+    mods = list(seq)
+    if not (2 <= len(mods) <= 3 and isinstance(mods[0], nn.Conv2d) and isinstance(mods[1], nn.BatchNorm2d)):
+        return None
+    conv, bn = mods[0], mods[1]
+    act = None
+    if len(mods) == 3:
+        if not isinstance(mods[2], (nn.ReLU, nn.ReLU6)):
+            return None
+        act = "relu6" if isinstance(mods[2], nn.ReLU6) else "relu"
+    if not (conv.in_channels == 3 and conv.out_channels == 32 and conv.kernel_size == (3, 3) and conv.stride == (2, 2)
+            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+            and conv.padding_mode == "zeros" and conv.weight.dtype == torch.float32 and bn.affine):
+        return None
+    if not (x.is_cuda and x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.float32 and x.is_contiguous()
+            and not x.requires_grad and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return None
+    batch = bn.training or bn.running_mean is None
+    if batch:
+        z, stats = _StemConvFn.apply(x, conv.weight)
+        return bn_act(z, bn, act, None, col_sums=stats)
+    if torch.is_grad_enabled() and (conv.weight.requires_grad or bn.weight.requires_grad):
+        return None                                              # eval-mode statistics with gradients: the library path
+    B, _, H, W = x.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    scale, shift, _, _ = _eval_affine(bn)
+    out = torch.empty(B, OH, OW, 32, dtype=torch.bfloat16, device=x.device)
+    call("kdf_stem_conv_fwd", ptr(x), ptr(conv.weight.detach().contiguous()), B, H, W, ptr(scale), ptr(shift), _ACT[act], ptr(out), None,
+         stream_ptr(x.device))
+    return out.permute(0, 3, 1, 2)
+
+
 def _conv_frozen(m, x: torch.Tensor) -> torch.Tensor:
     """``m(x)``; for a convolution run without autograd under bf16 autocast (the frozen teacher) the bf16 copy of its
     weight is cached until the weight changes, instead of being re-cast by autocast on every step."""
@@ -300,7 +372,8 @@ class _PwConvFn(torch.autograd.Function):
         N, K = ctx.wshape[0], x_rows.shape[1]
         w16 = wb[:N, :K]                                      # the bf16 operand the forward used (first diagonal block when packed)
         gx = torch.mm(g, w16) if ctx.needs_input_grad[0] else None
-        gw = torch.mm(g.t(), x_rows).float().view(ctx.wshape) if ctx.needs_input_grad[1] else None
+        # fp32 straight out of the GEMM (aten::mm.dtype): no bf16 rounding of the weight gradient and no conversion launch
+        gw = torch.mm(g.t(), x_rows, out_dtype=torch.float32).view(ctx.wshape) if ctx.needs_input_grad[1] else None
         return gx, gw, None, None
 
 

@@ -755,3 +755,78 @@ def test_range_project_matches_torch_scatter_on_its_cells(ops, dtype, reduce):
     ref.backward(gout.permute(0, 2, 3, 1).reshape(B * H * W, C).float())
     assert rel_err(feats.grad.float().cpu(), fr.grad.view(B, N, C).cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
     assert (feats.grad[~(cell >= 0)] == 0).all()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 37, 51), (1, 256, 256), (2, 9, 130)])
+def test_stem_conv_vs_torch_conv2d(ops, B, H, W):
+    """The camera stem (camera_encoder.py:63-67) from the fp32 NCHW image: rows + BatchNorm column sums in training,
+    folded BatchNorm + ReLU6 in inference, weight gradient -- against nn.Conv2d on the bf16-rounded image and taps
+    (what the autocast convolution sees), fp32 accumulation."""
+    import torch.nn as nn
+    from src.native import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(H * 7 + W)
+    conv = nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(32, 3, 3, 3, generator=g) * 0.3)
+    x = torch.rand(B, 3, H, W, generator=g)
+    xr, wr = x.bfloat16().float(), conv.weight.detach().bfloat16().float()
+    ref_w = wr.clone().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, ref_w, None, 2, 1)
+    OH, OW = ref.shape[2:]
+    gout = torch.randn(ref.shape, generator=g).bfloat16()
+    ref.backward(gout.float())
+    dev = "cuda"
+    xc, wc = x.to(dev), conv.weight.detach().to(dev)
+    out = torch.empty(B, OH, OW, 32, dtype=torch.bfloat16, device=dev)
+    stats = torch.empty(2, 32, dtype=torch.float64, device=dev)
+    call("kdf_stem_conv_fwd", ptr(xc), ptr(wc), B, H, W, None, None, 0, ptr(out), ptr(stats), stream_ptr(xc.device))
+    got = out.permute(0, 3, 1, 2).float().cpu()
+    assert rel_err(got, ref.detach()) < 4e-3                       # bf16 storage of an fp32 accumulation
+    assert (got - ref.detach()).abs().max() <= 2.0 ** -7 * ref.detach().abs().max()
+    st = torch.stack([got.double().sum((0, 2, 3)), (got.double() ** 2).sum((0, 2, 3))])
+    np.testing.assert_allclose(stats.cpu().numpy(), st.numpy(), rtol=2e-6, atol=1e-6)
+    gw = torch.empty(32, 27, dtype=torch.float32, device=dev)
+    gr = gout.to(dev).permute(0, 2, 3, 1).contiguous()
+    call("kdf_stem_conv_bwd_weight", ptr(xc), ptr(gr), B, H, W, ptr(gw), stream_ptr(xc.device))
+    assert rel_err(gw.view(32, 3, 3, 3).cpu(), ref_w.grad) < 2e-5
+    # inference: folded BatchNorm + ReLU6 in the same kernel == the two-step sequence on the stored rows
+    scale, shift = (torch.rand(32, generator=g) + 0.5).to(dev), torch.randn(32, generator=g).to(dev)
+    fused = torch.empty_like(out)
+    call("kdf_stem_conv_fwd", ptr(xc), ptr(wc), B, H, W, ptr(scale), ptr(shift), 2, ptr(fused), None, stream_ptr(xc.device))
+    two = torch.clamp(torch.addcmul(shift, out.float(), scale), 0, 6).to(torch.bfloat16)
+    assert torch.equal(fused, two)
+
+
+def test_stem_module_path_matches_library_path(ops):
+    """TwinLiteEncoder.stem through ops.stem_conv (training and inference) against the same Sequential on the library
+    convolution (run_fused over the channels-last image): outputs and parameter gradients within bf16 noise."""
+    import copy
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(3)
+    stem = nn.Sequential(nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(32), nn.ReLU6()).cuda()
+    with torch.no_grad():
+        stem[1].weight.copy_(torch.rand(32, generator=g) + 0.5)
+        stem[1].bias.copy_(torch.randn(32, generator=g) * 0.2)
+    lib = copy.deepcopy(stem)
+    x = torch.rand(4, 3, 96, 128, generator=g).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.stem_conv(stem, x)
+        y_lib = ops.run_fused(lib, x.contiguous(memory_format=torch.channels_last))
+    assert y is not None and y.dtype == torch.bfloat16 and y.shape == y_lib.shape
+    assert rel_err(y.float().cpu(), y_lib.float().cpu()) < 1e-2
+    gy = torch.randn(y.shape, generator=g).cuda().to(torch.bfloat16)
+    y.backward(gy)
+    y_lib.backward(gy)
+    for a, b in zip(stem.parameters(), lib.parameters()):
+        assert rel_err(a.grad.cpu(), b.grad.cpu()) < 2e-2
+    for a, b in zip(stem.buffers(), lib.buffers()):
+        assert torch.allclose(a.float().cpu(), b.float().cpu(), rtol=1e-3, atol=1e-4)
+    stem.eval(); lib.eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        e = ops.stem_conv(stem, x)
+        e_lib = ops.run_fused(lib, x.contiguous(memory_format=torch.channels_last))
+    assert e is not None and rel_err(e.float().cpu(), e_lib.float().cpu()) < 1e-2
+    # not the stem's shape / dtype: declined
+    assert ops.stem_conv(stem, x.double()) is None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert ops.stem_conv(nn.Sequential(nn.Conv2d(3, 16, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(16)).cuda(), x) is None

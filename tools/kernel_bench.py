@@ -146,6 +146,18 @@ if "sorted" in only:
     timeit("mlp_layer_bwd mode1 (dy rows)", lambda: ops.mlp_layer_bwd(1, dy0, z3, gs, ga, gb, zprev, sc, sh, W3, row_cell=cell0.view(-1)), M * 1024)
     timeit("mlp_layer_bwd_share", lambda: point_mlp.mlp_layer_bwd_share(cs.view(-1), share, bits, z3, gs, ga, gb, zprev, sc, sh, W3), M * (768 + 16 + 4))
     del z3, zprev, dy0
+if "stem" in only:
+    img = torch.rand(B, 3, 256, 256, device=dev); w = torch.randn(32, 3, 3, 3, device=dev) * 0.3
+    out = torch.empty(B, 128, 128, 32, device=dev, dtype=dt); sts = torch.empty(2, 32, dtype=torch.float64, device=dev)
+    gw = torch.empty(32, 27, device=dev); gr = torch.randn(B, 128, 128, 32, device=dev, dtype=dt)
+    scl, shf = torch.rand(32, device=dev) + 0.5, torch.randn(32, device=dev)
+    nb = img.numel() * 4 + out.numel() * 2
+    timeit("stem fwd + stats", lambda: native.call("kdf_stem_conv_fwd", p(img), p(w), B, 256, 256, None, None, 0, p(out), p(sts), st), nb)
+    timeit("stem fwd + folded BN + ReLU6", lambda: native.call("kdf_stem_conv_fwd", p(img), p(w), B, 256, 256, p(scl), p(shf), 2, p(out), None, st), nb)
+    timeit("stem wgrad", lambda: native.call("kdf_stem_conv_bwd_weight", p(img), p(gr), B, 256, 256, p(gw), st), nb)
+    wb = w.to(dt)
+    with torch.autocast("cuda", dtype=dt):
+        timeit("library: channels_last + cast + cudnn fwd", lambda: torch.nn.functional.conv2d(img.contiguous(memory_format=torch.channels_last), w, None, 2, 1), nb)
 if "dw" in only:
     import torch.nn as nn
     for (Cc, Hh, st_) in (tuple(int(v) for v in t.split(":")) for t in a.dw_shapes.split(",")):
