@@ -398,6 +398,15 @@ int kdf_kd_loss_fwd_bwd_counted(const void *s_logits, const void *t_logits, cons
  * fusion backward; bc / ac f32 [C] are formed by the caller from those sums. */
 int kdf_rows_axpb(void *g, const void *x, int dtype, int64_t M, int C, const float *bc, const float *ac, void *stream);
 
+/* The classifier of the BEV-resolution head (fusion_module.py:162-173): nn.Conv2d(32, K, 1) with bias over bf16 pixel rows
+ * x [M,32] (M = frames x HW), taps rounded to bf16 as the autocast convolution does, fp32 accumulation, written as planar
+ * logits bf16 [B,K,HW] (what the loss reads).  K = 1..4.  kdf_cls_conv_bwd: dx bf16 [M,32] (nullable), grad_weight f32
+ * [K,32] and grad_bias f32 [K] (nullable) -- both zeroed by the call -- from planar dlogits bf16 [B,K,HW]. */
+int kdf_cls_conv_fwd(const void *x_bf16, const float *weight, const float *bias, int64_t M, int Cin, int K, int HW,
+                     void *logits_bf16, void *stream);
+int kdf_cls_conv_bwd(const void *x_bf16, const void *dlogits_bf16, const float *weight, int64_t M, int Cin, int K, int HW,
+                     void *dx_bf16, float *grad_weight, float *grad_bias, void *stream);
+
 /* The camera stem (camera_encoder.py:63-67): Conv2d(3, 32, 3, stride 2, padding 1, bias=False) read straight from the fp32
  * NCHW image [B,3,H,W] (inputs and taps rounded to bf16 as the autocast convolution does, fp32 accumulation) into bf16
  * pixel-major rows out [B,OH,OW,32].  stats (nullable, f64 [2,32], zeroed by the call): column sums of the stored values

@@ -220,7 +220,9 @@ class SameResolutionSegmentationHead(nn.Module):
         self.cls = nn.Conv2d(32, num_classes, kernel_size=1)
 
     def forward(self, x):
-        return self.cls(self.block(x))
+        h = self.block(x)
+        y = ops.cls_conv(self.cls, h)              # 32 -> K classes: one kernel, planar logits (None: not the bf16 path)
+        return self.cls(h) if y is None else y
 
 
 # ----------------------------------------------------------------------------- complete model

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "kdf_rowbn_bwd": (C.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_bev_reduce_affine": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "kdf_bev_bwd_affine": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "kdf_cls_conv_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "kdf_cls_conv_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kdf_stem_conv_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "kdf_stem_conv_bwd_weight": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "kdf_bev_build_sorted": (C.c_int, [_vp, _i, _i64, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -109,7 +111,7 @@ KERNELS_PER_CALL = {
     "kdf_kd_loss_fwd_bwd": 2, "kdf_kd_label_count": 1, "kdf_kd_loss_fwd_bwd_counted": 1, "kdf_confusion_matrix": 1, "kdf_adamw_flat": 1,
     "kdf_rowbn_stats": 1, "kdf_rowbn_apply_fwd": 1, "kdf_rowbn_bwd": 2,
     "kdf_mlp_layer_fwd": 1, "kdf_mlp_eval3_fwd": 1, "kdf_mlp_layer_bwd": 1, "kdf_bn_finalize": 1, "kdf_bev_reduce_affine": 1, "kdf_bev_bwd_affine": 1,
-    "kdf_bev_build_sorted": 3, "kdf_bev_bwd_share": 1, "kdf_mlp_layer_bwd_share": 1, "kdf_stem_conv_fwd": 1, "kdf_stem_conv_bwd_weight": 1,
+    "kdf_bev_build_sorted": 3, "kdf_bev_bwd_share": 1, "kdf_mlp_layer_bwd_share": 1, "kdf_stem_conv_fwd": 1, "kdf_stem_conv_bwd_weight": 1, "kdf_cls_conv_fwd": 1, "kdf_cls_conv_bwd": 1,
     "kdf_point_moments": 1, "kdf_bev_build_order": 3, "kdf_fpn_merge_fwd": 1, "kdf_fpn_up2_bwd": 1, "kdf_rows_axpb": 1, "kdf_mlp_l1_stats": 1, "kdf_bn_bwd_coeffs": 1, "kdf_mlp_l1_bwd": 1, "kdf_dwconv3x3_fwd": 1, "kdf_dwconv3x3_affine_fwd": 1, "kdf_dwconv3x3_bwd_data": 1, "kdf_dwconv3x3_bwd_weight": 1,
 }
 launch_stats = {"kernels": 0, "calls": 0}

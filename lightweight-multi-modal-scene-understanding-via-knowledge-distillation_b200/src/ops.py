@@ -298,6 +298,50 @@ def stem_conv(seq, x: torch.Tensor) -> Optional[torch.Tensor]:
     return out.permute(0, 3, 1, 2)
 
 
+# ----------------------------------------------------------------------------- the head's classifier
+class _ClsConvFn(torch.autograd.Function):
+    """nn.Conv2d(32, K, 1) (+ bias) over channels-last bf16 maps -> planar bf16 logits [B,K,H,W]; backward in one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B, C, H, W = x.shape
+        K = weight.shape[0]
+        rows = _nhwc_rows(x)
+        w = weight.detach().reshape(K, C).float().contiguous()
+        out = torch.empty(B, K, H, W, dtype=torch.bfloat16, device=x.device)
+        call("kdf_cls_conv_fwd", ptr(rows), ptr(w), ptr(bias.detach().float().contiguous()) if bias is not None else None,
+             B * H * W, C, K, H * W, ptr(out), stream_ptr(x.device))
+        ctx.save_for_backward(x, w)
+        ctx.wshape, ctx.has_bias = weight.shape, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, C, H, W = x.shape
+        K = w.shape[0]
+        g = g.to(torch.bfloat16).contiguous()
+        dev = x.device
+        gx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev) if ctx.needs_input_grad[0] else None
+        gw = torch.empty(K, C, dtype=torch.float32, device=dev)
+        gb = torch.empty(K, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        call("kdf_cls_conv_bwd", ptr(_nhwc_rows(x)), ptr(g), ptr(w), B * H * W, C, K, H * W, ptr(gx), ptr(gw), ptr(gb), stream_ptr(dev))
+        return (gx.permute(0, 3, 1, 2) if gx is not None else None), gw.view(ctx.wshape), gb
+
+
+def cls_conv(conv, x: torch.Tensor) -> Optional[torch.Tensor]:
+    """The head's 1x1 classifier ``nn.Conv2d(32, K <= 4, 1)`` on the classifier kernel for dense channels-last bf16 CUDA maps
+    under bf16 autocast (planar bf16 logits, as the autocast convolution returns them in value); None otherwise."""
+    import torch.nn as nn
+    if not (isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
+            and conv.groups == 1 and conv.in_channels == 32 and 1 <= conv.out_channels <= 4 and conv.weight.dtype == torch.float32):
+        return None
+    if not (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and _nhwc_rows(x) is not None
+            and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return None
+    return _ClsConvFn.apply(x, conv.weight, conv.bias)
+
+
 def _conv_frozen(m, x: torch.Tensor) -> torch.Tensor:
     """``m(x)``; for a convolution run without autograd under bf16 autocast (the frozen teacher) the bf16 copy of its
     weight is cached until the weight changes, instead of being re-cast by autocast on every step."""

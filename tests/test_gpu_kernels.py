@@ -830,3 +830,35 @@ def test_stem_module_path_matches_library_path(ops):
     assert ops.stem_conv(stem, x.double()) is None
     with torch.autocast("cuda", dtype=torch.bfloat16):
         assert ops.stem_conv(nn.Sequential(nn.Conv2d(3, 16, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(16)).cuda(), x) is None
+
+
+@pytest.mark.parametrize("K,B,H,W", [(2, 3, 64, 64), (1, 2, 5, 7), (4, 2, 16, 24), (3, 1, 33, 9)])
+def test_cls_conv_vs_torch_conv2d(ops, K, B, H, W):
+    """The head's classifier nn.Conv2d(32, K, 1) with bias (fusion_module.py:162-173) on the classifier kernel: planar
+    bf16 logits, data / weight / bias gradients, against fp32 torch on the bf16-rounded operands."""
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(K * 100 + H)
+    conv = nn.Conv2d(32, K, 1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(K, 32, 1, 1, generator=g) * 0.3)
+        conv.bias.copy_(torch.randn(K, generator=g))
+    x = torch.randn(B, 32, H, W, generator=g).to(torch.bfloat16)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.cls_conv(conv, xc)
+    assert y is not None and y.dtype == torch.bfloat16 and y.is_contiguous() and tuple(y.shape) == (B, K, H, W)
+    ref_x = x.float().requires_grad_(True)
+    ref_w = conv.weight.detach().cpu().bfloat16().float().requires_grad_(True)
+    ref_b = conv.bias.detach().cpu().clone().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(ref_x, ref_w, ref_b)
+    assert rel_err(y.float().cpu(), ref.detach()) < 4e-3
+    gout = torch.randn(ref.shape, generator=g).to(torch.bfloat16)
+    y.backward(gout.cuda())
+    ref.backward(gout.float())
+    assert rel_err(xc.grad.float().cpu(), ref_x.grad) < 4e-3
+    assert rel_err(conv.weight.grad.cpu(), ref_w.grad) < 2e-5
+    assert rel_err(conv.bias.grad.cpu(), ref_b.grad) < 2e-5
+    # other shapes / dtypes are declined (the module then runs)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert ops.cls_conv(nn.Conv2d(64, 2, 1).cuda(), xc) is None
+    assert ops.cls_conv(conv, xc.float()) is None
