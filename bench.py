@@ -272,7 +272,7 @@ def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each hand-written kernel at the bench
     shapes, from the committed `ncu --set full` captures (profiles/r01_ncu_traffic.json names the capture files)."""
     out = {}
-    for name in ("r01_ncu_traffic.json", "r02_ncu_traffic.json"):          # the later capture wins for kernels it covers
+    for name in ("r01_ncu_traffic.json", "r02_ncu_traffic.json", "r02b_ncu_traffic.json"):          # the later capture wins for kernels it covers
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 out.update(json.load(f)["bytes_per_launch"])
@@ -478,6 +478,81 @@ def kernel_rooflines(args, device, fp32):
             del x
         add("pw_conv_fwd, the 17 1x1 convolutions of the student's forward (sum)", tot_ms, tot_bytes,
             "sum over the layers of rows in + rows out; batch statistics come out of the same kernels")
+        # ---- depthwise 3x3 (TMA-staged tiles, packed fp32 FMAs): the eight layers of the student, forward (+ statistics), data
+        #      gradient and weight gradient; two representative layers by name, all of them summed
+        dw_layers = (("stage1", 32, 128, 1), ("stage2", 192, 128, 2), ("stage3", 384, 64, 1), ("stage4", 384, 64, 2),
+                     ("stage5", 768, 32, 1), ("fpn smooth", 128, 64, 1), ("head dw0", 128, 64, 1), ("head dw1", 64, 64, 1))
+        tot = {"fwd": [0.0, 0], "dgrad": [0.0, 0], "wgrad": [0.0, 0]}
+        for lname, Cc, Hh, st_ in dw_layers:
+            OHh = (Hh - 1) // st_ + 1
+            xin = torch.randn(B, Hh, Hh, Cc, device=device).to(dt)
+            yo = torch.empty(B, OHh, OHh, Cc, device=device, dtype=dt)
+            gr = torch.randn(B, OHh, OHh, Cc, device=device).to(dt)
+            gx = torch.empty_like(xin)
+            w9 = torch.randn(Cc, 9, **f32) * 0.3
+            gw = torch.empty(Cc, 9, **f32)
+            sts = torch.empty(2, Cc, dtype=torch.float64, device=device)
+            nb = (xin.numel() + yo.numel()) * s
+            t_f = time_kernel(with_flush(lambda: native.call("kdf_dwconv3x3_fwd", p(xin), p(w9), 1, B, Hh, Hh, Cc, st_, 0, p(yo), p(sts), st))) - t_flush
+            t_d = time_kernel(with_flush(lambda: native.call("kdf_dwconv3x3_bwd_data", p(gr), p(w9), 1, B, Hh, Hh, Cc, st_, p(gx), st))) - t_flush
+            t_w = time_kernel(with_flush(lambda: native.call("kdf_dwconv3x3_bwd_weight", p(xin), p(gr), 1, B, Hh, Hh, Cc, st_, p(gw), st))) - t_flush
+            for key, t in (("fwd", t_f), ("dgrad", t_d), ("wgrad", t_w)):
+                tot[key][0] += t
+                tot[key][1] += nb
+            if lname in ("stage2", "stage3"):
+                shape = f"{Cc} ch @{Hh}x{Hh} stride {st_}"
+                add(f"dwconv3x3 forward + statistics, {lname} ({shape})", t_f, nb, "map in + map out, once; L2 flushed between launches")
+                add(f"dwconv3x3 data gradient, {lname} ({shape})", t_d, nb, "gradient map in + gradient map out, once")
+                add(f"dwconv3x3 weight gradient, {lname} ({shape})", t_w, nb, "input map + gradient map in, once")
+            del xin, yo, gr, gx
+        add("dwconv3x3 forward + statistics, the 8 depthwise layers of the student (sum)", tot["fwd"][0], tot["fwd"][1], "sum over the layers")
+        add("dwconv3x3 data gradients, the 8 depthwise layers (sum)", tot["dgrad"][0], tot["dgrad"][1], "sum over the layers")
+        add("dwconv3x3 weight gradients, the 8 depthwise layers (sum)", tot["wgrad"][0], tot["wgrad"][1], "sum over the layers")
+        # ---- camera stem (fp32 NCHW image -> bf16 rows) and the head's classifier
+        img = torch.rand(B, 3, 256, 256, **f32)
+        wst = torch.randn(32, 3, 3, 3, **f32) * 0.3
+        so = torch.empty(B, 128, 128, 32, device=device, dtype=dt)
+        sst = torch.empty(2, 32, dtype=torch.float64, device=device)
+        sgw = torch.empty(32, 27, **f32)
+        sgr = torch.randn(B, 128, 128, 32, device=device).to(dt)
+        nb = img.numel() * 4 + so.numel() * s
+        add("stem_conv_fwd_kernel (3x3 s2, 3->32, image fp32 NCHW -> bf16 rows + statistics)",
+            time_kernel(with_flush(lambda: native.call("kdf_stem_conv_fwd", p(img), p(wst), B, 256, 256, None, None, 0, p(so), p(sst), st))) - t_flush,
+            nb, "image in (4 B/value) + rows out; 864 multiply-adds per output pixel on the CUDA cores: shared-memory bound, not HBM bound")
+        add("stem_conv_wgrad_kernel", time_kernel(with_flush(lambda: native.call("kdf_stem_conv_bwd_weight", p(img), p(sgr), B, 256, 256, p(sgw), st))) - t_flush,
+            nb, "image + gradient rows in")
+        del img, so, sgr
+        xr = torch.randn(M, 32, device=device).to(dt)
+        wc, bc = torch.randn(2, 32, **f32) * 0.3, torch.randn(2, **f32)
+        lo = torch.empty(B, 2, H, W, device=device, dtype=dt)
+        dl = torch.randn(B, 2, H, W, device=device).to(dt)
+        dxr, gwc, gbc = torch.empty_like(xr), torch.empty(2, 32, **f32), torch.empty(2, **f32)
+        add("cls_conv_fwd_kernel (32 -> 2 classes, planar logits)",
+            time_kernel(with_flush(lambda: native.call("kdf_cls_conv_fwd", p(xr), p(wc), p(bc), M, 32, 2, H * W, p(lo), st))) - t_flush,
+            M * (32 + 2) * s, "64 B row in, 2 logits out per pixel (8.9 MB: launch-latency bound)")
+        add("cls_conv_bwd_kernel", time_kernel(with_flush(lambda: native.call("kdf_cls_conv_bwd", p(xr), p(dl), p(wc), M, 32, 2, H * W, p(dxr), p(gwc), p(gbc), st))) - t_flush,
+            M * (64 + 2) * s, "row + 2 logit gradients in, gradient row out per pixel")
+        # ---- the cell-sorted form of the LiDAR projection: built and tested, not in the step (slower in total)
+        cell_s, count_s, offsets_s, spts, cs, _ = point_mlp.bev_build_sorted(pts, geom, (H, W))
+        add("bev_build_sorted (index+scan+permute: the points in cell order)", time_kernel(lambda: point_mlp.bev_build_sorted(pts, geom, (H, W)), 10),
+            B * (16 * N + 4 * N + 4 * N + 4 * N + 16 * N + 4 * N + 8 * H * W), "as bev_build_order + 16N sorted points and 4N cell ids out", in_step=False)
+        z3 = torch.randn(Mpts, 128, device=device).to(dt)
+        z2 = torch.randn(Mpts, 128, device=device).to(dt)
+        sc3, sh3 = torch.rand(128, **f32) + 0.5, torch.randn(128, **f32) * 0.1
+        add("bev_reduce_affine_kernel over cell-sorted rows (contiguous segments)",
+            time_kernel(lambda: point_mlp.bev_reduce_affine(z3, sc3, sh3, None, offsets_s, B, N, (H, W), True), 10),
+            B * (C * s * v * N + 2 * C * s * H * W), "rows of valid points once; grid and extreme out", in_step=False)
+        grid_s, gz_s = point_mlp.bev_reduce_affine(z3, sc3, sh3, None, offsets_s, B, N, (H, W), True)
+        gg = torch.randn(B, H, W, C, device=device, dtype=dt)
+        add("bev_bwd_share_kernel (per-cell shares + per-row tie bits, no gradient rows)",
+            time_kernel(lambda: point_mlp.bev_bwd_share(gg, z3, grid_s, gz_s, offsets_s, B, N, (H, W)), 10),
+            B * (C * s * v * N + (C // 8) * v * N + 4 * C * s * H * W), "rows of valid points once, C/8 bytes of tie bits per valid row out, 4 rows per cell", in_step=False)
+        share, bits, _s3 = point_mlp.bev_bwd_share(gg, z3, grid_s, gz_s, offsets_s, B, N, (H, W))
+        gs, ga, gb = torch.rand(128, **f32) + 0.5, torch.randn(128, **f32) * 0.01, torch.randn(128, **f32) * 0.01
+        add("mlp_layer_bwd_kernel<1, share> (layer 3 backward forming dy from shares + tie bits)",
+            time_kernel(lambda: point_mlp.mlp_layer_bwd_share(cs.view(-1), share, bits, z3, gs, ga, gb, z2, sc3, sh3, W3), 10),
+            Mpts * (3 * C * s + C // 8 + 4), "z, z_prev rows in, dy_prev row out, 16 B of tie bits + 4 B cell id per point", in_step=False)
+        del z3, z2, gg, share, bits
     return out, v
 
 

@@ -158,6 +158,13 @@ if "stem" in only:
     wb = w.to(dt)
     with torch.autocast("cuda", dtype=dt):
         timeit("library: channels_last + cast + cudnn fwd", lambda: torch.nn.functional.conv2d(img.contiguous(memory_format=torch.channels_last), w, None, 2, 1), nb)
+if "cls" in only:
+    Mc = B * H * W
+    xr = torch.randn(Mc, 32, device=dev).to(dt); wc = torch.randn(2, 32, device=dev) * 0.3; bc = torch.randn(2, device=dev)
+    lo = torch.empty(B, 2, H, W, device=dev, dtype=dt); dl = torch.randn(B, 2, H, W, device=dev).to(dt)
+    dxr = torch.empty_like(xr); gwc = torch.empty(2, 32, device=dev); gbc = torch.empty(2, device=dev)
+    timeit("cls_conv fwd", lambda: native.call("kdf_cls_conv_fwd", p(xr), p(wc), p(bc), Mc, 32, 2, H * W, p(lo), st), Mc * 68)
+    timeit("cls_conv bwd", lambda: native.call("kdf_cls_conv_bwd", p(xr), p(dl), p(wc), Mc, 32, 2, H * W, p(dxr), p(gwc), p(gbc), st), Mc * 132)
 if "dw" in only:
     import torch.nn as nn
     for (Cc, Hh, st_) in (tuple(int(v) for v in t.split(":")) for t in a.dw_shapes.split(",")):
