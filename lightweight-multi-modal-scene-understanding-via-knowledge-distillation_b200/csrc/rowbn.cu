@@ -612,7 +612,7 @@ int kdf_rowbn_bwd(const void *grad_out, const void *x, int dtype, int64_t M, int
         const int rows = RB_THREADS / (C / vec);
         size_t smem = sizeof(float) * (size_t)rows * (C / vec) * 2 * vec;
         if (smem < sizeof(float) * 4 * (size_t)C) smem = sizeof(float) * 4 * (size_t)C;
-        const int cblocks = rb_blocks(M, C, vec, 4, 2 * sm_count());                    // co-resident by construction (<= 2 CTAs/SM)
+        const int cblocks = rb_blocks(M, C, vec, 4, 3 * sm_count());                    // co-resident by construction (<= 3 CTAs/SM: the launch bounds)
         KDF_CUDA(cudaMemsetAsync(a.ws, 0, sizeof(RowBnWs) + sizeof(double) * 2 * RB_COPIES * (size_t)a.C, st));
         if (dtype == KDF_F32) return launch_bwd_coop<float, 4>(a, grad_x, cblocks, smem, st);
         if (vec == 8) return launch_bwd_coop<__nv_bfloat16, 8>(a, grad_x, cblocks, smem, st);
