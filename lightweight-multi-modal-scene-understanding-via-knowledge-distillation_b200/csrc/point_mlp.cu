@@ -309,17 +309,19 @@ struct MlpEvalArgs {
 struct MlpEvalSmem {
     static constexpr int OFF_W2 = 0;                                   // 1 panel  [128 n][64 k]
     static constexpr int OFF_W3 = OFF_W2 + PM_N * 64 * 2;              // 2 panels [128 n][128 k]
+    // Two CTAs share an SM (99 KB and 256 TMEM columns each): one CTA's TMEM epilogues overlap the other's MMAs and loads.
+    // That needs the A1 tile single-buffered (it is re-staged after MMA 1 has been waited for) and the staging tile of the
+    // output rows ALIASED onto the A2 operand tile (free once MMA 2 has completed, which is what epilogue 2 waits for).
     static constexpr int OFF_A1_0 = OFF_W3 + PM_N * 128 * 2;
-    static constexpr int OFF_A1_1 = OFF_A1_0 + PM_ROWS * 64 * 2;
-    static constexpr int OFF_A2 = OFF_A1_1 + PM_ROWS * 64 * 2;
-    static constexpr int OFF_STAGE = OFF_A2 + PM_ROWS * 128 * 2;
-    static constexpr int OFF_MISC = OFF_STAGE + PM_ROWS * PM_N * 2;
+    static constexpr int OFF_A2 = OFF_A1_0 + PM_ROWS * 64 * 2;
+    static constexpr int OFF_STAGE = OFF_A2;
+    static constexpr int OFF_MISC = OFF_A2 + PM_ROWS * 128 * 2;
     static constexpr int MISC_BYTES = 64 + 4 * (64 * 4 + 64 + 2 * 128);
     static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 mlp_eval3_kernel(MlpEvalArgs a) {
     KDF_PM_DERIVED(NT);
     using L = MlpEvalSmem;
@@ -331,7 +333,7 @@ mlp_eval3_kernel(MlpEvalArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = tc::align_smem_1024(smem_raw);
     uint8_t *sW2 = smem + L::OFF_W2, *sW3 = smem + L::OFF_W3;
-    auto sA1 = [smem](int b) -> uint8_t * { return smem + (b ? L::OFF_A1_1 : L::OFF_A1_0); };
+    uint8_t *sA1 = smem + L::OFF_A1_0;
     uint8_t *sA2 = smem + L::OFF_A2, *sStage = smem + L::OFF_STAGE;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_MISC);          // [0] MMA 1 done, [1] MMA 2 done
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_MISC + 16);
@@ -403,8 +405,8 @@ mlp_eval3_kernel(MlpEvalArgs a) {
         }
         tc::fence_async_smem();
     };
-    auto issue_mma1 = [&](int buf) {                                       // one thread
-        const uint32_t a_base = tc::smem_u32(sA1(buf)), w_base = tc::smem_u32(sW2);
+    auto issue_mma1 = [&]() {                                              // one thread
+        const uint32_t a_base = tc::smem_u32(sA1), w_base = tc::smem_u32(sW2);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             tc::mma_bf16(tmem_base, tc::desc_kmajor(a_base + (uint32_t)k * 32u), tc::desc_kmajor(w_base + (uint32_t)k * 32u), IDESC, k > 0);
@@ -486,23 +488,25 @@ mlp_eval3_kernel(MlpEvalArgs a) {
     int64_t tile = blockIdx.x;
     if (tile < n_tiles) {
         load_tile(tile);
-        stage_tile(tile, sA1(0));
+        stage_tile(tile, sA1);
     }
     __syncthreads();
     int it = 0;
     int64_t prev_tile = -1;
     for (; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
         if (tid == 0) {
             tc::fence_after_sync();
-            issue_mma1(buf);
+            issue_mma1();
         }
         const int64_t next = tile + gridDim.x;
         if (next < n_tiles) load_tile(next);
         if (tid == 32) l2_prefetch(next + gridDim.x);
-        if (it > 0) epilogue2(prev_tile, (uint32_t)((it - 1) & 1));        // also: MMA 2 of the previous tile has consumed A2
-        if (next < n_tiles) stage_tile(next, sA1(buf ^ 1));
-        epilogue1((uint32_t)(it & 1));
+        if (it > 0) {
+            epilogue2(prev_tile, (uint32_t)((it - 1) & 1));                // waits for MMA 2 of the previous tile: A2 is free, the rows go out
+            __syncthreads();                                               // ... through the staging tile that IS the A2 tile: drained before epilogue 1 refills it
+        }
+        epilogue1((uint32_t)(it & 1));                                     // waits for MMA 1: the A1 tile is free for the next tile's rows
+        if (next < n_tiles) stage_tile(next, sA1);
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
@@ -1395,7 +1399,7 @@ int kdf_mlp_eval3_fwd(const float *points, int64_t M, const float *q, const floa
     MlpEvalArgs a{points, M, q, r, reinterpret_cast<const __nv_bfloat16 *>(W2_bf16), scale2, shift2,
                   reinterpret_cast<const __nv_bfloat16 *>(W3_bf16), reinterpret_cast<__nv_bfloat16 *>(z3_out)};
     const int64_t n_tiles = (M + PM_ROWS - 1) / PM_ROWS;
-    int blocks = sm_count();
+    int blocks = 2 * sm_count();                                        // two co-resident CTAs per SM
     if (n_tiles < blocks) blocks = (int)n_tiles;
     const int smem = MlpEvalSmem::TOTAL;
     KDF_CUDA(cudaFuncSetAttribute(mlp_eval3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
