@@ -72,6 +72,25 @@ struct PwSmem {
     }
 };
 
+// (a, b) = (a, b) * (s0, s1) + (h0, h1) as one packed fp32 FMA (same rounding as two scalar ones)
+__device__ __forceinline__ void pw_fma2(float &a, float &b, float s0, float s1, float h0, float h1) {
+    unsigned long long x, sc, sh, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(s0), "f"(s1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sh) : "f"(h0), "f"(h1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(sc), "l"(sh));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+__device__ __forceinline__ uint32_t pw_max2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t pw_min2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 __device__ __forceinline__ float pw_act(float v, int act) {
     if (act == 1) return fmaxf(v, 0.f);
     if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);
@@ -194,17 +213,23 @@ pw_conv_fwd_kernel(PwArgs a, const __grid_constant__ CUtensorMap tmA) {
                         float v[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[h][8 * j + e]);
-                        if (EPI == 1) {
+                        if (EPI == 1) {                                // folded BatchNorm as four packed FMAs (two channels each)
                             const int c0 = s * 64 + h * 32 + 8 * j;
                             const float4 sa = *reinterpret_cast<const float4 *>(t_esc + c0), sb = *reinterpret_cast<const float4 *>(t_esc + c0 + 4);
                             const float4 ha = *reinterpret_cast<const float4 *>(t_esh + c0), hb = *reinterpret_cast<const float4 *>(t_esh + c0 + 4);
-                            const float cs[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                            const float ch_[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = pw_act(fmaf(v[e], cs[e], ch_[e]), a.epi_act);
+                            pw_fma2(v[0], v[1], sa.x, sa.y, ha.x, ha.y);
+                            pw_fma2(v[2], v[3], sa.z, sa.w, ha.z, ha.w);
+                            pw_fma2(v[4], v[5], sb.x, sb.y, hb.x, hb.y);
+                            pw_fma2(v[6], v[7], sb.z, sb.w, hb.z, hb.w);
                         }
                         const uint32_t chunk = (uint32_t)(h * 4 + j);  // 16-byte chunk of the 128-byte slab row
-                        const uint32_t p0 = pack_bf16(v[0], v[1]), p1 = pack_bf16(v[2], v[3]), p2 = pack_bf16(v[4], v[5]), p3 = pack_bf16(v[6], v[7]);
+                        uint32_t p0 = pack_bf16(v[0], v[1]), p1 = pack_bf16(v[2], v[3]), p2 = pack_bf16(v[4], v[5]), p3 = pack_bf16(v[6], v[7]);
+                        if (EPI == 1) {
+                            // the activation on the packed bf16 pairs: 0 and 6 are bf16 numbers and the rounding is monotonic, so
+                            // clamp(round(x)) == round(clamp(x)) -- one instruction per two channels instead of two per channel
+                            if (a.epi_act >= 1) { p0 = pw_max2(p0, 0u); p1 = pw_max2(p1, 0u); p2 = pw_max2(p2, 0u); p3 = pw_max2(p3, 0u); }
+                            if (a.epi_act == 2) { p0 = pw_min2(p0, 0x40C040C0u); p1 = pw_min2(p1, 0x40C040C0u); p2 = pw_min2(p2, 0x40C040C0u); p3 = pw_min2(p3, 0x40C040C0u); }
+                        }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_w + ((chunk ^ (uint32_t)(erow & 7)) << 4)),
                                      "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
                     }
