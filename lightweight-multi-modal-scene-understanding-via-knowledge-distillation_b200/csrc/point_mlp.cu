@@ -62,26 +62,59 @@ struct MlpSmem {
 };
 
 // MODE 0: a1[c] = relu(q[c,:] . (x,y,z,i) + r[c])  for 8 channels c0..c0+7 of one point
-__device__ __forceinline__ uint4 first_layer_chunk(const float4 &p, const float *q, const float *r) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float acc = r[j];
-        acc = fmaf(q[4 * j + 0], p.x, acc);
-        acc = fmaf(q[4 * j + 1], p.y, acc);
-        acc = fmaf(q[4 * j + 2], p.z, acc);
-        acc = fmaf(q[4 * j + 3], p.w, acc);
-        v[j] = fmaxf(acc, 0.f);
-    }
-    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+// packed fp32 pairs: `fma.rn.f32x2` does two channels per instruction with the rounding of two scalar FMAs, and ReLU is taken
+// on the packed bf16 pair after the conversion (0 is a bf16 number and the rounding is monotonic: max(round(x), 0) ==
+// round(max(x, 0))) -- the prologues below are bit-identical to their scalar form at 55-70 % of its instructions
+typedef unsigned long long pm_u64;
+__device__ __forceinline__ pm_u64 pm_pk2(float lo, float hi) {
+    pm_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-
-// MODE 1: relu(z*scale + shift) on 8 bf16 values
-__device__ __forceinline__ uint4 affine_relu_chunk(const uint4 &u, const float *sc, const float *sh) {
-    float v[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+__device__ __forceinline__ pm_u64 pm_fma2(pm_u64 a, pm_u64 b, pm_u64 c) {
+    pm_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ pm_u64 pm_add2(pm_u64 a, pm_u64 b) {
+    pm_u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pm_u64 pm_unpack2(uint32_t w) { return pm_pk2(bf16_lo(w), bf16_hi(w)); }
+__device__ __forceinline__ void pm_store8(float *dst, const pm_u64 (&v)[4]) {          // 4 pairs -> 8 consecutive floats
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
-    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    for (int i = 0; i < 4; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(dst[2 * i]), "=f"(dst[2 * i + 1]) : "l"(v[i]));
+}
+__device__ __forceinline__ uint32_t pm_pack_relu(pm_u64 v) {               // bf16x2(relu(lo), relu(hi))
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    uint32_t r;
+    const uint32_t p = pack_bf16(lo, hi);
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(p), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ uint4 first_layer_chunk(const float4 &p, const float *q, const float *r) {
+    const pm_u64 px = pm_pk2(p.x, p.x), py = pm_pk2(p.y, p.y), pz = pm_pk2(p.z, p.z), pw = pm_pk2(p.w, p.w);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                                          // channels 2i, 2i+1 of the chunk
+        pm_u64 acc = pm_pk2(r[2 * i], r[2 * i + 1]);
+        acc = pm_fma2(pm_pk2(q[8 * i + 0], q[8 * i + 4]), px, acc);
+        acc = pm_fma2(pm_pk2(q[8 * i + 1], q[8 * i + 5]), py, acc);
+        acc = pm_fma2(pm_pk2(q[8 * i + 2], q[8 * i + 6]), pz, acc);
+        acc = pm_fma2(pm_pk2(q[8 * i + 3], q[8 * i + 7]), pw, acc);
+        o[i] = pm_pack_relu(acc);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ uint4 affine_relu_chunk(const uint4 &u, const float *sc, const float *sh) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        o[i] = pm_pack_relu(pm_fma2(pm_pk2(bf16_lo(w[i]), bf16_hi(w[i])), pm_pk2(sc[2 * i], sc[2 * i + 1]), pm_pk2(sh[2 * i], sh[2 * i + 1])));
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // MINB = 2: two co-resident CTAs per SM (layers 1+2: 85 KB of shared memory, 256 TMEM columns and <= 128 registers each),
@@ -144,7 +177,7 @@ mlp_layer_fwd_kernel(MlpFwdArgs a) {
     }
     // fixed per-thread output chunk for the store / statistics phase: 16 chunks per 256-byte row
     const int och = tid & 15, orow0 = tid >> 4;
-    float s_sum[8], s_sq[8];
+    float s_sum[8], s_sq[8];                          // (scalar on purpose: as packed pairs the 256-thread variant spills, 0.34 -> 0.39 ms)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_sum[j] = 0.f; s_sq[j] = 0.f; }
 
@@ -445,9 +478,7 @@ mlp_eval3_kernel(MlpEvalArgs a) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const uint32_t zz = pack_bf16(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));   // z2 as stored
-                    const float v0 = fmaxf(fmaf(bf16_lo(zz), cs[2 * e], ch_[2 * e]), 0.f);
-                    const float v1 = fmaxf(fmaf(bf16_hi(zz), cs[2 * e + 1], ch_[2 * e + 1]), 0.f);
-                    o[e] = pack_bf16(v0, v1);
+                    o[e] = pm_pack_relu(pm_fma2(pm_unpack2(zz), pm_pk2(cs[2 * e], cs[2 * e + 1]), pm_pk2(ch_[2 * e], ch_[2 * e + 1])));
                 }
                 *reinterpret_cast<uint4 *>(sA2 + (uint32_t)(chunk >> 3) * PANEL + tc::sw128_offset(erow, chunk & 7)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -738,9 +769,16 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                         unpack8(raw_cell[p] >= 0 ? raw_dy[p] : make_uint4(0u, 0u, 0u, 0u), g);
                     }
                     unpack8(raw_z[p], zz);
+                    uint32_t o4[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = fmaf(gs[j], g[j], fmaf(gb[j], zz[j], ga[j]));
-                    v = pack8(g);
+                    for (int j = 0; j < 4; ++j) {                          // dz = gs*dy + (gb*z + ga), two channels per instruction
+                        const pm_u64 t2 = pm_fma2(pm_pk2(gb[2 * j], gb[2 * j + 1]), pm_pk2(zz[2 * j], zz[2 * j + 1]), pm_pk2(ga[2 * j], ga[2 * j + 1]));
+                        const pm_u64 d2 = pm_fma2(pm_pk2(gs[2 * j], gs[2 * j + 1]), pm_pk2(g[2 * j], g[2 * j + 1]), t2);
+                        float lo, hi;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d2));
+                        o4[j] = pack_bf16(lo, hi);
+                    }
+                    v = make_uint4(o4[0], o4[1], o4[2], o4[3]);
                 }
                 *reinterpret_cast<uint4 *>(sD(buf) + (dch >> 3) * PANEL + tc::sw128_offset(r, dch & 7)) = v;
             }
@@ -794,10 +832,11 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     };
 
     // accumulators of the column sums, fixed per thread for the whole kernel
-    constexpr int NACC = MODE == 1 ? 16 : 5;
+    constexpr int NACC = MODE == 1 ? 1 : 5;                                // MODE 1 accumulates channel pairs (acc2)
     float acc[NACC];
 #pragma unroll
     for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+    pm_u64 acc2[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};     // MODE 1: sum dy_prev (4 pairs), sum dy_prev * z_prev (4 pairs)
     const int och = tid & 15, orow0 = tid >> 4;                            // MODE 1 store phase
     const int ccol = tid & 63, crq = tid >> 6;                             // MODE 0 column-owner phase
     constexpr int CRQ_ROWS = PM_ROWS / (PM_THREADS / 64);                  // rows per column-owner group
@@ -869,11 +908,13 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                 if (r0 + r < a.M) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(sStage + r * 256 + ((och ^ (r & 7)) << 4));
                     *reinterpret_cast<uint4 *>(a.dy_prev + (r0 + r) * PM_N + och * 8) = v;
-                    float f[8], zz[8];
-                    unpack8(v, f);
-                    unpack8(zk[p], zz);
+                    const uint32_t fw[4] = {v.x, v.y, v.z, v.w}, zw[4] = {zk[p].x, zk[p].y, zk[p].z, zk[p].w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] = fmaf(f[j], zz[j], acc[8 + j]); }
+                    for (int j = 0; j < 4; ++j) {
+                        const pm_u64 f2 = pm_unpack2(fw[j]);
+                        acc2[j] = pm_add2(acc2[j], f2);
+                        acc2[4 + j] = pm_fma2(f2, pm_unpack2(zw[j]), acc2[4 + j]);
+                    }
                 }
             }
         } else {
@@ -925,8 +966,11 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
     // ---- column sums -> fp64 atomics
     float *red = reinterpret_cast<float *>(sD(0));
     if (MODE == 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) red[(orow0 * 16 + och) * 16 + j] = acc[j];
+        {
+            const pm_u64 lo4[4] = {acc2[0], acc2[1], acc2[2], acc2[3]}, hi4[4] = {acc2[4], acc2[5], acc2[6], acc2[7]};
+            pm_store8(red + (orow0 * 16 + och) * 16, lo4);
+            pm_store8(red + (orow0 * 16 + och) * 16 + 8, hi4);
+        }
         __syncthreads();
         if (tid < 16 * 16) {
             const int ch = tid >> 4, j = tid & 15;
