@@ -1030,8 +1030,8 @@ struct MlpBwd0TmaSmem {
     static constexpr int OFF_A0 = OFF_Z1 + 2 * PANEL;                // a1 tile, 1 panel, x 2 stages
     static constexpr int OFF_A1 = OFF_A0 + PANEL;
     static constexpr int OFF_STAGE = OFF_A1 + PANEL;                 // dy1 staging, bf16 [128 x 64]
-    static constexpr int OFF_PTS = OFF_STAGE + PANEL;                // raw points, 2 x 128 float4
-    static constexpr int OFF_MISC = OFF_PTS + 2 * PM_ROWS * 16;
+    static constexpr int OFF_PTS = OFF_STAGE + PANEL;                // raw points, 3 x 128 float4 (tile i-1 is summed while tile i+1 is staged)
+    static constexpr int OFF_MISC = OFF_PTS + 3 * PM_ROWS * 16;
     // 4 mbarriers + tmem slot, then floats: ga[128] gs[128] gb[128] q[8*36] r[64] cvec[64] asum[64]
     static constexpr int MISC_BYTES = 64 + 4 * (3 * 128 + 8 * 36 + 64 + 64 + 64);
     static constexpr int TOTAL = OFF_MISC + MISC_BYTES + 1024;
@@ -1124,7 +1124,7 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
             if (tile < n_tiles && row < a.M) rpt[p] = ldg_stream_u4(reinterpret_cast<const uint4 *>(a.input) + row);
         }
     };
-    auto stage_a = [&](int64_t tile, int buf) {
+    auto stage_a = [&](int64_t tile, int buf, int slot) {
         const int64_t r0 = tile * PM_ROWS;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
@@ -1138,7 +1138,7 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
                 unpack8(v, f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a_sum[j] += f[j];
-                if (ach == 0) sPts[buf * PM_ROWS + r] = pt;
+                if (ach == 0) sPts[slot * PM_ROWS + r] = pt;
             }
             *reinterpret_cast<uint4 *>(sA(buf) + tc::sw128_offset(r, ach)) = v;
         }
@@ -1177,8 +1177,10 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
 #pragma unroll
     for (int j = 0; j < 5; ++j) acc[j] = 0.f;
     const int ccol = tid & 63, crq = tid >> 6;                           // column-owner phase: 8 groups x 16 rows
-    auto epilogue = [&](int64_t tile, int buf, uint32_t parity, int64_t refill_tile) {
-        const int64_t r0 = tile * PM_ROWS;
+    // part 1: accumulator -> ReLU mask -> bf16 staging tile;  part 2 (after a CTA barrier): column sums from the staging tile.
+    // Part 2 shares its barrier interval with the staging of the NEXT tile's activation (two barriers per tile instead of three:
+    // 43 % of this kernel's stall samples sat at CTA barriers), which is why the raw points are triple-buffered.
+    auto epilogue1 = [&](int64_t tile, int buf, uint32_t parity, int64_t refill_tile) {
         tc::mbar_wait(&bar_mma[buf], parity);
         tc::fence_after_sync();
         // the tensor cores are done with this stage's dy / z tiles: refill them right away
@@ -1200,27 +1202,26 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
             }
         }
         tc::fence_before_sync();
-        __syncthreads();
-        {
-            const int rows = (int)((a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS);
-            const int rbeg = crq * 16, rend = (rbeg + 16 < rows) ? rbeg + 16 : rows;
-            for (int r = rbeg; r < rend; ++r) {
-                const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16 *>(sStage + tc::sw128_offset(r, ccol >> 3) + (ccol & 7) * 2);
-                const float v = __bfloat162float(hv);
-                const float4 pt = sPts[buf * PM_ROWS + r];
-                acc[0] += v;
-                acc[1] = fmaf(v, pt.x, acc[1]); acc[2] = fmaf(v, pt.y, acc[2]);
-                acc[3] = fmaf(v, pt.z, acc[3]); acc[4] = fmaf(v, pt.w, acc[4]);
-            }
+    };
+    auto epilogue2 = [&](int64_t tile, int slot) {
+        const int64_t r0 = tile * PM_ROWS;
+        const int rows = (int)((a.M - r0 < PM_ROWS) ? (a.M - r0) : PM_ROWS);
+        const int rbeg = crq * 16, rend = (rbeg + 16 < rows) ? rbeg + 16 : rows;
+        for (int r = rbeg; r < rend; ++r) {
+            const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16 *>(sStage + tc::sw128_offset(r, ccol >> 3) + (ccol & 7) * 2);
+            const float v = __bfloat162float(hv);
+            const float4 pt = sPts[slot * PM_ROWS + r];
+            acc[0] += v;
+            acc[1] = fmaf(v, pt.x, acc[1]); acc[2] = fmaf(v, pt.y, acc[2]);
+            acc[3] = fmaf(v, pt.z, acc[3]); acc[4] = fmaf(v, pt.w, acc[4]);
         }
-        __syncthreads();                                                 // staging tile, a1 tile and points of this stage are free again
     };
 
     // ---- pipeline: MMA(i) | points(i+1) in flight | epilogue(i-1) + TMA refill | a1(i+1)
     int64_t tile = blockIdx.x;
     if (tile < n_tiles) {
         load_pts(tile);
-        stage_a(tile, 0);
+        stage_a(tile, 0, 0);
     }
     __syncthreads();
     int it = 0;
@@ -1230,12 +1231,19 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
         if (tid == 0) issue_mma(buf, it == 0, (uint32_t)((it >> 1) & 1));
         const int64_t next = tile + gridDim.x;
         load_pts(next);
-        if (it > 0) epilogue(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1), next);   // refills stage buf^1 with tile i+1
-        if (next < n_tiles) stage_a(next, buf ^ 1);
+        if (it > 0) epilogue1(prev_tile, buf ^ 1, (uint32_t)(((it - 1) >> 1) & 1), next);  // refills stage buf^1 with tile i+1
+        __syncthreads();                                                 // staging tile written; the a1 tile of tile i-1 has been read
+        if (it > 0) epilogue2(prev_tile, (it + 2) % 3);                  // points of tile i-1: slot (i-1) mod 3
+        if (next < n_tiles) stage_a(next, buf ^ 1, (it + 1) % 3);
         __syncthreads();
         prev_tile = tile;
     }
-    if (it > 0) epilogue(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1), n_tiles);
+    if (it > 0) {
+        epilogue1(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1), n_tiles);
+        __syncthreads();
+        epilogue2(prev_tile, (it + 2) % 3);
+        __syncthreads();
+    }
 
     // ---- column sums -> fp64 atomics
 #pragma unroll
