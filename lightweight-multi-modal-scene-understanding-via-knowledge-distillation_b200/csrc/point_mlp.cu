@@ -86,6 +86,11 @@ __device__ __forceinline__ void pm_store8(float *dst, const pm_u64 (&v)[4]) {   
 #pragma unroll
     for (int i = 0; i < 4; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(dst[2 * i]), "=f"(dst[2 * i + 1]) : "l"(v[i]));
 }
+__device__ __forceinline__ uint32_t pm_gt0_mask(uint32_t a) {              // 0xFFFF per bf16 half of `a` that is > 0
+    uint32_t d;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(0u));
+    return d;
+}
 __device__ __forceinline__ uint32_t pm_pack_relu(pm_u64 v) {               // bf16x2(relu(lo), relu(hi))
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
@@ -868,11 +873,13 @@ mlp_layer_bwd_kernel(MlpBwdArgs a) {
                 for (int j = 0; j < 4; ++j) {
                     const int chunk = (warp >> 2) * (COLS_W / 8) + half * 4 + j;   // 16-byte chunk of the 256-byte row
                     const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + (chunk >> 3) * PANEL + tc::sw128_offset(row, chunk & 7));
-                    float act[8], v[8];
-                    unpack8(av, act);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = act[e] > 0.f ? __uint_as_float(r[8 * j + e]) : 0.f;
-                    *reinterpret_cast<uint4 *>(sStage + row * 256 + ((chunk ^ (row & 7)) << 4)) = pack8(v);
+                    // ReLU mask on the packed pairs: convert, then AND with `activation > 0` (rounding a masked-out value is moot)
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])) & pm_gt0_mask(av.x);
+                    o.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])) & pm_gt0_mask(av.y);
+                    o.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])) & pm_gt0_mask(av.z);
+                    o.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])) & pm_gt0_mask(av.w);
+                    *reinterpret_cast<uint4 *>(sStage + row * 256 + ((chunk ^ (row & 7)) << 4)) = o;
                 }
             }
         } else {
@@ -1194,11 +1201,18 @@ mlp_layer_bwd0_tma_kernel(MlpBwdArgs a, const __grid_constant__ CUtensorMap tm_d
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int chunk = (col0 >> 3) + j;
-                float act[8], v[8];
-                unpack8(*reinterpret_cast<const uint4 *>(sA(buf) + tc::sw128_offset(row, chunk)), act);
+                const uint4 av = *reinterpret_cast<const uint4 *>(sA(buf) + tc::sw128_offset(row, chunk));
+                const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+                uint32_t o[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = act[e] > 0.f ? __uint_as_float(r[8 * j + e]) + cvec[chunk * 8 + e] : 0.f;
-                *reinterpret_cast<uint4 *>(sStage + tc::sw128_offset(row, chunk)) = pack8(v);
+                for (int e = 0; e < 4; ++e) {                            // (accumulator + constant row) on pairs, ReLU mask as an AND
+                    const pm_u64 v2 = pm_add2(pm_pk2(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1])),
+                                              pm_pk2(cvec[chunk * 8 + 2 * e], cvec[chunk * 8 + 2 * e + 1]));
+                    float lo, hi;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v2));
+                    o[e] = pack_bf16(lo, hi) & pm_gt0_mask(aw[e]);
+                }
+                *reinterpret_cast<uint4 *>(sStage + tc::sw128_offset(row, chunk)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
         tc::fence_before_sync();
