@@ -342,7 +342,15 @@ rowbn_apply_bwd_kernel(const T *__restrict__ g, const T *__restrict__ x, T *__re
 // grid-wide barrier, per-channel coefficients (every CTA, from the accumulator sets), apply.  Same arithmetic as
 // rowbn_reduce_kernel<MODE 1> + rowbn_apply_bwd_kernel; what it saves is a launch, the last-CTA finalisation round
 // trip and the second kernel's ramp -- ~10 us of the ~40 us such a pair costs on a 30 MB tensor.
-template <typename T, int VEC>
+// (the activation is a template parameter here: with a run-time `act` both loops carried the selects of all three cases)
+template <int ACT>
+__device__ __forceinline__ bool act_open_t(float y) {
+    if (ACT == 1) return y > 0.f;
+    if (ACT == 2) return y > 0.f && y < 6.f;
+    return true;
+}
+
+template <typename T, int VEC, int ACT>
 __global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
 rowbn_bwd_coop_kernel(ReduceArgs a, T *__restrict__ dx) {
     extern __shared__ float sm[];                     // phase 1: [rows][G][2*VEC]; phase 2: scale, shift, A, B [4][C]
@@ -378,7 +386,7 @@ rowbn_bwd_coop_kernel(ReduceArgs a, T *__restrict__ dx) {
                         IO::unpack(gr[u], gv);
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) {
-                            const float dy = act_open(fmaf(xv[q], sc[q], sh[q]), a.act) ? gv[q] : 0.f;
+                            const float dy = act_open_t<ACT>(fmaf(xv[q], sc[q], sh[q])) ? gv[q] : 0.f;
                             s0[q] += dy;
                             s1[q] = fmaf(dy, xv[q], s1[q]);
                         }
@@ -456,7 +464,7 @@ rowbn_bwd_coop_kernel(ReduceArgs a, T *__restrict__ dx) {
                 ld_coef<VEC>(csc + c, vsc); ld_coef<VEC>(csh + c, vsh); ld_coef<VEC>(cA + c, vA); ld_coef<VEC>(cB + c, vB);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    const float dy = act_open(fmaf(xv[q], vsc[q], vsh[q]), a.act) ? gv[q] : 0.f;
+                    const float dy = act_open_t<ACT>(fmaf(xv[q], vsc[q], vsh[q])) ? gv[q] : 0.f;
                     o[q] = fmaf(dy, vsc[q], fmaf(vB[q], xv[q], vA[q]));
                 }
                 IO::store(dx + rr * a.C + c, o);
@@ -469,8 +477,10 @@ template <typename T, int VEC>
 static int launch_bwd_coop(ReduceArgs a, void *dx, int blocks, size_t smem, cudaStream_t st) {
     T *dxp = reinterpret_cast<T *>(dx);
     void *args[] = {&a, &dxp};
-    KDF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&rowbn_bwd_coop_kernel<T, VEC>), dim3(blocks), dim3(RB_THREADS),
-                                         args, smem, st));
+    const void *fn = a.act == 1 ? reinterpret_cast<const void *>(&rowbn_bwd_coop_kernel<T, VEC, 1>)
+                   : a.act == 2 ? reinterpret_cast<const void *>(&rowbn_bwd_coop_kernel<T, VEC, 2>)
+                                : reinterpret_cast<const void *>(&rowbn_bwd_coop_kernel<T, VEC, 0>);
+    KDF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(RB_THREADS), args, smem, st));
     return KDF_OK;
 }
 
