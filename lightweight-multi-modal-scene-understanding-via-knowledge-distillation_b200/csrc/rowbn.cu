@@ -247,11 +247,17 @@ rowbn_reduce_kernel(ReduceArgs a) {
     }
 }
 
-// y = act(x*scale + shift) [+ residual]
-template <typename T, int VEC>
+// y = act(x*scale + shift) [+ residual]   (activation as a template parameter: no per-element selects of the other cases)
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float y) {
+    if (ACT == 1) return fmaxf(y, 0.f);
+    if (ACT == 2) return fminf(fmaxf(y, 0.f), 6.f);
+    return y;
+}
+template <typename T, int VEC, int ACT>
 __global__ void __launch_bounds__(RB_THREADS, (VEC == 8 ? 3 : 4))
 rowbn_apply_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, T *__restrict__ y, int64_t M, int C,
-                       const float *__restrict__ scale, const float *__restrict__ shift, int act) {
+                       const float *__restrict__ scale, const float *__restrict__ shift) {
     const RowMap m = row_map<VEC>(C);
     if (!m.active) return;
     const int c = m.g * VEC;
@@ -280,7 +286,7 @@ rowbn_apply_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, T *__
                 if (res) IO::unpack(rr_[u], rv);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    o[q] = act_fwd(fmaf(xv[q], sc[q], sh[q]), act);
+                    o[q] = act_fwd_t<ACT>(fmaf(xv[q], sc[q], sh[q]));
                     if (res) o[q] += rv[q];
                 }
                 IO::store(y + rr * C + c, o);
@@ -585,12 +591,16 @@ int kdf_rowbn_apply_fwd(const void *x, const void *residual, int dtype, int64_t 
     const int vec = rb_vec(dtype, C);
     const int blocks = rb_blocks(M, C, vec, 8);
     cudaStream_t st = as_stream(stream);
-    if (dtype == KDF_F32)
-        rowbn_apply_fwd_kernel<float, 4><<<blocks, RB_THREADS, 0, st>>>((const float *)x, (const float *)residual, (float *)y, M, C, scale, shift, act);
-    else if (vec == 8)
-        rowbn_apply_fwd_kernel<__nv_bfloat16, 8><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)residual, (__nv_bfloat16 *)y, M, C, scale, shift, act);
-    else
-        rowbn_apply_fwd_kernel<__nv_bfloat16, 4><<<blocks, RB_THREADS, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)residual, (__nv_bfloat16 *)y, M, C, scale, shift, act);
+#define KDF_RB_APPLY(T, V)                                                                                                      \
+    do {                                                                                                                        \
+        if (act == 1) rowbn_apply_fwd_kernel<T, V, 1><<<blocks, RB_THREADS, 0, st>>>((const T *)x, (const T *)residual, (T *)y, M, C, scale, shift);      \
+        else if (act == 2) rowbn_apply_fwd_kernel<T, V, 2><<<blocks, RB_THREADS, 0, st>>>((const T *)x, (const T *)residual, (T *)y, M, C, scale, shift); \
+        else rowbn_apply_fwd_kernel<T, V, 0><<<blocks, RB_THREADS, 0, st>>>((const T *)x, (const T *)residual, (T *)y, M, C, scale, shift);               \
+    } while (0)
+    if (dtype == KDF_F32) KDF_RB_APPLY(float, 4);
+    else if (vec == 8) KDF_RB_APPLY(__nv_bfloat16, 8);
+    else KDF_RB_APPLY(__nv_bfloat16, 4);
+#undef KDF_RB_APPLY
     KDF_LAUNCH_CHECK();
     return KDF_OK;
 }
