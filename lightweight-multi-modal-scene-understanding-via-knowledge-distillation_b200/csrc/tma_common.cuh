@@ -33,11 +33,6 @@ __device__ __forceinline__ void load_4d(void *smem_dst, const CUtensorMap *tmap,
         ::"r"(tc::smem_u32(smem_dst)), "l"(tmap), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-// the same box DRAM -> L2 only (no shared memory, no barrier): issued well ahead of the load that will want it
-__device__ __forceinline__ void prefetch_2d(const CUtensorMap *tmap, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
