@@ -278,3 +278,18 @@ def test_eval_caches_follow_the_parameter_generation():
     g0 = native._generation
     native.bump_batch_counter(nn.BatchNorm2d(4))
     assert native._generation == g0 + 1
+
+
+def test_activation_commutes_with_bf16_rounding():
+    """The kernels take ReLU / ReLU6 AFTER the conversion to bf16, on the packed pair (`max/min.bf16x2`), where the layer-by-
+    layer form clamps in fp32 and then rounds.  Both agree exactly because 0 and 6 are bf16 numbers and round-to-nearest-even is
+    monotonic: clamp(round(x)) == round(clamp(x)) for every fp32 x (checked on a dense sample around the thresholds, the
+    rounding boundaries next to them, and random values)."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    near = torch.cat([torch.linspace(-1e-2, 1e-2, 20001), 6 + torch.linspace(-5e-2, 5e-2, 20001),
+                      torch.randn(200000, generator=g) * 4, torch.tensor([0.0, -0.0, 6.0, 5.984375, 6.03125, float("inf"), -float("inf")])])
+    for lo, hi in ((0.0, float("inf")), (0.0, 6.0)):
+        a = near.clamp(lo, hi).to(torch.bfloat16)
+        b = near.to(torch.bfloat16).clamp(lo, hi)
+        assert torch.equal(a.float(), b.float())                     # (value equality: +0 and -0 are the same activation)
